@@ -1,0 +1,143 @@
+/* slip_b200_device.h -- thin C ABI between the C host code (slip_lu_b200/csrc/host) and the
+ * CUDA kernels for sm_100a (slip_lu_b200/csrc/cuda/slipcu.cu).
+ *
+ * Plain pointers and sizes only.  Big integers cross this boundary as sign + little-endian
+ * 32-bit limb strings (two of them make one GMP limb on x86-64).  Everything behind it runs
+ * on the GPU in a residue number system (31-bit prime channels, Montgomery form) plus
+ * positional 32-bit-limb reconstruction; see DESIGN.md.
+ *
+ * Each entry point names the reference routine whose work it takes over.
+ */
+#ifndef SLIP_B200_DEVICE_H
+#define SLIP_B200_DEVICE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SLIPCU_OK            0
+#define SLIPCU_OUT_OF_MEMORY (-1)
+#define SLIPCU_SINGULAR      (-2)
+#define SLIPCU_BAD_INPUT     (-3)
+#define SLIPCU_CUDA_ERROR    (-10)   /* no device, launch failure, ...: the caller must fail loudly */
+#define SLIPCU_BAD_PRIME     (-11)   /* a pivot vanished modulo a channel prime: retire it and retry */
+
+typedef struct slipcu_factor slipcu_factor;     /* one factorization; keeps L, U, rho resident in HBM */
+
+/* result of the exact pivot scan of one column (slip_get_pivot.c:46-150 and the three
+ * slip_get_*_pivot.c scans).  Slots index the column's pattern (sorted by row position). */
+typedef struct
+{
+    int32_t best_slot;      /* extreme (smallest / largest / first nonzero) eligible entry, -1: none */
+    int32_t best_sign;      /* sign of that entry */
+    int32_t diag_eligible;  /* 1 if the diagonal candidate is in the L part and nonzero */
+    int32_t diag_vs_best;   /* cmp(|diag|, |best|): -1, 0, +1 (valid if diag_eligible) */
+    int32_t bad_channel;    /* 0, or 1 + index of a channel whose prime divides an earlier pivot */
+    int32_t reserved[3];
+} slipcu_pivot_info;
+
+/* receives column k of the factorization as positional integers.  `limbs` holds `cnt` rows of
+ * `stride` 32-bit limbs (|value|, little endian, zero padded, stride even); nlimbs32[e] is the
+ * number of significant 32-bit limbs, sign[e] in {-1,0,1}.  The pointers are only valid during
+ * the call. */
+typedef int (*slipcu_column_sink) (void *user, int k, int cnt, int stride,
+                                   const uint32_t *limbs, const int32_t *nlimbs32, const int8_t *sign);
+
+const char *slipcu_last_error (void);
+int  slipcu_device_count (void);
+/* set the CUDA device used by this thread's subsequent calls (multi-GPU sharding, one rank per GPU) */
+int  slipcu_set_device (int device);
+
+/* -- factorization session -------------------------------------------------------------------
+ * slipcu_factor_begin: uploads A (CSC; values as limb strings) and reduces it into `channels`
+ *   residue channels.  Takes over the workspace set-up of SLIP_LU_factorize.c:60-189.
+ *   Avalue_off has nz+1 entries: limbs of entry a are Alimbs[Avalue_off[a] .. Avalue_off[a+1]). */
+int slipcu_factor_begin (slipcu_factor **F, int n, int nz, const int32_t *Ap, const int32_t *Ai,
+                         const uint32_t *Alimbs, const int64_t *Avalue_off, const int8_t *Asign,
+                         int channels, int keep_positional);
+/* keep_positional = 1: every entry of L and U is reconstructed as a positional integer and kept
+ *   for slipcu_factor_download (SLIP_LU_factorize).  0: only what the pivot scan needs is
+ *   reconstructed (SLIP_solve_*: the factors never leave the GPU). */
+
+/* slipcu_factor_column: the sparse REF triangular solve of column k (slip_REF_triangular_solve.c:
+ *   84-262) on the pattern computed by the host, followed by exact reconstruction of the column and
+ *   the exact nonzero/magnitude pivot scan (slip_get_pivot.c).
+ *   rows[0..cnt): pattern, original row indices, sorted by current position; the first nU are
+ *   already pivotal and upos[u] is the pivot position of rows[u].  recon_channels: number of
+ *   channels that bound the column's entries.  scheme: SLIP_pivot code.  diag_slot: slot of row
+ *   `col` in the pattern if it is a candidate, else -1.  Blocks until the scan result is back. */
+int slipcu_factor_column (slipcu_factor *F, int k, int col, int cnt, int nU,
+                          const int32_t *rows, const int32_t *upos, int recon_channels,
+                          int scheme, int diag_slot, slipcu_pivot_info *info);
+
+/* one reconstructed entry of the current column (used only for the rational tolerance test of
+ * SLIP_TOL_SMALLEST / SLIP_TOL_LARGEST, slip_get_pivot.c:94-143).  limbs must hold stride words. */
+int slipcu_factor_fetch_entry (slipcu_factor *F, int k, int slot, uint32_t *limbs,
+                               int32_t *nlimbs32, int8_t *sign);
+int slipcu_factor_column_stride (slipcu_factor *F, int k);
+
+/* commits the pivot of column k: rho_k, its modular inverses, the L column descriptor
+ * (slip_get_pivot.c:152-175). */
+int slipcu_factor_set_pivot (slipcu_factor *F, int k, int slot);
+
+/* streams every column of the finished factorization to the host (SLIP_LU_factorize.c:224-262,
+ * where the reference copies x into L and U). */
+int slipcu_factor_download (slipcu_factor *F, slipcu_column_sink sink, void *user);
+
+/* slipcu_factor_upload: a resident session built from factors held by the host (SLIP_LU_solve on
+ *   L, U that are not resident, or whose right-hand side needs more channels).  Column k has
+ *   colcnt[k] entries in slot order: colnU[k] entries of U(:,k) above the diagonal, then the
+ *   entries of L(:,k) (the diagonal, slot colpiv[k], is among them); rows[] are FINAL positions;
+ *   values are limb strings like A. */
+int slipcu_factor_upload (slipcu_factor **F, int n, int channels, const int32_t *colcnt,
+                          const int32_t *colnU, const int32_t *colpiv, const int32_t *rows,
+                          const uint32_t *limbs, const int64_t *value_off, const int8_t *sign);
+
+/* -- solve ------------------------------------------------------------------------------------
+ * slipcu_solve: exact forward substitution, scaling by det and back substitution
+ *   (SLIP_LU_solve.c:74-91, slip_forward_sub.c, slip_array_mul.c, slip_back_sub.c) for nrhs
+ *   right-hand sides against the resident factors.  b is row-major n x nrhs in ORIGINAL row
+ *   order; pinv is the final inverse row permutation.  The sink receives one "column" per
+ *   right-hand side: cnt = n entries in factor (position) order holding det * x_i, the numerators
+ *   of slip_array_div.c. */
+int slipcu_solve (slipcu_factor *F, int nrhs, const uint32_t *blimbs, const int64_t *bvalue_off,
+                  const int8_t *bsign, const int32_t *pinv, int recon_channels,
+                  slipcu_column_sink sink, void *user, int32_t *top_digit_max);
+/* top_digit_max (may be NULL): receives the highest mixed-radix digit index any result uses, so a
+ * caller that only has an ESTIMATE of the result size can verify that the top channels stayed
+ * empty (and retry with more channels otherwise). */
+
+/* channels available in the session (>= the count passed to begin, rounded up) */
+int  slipcu_factor_channels (const slipcu_factor *F);
+/* log2 of the product of the first `count` channel primes, rounded down (for sizing) */
+double slipcu_channel_bits (int count);
+void slipcu_factor_free (slipcu_factor *F);
+
+/* after SLIPCU_BAD_PRIME: which channel (index into the prime list) failed; then retire it so
+ * that the next session does not use it */
+int  slipcu_factor_bad_channel (slipcu_factor *F, int *channel);
+int  slipcu_retire_channel (int channel);
+
+/* counters for bench.py: kernels launched by this library since process start, and the
+ * accumulated device time (ms, CUDA events) and algorithmic bytes of the triangular-solve kernel */
+typedef struct
+{
+    uint64_t launches;            /* all kernels */
+    uint64_t trisolve_launches;
+    double   trisolve_ms;         /* only accumulated while profiling is enabled */
+    double   trisolve_bytes;      /* algorithmic bytes: L entries streamed + column written */
+    double   trisolve_modmul;     /* 32-bit limb (modular) multiplies: 4 per entry update */
+    double   recon_ms;            /* garner + to_limbs */
+    double   recon_mac;           /* 32x32 multiply-accumulates in reconstruction */
+} slipcu_counters;
+void slipcu_get_counters (slipcu_counters *out);
+void slipcu_reset_counters (void);
+void slipcu_set_profiling (int enabled);   /* 1: bracket kernels with CUDA events (adds syncs) */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,1357 @@
+// slipcu.cu -- CUDA kernels (sm_100a) and the thin C ABI of include/slip_b200_device.h.
+//
+// Exact sparse left-looking REF LU on the GPU.  Every integer of the factorization lives in HBM
+// as its residues modulo S 31-bit primes ("channels", Montgomery form, channel-blocked layout);
+// the REF update  x_i <- (rho_j * x_i - l_ij * x_j) / rho_{j-1}  becomes one fused
+// multiply-add-reduce per channel, the exact division being a multiplication by the inverse of
+// the previous pivot.  Exact values (for the pivot scan and for the mpz_t output of the C
+// interface) are reconstructed per column with a mixed-radix (Garner) pass and a positional
+// 32-bit-limb carry-chain pass.  See DESIGN.md for layout, bounds and rooflines.
+//
+// Reference routines replaced (cjh10644/SLIP_LU):
+//   k_trisolve        slip_REF_triangular_solve.c:84-262, slip_forward_sub.c:64-155
+//   k_backsub         slip_array_mul.c, slip_back_sub.c:30-56
+//   k_garner,k_limbs  (GMP keeps values positional; here reconstruction is explicit)
+//   k_pivot_scan      slip_get_pivot.c:46-150, slip_get_{smallest,largest,nonzero}_pivot.c
+//   k_pivot_commit    slip_get_pivot.c:152-175
+//   k_residues        slip_get_column.c (input side)
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <atomic>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "slip_b200_device.h"
+
+typedef unsigned long long u64;
+typedef uint32_t u32;
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail (int code, const char *what, const char *detail)
+{
+    g_err = std::string (what) + ": " + (detail ? detail : "");
+    return code;
+}
+#define CU(call)                                                                          \
+    do { cudaError_t e_ = (call); if (e_ != cudaSuccess)                                  \
+         return fail (e_ == cudaErrorMemoryAllocation ? SLIPCU_OUT_OF_MEMORY : SLIPCU_CUDA_ERROR, \
+                      #call, cudaGetErrorString (e_)); } while (0)
+
+extern "C" const char *slipcu_last_error (void) { return g_err.c_str (); }
+
+static std::atomic<uint64_t> g_launches{0}, g_tri_launches{0};
+static double g_tri_ms = 0, g_tri_bytes = 0, g_tri_modmul = 0, g_recon_ms = 0, g_recon_mac = 0;
+static int g_profiling = 0;
+
+// ------------------------------------------------------------------------------------------------
+// Montgomery arithmetic modulo a prime p < 2^31, R = 2^32
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ u32 mont_redc (u64 T, u32 p, u32 ninv)
+{   // requires T < p * 2^32; returns T / R mod p in [0, p)
+    u32 m = (u32) T * ninv;
+    u64 t = T + (u64) m * p;
+    u32 r = (u32) (t >> 32);
+    return r >= p ? r - p : r;
+}
+__host__ __device__ __forceinline__ u32 mont_mul (u32 a, u32 b, u32 p, u32 ninv)
+{
+    return mont_redc ((u64) a * b, p, ninv);
+}
+__host__ __device__ __forceinline__ u32 mont_pow (u32 a_m, u32 e, u32 one_m, u32 p, u32 ninv)
+{
+    u32 r = one_m;
+    while (e) { if (e & 1) r = mont_mul (r, a_m, p, ninv); a_m = mont_mul (a_m, a_m, p, ninv); e >>= 1; }
+    return r;
+}
+__host__ __device__ __forceinline__ u32 reduce_word (u32 w, u32 p)
+{   // w < 2^32 < 4p  (p > 2^30)
+    if (w >= p) w -= p;
+    if (w >= p) w -= p;
+    if (w >= p) w -= p;
+    return w;
+}
+// 64-bit lazy accumulator for sums of products of 31-bit factors.  Invariant: T < 2^63.
+__device__ __forceinline__ void lazy_mac (u64 &T, u32 a, u32 b, u32 p)
+{
+    T += (u64) a * b;                       // < 2^63 + 2^62
+    if (T >> 63) T -= ((u64) p << 32);      // p * 2^32 >= 2^62, keeps T < 2^63 and T mod p
+}
+__device__ __forceinline__ u32 lazy_redc (u64 T, u32 p, u32 ninv)
+{
+    u32 hi = reduce_word ((u32) (T >> 32), p);
+    return mont_redc (((u64) hi << 32) | (u32) T, p, ninv);
+}
+
+// ------------------------------------------------------------------------------------------------
+// channel primes and reconstruction tables (shared by all sessions, immutable once built)
+// ------------------------------------------------------------------------------------------------
+struct Tables
+{
+    int S = 0;                 // channels covered
+    std::vector<u32> hp;       // host copy of the primes
+    std::vector<double> cumbits;   // cumbits[c] = log2(p_0 ... p_{c-1})
+    u32 *p = nullptr, *ninv = nullptr, *r2 = nullptr, *one = nullptr;
+    u32 *C = nullptr;          // [S][S]  C[u][t] = (p_0..p_{u-1}) mod p_t, Montgomery form, u < t
+    u32 *invB = nullptr;       // [S]     (p_0..p_{t-1})^-1 mod p_t, Montgomery form
+    u32 *Bpos = nullptr;       // [S][LB] limbs of p_0..p_{t-1}
+    int LB = 0;
+    ~Tables ()
+    {
+        cudaFree (p); cudaFree (ninv); cudaFree (r2); cudaFree (one);
+        cudaFree (C); cudaFree (invB); cudaFree (Bpos);
+    }
+};
+
+static std::mutex g_tab_mutex;
+static std::vector<u32> g_primes;          // descending from 2^31 - 1, retired ones removed
+static u32 g_next_candidate = 0x7fffffffu;
+static std::shared_ptr<Tables> g_tables;
+
+static bool is_prime_u32 (u32 x)
+{
+    if (x < 2) return false;
+    if ((x & 1) == 0) return x == 2;
+    for (u32 d = 3; (u64) d * d <= x; d += 2) if (x % d == 0) return false;
+    return true;
+}
+static void extend_primes (size_t count)
+{
+    while (g_primes.size () < count)
+    {
+        while (!is_prime_u32 (g_next_candidate)) g_next_candidate -= 2;
+        g_primes.push_back (g_next_candidate);
+        g_next_candidate -= 2;
+    }
+}
+
+__global__ void k_build_tables (int S, const u32 *p, const u32 *ninv, const u32 *r2, const u32 *one,
+                                u32 *C, u32 *invB)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= S) return;
+    const u32 pt = p[t], ni = ninv[t], rr = r2[t];
+    u32 acc = one[t];
+    for (int u = 0; u < t; ++u)
+    {
+        C[(size_t) u * S + t] = acc;
+        u32 pu = mont_mul (reduce_word (p[u], pt), rr, pt, ni);
+        acc = mont_mul (acc, pu, pt, ni);
+    }
+    invB[t] = mont_pow (acc, pt - 2, one[t], pt, ni);
+}
+
+static int build_tables (int S, std::shared_ptr<Tables> &out)
+{
+    auto T = std::make_shared<Tables> ();
+    T->S = S;
+    extend_primes ((size_t) S);
+    T->hp.assign (g_primes.begin (), g_primes.begin () + S);
+    std::vector<u32> ninv (S), r2 (S), one (S);
+    T->cumbits.resize (S + 1);
+    T->cumbits[0] = 0.0;
+    for (int c = 0; c < S; ++c)
+    {
+        u32 p = T->hp[c];
+        u32 inv = 1;                          // Newton: inv = p^-1 mod 2^32
+        for (int it = 0; it < 5; ++it) inv *= 2u - p * inv;
+        ninv[c] = (u32) (0u - inv);
+        u64 r = ((u64) 1 << 32) % p;
+        one[c] = (u32) r;
+        r2[c] = (u32) ((r * r) % p);
+        T->cumbits[c + 1] = T->cumbits[c] + log2 ((double) p);
+    }
+    // prefix products as limb strings: row t = p_0 .. p_{t-1}  (t limbs at most)
+    T->LB = S + 1;
+    std::vector<u32> B ((size_t) S * T->LB, 0u);
+    {
+        std::vector<u32> cur (T->LB, 0u);
+        cur[0] = 1; int len = 1;
+        for (int t = 0; t < S; ++t)
+        {
+            memcpy (&B[(size_t) t * T->LB], cur.data (), (size_t) len * sizeof (u32));
+            u64 carry = 0;
+            for (int l = 0; l < len; ++l)
+            {
+                u64 v = (u64) cur[l] * T->hp[t] + carry;
+                cur[l] = (u32) v; carry = v >> 32;
+            }
+            if (carry) cur[len++] = (u32) carry;
+        }
+    }
+    CU (cudaMalloc (&T->p, S * sizeof (u32)));
+    CU (cudaMalloc (&T->ninv, S * sizeof (u32)));
+    CU (cudaMalloc (&T->r2, S * sizeof (u32)));
+    CU (cudaMalloc (&T->one, S * sizeof (u32)));
+    CU (cudaMalloc (&T->invB, S * sizeof (u32)));
+    CU (cudaMalloc (&T->C, (size_t) S * S * sizeof (u32)));
+    CU (cudaMalloc (&T->Bpos, (size_t) S * T->LB * sizeof (u32)));
+    CU (cudaMemcpy (T->p, T->hp.data (), S * sizeof (u32), cudaMemcpyHostToDevice));
+    CU (cudaMemcpy (T->ninv, ninv.data (), S * sizeof (u32), cudaMemcpyHostToDevice));
+    CU (cudaMemcpy (T->r2, r2.data (), S * sizeof (u32), cudaMemcpyHostToDevice));
+    CU (cudaMemcpy (T->one, one.data (), S * sizeof (u32), cudaMemcpyHostToDevice));
+    CU (cudaMemcpy (T->Bpos, B.data (), B.size () * sizeof (u32), cudaMemcpyHostToDevice));
+    CU (cudaMemset (T->C, 0, (size_t) S * S * sizeof (u32)));
+    k_build_tables<<<(S + 127) / 128, 128>>> (S, T->p, T->ninv, T->r2, T->one, T->C, T->invB);
+    g_launches++;
+    CU (cudaGetLastError ());
+    CU (cudaDeviceSynchronize ());
+    out = T;
+    return SLIPCU_OK;
+}
+
+static int get_tables (int S, std::shared_ptr<Tables> &out)
+{
+    std::lock_guard<std::mutex> lk (g_tab_mutex);
+    if (g_tables && g_tables->S >= S) { out = g_tables; return SLIPCU_OK; }
+    int want = S;
+    if (g_tables) want = std::max (S, g_tables->S + g_tables->S / 4);
+    want = (want + 31) & ~31;
+    std::shared_ptr<Tables> T;
+    int rc = build_tables (want, T);
+    if (rc) return rc;
+    g_tables = T; out = T;
+    return SLIPCU_OK;
+}
+
+extern "C" double slipcu_channel_bits (int count)
+{
+    std::lock_guard<std::mutex> lk (g_tab_mutex);
+    extend_primes ((size_t) std::max (count, 0));
+    double b = 0;
+    for (int c = 0; c < count; ++c) b += log2 ((double) g_primes[c]);
+    return b;
+}
+
+extern "C" int slipcu_retire_channel (int channel)
+{
+    std::lock_guard<std::mutex> lk (g_tab_mutex);
+    if (channel < 0 || (size_t) channel >= g_primes.size ()) return SLIPCU_BAD_INPUT;
+    g_primes.erase (g_primes.begin () + channel);
+    g_tables.reset ();          // live sessions keep their own reference
+    return SLIPCU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device memory arena (bump allocation in large chunks; columns never straddle a chunk)
+// ------------------------------------------------------------------------------------------------
+struct Arena
+{
+    std::vector<std::pair<char *, size_t>> chunks;     // base, bytes
+    size_t chunk_bytes; char *cur = nullptr; size_t left = 0; size_t total = 0;
+    explicit Arena (size_t cb) : chunk_bytes (cb) {}
+    void *alloc (size_t bytes)
+    {
+        bytes = (bytes + 255) & ~(size_t) 255;
+        if (bytes > left)
+        {
+            size_t cb = std::max (chunk_bytes, bytes);
+            char *ptr = nullptr;
+            if (cudaMalloc (&ptr, cb) != cudaSuccess) { cudaGetLastError (); return nullptr; }
+            chunks.push_back ({ptr, cb}); cur = ptr; left = cb; total += cb;
+        }
+        void *r = cur; cur += bytes; left -= bytes;
+        return r;
+    }
+    ~Arena () { for (auto &c : chunks) cudaFree (c.first); }
+};
+
+// ------------------------------------------------------------------------------------------------
+// session
+// ------------------------------------------------------------------------------------------------
+struct ColDesc            // one finished column, as the kernels see it
+{
+    const u32 *base;      // residues, [S/CH][cnt][CH]
+    const int32_t *rows;  // original row index of every slot
+    int32_t cnt;          // slots in the column (U part first, then L part)
+    int32_t nU;           // size of the U part (the pivot itself is an L-part slot)
+    int32_t pivslot;      // slot of the pivot
+    int32_t pad;
+};
+
+struct HostCol
+{
+    u32 *base = nullptr; int32_t *rows = nullptr; int cnt = 0, nU = 0, s = 0, stride = 0;
+    u32 *limbs = nullptr; int32_t *nl = nullptr; int8_t *sign = nullptr;
+};
+
+struct slipcu_factor
+{
+    int n = 0, nz = 0, S = 0, CH = 16, threads = 512, device = 0;
+    std::shared_ptr<Tables> tab;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev = nullptr, ev0 = nullptr, ev1 = nullptr;
+    int32_t *dAp = nullptr, *dAi = nullptr;
+    u32 *dA = nullptr;                       // residues of A, [S/CH][nz][CH]
+    u32 *rho = nullptr, *invrho = nullptr, *ratio = nullptr;    // [n][S]
+    ColDesc *desc = nullptr;                 // [n]
+    int32_t *pos = nullptr;                  // [n]
+    int32_t *bad = nullptr;                  // device flag
+    u32 *dig = nullptr; size_t dig_rows = 0; // [dig_rows][S] digit scratch
+    int32_t *topd = nullptr;                 // [dig_rows]
+    Arena resid, ints, limbs;
+    std::vector<HostCol> cols;
+    std::vector<int32_t> hAp;
+    int32_t *h_packet = nullptr;             // pinned staging for the per-column pattern
+    slipcu_pivot_info *h_info = nullptr;     // pinned
+    slipcu_pivot_info *d_info = nullptr;
+    size_t smem_limit = 0;
+    int keep_positional = 1, rows_are_positions = 0, x_global = 0, cur = -1;
+    u32 *tmp_limbs = nullptr; int32_t *tmp_nl = nullptr; int tmp_stride = 0;
+    slipcu_factor () : resid ((size_t) 512 << 20), ints ((size_t) 16 << 20), limbs ((size_t) 256 << 20) {}
+};
+
+// ------------------------------------------------------------------------------------------------
+// k_residues: positional limb strings -> Montgomery residues, channel-blocked
+//   out[(cb * count + e) * CH + ch]   e = entry, c = cb*CH + ch
+// ------------------------------------------------------------------------------------------------
+__global__ void k_residues (int count, int CH, const u32 *limbs, const int64_t *off, const int8_t *sign,
+                            const u32 *p, const u32 *ninv, const u32 *r2, u32 *out)
+{
+    const int per = blockDim.x / CH;
+    const int e = blockIdx.x * per + threadIdx.x / CH;
+    const int ch = threadIdx.x % CH;
+    const int cb = blockIdx.y;
+    if (e >= count) return;
+    const int c = cb * CH + ch;
+    const u32 pc = p[c], ni = ninv[c], rr = r2[c];
+    u32 r = 0;
+    for (int64_t l = off[e + 1] - 1; l >= off[e]; --l)
+    {
+        r = mont_mul (r, rr, pc, ni);                 // r * 2^32 mod p
+        r += reduce_word (limbs[l], pc);
+        if (r >= pc) r -= pc;
+    }
+    r = mont_mul (r, rr, pc, ni);                     // to Montgomery form
+    if (sign[e] < 0 && r) r = pc - r;
+    out[((size_t) cb * count + e) * CH + ch] = r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_trisolve: sparse REF triangular solve of one column (or of one dense right-hand side), one
+// CTA per block of CH channels, all channels independent.  Slots 0..nU-1 of the pattern are rows
+// that are already pivotal (sorted by pivot position upos[u]); slots nU..cnt-1 are candidate rows.
+// hist[] is the symbolic history vector of the reference; it is identical in every channel.
+// ------------------------------------------------------------------------------------------------
+struct TriArgs
+{
+    int k;                   // level the L part is brought to (column index; n for a rhs)
+    int S, cnt, nU;
+    const int32_t *rows;     // [cnt] original row of each slot
+    const int32_t *upos;     // [nU] pivot position of each U-part slot
+    // source vector to scatter: src_cnt entries, entry e at residue index src_first + e*src_step,
+    // going to the slot of row src_rows[e] (or row e when src_rows == nullptr)
+    const u32 *src; int src_total; int src_first, src_step, src_cnt; const int32_t *src_rows;
+    size_t src_y_stride;     // added to src_first per blockIdx.y (multiple right-hand sides)
+    u32 *out;                // [S/CH][cnt][CH] result region (+ blockIdx.y * out_y_stride words)
+    size_t out_y_stride;
+    const ColDesc *desc;
+    const u32 *rho, *invrho, *ratio, *p, *ninv;
+    int32_t *pos;            // [n] row -> slot
+    int x_in_smem;
+};
+
+template <int CH>
+__global__ void __launch_bounds__ (512) k_trisolve (TriArgs a)
+{
+    extern __shared__ __align__ (16) unsigned char smem_raw[];
+    int32_t *hist = (int32_t *) smem_raw;
+    u32 *xsm = (u32 *) (smem_raw + (((size_t) a.cnt * sizeof (int32_t) + 15) & ~(size_t) 15));
+
+    const int tid = threadIdx.x, ch = tid % CH, rg = tid / CH, RG = blockDim.x / CH;
+    const int cb = blockIdx.x, c = cb * CH + ch, S = a.S, cnt = a.cnt, nU = a.nU;
+    const u32 p = a.p[c], ni = a.ninv[c];
+    u32 *xg = a.out + (size_t) blockIdx.y * a.out_y_stride + (size_t) cb * cnt * CH;
+    u32 *xs = a.x_in_smem ? xsm : xg;
+
+    for (int t = rg; t < cnt; t += RG)
+    {
+        xs[t * CH + ch] = 0;
+        if (ch == 0) { hist[t] = -1; a.pos[a.rows[t]] = t; }
+    }
+    __syncthreads ();
+    {
+        const u32 *src = a.src + (size_t) cb * a.src_total * CH;
+        const int first = a.src_first + (int) (blockIdx.y * a.src_y_stride);
+        for (int e = rg; e < a.src_cnt; e += RG)
+        {
+            const int row = a.src_rows ? a.src_rows[e] : e;
+            xs[a.pos[row] * CH + ch] = src[((size_t) first + (size_t) e * a.src_step) * CH + ch];
+        }
+    }
+    __syncthreads ();
+
+    u32 pend_val = 0; int pend_slot = -1;
+    for (int u = 0; u < nU; ++u)
+    {
+        if (pend_slot >= 0) { xs[pend_slot * CH + ch] = pend_val; pend_slot = -1; }
+        const int j = a.upos[u];
+        const ColDesc d = a.desc[j];
+        u32 xj = xs[u * CH + ch];
+        const int hj = hist[u];
+        if (hj < j - 1)
+        {   // history update of the finished U entry: level hj+1 -> level j
+            xj = mont_mul (xj, a.rho[(size_t) (j - 1) * S + c], p, ni);
+            if (hj >= 0) xj = mont_mul (xj, a.invrho[(size_t) hj * S + c], p, ni);
+            if (rg == 0) { pend_slot = u; pend_val = xj; }
+        }
+        const u32 y = (j >= 1) ? mont_mul (xj, a.invrho[(size_t) (j - 1) * S + c], p, ni) : xj;
+        const u32 negy = y ? p - y : 0u;
+        const u32 rj = a.ratio[(size_t) j * S + c];
+        const u32 rhoj = a.rho[(size_t) j * S + c];
+        const u32 *Lb = d.base + (size_t) cb * d.cnt * CH;
+        const int len = d.cnt - d.nU;
+        const int iters = (len + RG - 1) / RG;
+#pragma unroll 2
+        for (int it = 0; it < iters; ++it)
+        {
+            const int m = d.nU + it * RG + rg;
+            const bool act = (m < d.cnt) && (m != d.pivslot);
+            int t = 0, h = 0;
+            if (act)
+            {
+                t = a.pos[d.rows[m]];
+                const u32 l = Lb[(size_t) m * CH + ch];
+                h = hist[t];
+                u32 f = rj;
+                if (h != j - 1)
+                {
+                    f = rhoj;
+                    if (h >= 0) f = mont_mul (f, a.invrho[(size_t) h * S + c], p, ni);
+                }
+                const u32 xv = xs[t * CH + ch];
+                xs[t * CH + ch] = mont_redc ((u64) xv * f + (u64) l * negy, p, ni);
+            }
+            __syncwarp ();
+            if (act && ch == 0) hist[t] = j;
+        }
+        __syncthreads ();
+    }
+    if (pend_slot >= 0) xs[pend_slot * CH + ch] = pend_val;
+    __syncthreads ();
+    // candidate rows: bring to level k; then publish the column
+    for (int t = rg; t < cnt; t += RG)
+    {
+        u32 v = xs[t * CH + ch];
+        if (t >= nU)
+        {
+            const int h = hist[t];
+            if (h < a.k - 1)
+            {
+                v = mont_mul (v, a.rho[(size_t) (a.k - 1) * S + c], p, ni);
+                if (h >= 0) v = mont_mul (v, a.invrho[(size_t) h * S + c], p, ni);
+            }
+        }
+        xg[t * CH + ch] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_backsub: z = det * y, then for j = n-1..0: z_j /= U_jj ; z_i -= U_ij * z_j  (slots = positions)
+// ------------------------------------------------------------------------------------------------
+struct BackArgs
+{
+    int n, S;
+    u32 *z; size_t z_y_stride;      // [S/CH][n][CH] per right-hand side
+    const ColDesc *desc; const u32 *rho, *invrho, *p, *ninv;
+    const int32_t *pos;             // row -> position (final pinv)
+};
+
+template <int CH>
+__global__ void __launch_bounds__ (512) k_backsub (BackArgs a)
+{
+    const int tid = threadIdx.x, ch = tid % CH, rg = tid / CH, RG = blockDim.x / CH;
+    const int cb = blockIdx.x, c = cb * CH + ch, S = a.S, n = a.n;
+    const u32 p = a.p[c], ni = a.ninv[c];
+    u32 *z = a.z + (size_t) blockIdx.y * a.z_y_stride + (size_t) cb * n * CH;
+    const u32 det = a.rho[(size_t) (n - 1) * S + c];
+    for (int t = rg; t < n; t += RG) z[t * CH + ch] = mont_mul (z[t * CH + ch], det, p, ni);
+    __syncthreads ();
+    u32 pend_val = 0; int pend_slot = -1;
+    for (int j = n - 1; j >= 0; --j)
+    {
+        if (pend_slot >= 0) { z[pend_slot * CH + ch] = pend_val; pend_slot = -1; }
+        const ColDesc d = a.desc[j];
+        const u32 zj = mont_mul (z[j * CH + ch], a.invrho[(size_t) j * S + c], p, ni);
+        if (rg == 0) { pend_slot = j; pend_val = zj; }
+        const u32 negz = zj ? p - zj : 0u;
+        const u32 *Ub = d.base + (size_t) cb * d.cnt * CH;
+        for (int m = rg; m < d.nU; m += RG)
+        {
+            const int t = a.pos[d.rows[m]];
+            const u32 uv = Ub[(size_t) m * CH + ch];
+            u32 zv = z[t * CH + ch] + mont_mul (uv, negz, p, ni);      // zv - uv * zj
+            if (zv >= p) zv -= p;
+            z[t * CH + ch] = zv;
+        }
+        __syncthreads ();
+    }
+    if (pend_slot >= 0) z[pend_slot * CH + ch] = pend_val;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_garner: residues -> mixed-radix digits of |x| (+ sign), one warp per entry.
+//   x mod M = d_0 + d_1 p_0 + d_2 p_0 p_1 + ...,   d_t = (x_t - sum_{u<t} d_u C[u][t]) / B_t mod p_t
+// ------------------------------------------------------------------------------------------------
+struct GarnerArgs
+{
+    int cnt;                    // entries per channel block in the region
+    int e0, ne;                 // entries e0 .. e0+ne-1 are reconstructed
+    int s, CH, S;
+    const u32 *base;            // [S/CH][cnt][CH]
+    u32 *dig; size_t dstride;   // digits out, row per entry
+    int32_t *topd;              // highest nonzero digit index of |x| (-1 for zero)
+    int8_t *sign;
+    const u32 *p, *ninv, *C, *invB;
+};
+
+__global__ void __launch_bounds__ (128) k_garner (GarnerArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= a.ne) return;
+    const int e = a.e0 + w;
+    const int s = a.s, S = a.S, CH = a.CH;
+    u32 *dg = a.dig + (size_t) e * a.dstride;
+    const unsigned full = 0xffffffffu;
+
+    for (int t0 = 0; t0 < s; t0 += 32)
+    {
+        const int t = t0 + lane;
+        const bool valid = t < s;
+        const int tt = valid ? t : s - 1;
+        const u32 p = a.p[tt], ni = a.ninv[tt];
+        const u32 vm = a.base[((size_t) (tt / CH) * a.cnt + e) * CH + (tt % CH)];
+        const u32 v = mont_redc (vm, p, ni);                 // plain residue
+        u64 T = 0;
+        const u32 *Ccol = a.C + tt;
+        for (int u = 0; u < t0; u += 4)
+        {
+            const uint4 d4 = *reinterpret_cast<const uint4 *> (dg + u);
+            const u32 c0 = Ccol[(size_t) (u + 0) * S], c1 = Ccol[(size_t) (u + 1) * S];
+            const u32 c2 = Ccol[(size_t) (u + 2) * S], c3 = Ccol[(size_t) (u + 3) * S];
+            lazy_mac (T, d4.x, c0, p); lazy_mac (T, d4.y, c1, p);
+            lazy_mac (T, d4.z, c2, p); lazy_mac (T, d4.w, c3, p);
+        }
+        u32 mine = 0;
+        for (int i = 0; i < 32; ++i)
+        {
+            u32 di = 0;
+            if (lane == i)
+            {
+                const u32 acc = lazy_redc (T, p, ni);
+                const u32 diff = v >= acc ? v - acc : v + p - acc;
+                di = mont_mul (diff, a.invB[tt], p, ni);
+                mine = di;
+            }
+            di = __shfl_sync (full, di, i);
+            if (lane > i && t0 + i < s) lazy_mac (T, di, Ccol[(size_t) (t0 + i) * S], p);
+        }
+        if (valid) dg[t] = mine;
+        __syncwarp ();
+    }
+    // sign: x is negative iff x mod M > (M-1)/2, whose digits are (p_t - 1)/2
+    bool neg = false;
+    for (int t0 = ((s - 1) / 32) * 32; t0 >= 0; t0 -= 32)
+    {
+        const int t = t0 + lane;
+        u32 d = 0, h = 0;
+        if (t < s) { d = dg[t]; h = (a.p[t] - 1) >> 1; }
+        const unsigned ne = __ballot_sync (full, d != h);
+        if (ne)
+        {
+            const int top = 31 - __clz (ne);
+            neg = __shfl_sync (full, (int) (d > h), top) != 0;
+            break;
+        }
+    }
+    if (neg)
+    {   // |x| = M - (x mod M): complement every digit, then add one
+        for (int t = lane; t < s; t += 32) dg[t] = a.p[t] - 1 - dg[t];
+        __syncwarp ();
+        if (lane == 0)
+        {
+            for (int t = 0; t < s; ++t)
+            {
+                u32 d = dg[t] + 1;
+                if (d == a.p[t]) dg[t] = 0; else { dg[t] = d; break; }
+            }
+        }
+        __syncwarp ();
+    }
+    int top = -1;
+    for (int t0 = ((s - 1) / 32) * 32; t0 >= 0; t0 -= 32)
+    {
+        const int t = t0 + lane;
+        const u32 d = (t < s) ? dg[t] : 0u;
+        const unsigned nzm = __ballot_sync (full, d != 0);
+        if (nzm) { top = t0 + 31 - __clz (nzm); break; }
+    }
+    // zero-pad the digit row up to the next multiple of 4 (vector loads in later passes)
+    for (int t = s + lane; t < ((s + 3) & ~3); t += 32) dg[t] = 0;
+    if (lane == 0) { a.topd[e] = top; a.sign[e] = top < 0 ? 0 : (neg ? -1 : 1); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_limbs: mixed-radix digits -> positional 32-bit limbs, one warp per entry.
+//   limb_l = sum_t d_t * B_t[l] accumulated in 96 bits per lane, then a carry chain across lanes.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mac96 (u32 &a0, u32 &a1, u32 &a2, u32 d, u32 b)
+{
+    asm ("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
+         "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+         "addc.u32 %2, %2, 0;"
+         : "+r"(a0), "+r"(a1), "+r"(a2) : "r"(d), "r"(b));
+}
+
+struct LimbArgs
+{
+    int e0, ne;                 // digit rows e0 .. e0+ne-1
+    int out0;                   // limb row of entry e0 (rows follow consecutively)
+    int stride, LB;
+    const u32 *dig; size_t dstride; const int32_t *topd;
+    const u32 *Bpos;
+    u32 *limbs; int32_t *nl;
+};
+
+__global__ void __launch_bounds__ (128) k_limbs (LimbArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= a.ne) return;
+    const int e = a.e0 + w;
+    const int eo = a.out0 + w;
+    const unsigned full = 0xffffffffu;
+    const int top = a.topd[e];
+    u32 *out = a.limbs + (size_t) eo * a.stride;
+    const u32 *dg = a.dig + (size_t) e * a.dstride;
+    if (top < 0)
+    {
+        for (int l = lane; l < a.stride; l += 32) out[l] = 0;
+        if (lane == 0) a.nl[eo] = 0;
+        return;
+    }
+    u32 in_a1 = 0, in_a2 = 0, in_b2 = 0;   // spill of the previous chunk: a1[31], a2[31], a2[30]
+    u32 carry_in = 0;
+    int nl = 0;
+    for (int l0 = 0; l0 < a.stride; l0 += 32)
+    {
+        const int l = l0 + lane;
+        const int lr = l < a.LB ? l : a.LB - 1;      // lanes past the row read a zero column
+        u32 a0 = 0, a1 = 0, a2 = 0;
+        // B_t has no limb l for t < l (p_i < 2^32); digits above `top` are zero
+        int t = l0 & ~3;
+        for (; t + 3 <= top; t += 4)
+        {
+            const uint4 d4 = *reinterpret_cast<const uint4 *> (dg + t);
+            const u32 *Bp = a.Bpos + (size_t) t * a.LB + lr;
+            mac96 (a0, a1, a2, d4.x, Bp[0]);
+            mac96 (a0, a1, a2, d4.y, Bp[a.LB]);
+            mac96 (a0, a1, a2, d4.z, Bp[2 * (size_t) a.LB]);
+            mac96 (a0, a1, a2, d4.w, Bp[3 * (size_t) a.LB]);
+        }
+        for (; t <= top; ++t) mac96 (a0, a1, a2, dg[t], a.Bpos[(size_t) t * a.LB + lr]);
+        // column sum for limb l: a0[l] + a1[l-1] + a2[l-2]
+        u32 p1 = __shfl_up_sync (full, a1, 1), p2 = __shfl_up_sync (full, a2, 2);
+        if (lane == 0) { p1 = in_a1; p2 = in_b2; }
+        if (lane == 1) { p2 = in_a2; }
+        const u64 sum = (u64) a0 + p1 + p2;
+        // carries are < 4: iterate the ripple until it settles
+        u32 cin = (lane == 0) ? carry_in : 0u, cout;
+        for (;;)
+        {
+            cout = (u32) ((sum + cin) >> 32);
+            u32 nin = __shfl_up_sync (full, cout, 1);
+            if (lane == 0) nin = carry_in;
+            const bool changed = nin != cin;
+            cin = nin;
+            if (!__any_sync (full, changed)) break;
+        }
+        const u32 limb = (u32) (sum + cin);
+        cout = (u32) ((sum + cin) >> 32);
+        if (l < a.stride) out[l] = limb;
+        const unsigned nzm = __ballot_sync (full, limb != 0 && l < a.stride);
+        if (nzm) nl = l0 + 32 - __clz (nzm);
+        carry_in = __shfl_sync (full, cout, 31);
+        in_a1 = __shfl_sync (full, a1, 31);
+        in_a2 = __shfl_sync (full, a2, 31);
+        in_b2 = __shfl_sync (full, a2, 30);
+    }
+    if (lane == 0) a.nl[eo] = nl;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_pivot_scan: exact nonzero / magnitude scan over the candidate slots (nU..cnt-1)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int cmp_mag (const u32 *dig, size_t ds, const int32_t *topd, int e1, int e2)
+{
+    const int t1 = topd[e1], t2 = topd[e2];
+    if (t1 != t2) return t1 < t2 ? -1 : 1;
+    for (int t = t1; t >= 0; --t)
+    {
+        const u32 d1 = dig[(size_t) e1 * ds + t], d2 = dig[(size_t) e2 * ds + t];
+        if (d1 != d2) return d1 < d2 ? -1 : 1;
+    }
+    return 0;
+}
+// mode: 0 smallest, 1 largest, 2 first nonzero.  Ties go to the earlier slot.
+__device__ __forceinline__ int better (const u32 *dig, size_t ds, const int32_t *topd, int mode, int x, int y)
+{
+    if (x < 0) return y;
+    if (y < 0) return x;
+    if (mode == 2) return x < y ? x : y;
+    int c = cmp_mag (dig, ds, topd, x, y);
+    if (mode == 1) c = -c;
+    if (c < 0) return x;
+    if (c > 0) return y;
+    return x < y ? x : y;
+}
+
+__global__ void __launch_bounds__ (256) k_pivot_scan (int cnt, int nU, int mode, int diag_slot,
+                                                       const u32 *dig, size_t ds, const int32_t *topd,
+                                                       const int8_t *sign, const int32_t *bad,
+                                                       slipcu_pivot_info *info)
+{
+    __shared__ int sbest[256];
+    int best = -1;
+    for (int e = nU + threadIdx.x; e < cnt; e += blockDim.x)
+        if (topd[e] >= 0) best = better (dig, ds, topd, mode, best, e);
+    sbest[threadIdx.x] = best;
+    __syncthreads ();
+    for (int w = blockDim.x >> 1; w > 0; w >>= 1)
+    {
+        if ((int) threadIdx.x < w)
+            sbest[threadIdx.x] = better (dig, ds, topd, mode, sbest[threadIdx.x], sbest[threadIdx.x + w]);
+        __syncthreads ();
+    }
+    if (threadIdx.x == 0)
+    {
+        best = sbest[0];
+        info->best_slot = best;
+        info->best_sign = best >= 0 ? sign[best] : 0;
+        const int de = (diag_slot >= nU && diag_slot < cnt && topd[diag_slot] >= 0) ? 1 : 0;
+        info->diag_eligible = de;
+        info->diag_vs_best = (de && best >= 0) ? cmp_mag (dig, ds, topd, diag_slot, best) : 0;
+        info->bad_channel = *bad;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_pivot_commit: rho_k, rho_k^-1, rho_k / rho_{k-1} in every channel; column descriptor
+// ------------------------------------------------------------------------------------------------
+__global__ void k_pivot_commit (int k, int S, int CH, int slot, ColDesc d, ColDesc *desc,
+                                u32 *rho, u32 *invrho, u32 *ratio,
+                                const u32 *p, const u32 *ninv, const u32 *one, int32_t *bad)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0) { d.pivslot = slot; desc[k] = d; }
+    if (c >= S) return;
+    const u32 pc = p[c], ni = ninv[c];
+    const u32 v = d.base[((size_t) (c / CH) * d.cnt + slot) * CH + (c % CH)];
+    if (v == 0) atomicCAS (bad, 0, c + 1);
+    const u32 inv = mont_pow (v, pc - 2, one[c], pc, ni);
+    rho[(size_t) k * S + c] = v;
+    invrho[(size_t) k * S + c] = inv;
+    ratio[(size_t) k * S + c] = k >= 1 ? mont_mul (v, invrho[(size_t) (k - 1) * S + c], pc, ni) : v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side of the C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" int slipcu_device_count (void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount (&n) != cudaSuccess) { cudaGetLastError (); return 0; }
+    return n;
+}
+extern "C" int slipcu_set_device (int device)
+{
+    CU (cudaSetDevice (device));
+    return SLIPCU_OK;
+}
+
+static int env_int (const char *name, int dflt)
+{
+    const char *v = getenv (name);
+    return (v && *v) ? atoi (v) : dflt;
+}
+
+extern "C" void slipcu_factor_free (slipcu_factor *F)
+{
+    if (!F) return;
+    cudaSetDevice (F->device);
+    if (F->st) cudaStreamSynchronize (F->st);
+    cudaFree (F->dAp); cudaFree (F->dAi); cudaFree (F->dA);
+    cudaFree (F->rho); cudaFree (F->invrho); cudaFree (F->ratio);
+    cudaFree (F->desc); cudaFree (F->pos); cudaFree (F->bad);
+    cudaFree (F->dig); cudaFree (F->topd); cudaFree (F->d_info);
+    cudaFree (F->tmp_limbs); cudaFree (F->tmp_nl);
+    if (F->h_packet) cudaFreeHost (F->h_packet);
+    if (F->h_info) cudaFreeHost (F->h_info);
+    if (F->ev) cudaEventDestroy (F->ev);
+    if (F->ev0) cudaEventDestroy (F->ev0);
+    if (F->ev1) cudaEventDestroy (F->ev1);
+    if (F->st) cudaStreamDestroy (F->st);
+    delete F;
+}
+
+extern "C" int slipcu_factor_channels (const slipcu_factor *F) { return F ? F->S : 0; }
+
+static int ensure_digits (slipcu_factor *F, size_t rows)
+{
+    if (rows <= F->dig_rows) return SLIPCU_OK;
+    size_t want = std::max (rows, F->dig_rows * 2);
+    want = std::min<size_t> (std::max<size_t> (want, 64), std::max<size_t> (rows, (size_t) F->n));
+    CU (cudaStreamSynchronize (F->st));
+    cudaFree (F->dig); cudaFree (F->topd); F->dig = nullptr; F->topd = nullptr; F->dig_rows = 0;
+    CU (cudaMalloc (&F->dig, want * (size_t) (F->S + 4) * sizeof (u32)));
+    CU (cudaMalloc (&F->topd, want * sizeof (int32_t)));
+    F->dig_rows = want;
+    return SLIPCU_OK;
+}
+
+// everything a session needs apart from the input matrix
+static int session_common_init (slipcu_factor *F, int n, int channels)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount (&ndev) != cudaSuccess || ndev == 0)
+    {
+        cudaGetLastError ();
+        return fail (SLIPCU_CUDA_ERROR, "slip_lu_b200", "no CUDA device: this library has no CPU path");
+    }
+    CU (cudaGetDevice (&F->device));
+    F->n = n;
+    const int S = (channels + 31) & ~31;
+    int rc = get_tables (S, F->tab);
+    if (rc) return rc;
+    F->S = S;
+    // channel block width: aim for at least ~one CTA per SM
+    int sms = 148;
+    cudaDeviceGetAttribute (&sms, cudaDevAttrMultiProcessorCount, F->device);
+    int CH = 32;
+    if (S / 32 < sms) CH = 16;
+    if (S / 16 < sms) CH = 8;
+    CH = env_int ("SLIP_B200_CH", CH);
+    if (CH != 8 && CH != 16 && CH != 32) CH = 16;
+    F->CH = CH;
+    F->threads = env_int ("SLIP_B200_THREADS", CH == 8 ? 256 : 512);
+    if (F->threads % 32 || F->threads < 32 || F->threads > 512) F->threads = 256;
+    F->x_global = env_int ("SLIP_B200_X_GLOBAL", 0);
+    int smem_optin = 0;
+    cudaDeviceGetAttribute (&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, F->device);
+    F->smem_limit = (size_t) smem_optin;
+    CU (cudaFuncSetAttribute (k_trisolve<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
+    CU (cudaFuncSetAttribute (k_trisolve<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
+    CU (cudaFuncSetAttribute (k_trisolve<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
+
+    CU (cudaStreamCreateWithFlags (&F->st, cudaStreamNonBlocking));
+    CU (cudaEventCreateWithFlags (&F->ev, cudaEventDisableTiming));
+    CU (cudaEventCreate (&F->ev0)); CU (cudaEventCreate (&F->ev1));
+    CU (cudaMalloc (&F->rho, (size_t) n * S * sizeof (u32)));
+    CU (cudaMalloc (&F->invrho, (size_t) n * S * sizeof (u32)));
+    CU (cudaMalloc (&F->ratio, (size_t) n * S * sizeof (u32)));
+    CU (cudaMalloc (&F->desc, (size_t) n * sizeof (ColDesc)));
+    CU (cudaMalloc (&F->pos, (size_t) n * sizeof (int32_t)));
+    CU (cudaMalloc (&F->bad, sizeof (int32_t)));
+    CU (cudaMalloc (&F->d_info, sizeof (slipcu_pivot_info)));
+    CU (cudaMemset (F->bad, 0, sizeof (int32_t)));
+    CU (cudaMemset (F->pos, 0, (size_t) n * sizeof (int32_t)));
+    CU (cudaHostAlloc (&F->h_packet, (size_t) 2 * n * sizeof (int32_t), cudaHostAllocDefault));
+    CU (cudaHostAlloc (&F->h_info, sizeof (slipcu_pivot_info), cudaHostAllocDefault));
+    F->cols.resize (n);
+    return SLIPCU_OK;
+}
+
+extern "C" int slipcu_factor_begin (slipcu_factor **out, int n, int nz, const int32_t *Ap,
+                                    const int32_t *Ai, const u32 *Alimbs, const int64_t *Aoff,
+                                    const int8_t *Asign, int channels, int keep_positional)
+{
+    if (!out || n <= 0 || nz <= 0 || !Ap || !Ai || !Alimbs || !Aoff || !Asign || channels <= 0)
+        return fail (SLIPCU_BAD_INPUT, "slipcu_factor_begin", "bad argument");
+    slipcu_factor *F = new slipcu_factor ();
+    *out = F;
+    int rc = session_common_init (F, n, channels);
+    if (rc) return rc;
+    F->nz = nz;
+    F->keep_positional = keep_positional ? 1 : 0;
+    const int S = F->S, CH = F->CH;
+    CU (cudaMalloc (&F->dAp, (size_t) (n + 1) * sizeof (int32_t)));
+    CU (cudaMalloc (&F->dAi, (size_t) nz * sizeof (int32_t)));
+    CU (cudaMalloc (&F->dA, (size_t) nz * S * sizeof (u32)));
+    F->hAp.assign (Ap, Ap + n + 1);
+    CU (cudaMemcpy (F->dAp, Ap, (size_t) (n + 1) * sizeof (int32_t), cudaMemcpyHostToDevice));
+    CU (cudaMemcpy (F->dAi, Ai, (size_t) nz * sizeof (int32_t), cudaMemcpyHostToDevice));
+    // reduce A into the channels
+    {
+        u32 *dl = nullptr; int64_t *doff = nullptr; int8_t *dsg = nullptr;
+        const size_t nl = (size_t) Aoff[nz];
+        CU (cudaMalloc (&dl, std::max<size_t> (nl, 1) * sizeof (u32)));
+        CU (cudaMalloc (&doff, (size_t) (nz + 1) * sizeof (int64_t)));
+        CU (cudaMalloc (&dsg, (size_t) nz));
+        CU (cudaMemcpy (dl, Alimbs, nl * sizeof (u32), cudaMemcpyHostToDevice));
+        CU (cudaMemcpy (doff, Aoff, (size_t) (nz + 1) * sizeof (int64_t), cudaMemcpyHostToDevice));
+        CU (cudaMemcpy (dsg, Asign, (size_t) nz, cudaMemcpyHostToDevice));
+        const int per = 256 / CH;
+        dim3 grid ((nz + per - 1) / per, S / CH);
+        k_residues<<<grid, 256, 0, F->st>>> (nz, CH, dl, doff, dsg, F->tab->p, F->tab->ninv, F->tab->r2, F->dA);
+        g_launches++;
+        CU (cudaGetLastError ());
+        CU (cudaStreamSynchronize (F->st));
+        cudaFree (dl); cudaFree (doff); cudaFree (dsg);
+    }
+    return SLIPCU_OK;
+}
+
+template <int CH>
+static cudaError_t launch_tri (const TriArgs &a, dim3 grid, int threads, size_t smem, cudaStream_t st)
+{
+    k_trisolve<CH><<<grid, threads, smem, st>>> (a);
+    return cudaGetLastError ();
+}
+static cudaError_t launch_tri_any (int CH, const TriArgs &a, dim3 grid, int threads, size_t smem, cudaStream_t st)
+{
+    g_launches++; g_tri_launches++;
+    if (CH == 8) return launch_tri<8> (a, grid, threads, smem, st);
+    if (CH == 16) return launch_tri<16> (a, grid, threads, smem, st);
+    return launch_tri<32> (a, grid, threads, smem, st);
+}
+
+static int check_channels (slipcu_factor *F);
+
+// timing helper for the optional profiling mode
+struct ScopedTimer
+{
+    slipcu_factor *F; double *acc;
+    ScopedTimer (slipcu_factor *F_, double *acc_) : F (F_), acc (acc_)
+    {
+        if (g_profiling) cudaEventRecord (F->ev0, F->st);
+    }
+    ~ScopedTimer ()
+    {
+        if (!g_profiling) return;
+        cudaEventRecord (F->ev1, F->st);
+        cudaEventSynchronize (F->ev1);
+        float ms = 0; cudaEventElapsedTime (&ms, F->ev0, F->ev1);
+        *acc += ms;
+    }
+};
+
+// mixed-radix digits + sign of entries e0..e0+ne-1 of a residue region (digit row = entry index)
+static int run_garner (slipcu_factor *F, const u32 *base, int region_cnt, int e0, int ne, int s, int8_t *sign)
+{
+    if (ne <= 0) return SLIPCU_OK;
+    const Tables &T = *F->tab;
+    GarnerArgs g;
+    g.cnt = region_cnt; g.e0 = e0; g.ne = ne; g.s = s; g.CH = F->CH; g.S = T.S;
+    g.base = base; g.dig = F->dig; g.dstride = (size_t) F->S + 4; g.topd = F->topd; g.sign = sign;
+    g.p = T.p; g.ninv = T.ninv; g.C = T.C; g.invB = T.invB;
+    ScopedTimer tm (F, &g_recon_ms);
+    k_garner<<<(ne + 3) / 4, 128, 0, F->st>>> (g);
+    g_launches++;
+    CU (cudaGetLastError ());
+    g_recon_mac += (double) ne * ((double) s * s * 0.5);
+    return SLIPCU_OK;
+}
+
+// positional limbs of digit rows e0..e0+ne-1 into limb rows out0.. of (limbs, nl)
+static int run_limbs (slipcu_factor *F, int e0, int ne, int out0, int stride, int s, u32 *limbs, int32_t *nl)
+{
+    if (ne <= 0) return SLIPCU_OK;
+    const Tables &T = *F->tab;
+    LimbArgs l;
+    l.e0 = e0; l.ne = ne; l.out0 = out0; l.stride = stride; l.LB = T.LB;
+    l.dig = F->dig; l.dstride = (size_t) F->S + 4; l.topd = F->topd; l.Bpos = T.Bpos;
+    l.limbs = limbs; l.nl = nl;
+    ScopedTimer tm (F, &g_recon_ms);
+    k_limbs<<<(ne + 3) / 4, 128, 0, F->st>>> (l);
+    g_launches++;
+    CU (cudaGetLastError ());
+    g_recon_mac += (double) ne * ((double) s * s * 0.5);
+    return SLIPCU_OK;
+}
+
+static int alloc_column (slipcu_factor *F, HostCol &hc, int cnt, int s)
+{
+    hc.cnt = cnt; hc.s = s;
+    hc.stride = (s + 1) & ~1;
+    hc.base = (u32 *) F->resid.alloc ((size_t) cnt * F->S * sizeof (u32));
+    hc.sign = (int8_t *) F->ints.alloc ((size_t) cnt);
+    if (F->keep_positional)
+    {
+        hc.limbs = (u32 *) F->limbs.alloc ((size_t) cnt * hc.stride * sizeof (u32));
+        hc.nl = (int32_t *) F->ints.alloc ((size_t) cnt * sizeof (int32_t));
+    }
+    if (!hc.base || !hc.sign || (F->keep_positional && (!hc.limbs || !hc.nl)))
+        return fail (SLIPCU_OUT_OF_MEMORY, "alloc_column", "device memory exhausted");
+    return SLIPCU_OK;
+}
+
+extern "C" int slipcu_factor_column (slipcu_factor *F, int k, int col, int cnt, int nU,
+                                     const int32_t *rows, const int32_t *upos, int recon_channels,
+                                     int scheme, int diag_slot, slipcu_pivot_info *info)
+{
+    if (!F || k < 0 || k >= F->n || cnt <= 0 || cnt > F->n || nU < 0 || nU >= cnt || !rows || !info)
+        return fail (SLIPCU_BAD_INPUT, "slipcu_factor_column", "bad argument");
+    const Tables &T = *F->tab;
+    const int S = F->S, CH = F->CH;
+    int s = std::min (std::max (recon_channels, 1), S);
+    HostCol &hc = F->cols[k];
+    hc.nU = nU;
+    int rc = alloc_column (F, hc, cnt, s);
+    if (rc) return rc;
+    hc.rows = (int32_t *) F->ints.alloc ((size_t) (cnt + nU) * sizeof (int32_t));
+    if (!hc.rows) return fail (SLIPCU_OUT_OF_MEMORY, "slipcu_factor_column", "device memory exhausted");
+    rc = ensure_digits (F, (size_t) cnt);
+    if (rc) return rc;
+    memcpy (F->h_packet, rows, (size_t) cnt * sizeof (int32_t));
+    if (nU) memcpy (F->h_packet + cnt, upos, (size_t) nU * sizeof (int32_t));
+    CU (cudaMemcpyAsync (hc.rows, F->h_packet, (size_t) (cnt + nU) * sizeof (int32_t),
+                         cudaMemcpyHostToDevice, F->st));
+
+    TriArgs a;
+    a.k = k; a.S = S; a.cnt = cnt; a.nU = nU;
+    a.rows = hc.rows; a.upos = hc.rows + cnt;
+    a.src = F->dA; a.src_total = F->nz; a.src_first = F->hAp[col]; a.src_step = 1;
+    a.src_cnt = F->hAp[col + 1] - F->hAp[col]; a.src_rows = F->dAi + F->hAp[col];
+    a.src_y_stride = 0;
+    a.out = hc.base; a.out_y_stride = 0;
+    a.desc = F->desc; a.rho = F->rho; a.invrho = F->invrho; a.ratio = F->ratio;
+    a.p = T.p; a.ninv = T.ninv; a.pos = F->pos;
+    size_t smem = (((size_t) cnt * sizeof (int32_t) + 15) & ~(size_t) 15);
+    const size_t xbytes = (size_t) cnt * CH * sizeof (u32);
+    a.x_in_smem = (smem + xbytes + 1024 <= F->smem_limit) && !F->x_global;
+    if (a.x_in_smem) smem += xbytes;
+    if (smem > F->smem_limit) return fail (SLIPCU_BAD_INPUT, "slipcu_factor_column", "pattern too large for shared history");
+    {
+        ScopedTimer tm (F, &g_tri_ms);
+        CU (launch_tri_any (CH, a, dim3 (S / CH, 1), F->threads, smem, F->st));
+    }
+    {   // algorithmic work of this launch
+        double upd = 0;
+        for (int u = 0; u < nU; ++u) { const HostCol &lj = F->cols[upos[u]]; upd += (double) (lj.cnt - lj.nU - 1); }
+        g_tri_bytes += (upd + (double) cnt) * (double) S * 4.0;
+        g_tri_modmul += upd * (double) S * 4.0;
+    }
+    // exact values: candidates always (pivot scan); the U part only if the factors go to the host
+    const int e0 = F->keep_positional ? 0 : nU;
+    rc = run_garner (F, hc.base, cnt, e0, cnt - e0, s, hc.sign);
+    if (rc) return rc;
+    const int mode = (scheme == 2) ? 2 : ((scheme == 4 || scheme == 5) ? 1 : 0);
+    k_pivot_scan<<<1, 256, 0, F->st>>> (cnt, nU, mode, diag_slot, F->dig, (size_t) F->S + 4, F->topd,
+                                        hc.sign, F->bad, F->d_info);
+    g_launches++;
+    CU (cudaGetLastError ());
+    CU (cudaMemcpyAsync (F->h_info, F->d_info, sizeof (slipcu_pivot_info), cudaMemcpyDeviceToHost, F->st));
+    CU (cudaEventRecord (F->ev, F->st));
+    if (F->keep_positional)
+    {   // positional limbs of the whole column; overlaps the host's pivot decision
+        rc = run_limbs (F, 0, cnt, 0, hc.stride, s, hc.limbs, hc.nl);
+        if (rc) return rc;
+    }
+    CU (cudaEventSynchronize (F->ev));
+    *info = *F->h_info;
+    F->cur = k;
+    if (info->bad_channel) return fail (SLIPCU_BAD_PRIME, "slipcu_factor_column", "channel prime divides a pivot");
+    return SLIPCU_OK;
+}
+
+extern "C" int slipcu_factor_column_stride (slipcu_factor *F, int k)
+{
+    return (F && k >= 0 && k < F->n) ? F->cols[k].stride : 0;
+}
+
+extern "C" int slipcu_factor_fetch_entry (slipcu_factor *F, int k, int slot, u32 *limbs,
+                                          int32_t *nlimbs32, int8_t *sign)
+{
+    if (!F || k < 0 || k >= F->n) return fail (SLIPCU_BAD_INPUT, "slipcu_factor_fetch_entry", "bad column");
+    HostCol &hc = F->cols[k];
+    if (slot < 0 || slot >= hc.cnt) return fail (SLIPCU_BAD_INPUT, "slipcu_factor_fetch_entry", "bad slot");
+    if (F->keep_positional)
+    {
+        CU (cudaMemcpyAsync (limbs, hc.limbs + (size_t) slot * hc.stride, (size_t) hc.stride * sizeof (u32),
+                             cudaMemcpyDeviceToHost, F->st));
+        CU (cudaMemcpyAsync (nlimbs32, hc.nl + slot, sizeof (int32_t), cudaMemcpyDeviceToHost, F->st));
+    }
+    else
+    {   // digits of the current column are still in the scratch: convert this one entry on demand
+        if (k != F->cur || slot < hc.nU)
+            return fail (SLIPCU_BAD_INPUT, "slipcu_factor_fetch_entry", "entry no longer reconstructible");
+        if (!F->tmp_limbs || F->tmp_stride < hc.stride)
+        {
+            cudaFree (F->tmp_limbs); cudaFree (F->tmp_nl); F->tmp_limbs = nullptr; F->tmp_nl = nullptr;
+            CU (cudaMalloc (&F->tmp_limbs, (size_t) (F->S + 2) * sizeof (u32)));
+            CU (cudaMalloc (&F->tmp_nl, sizeof (int32_t)));
+            F->tmp_stride = F->S + 2;
+        }
+        int rc = run_limbs (F, slot, 1, 0, hc.stride, hc.s, F->tmp_limbs, F->tmp_nl);
+        if (rc) return rc;
+        CU (cudaMemcpyAsync (limbs, F->tmp_limbs, (size_t) hc.stride * sizeof (u32), cudaMemcpyDeviceToHost, F->st));
+        CU (cudaMemcpyAsync (nlimbs32, F->tmp_nl, sizeof (int32_t), cudaMemcpyDeviceToHost, F->st));
+    }
+    CU (cudaMemcpyAsync (sign, hc.sign + slot, 1, cudaMemcpyDeviceToHost, F->st));
+    CU (cudaStreamSynchronize (F->st));
+    return SLIPCU_OK;
+}
+
+extern "C" int slipcu_factor_set_pivot (slipcu_factor *F, int k, int slot)
+{
+    if (!F || k < 0 || k >= F->n) return fail (SLIPCU_BAD_INPUT, "slipcu_factor_set_pivot", "bad column");
+    HostCol &hc = F->cols[k];
+    if (slot < hc.nU || slot >= hc.cnt) return fail (SLIPCU_BAD_INPUT, "slipcu_factor_set_pivot", "bad slot");
+    const Tables &T = *F->tab;
+    ColDesc d;
+    d.base = hc.base; d.rows = hc.rows; d.cnt = hc.cnt; d.nU = hc.nU; d.pivslot = slot; d.pad = 0;
+    k_pivot_commit<<<(F->S + 255) / 256, 256, 0, F->st>>> (k, F->S, F->CH, slot, d, F->desc, F->rho,
+                                                           F->invrho, F->ratio, T.p, T.ninv, T.one, F->bad);
+    g_launches++;
+    CU (cudaGetLastError ());
+    return SLIPCU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// slipcu_factor_upload: build a resident session from factors that live on the host (a
+// SLIP_LU_solve call whose L and U did not come from this process' last factorization, or whose
+// right-hand side needs more channels than the factorization kept).  Columns are given in slot
+// order (U part, then L part); rows are FINAL positions.
+// ------------------------------------------------------------------------------------------------
+extern "C" int slipcu_factor_upload (slipcu_factor **out, int n, int channels, const int32_t *colcnt,
+                                     const int32_t *colnU, const int32_t *colpiv, const int32_t *rows,
+                                     const u32 *limbs, const int64_t *off, const int8_t *sign)
+{
+    if (!out || n <= 0 || channels <= 0 || !colcnt || !colnU || !colpiv || !rows || !limbs || !off || !sign)
+        return fail (SLIPCU_BAD_INPUT, "slipcu_factor_upload", "bad argument");
+    slipcu_factor *F = new slipcu_factor ();
+    *out = F;
+    int rc = session_common_init (F, n, channels);
+    if (rc) return rc;
+    F->rows_are_positions = 1;
+    F->keep_positional = 0;
+    const Tables &T = *F->tab;
+    const int S = F->S, CH = F->CH;
+    size_t total = 0;
+    for (int k = 0; k < n; ++k) total += (size_t) colcnt[k];
+    u32 *dl = nullptr; int64_t *doff = nullptr; int8_t *dsg = nullptr; int32_t *drows = nullptr;
+    const size_t nl = (size_t) off[total];
+    CU (cudaMalloc (&dl, std::max<size_t> (nl, 1) * sizeof (u32)));
+    CU (cudaMalloc (&doff, (total + 1) * sizeof (int64_t)));
+    CU (cudaMalloc (&dsg, total));
+    drows = (int32_t *) F->ints.alloc (total * sizeof (int32_t));
+    if (!drows) return fail (SLIPCU_OUT_OF_MEMORY, "slipcu_factor_upload", "device memory exhausted");
+    CU (cudaMemcpyAsync (dl, limbs, nl * sizeof (u32), cudaMemcpyHostToDevice, F->st));
+    CU (cudaMemcpyAsync (doff, off, (total + 1) * sizeof (int64_t), cudaMemcpyHostToDevice, F->st));
+    CU (cudaMemcpyAsync (dsg, sign, total, cudaMemcpyHostToDevice, F->st));
+    CU (cudaMemcpyAsync (drows, rows, total * sizeof (int32_t), cudaMemcpyHostToDevice, F->st));
+    size_t e = 0;
+    for (int k = 0; k < n; ++k)
+    {
+        HostCol &hc = F->cols[k];
+        const int cnt = colcnt[k];
+        hc.cnt = cnt; hc.nU = colnU[k]; hc.s = S; hc.stride = 0;
+        hc.rows = drows + e;
+        hc.base = (u32 *) F->resid.alloc ((size_t) cnt * S * sizeof (u32));
+        if (!hc.base) return fail (SLIPCU_OUT_OF_MEMORY, "slipcu_factor_upload", "device memory exhausted");
+        const int per = 256 / CH;
+        dim3 grid ((cnt + per - 1) / per, S / CH);
+        k_residues<<<grid, 256, 0, F->st>>> (cnt, CH, dl, doff + e, dsg + e, T.p, T.ninv, T.r2, hc.base);
+        g_launches++;
+        CU (cudaGetLastError ());
+        rc = slipcu_factor_set_pivot (F, k, colpiv[k]);
+        if (rc) return rc;
+        e += (size_t) cnt;
+    }
+    CU (cudaStreamSynchronize (F->st));
+    cudaFree (dl); cudaFree (doff); cudaFree (dsg);
+    return check_channels (F);
+}
+
+// D2H of a column's limbs through pinned staging, handed to the sink
+static int stream_column (slipcu_factor *F, int k, const HostCol &hc, slipcu_column_sink sink, void *user,
+                          u32 *h_limbs, int32_t *h_nl, int8_t *h_sign)
+{
+    CU (cudaMemcpyAsync (h_limbs, hc.limbs, (size_t) hc.cnt * hc.stride * sizeof (u32), cudaMemcpyDeviceToHost, F->st));
+    CU (cudaMemcpyAsync (h_nl, hc.nl, (size_t) hc.cnt * sizeof (int32_t), cudaMemcpyDeviceToHost, F->st));
+    CU (cudaMemcpyAsync (h_sign, hc.sign, (size_t) hc.cnt, cudaMemcpyDeviceToHost, F->st));
+    CU (cudaStreamSynchronize (F->st));
+    int rc = sink (user, k, hc.cnt, hc.stride, h_limbs, h_nl, h_sign);
+    if (rc) return fail (rc, "column sink", "host sink failed");
+    return SLIPCU_OK;
+}
+
+// a channel prime that divides a pivot makes that channel's inverses meaningless
+static int check_channels (slipcu_factor *F)
+{
+    int32_t bad = 0;
+    CU (cudaMemcpyAsync (&bad, F->bad, sizeof (bad), cudaMemcpyDeviceToHost, F->st));
+    CU (cudaStreamSynchronize (F->st));
+    if (bad) return fail (SLIPCU_BAD_PRIME, "check_channels", "channel prime divides a pivot");
+    return SLIPCU_OK;
+}
+
+extern "C" int slipcu_factor_bad_channel (slipcu_factor *F, int *channel)
+{
+    int32_t bad = 0;
+    CU (cudaMemcpyAsync (&bad, F->bad, sizeof (bad), cudaMemcpyDeviceToHost, F->st));
+    CU (cudaStreamSynchronize (F->st));
+    if (channel) *channel = bad - 1;
+    return SLIPCU_OK;
+}
+
+extern "C" int slipcu_factor_download (slipcu_factor *F, slipcu_column_sink sink, void *user)
+{
+    if (!F || !sink) return fail (SLIPCU_BAD_INPUT, "slipcu_factor_download", "bad argument");
+    { int rcb = check_channels (F); if (rcb) return rcb; }
+    size_t maxw = 0; int maxc = 0;
+    for (auto &hc : F->cols) { maxw = std::max (maxw, (size_t) hc.cnt * hc.stride); maxc = std::max (maxc, hc.cnt); }
+    u32 *h_limbs = nullptr; int32_t *h_nl = nullptr; int8_t *h_sign = nullptr;
+    CU (cudaHostAlloc (&h_limbs, std::max<size_t> (maxw, 1) * sizeof (u32), cudaHostAllocDefault));
+    CU (cudaHostAlloc (&h_nl, (size_t) std::max (maxc, 1) * sizeof (int32_t), cudaHostAllocDefault));
+    CU (cudaHostAlloc (&h_sign, (size_t) std::max (maxc, 1), cudaHostAllocDefault));
+    int rc = SLIPCU_OK;
+    for (int k = 0; k < F->n && rc == SLIPCU_OK; ++k)
+        rc = stream_column (F, k, F->cols[k], sink, user, h_limbs, h_nl, h_sign);
+    cudaFreeHost (h_limbs); cudaFreeHost (h_nl); cudaFreeHost (h_sign);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// solve
+// ------------------------------------------------------------------------------------------------
+extern "C" int slipcu_solve (slipcu_factor *F, int nrhs, const u32 *blimbs, const int64_t *boff,
+                             const int8_t *bsign, const int32_t *pinv, int recon_channels,
+                             slipcu_column_sink sink, void *user, int32_t *top_digit_max)
+{
+    if (!F || nrhs <= 0 || !blimbs || !boff || !bsign || !pinv || !sink)
+        return fail (SLIPCU_BAD_INPUT, "slipcu_solve", "bad argument");
+    CU (cudaSetDevice (F->device));
+    { int rcb = check_channels (F); if (rcb) return rcb; }
+    const Tables &T = *F->tab;
+    const int n = F->n, S = F->S, CH = F->CH;
+    const int s = std::min (std::max (recon_channels, 1), S);
+    if (recon_channels > S) return fail (SLIPCU_BAD_INPUT, "slipcu_solve", "right-hand side needs more channels than the session holds");
+    const int total = n * nrhs;
+    // right-hand sides handled per batch so that the work vectors stay within a memory budget
+    size_t budget = (size_t) env_int ("SLIP_B200_SOLVE_BATCH_MB", 4096) << 20;
+    int batch = (int) std::max<size_t> (1, std::min<size_t> ((size_t) nrhs, budget / ((size_t) n * S * sizeof (u32))));
+
+    u32 *dl = nullptr, *dB = nullptr, *dz = nullptr, *dlimbs = nullptr; int64_t *doff = nullptr; int8_t *dsg = nullptr;
+    int32_t *drow_at = nullptr, *dident = nullptr, *dnl = nullptr; int8_t *dsign = nullptr;
+    u32 *h_limbs = nullptr; int32_t *h_nl = nullptr; int8_t *h_sign = nullptr;
+    const int stride = (s + 1) & ~1;
+    int rc = SLIPCU_OK;
+    if (top_digit_max) *top_digit_max = -1;
+    std::vector<int32_t> row_at (n), ident (n);
+    for (int r = 0; r < n; ++r) { row_at[pinv[r]] = r; ident[r] = r; }
+    int32_t *dpinv = nullptr;
+    const size_t nl = (size_t) boff[total];
+#define CUG(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail (e_ == cudaErrorMemoryAllocation ? SLIPCU_OUT_OF_MEMORY : SLIPCU_CUDA_ERROR, #call, cudaGetErrorString (e_)); goto done; } } while (0)
+    CUG (cudaMalloc (&dl, std::max<size_t> (nl, 1) * sizeof (u32)));
+    CUG (cudaMalloc (&doff, (size_t) (total + 1) * sizeof (int64_t)));
+    CUG (cudaMalloc (&dsg, (size_t) total));
+    CUG (cudaMalloc (&dB, (size_t) total * S * sizeof (u32)));
+    CUG (cudaMalloc (&dz, (size_t) batch * n * S * sizeof (u32)));
+    CUG (cudaMalloc (&dlimbs, (size_t) n * stride * sizeof (u32)));
+    CUG (cudaMalloc (&drow_at, (size_t) n * sizeof (int32_t)));
+    CUG (cudaMalloc (&dident, (size_t) n * sizeof (int32_t)));
+    CUG (cudaMalloc (&dpinv, (size_t) n * sizeof (int32_t)));
+    CUG (cudaMalloc (&dnl, (size_t) n * sizeof (int32_t)));
+    CUG (cudaMalloc (&dsign, (size_t) n));
+    CUG (cudaHostAlloc (&h_limbs, (size_t) n * stride * sizeof (u32), cudaHostAllocDefault));
+    CUG (cudaHostAlloc (&h_nl, (size_t) n * sizeof (int32_t), cudaHostAllocDefault));
+    CUG (cudaHostAlloc (&h_sign, (size_t) n, cudaHostAllocDefault));
+    CUG (cudaMemcpyAsync (dl, blimbs, nl * sizeof (u32), cudaMemcpyHostToDevice, F->st));
+    CUG (cudaMemcpyAsync (doff, boff, (size_t) (total + 1) * sizeof (int64_t), cudaMemcpyHostToDevice, F->st));
+    CUG (cudaMemcpyAsync (dsg, bsign, (size_t) total, cudaMemcpyHostToDevice, F->st));
+    CUG (cudaMemcpyAsync (drow_at, row_at.data (), (size_t) n * sizeof (int32_t), cudaMemcpyHostToDevice, F->st));
+    CUG (cudaMemcpyAsync (dident, ident.data (), (size_t) n * sizeof (int32_t), cudaMemcpyHostToDevice, F->st));
+    CUG (cudaMemcpyAsync (dpinv, pinv, (size_t) n * sizeof (int32_t), cudaMemcpyHostToDevice, F->st));
+    rc = ensure_digits (F, (size_t) n);
+    if (rc) goto done;
+    {
+        const int per = 256 / CH;
+        dim3 grid ((total + per - 1) / per, S / CH);
+        k_residues<<<grid, 256, 0, F->st>>> (total, CH, dl, doff, dsg, T.p, T.ninv, T.r2, dB);
+        g_launches++;
+        CUG (cudaGetLastError ());
+    }
+    for (int r0 = 0; r0 < nrhs; r0 += batch)
+    {
+        const int nb = std::min (batch, nrhs - r0);
+        TriArgs a;
+        a.k = n; a.S = S; a.cnt = n; a.nU = n;
+        // slots are positions.  Resident sessions store original rows (slot of row r = pinv[r]);
+        // uploaded sessions store positions (identity map), b rows are then routed through pinv.
+        a.rows = F->rows_are_positions ? dident : drow_at; a.upos = dident;
+        a.src = dB; a.src_total = total; a.src_first = r0; a.src_step = nrhs; a.src_cnt = n;
+        a.src_rows = F->rows_are_positions ? dpinv : nullptr;
+        a.src_y_stride = 1;
+        a.out = dz; a.out_y_stride = (size_t) n * S;
+        a.desc = F->desc; a.rho = F->rho; a.invrho = F->invrho; a.ratio = F->ratio;
+        a.p = T.p; a.ninv = T.ninv; a.pos = F->pos;
+        size_t smem = (((size_t) n * sizeof (int32_t) + 15) & ~(size_t) 15);
+        const size_t xbytes = (size_t) n * CH * sizeof (u32);
+        a.x_in_smem = (smem + xbytes + 1024 <= F->smem_limit) && !F->x_global;
+        if (a.x_in_smem) smem += xbytes;
+        if (smem > F->smem_limit) { rc = fail (SLIPCU_BAD_INPUT, "slipcu_solve", "n too large for shared history"); goto done; }
+        CUG (launch_tri_any (CH, a, dim3 (S / CH, nb), F->threads, smem, F->st));
+        BackArgs b;
+        b.n = n; b.S = S; b.z = dz; b.z_y_stride = (size_t) n * S;
+        b.desc = F->desc; b.rho = F->rho; b.invrho = F->invrho; b.p = T.p; b.ninv = T.ninv; b.pos = F->pos;
+        g_launches++;
+        if (CH == 8) k_backsub<8><<<dim3 (S / CH, nb), F->threads, 0, F->st>>> (b);
+        else if (CH == 16) k_backsub<16><<<dim3 (S / CH, nb), F->threads, 0, F->st>>> (b);
+        else k_backsub<32><<<dim3 (S / CH, nb), F->threads, 0, F->st>>> (b);
+        CUG (cudaGetLastError ());
+        for (int r = 0; r < nb; ++r)
+        {
+            HostCol hc;
+            hc.cnt = n; hc.s = s; hc.stride = stride; hc.limbs = dlimbs; hc.nl = dnl; hc.sign = dsign;
+            rc = run_garner (F, dz + (size_t) r * n * S, n, 0, n, s, dsign);
+            if (rc) goto done;
+            rc = run_limbs (F, 0, n, 0, stride, s, dlimbs, dnl);
+            if (rc) goto done;
+            if (top_digit_max)
+            {   // highest mixed-radix digit in use: lets the caller verify an estimated bound
+                CUG (cudaMemcpyAsync (h_nl, F->topd, (size_t) n * sizeof (int32_t), cudaMemcpyDeviceToHost, F->st));
+                CUG (cudaStreamSynchronize (F->st));
+                for (int t = 0; t < n; ++t) *top_digit_max = std::max (*top_digit_max, h_nl[t]);
+            }
+            rc = stream_column (F, r0 + r, hc, sink, user, h_limbs, h_nl, h_sign);
+            if (rc) goto done;
+        }
+    }
+done:
+    cudaStreamSynchronize (F->st);
+    cudaFree (dl); cudaFree (doff); cudaFree (dsg); cudaFree (dB); cudaFree (dz); cudaFree (dlimbs);
+    cudaFree (drow_at); cudaFree (dident); cudaFree (dpinv); cudaFree (dnl); cudaFree (dsign);
+    if (h_limbs) cudaFreeHost (h_limbs);
+    if (h_nl) cudaFreeHost (h_nl);
+    if (h_sign) cudaFreeHost (h_sign);
+#undef CUG
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// counters
+// ------------------------------------------------------------------------------------------------
+extern "C" void slipcu_get_counters (slipcu_counters *o)
+{
+    if (!o) return;
+    o->launches = g_launches.load (); o->trisolve_launches = g_tri_launches.load ();
+    o->trisolve_ms = g_tri_ms; o->trisolve_bytes = g_tri_bytes; o->trisolve_modmul = g_tri_modmul;
+    o->recon_ms = g_recon_ms; o->recon_mac = g_recon_mac;
+}
+extern "C" void slipcu_reset_counters (void)
+{
+    g_launches = 0; g_tri_launches = 0;
+    g_tri_ms = g_tri_bytes = g_tri_modmul = g_recon_ms = g_recon_mac = 0;
+}
+extern "C" void slipcu_set_profiling (int enabled) { g_profiling = enabled; }

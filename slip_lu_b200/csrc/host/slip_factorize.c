@@ -1,0 +1,366 @@
+/* slip_factorize.c -- SLIP_LU_factorize: left-looking REF LU, P A Q = L D^-1 U.
+ *
+ * Mirrors SLIP_LU/Source/SLIP_LU_factorize.c:34-323.  Division of labour:
+ *   host (this file)   the symbolic side of each column: reach of A(:,q[k]) in the graph of L
+ *                      (slip_reach.c / slip_dfs.c), ordering of the pattern by the current row
+ *                      permutation (slip_sort_xi.c), the row-permutation bookkeeping of
+ *                      slip_get_pivot.c:152-172 and the final assembly of L, U, rhos as mpz_t.
+ *   GPU (slipcu_*)     all arithmetic: the sparse REF triangular solve, exact reconstruction and
+ *                      the exact pivot scan.
+ * The only arithmetic left on the host is the rational tolerance comparison of
+ * SLIP_TOL_SMALLEST / SLIP_TOL_LARGEST on two already-reconstructed integers, done with the very
+ * GMP call the reference uses (slip_get_pivot.c:94-143) so that its outcome is reproduced. */
+#include "slip_internal.h"
+
+/* ---- host copy of the patterns of the finished columns ---- */
+typedef struct
+{
+    int32_t *rows ;      /* all patterns back to back (original row indices) */
+    int64_t cap, used ;
+    int64_t *ptr ;       /* n+1 */
+    int32_t *nU ;        /* n: size of the U part of each pattern */
+    int32_t *piv ;       /* n: slot of the pivot */
+} pattern_store ;
+
+static void patterns_free (pattern_store *P)
+{
+    SLIP_free (P->rows) ; SLIP_free (P->ptr) ; SLIP_free (P->nU) ; SLIP_free (P->piv) ;
+    memset (P, 0, sizeof (*P)) ;
+}
+
+static SLIP_info patterns_init (pattern_store *P, int32_t n, int64_t guess)
+{
+    memset (P, 0, sizeof (*P)) ;
+    P->cap = guess > 4 * (int64_t) n ? guess : 4 * (int64_t) n ;
+    P->rows = (int32_t *) SLIP_malloc ((size_t) P->cap * sizeof (int32_t)) ;
+    P->ptr = (int64_t *) SLIP_calloc ((size_t) n + 1, sizeof (int64_t)) ;
+    P->nU = (int32_t *) SLIP_calloc ((size_t) n, sizeof (int32_t)) ;
+    P->piv = (int32_t *) SLIP_calloc ((size_t) n, sizeof (int32_t)) ;
+    if (!P->rows || !P->ptr || !P->nU || !P->piv) { patterns_free (P) ; return SLIP_OUT_OF_MEMORY ; }
+    return SLIP_OK ;
+}
+
+static SLIP_info patterns_reserve (pattern_store *P, int64_t extra)
+{
+    if (P->used + extra <= P->cap) return SLIP_OK ;
+    int64_t ncap = P->cap ;
+    while (ncap < P->used + extra) ncap *= 2 ;
+    int32_t *nr = (int32_t *) realloc (P->rows, (size_t) ncap * sizeof (int32_t)) ;
+    if (!nr) return SLIP_OUT_OF_MEMORY ;
+    P->rows = nr ; P->cap = ncap ;
+    return SLIP_OK ;
+}
+
+static int cmp_i32 (const void *a, const void *b)
+{
+    int32_t x = *(const int32_t *) a, y = *(const int32_t *) b ;
+    return (x > y) - (x < y) ;
+}
+
+/* pattern of column k: rows reachable from the rows of A(:,col) through the finished columns of
+ * L, written to out[] sorted by current position.  Returns the count. */
+static int32_t column_pattern (const SLIP_sparse *A, int32_t col, int32_t k, const pattern_store *P,
+    const int32_t *pinv, const int32_t *row_at, int32_t *mark, int32_t *stack, int32_t *out)
+{
+    int32_t cnt = 0 ;
+    const int32_t stamp = k + 1 ;
+    for (int32_t a = A->p [col] ; a < A->p [col + 1] ; a++)
+    {
+        int32_t r0 = A->i [a] ;
+        if (mark [r0] == stamp) continue ;
+        int32_t sp = 0 ;
+        mark [r0] = stamp ; stack [sp++] = r0 ;
+        while (sp > 0)
+        {
+            const int32_t r = stack [--sp] ;
+            const int32_t pos = pinv [r] ;
+            out [cnt++] = pos ;
+            if (pos < k)
+            {   /* row r is the pivot of column pos: follow the L part of that column */
+                const int32_t *rows = P->rows + P->ptr [pos] ;
+                const int32_t len = (int32_t) (P->ptr [pos + 1] - P->ptr [pos]) ;
+                for (int32_t m = P->nU [pos] ; m < len ; m++)
+                {
+                    const int32_t rr = rows [m] ;
+                    if (mark [rr] != stamp) { mark [rr] = stamp ; stack [sp++] = rr ; }
+                }
+            }
+        }
+    }
+    qsort (out, (size_t) cnt, sizeof (int32_t), cmp_i32) ;
+    for (int32_t t = 0 ; t < cnt ; t++) out [t] = row_at [out [t]] ;
+    return cnt ;
+}
+
+/* ---- the rational tolerance test on two reconstructed entries ---- */
+static SLIP_info tolerance_prefers_diagonal (slipcu_factor *dev, int32_t k, int scheme, double tol,
+    int32_t best_slot, int32_t diag_slot, int *prefer)
+{
+    SLIP_info status = SLIP_OK ;
+    const int stride = slipcu_factor_column_stride (dev, k) ;
+    uint32_t *wb = (uint32_t *) SLIP_malloc ((size_t) (stride + 2) * sizeof (uint32_t)) ;
+    uint32_t *wd = (uint32_t *) SLIP_malloc ((size_t) (stride + 2) * sizeof (uint32_t)) ;
+    mpz_t vb, vd ; mpq_t ratio, t ;
+    mpz_init (vb) ; mpz_init (vd) ; mpq_init (ratio) ; mpq_init (t) ;
+    if (!wb || !wd) { status = SLIP_OUT_OF_MEMORY ; goto cleanup ; }
+    {
+        int32_t nb = 0, nd = 0 ; int8_t sb = 0, sd = 0 ;
+        SLIP_TRY (slip_from_device_status (slipcu_factor_fetch_entry (dev, k, best_slot, wb, &nb, &sb))) ;
+        SLIP_TRY (slip_from_device_status (slipcu_factor_fetch_entry (dev, k, diag_slot, wd, &nd, &sd))) ;
+        slip_mpz_from_words (vb, wb, nb, sb) ;
+        slip_mpz_from_words (vd, wd, nd, sd) ;
+    }
+    if (scheme == SLIP_TOL_SMALLEST)
+    {   /* |smallest| / |diagonal| */
+        mpz_abs (mpq_numref (ratio), vb) ;
+        mpz_abs (mpq_denref (ratio), vd) ;
+    }
+    else
+    {   /* the reference takes mpq_abs of diagonal/largest without canonicalising: the operand
+           of the comparison is |diagonal| over the SIGNED largest entry (slip_get_pivot.c:131-137) */
+        mpz_abs (mpq_numref (ratio), vd) ;
+        mpz_set (mpq_denref (ratio), vb) ;
+    }
+    mpq_set_d (t, tol) ;
+    *prefer = (mpq_cmp (ratio, t) >= 0) ;
+cleanup:
+    mpz_clear (vb) ; mpz_clear (vd) ; mpq_clear (ratio) ; mpq_clear (t) ;
+    SLIP_free (wb) ; SLIP_free (wd) ;
+    return status ;
+}
+
+static SLIP_info decide_pivot (slipcu_factor *dev, int32_t k, int scheme, double tol, int32_t diag_slot,
+    const slipcu_pivot_info *info, int32_t *slot)
+{
+    const int32_t best = info->best_slot ;
+    *slot = best ;
+    if (best < 0) return SLIP_SINGULAR ;          /* every candidate is zero */
+    if (!info->diag_eligible || diag_slot == best) return SLIP_OK ;
+    switch (scheme)
+    {
+        case SLIP_DIAGONAL:
+            *slot = diag_slot ;
+            return SLIP_OK ;
+        case SLIP_TOL_SMALLEST:
+            /* ratio = |smallest|/|diagonal| lies in (0,1]; most tolerances need no arithmetic */
+            if (tol != tol) return SLIP_OK ;
+            if (tol <= 0.0 || info->diag_vs_best == 0) { if (tol <= 1.0) *slot = diag_slot ; return SLIP_OK ; }
+            if (tol >= 1.0) return SLIP_OK ;
+            /* fall through: 0 < tol < 1 and |diagonal| > |smallest| */
+        case SLIP_TOL_LARGEST:
+        {
+            if (tol != tol) return SLIP_OK ;
+            int prefer = 0 ;
+            SLIP_info status = tolerance_prefers_diagonal (dev, k, scheme, tol, best, diag_slot, &prefer) ;
+            if (status != SLIP_OK) return status ;
+            if (prefer) *slot = diag_slot ;
+            return SLIP_OK ;
+        }
+        default:
+            return SLIP_OK ;
+    }
+}
+
+/* ---- assembling L, U, rhos on the host from the streamed columns ---- */
+typedef struct
+{
+    SLIP_sparse *L, *U ;
+    mpz_t *rhos ;
+    const pattern_store *P ;
+} assemble_ctx ;
+
+static int assemble_column (void *user, int k, int cnt, int stride, const uint32_t *limbs,
+    const int32_t *nl, const int8_t *sign)
+{
+    assemble_ctx *c = (assemble_ctx *) user ;
+    const int32_t nU = c->P->nU [k], piv = c->P->piv [k] ;
+    mpz_t *Ux = c->U->x + c->U->p [k] ;
+    mpz_t *Lx = c->L->x + c->L->p [k] ;
+    #pragma omp parallel for schedule(dynamic, 16) if (cnt > 32)
+    for (int t = 0 ; t < cnt ; t++)
+    {
+        mpz_ptr dst = (t < nU) ? Ux [t] : Lx [t - nU] ;
+        mpz_init (dst) ;
+        slip_mpz_from_words (dst, limbs + (size_t) t * stride, nl [t], sign [t]) ;
+    }
+    mpz_init_set (Ux [nU], Lx [piv - nU]) ;       /* the pivot closes the column of U */
+    mpz_set (c->rhos [k], Lx [piv - nU]) ;
+    return 0 ;
+}
+
+SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A, SLIP_LU_analysis *S,
+    mpz_t *rhos, int32_t *pinv, SLIP_options *option, int want_host_factors, slip_resident **resident,
+    double rhs_bits)
+{
+    if (!A || !S || !pinv || !option || !A->p || !A->x || !A->i || !S->q || A->n <= 0 || A->n != A->m)
+        return SLIP_INCORRECT_INPUT ;
+    if (want_host_factors && (!L || !U || !rhos)) return SLIP_INCORRECT_INPUT ;
+    const int32_t n = A->n, nz = A->p [n] ;
+    if (nz <= 0) return SLIP_INCORRECT_INPUT ;
+    const int scheme = (int) option->pivot ;
+    SLIP_info status = SLIP_OK ;
+    slip_limbs Al = {0} ;
+    pattern_store P = {0} ;
+    slipcu_factor *dev = NULL ;
+    slip_resident *res = NULL ;
+    double *colbits = (double *) SLIP_malloc ((size_t) n * sizeof (double)) ;
+    int32_t *row_at = (int32_t *) SLIP_malloc ((size_t) n * sizeof (int32_t)) ;
+    int32_t *mark = (int32_t *) SLIP_calloc ((size_t) n, sizeof (int32_t)) ;
+    int32_t *stack = (int32_t *) SLIP_malloc ((size_t) n * sizeof (int32_t)) ;
+    int32_t *pat = (int32_t *) SLIP_malloc ((size_t) n * sizeof (int32_t)) ;
+    int32_t *upos = (int32_t *) SLIP_malloc ((size_t) n * sizeof (int32_t)) ;
+    if (!colbits || !row_at || !mark || !stack || !pat || !upos) { status = SLIP_OUT_OF_MEMORY ; goto cleanup ; }
+
+    for (int32_t a = 0 ; a < nz ; a++)
+        if (A->i [a] < 0 || A->i [a] >= n) { status = SLIP_INCORRECT_INPUT ; goto cleanup ; }
+    for (int32_t k = 0 ; k < n ; k++)
+        if (S->q [k] < 0 || S->q [k] >= n) { status = SLIP_INCORRECT_INPUT ; goto cleanup ; }
+
+    /* sizing (replaces the allocation bound of SLIP_LU_factorize.c:102-163 by a true bound) */
+    SLIP_TRY (slip_column_bits (A, colbits)) ;
+    double total_bits = 0, min_bits = 1e300 ;
+    for (int32_t j = 0 ; j < n ; j++) { total_bits += colbits [j] ; if (colbits [j] < min_bits) min_bits = colbits [j] ; }
+    /* a right-hand side known up front (SLIP_solve_*) may need more room than the factors */
+    const double extra = rhs_bits > min_bits ? rhs_bits - min_bits : 0.0 ;
+    const int channels = slip_channels_for_bits (total_bits + extra) + SLIP_B200_SPARE_CHANNELS ;
+
+    {   /* A as limb strings */
+        int64_t words = 0 ;
+        for (int32_t a = 0 ; a < nz ; a++) words += slip_mpz_words (A->x [a]) ;
+        SLIP_TRY (slip_limbs_begin (&Al, nz, words)) ;
+        for (int32_t a = 0 ; a < nz ; a++) slip_limbs_put (&Al, a, A->x [a]) ;
+    }
+
+    for (int attempt = 0 ; ; attempt++)
+    {
+        int retry = 0 ;
+        SLIP_TRY (patterns_init (&P, n, (int64_t) S->lnz + S->unz)) ;
+        SLIP_TRY (slip_from_device_status (slipcu_factor_begin (&dev, n, nz, A->p, A->i, Al.limbs, Al.off,
+            Al.sign, channels, want_host_factors))) ;
+        const int S_dev = slipcu_factor_channels (dev) ;
+        for (int32_t r = 0 ; r < n ; r++) { pinv [r] = r ; row_at [r] = r ; mark [r] = 0 ; }
+        double cum_bits = 0 ;
+        for (int32_t k = 0 ; k < n ; k++)
+        {
+            const int32_t col = S->q [k] ;
+            cum_bits += colbits [col] ;
+            int s_k = slip_channels_for_bits (cum_bits) ;
+            if (s_k > S_dev) s_k = S_dev ;
+            const int32_t cnt = column_pattern (A, col, k, &P, pinv, row_at, mark, stack, pat) ;
+            int32_t nU = 0, diag_slot = -1 ;
+            for (int32_t t = 0 ; t < cnt ; t++)
+            {
+                const int32_t pos = pinv [pat [t]] ;
+                if (pos < k) upos [nU++] = pos ;
+                else if (pat [t] == col) diag_slot = t ;
+            }
+            if (cnt == nU) { status = SLIP_SINGULAR ; goto cleanup ; }    /* no candidate row at all */
+            slipcu_pivot_info info ;
+            int rc = slipcu_factor_column (dev, k, col, cnt, nU, pat, upos, s_k, scheme, diag_slot, &info) ;
+            if (rc == SLIPCU_BAD_PRIME) { retry = 1 ; break ; }
+            SLIP_TRY (slip_from_device_status (rc)) ;
+            int32_t slot = -1 ;
+            SLIP_TRY (decide_pivot (dev, k, scheme, option->tol, diag_slot, &info, &slot)) ;
+            {   /* move the pivot row to position k (slip_get_pivot.c:152-172) */
+                const int32_t prow = pat [slot], oldpos = pinv [prow], displaced = row_at [k] ;
+                row_at [k] = prow ; row_at [oldpos] = displaced ;
+                pinv [prow] = k ; pinv [displaced] = oldpos ;
+            }
+            SLIP_TRY (slip_from_device_status (slipcu_factor_set_pivot (dev, k, slot))) ;
+            SLIP_TRY (patterns_reserve (&P, cnt)) ;
+            memcpy (P.rows + P.used, pat, (size_t) cnt * sizeof (int32_t)) ;
+            P.used += cnt ;
+            P.ptr [k + 1] = P.used ; P.nU [k] = nU ; P.piv [k] = slot ;
+            if (k == n - 1)
+            {   /* det = rho[n-1], kept with the resident factors for the rational solve */
+                res = (slip_resident *) SLIP_calloc (1, sizeof (slip_resident)) ;
+                if (!res) { status = SLIP_OUT_OF_MEMORY ; goto cleanup ; }
+                mpz_init (res->det) ;
+                const int stride = slipcu_factor_column_stride (dev, k) ;
+                uint32_t *w = (uint32_t *) SLIP_malloc ((size_t) (stride + 2) * sizeof (uint32_t)) ;
+                if (!w) { status = SLIP_OUT_OF_MEMORY ; goto cleanup ; }
+                int32_t nw = 0 ; int8_t sg = 0 ;
+                rc = slipcu_factor_fetch_entry (dev, k, slot, w, &nw, &sg) ;
+                if (rc == SLIPCU_OK) slip_mpz_from_words (res->det, w, nw, sg) ;
+                SLIP_free (w) ;
+                SLIP_TRY (slip_from_device_status (rc)) ;
+            }
+        }
+        if (!retry)
+        {   /* the last pivot is only checked against the channel primes here */
+            int bad = -1 ;
+            SLIP_TRY (slip_from_device_status (slipcu_factor_bad_channel (dev, &bad))) ;
+            if (bad >= 0) retry = 1 ;
+        }
+        if (!retry) break ;
+        {   /* a channel prime divides a pivot (probability ~ n*S/2^31): retire it and start over */
+            int bad = -1 ;
+            slipcu_factor_bad_channel (dev, &bad) ;
+            slipcu_factor_free (dev) ; dev = NULL ;
+            if (res) { slip_resident_free (res) ; res = NULL ; }
+            patterns_free (&P) ;
+            if (bad < 0 || attempt >= 4) { slip_set_error ("could not find usable channel primes") ; status = SLIP_INCORRECT ; goto cleanup ; }
+            slipcu_retire_channel (bad) ;
+        }
+    }
+
+    if (want_host_factors)
+    {
+        int64_t lnz = 0, unz = 0 ;
+        for (int32_t k = 0 ; k < n ; k++)
+        {
+            const int32_t cnt = (int32_t) (P.ptr [k + 1] - P.ptr [k]) ;
+            lnz += cnt - P.nU [k] ; unz += P.nU [k] + 1 ;
+        }
+        if (lnz > INT32_MAX || unz > INT32_MAX) { status = SLIP_OUT_OF_MEMORY ; goto cleanup ; }
+        SLIP_sparse *M [2] = { L, U } ;
+        int64_t mnz [2] = { lnz, unz } ;
+        for (int w = 0 ; w < 2 ; w++)
+        {
+            M [w]->m = M [w]->n = n ;
+            M [w]->nz = M [w]->nzmax = (int32_t) mnz [w] ;
+            M [w]->p = (int32_t *) SLIP_calloc ((size_t) n + 1, sizeof (int32_t)) ;
+            M [w]->i = (int32_t *) SLIP_calloc ((size_t) mnz [w], sizeof (int32_t)) ;
+            M [w]->x = (mpz_t *) SLIP_calloc ((size_t) mnz [w], sizeof (mpz_t)) ;
+            if (!M [w]->p || !M [w]->i || !M [w]->x) { status = SLIP_OUT_OF_MEMORY ; goto cleanup ; }
+        }
+        for (int32_t k = 0 ; k < n ; k++)
+        {
+            const int32_t *rows = P.rows + P.ptr [k] ;
+            const int32_t cnt = (int32_t) (P.ptr [k + 1] - P.ptr [k]), nU = P.nU [k] ;
+            int32_t *Ui = U->i + U->p [k], *Li = L->i + L->p [k] ;
+            for (int32_t t = 0 ; t < nU ; t++) Ui [t] = pinv [rows [t]] ;
+            Ui [nU] = k ;
+            for (int32_t t = nU ; t < cnt ; t++) Li [t - nU] = pinv [rows [t]] ;
+            U->p [k + 1] = U->p [k] + nU + 1 ;
+            L->p [k + 1] = L->p [k] + (cnt - nU) ;
+        }
+        assemble_ctx ctx = { L, U, rhos, &P } ;
+        SLIP_TRY (slip_from_device_status (slipcu_factor_download (dev, assemble_column, &ctx))) ;
+    }
+
+    res->dev = dev ; dev = NULL ;
+    res->n = n ;
+    res->total_bits = total_bits ;
+    res->min_col_bits = min_bits ;
+    res->Lx = want_host_factors ? (const void *) L->x : NULL ;
+    if (resident) { *resident = res ; res = NULL ; }
+    else if (want_host_factors) { slip_resident_add (res) ; res = NULL ; }
+
+cleanup:
+    if (dev) slipcu_factor_free (dev) ;
+    if (res) slip_resident_free (res) ;
+    slip_limbs_free (&Al) ;
+    patterns_free (&P) ;
+    SLIP_free (colbits) ; SLIP_free (row_at) ; SLIP_free (mark) ; SLIP_free (stack) ;
+    SLIP_free (pat) ; SLIP_free (upos) ;
+    return status ;
+}
+
+SLIP_info SLIP_LU_factorize (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A, SLIP_LU_analysis *S,
+    mpz_t *rhos, int32_t *pinv, SLIP_options *option)
+{
+    if (!A || !L || !U || !S || !rhos || !pinv || !option || !A->p || !A->x || !A->i)
+        return SLIP_INCORRECT_INPUT ;
+    return slip_factorize_driver (L, U, A, S, rhos, pinv, option, 1, NULL, 0.0) ;
+}

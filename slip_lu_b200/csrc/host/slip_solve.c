@@ -1,0 +1,295 @@
+/* slip_solve.c -- SLIP_LU_solve and the SLIP_solve_* drivers.
+ *
+ * Mirrors SLIP_LU/Source/SLIP_LU_solve.c:44-94 (permute b, forward substitution, scale by det,
+ * back substitution, divide by det), SLIP_solve_mpq.c / SLIP_solve_double.c, SLIP_permute_x.c,
+ * SLIP_scale_x.c, SLIP_check_solution.c, SLIP_get_double_soln.c.  The substitutions run on the
+ * GPU against the resident factors; the host turns the integer numerators det*x_i into canonical
+ * rationals (the mpq_div of slip_array_div.c) and applies the permutation and the scale. */
+#include "slip_internal.h"
+
+/* ---- numerators det*x_i streamed from the device: x[i][c] = num / det, canonical ---- */
+typedef struct
+{
+    mpq_t **x ;
+    mpz_srcptr det ;
+} rational_ctx ;
+
+static int rational_column (void *user, int c, int cnt, int stride, const uint32_t *limbs,
+    const int32_t *nl, const int8_t *sign)
+{
+    rational_ctx *ctx = (rational_ctx *) user ;
+    #pragma omp parallel for schedule(dynamic, 8) if (cnt > 16)
+    for (int t = 0 ; t < cnt ; t++)
+    {
+        mpq_ptr q = ctx->x [t][c] ;
+        slip_mpz_from_words (mpq_numref (q), limbs + (size_t) t * stride, nl [t], sign [t]) ;
+        mpz_set (mpq_denref (q), ctx->det) ;
+        mpq_canonicalize (q) ;
+    }
+    return 0 ;
+}
+
+/* verified = 0: the channel count behind r is only an estimate of the result size; the solve then
+ * reconstructs over every channel and reports SLIP_INCORRECT if the two top channels were needed */
+static SLIP_info solve_on_device (mpq_t **x, SLIP_dense *b, slip_resident *r, const int32_t *pinv, int verified)
+{
+    SLIP_info status = SLIP_OK ;
+    const int32_t n = r->n, nrhs = b->n ;
+    slip_limbs bl = {0} ;
+    if (b->m != n || nrhs <= 0) return SLIP_INCORRECT_INPUT ;
+    if (mpz_sgn (r->det) == 0) return SLIP_SINGULAR ;
+    {
+        int64_t words = 0 ;
+        for (int32_t i = 0 ; i < n ; i++)
+            for (int32_t c = 0 ; c < nrhs ; c++) words += slip_mpz_words (b->x [i][c]) ;
+        SLIP_TRY (slip_limbs_begin (&bl, (int64_t) n * nrhs, words)) ;
+        for (int32_t i = 0 ; i < n ; i++)
+            for (int32_t c = 0 ; c < nrhs ; c++) slip_limbs_put (&bl, (int64_t) i * nrhs + c, b->x [i][c]) ;
+    }
+    {
+        const int have = slipcu_factor_channels (r->dev) ;
+        int s = have ;
+        if (verified)
+        {   /* Cramer: det*x_i is the determinant of A with one column replaced by b */
+            s = slip_channels_for_bits (r->total_bits - r->min_col_bits + slip_dense_max_column_bits (b)) ;
+            if (s > have) { status = SLIP_INCORRECT_INPUT ; goto cleanup ; }
+        }
+        int32_t top = -1 ;
+        rational_ctx ctx = { x, r->det } ;
+        SLIP_TRY (slip_from_device_status (slipcu_solve (r->dev, nrhs, bl.limbs, bl.off, bl.sign, pinv, s,
+            rational_column, &ctx, &top))) ;
+        if (!verified && top >= have - 2) status = SLIP_INCORRECT ;
+    }
+cleanup:
+    slip_limbs_free (&bl) ;
+    return status ;
+}
+
+SLIP_info slip_solve_resident (mpq_t **x, SLIP_dense *b, slip_resident *r, const int32_t *pinv)
+{
+    return solve_on_device (x, b, r, pinv, 1) ;
+}
+
+/* resident session from host-side factors (L, U, rhos given as mpz_t) */
+static SLIP_info upload_factors (slip_resident **out, const SLIP_sparse *L, const SLIP_sparse *U,
+    const mpz_t *rhos, int channels)
+{
+    SLIP_info status = SLIP_OK ;
+    const int32_t n = L->n ;
+    slip_limbs vl = {0} ;
+    slip_resident *res = NULL ;
+    int32_t *cnt = (int32_t *) SLIP_malloc ((size_t) n * sizeof (int32_t)) ;
+    int32_t *nU = (int32_t *) SLIP_malloc ((size_t) n * sizeof (int32_t)) ;
+    int32_t *piv = (int32_t *) SLIP_malloc ((size_t) n * sizeof (int32_t)) ;
+    const int64_t total = (int64_t) L->p [n] + U->p [n] - n ;
+    int32_t *rows = (int32_t *) SLIP_malloc ((size_t) (total > 0 ? total : 1) * sizeof (int32_t)) ;
+    if (!cnt || !nU || !piv || !rows) { status = SLIP_OUT_OF_MEMORY ; goto cleanup ; }
+    {
+        int64_t words = 0 ;
+        for (int32_t m = 0 ; m < L->p [n] ; m++) words += slip_mpz_words (L->x [m]) ;
+        for (int32_t m = 0 ; m < U->p [n] ; m++) words += slip_mpz_words (U->x [m]) ;
+        SLIP_TRY (slip_limbs_begin (&vl, total, words)) ;
+    }
+    int64_t e = 0 ;
+    for (int32_t k = 0 ; k < n ; k++)
+    {
+        const int32_t u0 = U->p [k], u1 = U->p [k + 1] - 1 ;     /* the diagonal closes the column */
+        const int32_t l0 = L->p [k], l1 = L->p [k + 1] ;
+        if (u1 < u0 || U->i [u1] != k) { status = SLIP_INCORRECT_INPUT ; goto cleanup ; }
+        nU [k] = u1 - u0 ; cnt [k] = (u1 - u0) + (l1 - l0) ; piv [k] = -1 ;
+        for (int32_t m = u0 ; m < u1 ; m++) { rows [e] = U->i [m] ; slip_limbs_put (&vl, e, U->x [m]) ; e++ ; }
+        for (int32_t m = l0 ; m < l1 ; m++)
+        {
+            if (L->i [m] == k) piv [k] = nU [k] + (m - l0) ;
+            rows [e] = L->i [m] ; slip_limbs_put (&vl, e, L->x [m]) ; e++ ;
+        }
+        if (piv [k] < 0) { status = SLIP_INCORRECT_INPUT ; goto cleanup ; }
+    }
+    res = (slip_resident *) SLIP_calloc (1, sizeof (slip_resident)) ;
+    if (!res) { status = SLIP_OUT_OF_MEMORY ; goto cleanup ; }
+    mpz_init_set (res->det, rhos [n - 1]) ;
+    res->n = n ;
+    res->total_bits = -1 ;               /* no A here: the solve reconstructs over every channel */
+    SLIP_TRY (slip_from_device_status (slipcu_factor_upload (&res->dev, n, channels, cnt, nU, piv, rows,
+        vl.limbs, vl.off, vl.sign))) ;
+    *out = res ; res = NULL ;
+cleanup:
+    if (res) slip_resident_free (res) ;
+    slip_limbs_free (&vl) ;
+    SLIP_free (cnt) ; SLIP_free (nU) ; SLIP_free (piv) ; SLIP_free (rows) ;
+    return status ;
+}
+
+/* largest entry of a SLIP_sparse / mpz array in bits */
+static double max_bits_sparse (const SLIP_sparse *M)
+{
+    size_t best = 0 ;
+    for (int32_t m = 0 ; m < M->p [M->n] ; m++)
+    {
+        size_t b = mpz_sgn (M->x [m]) ? mpz_sizeinbase (M->x [m], 2) : 0 ;
+        if (b > best) best = b ;
+    }
+    return (double) best ;
+}
+
+SLIP_info SLIP_LU_solve (mpq_t **x, SLIP_dense *b, const mpz_t *rhos, const SLIP_sparse *L,
+    const SLIP_sparse *U, const int32_t *pinv)
+{
+    if (!x || !b || !rhos || !pinv || !L || !U || !b->x || !L->p || !L->i || !L->x || !U->p || !U->i || !U->x)
+        return SLIP_INCORRECT_INPUT ;
+    SLIP_info status = SLIP_OK ;
+    slip_resident *r = slip_resident_find (L->x), *tmp = NULL ;
+    const double bbits = slip_dense_max_column_bits (b) ;
+    int need = -1 ;
+    if (r)
+    {   /* do the resident factors carry enough channels for this right-hand side? */
+        need = slip_channels_for_bits (r->total_bits - r->min_col_bits + bbits) ;
+        if (need <= slipcu_factor_channels (r->dev)) return solve_on_device (x, b, r, pinv, 1) ;
+    }
+    /* Factors that are not resident (or too narrow) are re-encoded from the host copies.  With
+     * the bound of the resident factorization at hand the channel count is exact.  Without it
+     * (L, U from elsewhere) there is no A to bound det*x with, so the count is estimated from
+     * the factors, the result is reconstructed over all channels, and the two top channels must
+     * stay empty; otherwise the channels are doubled and the solve repeated. */
+    const int32_t n = L->n ;
+    int channels = need > 0 ? need + SLIP_B200_SPARE_CHANNELS
+        : slip_channels_for_bits (max_bits_sparse (L) + max_bits_sparse (U) + bbits + 2.0 * log2 ((double) n + 1.0) + 64.0) + 2 ;
+    for (int attempt = 0 ; attempt < 8 ; attempt++)
+    {
+        SLIP_TRY (upload_factors (&tmp, L, U, rhos, channels)) ;
+        if (need > 0) { tmp->total_bits = r->total_bits ; tmp->min_col_bits = r->min_col_bits ; }
+        status = solve_on_device (x, b, tmp, pinv, need > 0) ;
+        slip_resident_free (tmp) ; tmp = NULL ;
+        if (status != SLIP_INCORRECT || need > 0) break ;
+        channels *= 2 ;
+    }
+cleanup:
+    if (tmp) slip_resident_free (tmp) ;
+    return status ;
+}
+
+SLIP_info SLIP_permute_x (mpq_t **x, int32_t n, int32_t numRHS, SLIP_LU_analysis *S)
+{
+    if (!x || !S || !S->q) return SLIP_INCORRECT_INPUT ;
+    /* x <- Q x: row i of the factor ordering is row q[i] of the original system.  Only the row
+       pointers move. */
+    mpq_t **tmp = (mpq_t **) SLIP_malloc ((size_t) n * sizeof (mpq_t *)) ;
+    if (!tmp) return SLIP_OUT_OF_MEMORY ;
+    (void) numRHS ;
+    for (int32_t i = 0 ; i < n ; i++) tmp [S->q [i]] = x [i] ;
+    memcpy (x, tmp, (size_t) n * sizeof (mpq_t *)) ;
+    SLIP_free (tmp) ;
+    return SLIP_OK ;
+}
+
+SLIP_info SLIP_scale_x (mpq_t **x, SLIP_sparse *A, SLIP_dense *b)
+{
+    if (!x || !A || !b) return SLIP_INCORRECT_INPUT ;
+    const int32_t n = A->m, nrhs = b->n ;
+    if (mpq_cmp_ui (A->scale, 1, 1) != 0 && mpq_cmp_ui (A->scale, 0, 1) != 0)
+        for (int32_t i = 0 ; i < n ; i++)
+            for (int32_t j = 0 ; j < nrhs ; j++) mpq_mul (x [i][j], x [i][j], A->scale) ;
+    if (mpq_cmp_ui (b->scale, 1, 1) != 0 && mpq_cmp_ui (b->scale, 0, 1) != 0)
+        for (int32_t i = 0 ; i < n ; i++)
+            for (int32_t j = 0 ; j < nrhs ; j++) mpq_div (x [i][j], x [i][j], b->scale) ;
+    return SLIP_OK ;
+}
+
+/* factor on the GPU, solve on the GPU; L and U never come to the host */
+static SLIP_info solve_exact (mpq_t **x, SLIP_sparse *A, SLIP_LU_analysis *S, SLIP_dense *b, SLIP_options *option)
+{
+    SLIP_info status = SLIP_OK ;
+    slip_resident *r = NULL ;
+    const int32_t n = A->n ;
+    int32_t *pinv = (int32_t *) SLIP_malloc ((size_t) n * sizeof (int32_t)) ;
+    if (!pinv) return SLIP_OUT_OF_MEMORY ;
+    SLIP_TRY (slip_factorize_driver (NULL, NULL, A, S, NULL, pinv, option, 0, &r, slip_dense_max_column_bits (b))) ;
+    SLIP_TRY (slip_solve_resident (x, b, r, pinv)) ;
+    SLIP_TRY (SLIP_permute_x (x, n, b->n, S)) ;
+    SLIP_TRY (SLIP_scale_x (x, A, b)) ;
+cleanup:
+    if (r) slip_resident_free (r) ;
+    SLIP_free (pinv) ;
+    return status ;
+}
+
+SLIP_info SLIP_solve_mpq (mpq_t **x_mpq, SLIP_sparse *A, SLIP_LU_analysis *S, SLIP_dense *b, SLIP_options *option)
+{
+    if (!x_mpq || !A || !A->p || !A->i || !A->x || !S || !S->q || !b || !b->x || !option)
+        return SLIP_INCORRECT_INPUT ;
+    return solve_exact (x_mpq, A, S, b, option) ;
+}
+
+SLIP_info SLIP_get_double_soln (double **x_doub, mpq_t **x_mpq, int32_t n, int32_t numRHS)
+{
+    if (!x_doub || !x_mpq) return SLIP_INCORRECT_INPUT ;
+    for (int32_t i = 0 ; i < n ; i++)
+        for (int32_t j = 0 ; j < numRHS ; j++) x_doub [i][j] = mpq_get_d (x_mpq [i][j]) ;
+    return SLIP_OK ;
+}
+
+SLIP_info SLIP_solve_double (double **x_doub, SLIP_sparse *A, SLIP_LU_analysis *S, SLIP_dense *b, SLIP_options *option)
+{
+    if (!x_doub || !A || !A->p || !A->i || !A->x || !S || !S->q || !b || !b->x || !option)
+        return SLIP_INCORRECT_INPUT ;
+    mpq_t **x = SLIP_create_mpq_mat (A->n, b->n) ;
+    if (!x) return SLIP_OUT_OF_MEMORY ;
+    SLIP_info status = solve_exact (x, A, S, b, option) ;
+    if (status == SLIP_OK) status = SLIP_get_double_soln (x_doub, x, A->n, b->n) ;
+    SLIP_delete_mpq_mat (&x, A->n, b->n) ;
+    return status ;
+}
+
+/* exact residual check A x == b in rational arithmetic, for the integer system (before scaling) */
+SLIP_info SLIP_check_solution (SLIP_sparse *A, mpq_t **x, SLIP_dense *b)
+{
+    if (!A || !x || !b || !b->x || !A->p || !A->i || !A->x) return SLIP_INCORRECT_INPUT ;
+    const int32_t n = A->n, nrhs = b->n ;
+    SLIP_info status = SLIP_OK ;
+    mpq_t **acc = SLIP_create_mpq_mat (n, nrhs) ;
+    if (!acc) return SLIP_OUT_OF_MEMORY ;
+    mpq_t t ;
+    mpq_init (t) ;
+    for (int32_t c = 0 ; c < nrhs ; c++)
+        for (int32_t j = 0 ; j < n ; j++)
+            for (int32_t a = A->p [j] ; a < A->p [j + 1] ; a++)
+            {
+                mpq_set_z (t, A->x [a]) ;
+                mpq_mul (t, t, x [j][c]) ;
+                mpq_add (acc [A->i [a]][c], acc [A->i [a]][c], t) ;
+            }
+    for (int32_t c = 0 ; c < nrhs && status == SLIP_OK ; c++)
+        for (int32_t i = 0 ; i < n ; i++)
+        {
+            mpq_set_z (t, b->x [i][c]) ;
+            if (!mpq_equal (t, acc [i][c])) { status = SLIP_INCORRECT ; break ; }
+        }
+    mpq_clear (t) ;
+    SLIP_delete_mpq_mat (&acc, n, nrhs) ;
+    return status ;
+}
+
+/* structural check of a CSC matrix (the reference also prints it; SLIP_spok.c) */
+SLIP_info SLIP_spok (SLIP_sparse *A, SLIP_options *option)
+{
+    if (!A || !option || !A->p || !A->i || !A->x) return SLIP_INCORRECT_INPUT ;
+    const int32_t n = A->n, m = A->m ;
+    if (n < 0 || m < 0 || A->nzmax < 0 || A->p [0] != 0 || A->p [n] < 0 || A->p [n] > A->nzmax)
+        return SLIP_INCORRECT_INPUT ;
+    int32_t *seen = (int32_t *) SLIP_malloc ((size_t) (m > 0 ? m : 1) * sizeof (int32_t)) ;
+    if (!seen) return SLIP_OUT_OF_MEMORY ;
+    for (int32_t i = 0 ; i < m ; i++) seen [i] = -1 ;
+    SLIP_info status = SLIP_OK ;
+    for (int32_t j = 0 ; j < n && status == SLIP_OK ; j++)
+    {
+        if (A->p [j] > A->p [j + 1]) { status = SLIP_INCORRECT_INPUT ; break ; }
+        for (int32_t a = A->p [j] ; a < A->p [j + 1] ; a++)
+        {
+            const int32_t i = A->i [a] ;
+            if (i < 0 || i >= m || seen [i] == j) { status = SLIP_INCORRECT_INPUT ; break ; }
+            seen [i] = j ;
+        }
+    }
+    SLIP_free (seen) ;
+    return status ;
+}

@@ -1,0 +1,49 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# COLAMD/AMD are SuiteSparse libraries the product loads at run time; in this image the only
+# build of them is inside the reference library compiled under oracle/_ref (checker side).
+_ref = os.path.join(ROOT, "oracle", "_ref", "libslip_ref.so")
+if os.path.exists(_ref):
+    os.environ.setdefault("SLIP_B200_ORDERING_LIB", _ref)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def product():
+    import __graft_entry__ as entry
+    entry.build()
+    import slip_lu_b200
+    return slip_lu_b200.lib()
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import binding
+    binding.build()
+    return binding
+
+
+@pytest.fixture(scope="session")
+def reference(oracle):
+    """The unmodified reference library (only where oracle/_ref was built)."""
+    from slip_lu_b200 import capi
+    if not os.path.exists(oracle.REF_SO):
+        pytest.skip("oracle/_ref/libslip_ref.so not built (needs /root/reference)")
+    return capi.SlipLib(oracle.REF_SO)
+
+
+@pytest.fixture(scope="session")
+def gpu(product):
+    if product.dll.SLIP_B200_device_count() < 1:
+        pytest.fail("no CUDA device visible: gpu tests must run on the B200 box")
+    return product

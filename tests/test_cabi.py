@@ -1,0 +1,138 @@
+"""CPU: the C-ABI library builds, loads, and exports every symbol the headers declare; the host
+logic that needs no GPU behaves like the reference; the compute entry points fail loudly
+without a device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+from slip_lu_b200 import capi, synth
+import cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared(header):
+    txt = open(os.path.join(ROOT, "include", header)).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(SLIP_[A-Za-z0-9_]+|slipcu_[a-z0-9_]+)\s*\(", txt))
+                  - {"SLIP_FREE", "SLIP_free (p) ; (p) = NULL ; }"})
+
+
+def test_exports_every_declared_symbol(product):
+    out = subprocess.check_output(["nm", "-D", "--defined-only", product.path], text=True)
+    exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
+    missing = [s for h in ("SLIP_LU.h", "slip_b200_device.h") for s in _declared(h)
+               if s not in exported and s not in ("SLIP_FREE",)]
+    assert not missing, f"declared but not exported: {missing}"
+
+
+def test_no_oracle_in_product(product):
+    """The product library must not depend on anything under oracle/."""
+    out = subprocess.check_output(["ldd", product.path], text=True)
+    assert "oracle" not in out and "libslip_ref" not in out and "libref_oracle" not in out
+    needed = subprocess.check_output(["readelf", "-d", product.path], text=True)
+    assert "libgmp" in needed
+
+
+def test_struct_layout_matches_interface(product):
+    assert C.sizeof(capi.SLIP_options) == 40
+    assert C.sizeof(capi.SLIP_sparse) == 72
+    assert C.sizeof(capi.SLIP_dense) == 48
+    o = product.default_options()
+    assert (o.contents.pivot, o.contents.order, o.contents.tol, o.contents.print_level,
+            o.contents.prec, o.contents.SLIP_MPFR_ROUND) == (3, 1, 1.0, 0, 128, 0)
+    product.free_options(o)
+
+
+def test_builders_roundtrip(product):
+    n, cp, ri, vals, b = synth.random_sparse(30, 4, 90, seed=4, nrhs=2, rhs_bits=70)
+    A = product.sparse_from_csc(n, cp, ri, vals)
+    assert product.sparse_to_py(A) == (cp, ri, vals)
+    assert capi.mpq_to_pair(A.contents.scale) == (1, 1)
+    I = [i for i in ri]
+    J = [j for j in range(n) for _ in range(cp[j], cp[j + 1])]
+    T = product.sparse_from_triplets(n, I, J, vals)
+    assert product.sparse_to_py(T) == (cp, ri, vals)
+    B = product.dense_from_rows(b)
+    assert [[capi.mpz_to_int(B.contents.x[r][c]) for c in range(2)] for r in range(n)] == b
+    assert product.dll.SLIP_spok(A, product.default_options()) == 0
+    product.free_sparse(A); product.free_sparse(T); product.free_dense(B)
+
+
+def test_double_builder_matches_reference_golden(product):
+    g = cases.load_golden("double_builders")
+    o = product.default_options()
+    for key in ("decimal", "tricky", "single"):
+        d = g[key]
+        vals = d["doubles"]
+        nz = len(vals)
+        if key == "decimal":
+            n, cp, ri = d["n"], d["colptr"], d["rowidx"]
+        else:
+            n, cp, ri = nz, list(range(nz + 1)), list(range(nz))
+        A = product.dll.SLIP_create_sparse()
+        rc = product.dll.SLIP_build_sparse_ccf_double(A, (C.c_int32 * (n + 1))(*cp), (C.c_int32 * nz)(*ri),
+                                                      (C.c_double * nz)(*vals), n, nz, o)
+        assert rc == 0
+        assert product.sparse_to_py(A)[2] == [int(v) for v in d["ints"]], key
+        assert capi.mpq_to_pair(A.contents.scale) == (int(d["scale"][0]), int(d["scale"][1])), key
+        product.free_sparse(A)
+
+
+def test_analyze_matches_golden_orderings(product):
+    """SLIP_LU_analyze (COLAMD / AMD through the SuiteSparse library found at run time, and the
+    nnz guesses) reproduces the reference's q."""
+    if not os.environ.get("SLIP_B200_ORDERING_LIB"):
+        pytest.skip("no SuiteSparse ordering library available here")
+    for name in ("10teams_default", "10teams_amd_largest", "rand120_colamd", "lap100_amd_tol"):
+        g = cases.load_golden(name)
+        n, cp, ri, vals, _ = cases.golden_system(g)
+        A = product.sparse_from_csc(n, cp, ri, vals)
+        o = product.default_options(order=g["options"]["order"])
+        S = product.analyze(A, o)
+        assert [S.contents.q[k] for k in range(n)] == g["q"], name
+        product.free_analysis(S); product.free_sparse(A)
+    A = product.sparse_from_csc(3, [0, 1, 2, 3], [0, 1, 2], [1, 2, 3])
+    S = product.analyze(A, product.default_options(order=capi.SLIP_NO_ORDERING))
+    assert [S.contents.q[k] for k in range(4)] == [0, 1, 2, 3] and S.contents.lnz == 5  # 10*nz clamped to ceil(n*n/2)
+
+
+def test_permute_and_scale(product):
+    n, nrhs = 4, 2
+    x = product.dll.SLIP_create_mpq_mat(n, nrhs)
+    for r in range(n):
+        for c in range(nrhs):
+            capi.int_to_mpz(x[r][c]._mp_num, 10 * r + c + 1)
+    S = product.dll.SLIP_create_LU_analysis(n + 1)
+    for k, v in enumerate([2, 0, 3, 1]):
+        S.contents.q[k] = v
+    assert product.dll.SLIP_permute_x(x, n, nrhs, S) == 0
+    got = product.mpq_mat_to_py(x, n, nrhs)
+    # x2[q[i]] = x[i]
+    assert [row[0][0] for row in got] == [11, 31, 1, 21]
+
+
+def test_compute_fails_loudly_without_gpu(product):
+    if product.dll.SLIP_B200_device_count() > 0:
+        pytest.skip("a GPU is present")
+    n, cp, ri, vals, b = synth.random_sparse(10, 3, 16, seed=1)
+    A = product.sparse_from_csc(n, cp, ri, vals)
+    o = product.default_options(order=capi.SLIP_NO_ORDERING)
+    S = product.analyze(A, o)
+    with pytest.raises(capi.SlipError):
+        product.factorize(A, S, o)
+    B = product.dense_from_rows(b)
+    with pytest.raises(capi.SlipError):
+        product.solve_mpq(A, S, B, o)
+    product.dll.SLIP_B200_last_error.restype = C.c_char_p
+    assert b"no CUDA device" in product.dll.SLIP_B200_last_error()
+
+
+def test_bad_arguments(product):
+    o = product.default_options()
+    assert product.dll.SLIP_LU_factorize(None, None, None, None, None, None, o) == capi.SLIP_INCORRECT_INPUT
+    assert product.dll.SLIP_LU_solve(None, None, None, None, None, None) == capi.SLIP_INCORRECT_INPUT
+    assert product.dll.SLIP_LU_analyze(None, None, o) == capi.SLIP_INCORRECT_INPUT

@@ -42,6 +42,16 @@ static int fail (int code, const char *what, const char *detail)
     g_err = std::string (what) + ": " + (detail ? detail : "");
     return code;
 }
+static int g_debug_sync = -1;     // SLIP_B200_DEBUG_SYNC=1: synchronize and check after every launch
+static int debug_check (const char *what, cudaStream_t st)
+{
+    if (g_debug_sync < 0) { const char *v = getenv ("SLIP_B200_DEBUG_SYNC"); g_debug_sync = (v && *v == '1') ? 1 : 0; }
+    if (!g_debug_sync) return 0;
+    cudaError_t e = cudaStreamSynchronize (st);
+    if (e == cudaSuccess) e = cudaGetLastError ();
+    if (e != cudaSuccess) { fprintf (stderr, "slipcu debug: %s failed: %s\n", what, cudaGetErrorString (e)); return 1; }
+    return 0;
+}
 #define CU(call)                                                                          \
     do { cudaError_t e_ = (call); if (e_ != cudaSuccess)                                  \
          return fail (e_ == cudaErrorMemoryAllocation ? SLIPCU_OUT_OF_MEMORY : SLIPCU_CUDA_ERROR, \
@@ -50,6 +60,7 @@ static int fail (int code, const char *what, const char *detail)
 extern "C" const char *slipcu_last_error (void) { return g_err.c_str (); }
 
 static std::atomic<uint64_t> g_launches{0}, g_tri_launches{0};
+static double g_h2d_bytes = 0;
 static double g_tri_ms = 0, g_tri_bytes = 0, g_tri_modmul = 0, g_recon_ms = 0, g_recon_mac = 0;
 static int g_profiling = 0;
 
@@ -278,6 +289,8 @@ struct ColDesc            // one finished column, as the kernels see it
     int32_t pad;
 };
 
+struct StepInfo;
+
 struct HostCol
 {
     u32 *base = nullptr; int32_t *rows = nullptr; int cnt = 0, nU = 0, s = 0, stride = 0;
@@ -307,6 +320,10 @@ struct slipcu_factor
     size_t smem_limit = 0;
     int keep_positional = 1, rows_are_positions = 0, x_global = 0, cur = -1;
     u32 *tmp_limbs = nullptr; int32_t *tmp_nl = nullptr; int tmp_stride = 0;
+    int32_t *slots = nullptr; size_t slots_cap = 0;      // slot lists of the current column
+    StepInfo *steps = nullptr; size_t steps_cap = 0;
+    int stages = 4;
+    int garner_mode = 1;
     slipcu_factor () : resid ((size_t) 512 << 20), ints ((size_t) 16 << 20), limbs ((size_t) 256 << 20) {}
 };
 
@@ -337,49 +354,163 @@ __global__ void k_residues (int count, int CH, const u32 *limbs, const int64_t *
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_trisolve: sparse REF triangular solve of one column (or of one dense right-hand side), one
-// CTA per block of CH channels, all channels independent.  Slots 0..nU-1 of the pattern are rows
-// that are already pivotal (sorted by pivot position upos[u]); slots nU..cnt-1 are candidate rows.
-// hist[] is the symbolic history vector of the reference; it is identical in every channel.
+// TMA bulk copy + mbarrier primitives (sm_90+; SASS: UBLKCP / SYNCS)
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 smem_u32 (const void *p) { return (u32) __cvta_generic_to_shared (p); }
+__device__ __forceinline__ void mbar_init (uint64_t *b, u32 cnt)
+{
+    asm volatile ("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32 (b)), "r"(cnt));
+}
+__device__ __forceinline__ void mbar_expect_tx (uint64_t *b, u32 bytes)
+{
+    asm volatile ("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32 (b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive (uint64_t *b)
+{
+    asm volatile ("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32 (b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait (uint64_t *b, u32 parity)
+{
+    asm volatile ("{\n .reg .pred p;\n WAIT_%=:\n"
+                  " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                  " @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}"
+                  :: "r"(smem_u32 (b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s (void *dst, const void *src, u32 bytes, uint64_t *b)
+{
+    asm volatile ("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                  :: "r"(smem_u32 (dst)), "l"(src), "r"(bytes), "r"(smem_u32 (b)) : "memory");
+}
+__device__ __forceinline__ void consumer_bar (int nthreads)
+{
+    asm volatile ("bar.sync 1, %0;" :: "r"(nthreads) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// symbolic pre-pass of a column: row -> slot map, then for every elimination step the list of
+// target slots (one per entry of the L column used), shared by all channel blocks.
+// ------------------------------------------------------------------------------------------------
+struct StepInfo           // one elimination step of a column: eliminate with column j of L
+{
+    const u32 *lbase;     // first L-part residue of column j for channel block 0
+    int32_t j;            // pivot position
+    int32_t len;          // entries in the L part of column j (the pivot row included)
+    int32_t cbstride;     // words between channel blocks of column j
+    int32_t slot_off;     // offset of this step's slot list (multiple of 4)
+    int32_t pad[2];
+};
+
+__global__ void k_setpos (int cnt, const int32_t *rows, int32_t *pos)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < cnt) pos[rows[t]] = t;
+}
+
+__global__ void k_slots (int nU, int total, int CH, const int32_t *upos, const int32_t *uoff,
+                         const ColDesc *desc, const int32_t *pos, int32_t *slots, StepInfo *steps)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int lo = 0, hi = nU - 1;                      // last u with uoff[u] <= i
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (uoff[mid] <= i) lo = mid; else hi = mid - 1; }
+    const int u = lo, r = i - uoff[u];
+    const ColDesc d = desc[upos[u]];
+    const int len = d.cnt - d.nU;
+    const int m = d.nU + r;
+    slots[i] = (r < len && m != d.pivslot) ? pos[d.rows[m]] : -1;
+    if (r == 0)
+    {
+        StepInfo si;
+        si.lbase = d.base + (size_t) d.nU * CH; si.j = upos[u]; si.len = len; si.cbstride = d.cnt * CH;
+        si.slot_off = uoff[u]; si.pad[0] = si.pad[1] = 0;
+        steps[u] = si;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_trisolve: sparse REF triangular solve of one column (or of one dense right-hand side).
+// One CTA per block of CH channels; channels are independent.  Warp 0 is the producer: it streams,
+// for every elimination step, the CH-wide rows of the L column, the slot list and the step's pivot
+// constants into a ring of shared-memory stages with TMA bulk copies (mbarrier completion).  The
+// consumer warps hold x (CH residues per pattern slot) and the symbolic history in shared memory
+// and apply   x_t <- x_t * f - l * (x_j / rho_{j-1})   per channel with one Montgomery reduction.
+// Slots 0..nU-1 of the pattern are rows that are already pivotal (in pivot order); slots
+// nU..cnt-1 are the candidate rows.
+// ------------------------------------------------------------------------------------------------
+#define TRI_ROWS 256          // rows per pipeline stage
+#define TRI_MAX_STAGES 8
+
 struct TriArgs
 {
     int k;                   // level the L part is brought to (column index; n for a rhs)
     int S, cnt, nU;
+    int stages;              // pipeline depth
     const int32_t *rows;     // [cnt] original row of each slot
-    const int32_t *upos;     // [nU] pivot position of each U-part slot
+    const StepInfo *steps;   // [nU]
+    const int32_t *slots;    // slot lists
     // source vector to scatter: src_cnt entries, entry e at residue index src_first + e*src_step,
     // going to the slot of row src_rows[e] (or row e when src_rows == nullptr)
     const u32 *src; int src_total; int src_first, src_step, src_cnt; const int32_t *src_rows;
     size_t src_y_stride;     // added to src_first per blockIdx.y (multiple right-hand sides)
     u32 *out;                // [S/CH][cnt][CH] result region (+ blockIdx.y * out_y_stride words)
     size_t out_y_stride;
-    const ColDesc *desc;
     const u32 *rho, *invrho, *ratio, *p, *ninv;
-    int32_t *pos;            // [n] row -> slot
+    const int32_t *pos;      // [n] row -> slot
     int x_in_smem;
 };
 
-template <int CH>
-__global__ void __launch_bounds__ (512) k_trisolve (TriArgs a)
-{
-    extern __shared__ __align__ (16) unsigned char smem_raw[];
-    int32_t *hist = (int32_t *) smem_raw;
-    u32 *xsm = (u32 *) (smem_raw + (((size_t) a.cnt * sizeof (int32_t) + 15) & ~(size_t) 15));
+struct StageMeta { int32_t j, nrows, first, last; };
 
-    const int tid = threadIdx.x, ch = tid % CH, rg = tid / CH, RG = blockDim.x / CH;
-    const int cb = blockIdx.x, c = cb * CH + ch, S = a.S, cnt = a.cnt, nU = a.nU;
-    const u32 p = a.p[c], ni = a.ninv[c];
+template <int CH>
+struct TriSmem
+{
+    // byte offsets inside the dynamic shared memory block
+    static __host__ __device__ size_t stage_bytes ()
+    {
+        return (size_t) TRI_ROWS * CH * 4 + (size_t) TRI_ROWS * 4 + 3 * CH * 4 + 32;   // L rows, slots, constants, meta
+    }
+    static __host__ __device__ size_t header_bytes () { return 2 * TRI_MAX_STAGES * sizeof (uint64_t); }
+    static __host__ __device__ size_t total (int cnt, int stages, bool x_in_smem)
+    {
+        size_t b = header_bytes ();
+        b += ((size_t) cnt * 4 + 127) & ~(size_t) 127;                        // history
+        if (x_in_smem) b += ((size_t) cnt * CH * 4 + 127) & ~(size_t) 127;     // x
+        b += (size_t) stages * ((stage_bytes () + 127) & ~(size_t) 127);
+        return b;
+    }
+};
+
+template <int CH>
+__global__ void __launch_bounds__ (544) k_trisolve (TriArgs a)
+{
+    extern __shared__ __align__ (128) unsigned char smem_raw[];
+    uint64_t *full = (uint64_t *) smem_raw;
+    uint64_t *empty = full + TRI_MAX_STAGES;
+    unsigned char *ptr = smem_raw + TriSmem<CH>::header_bytes ();
+    int32_t *hist = (int32_t *) ptr;
+    ptr += ((size_t) a.cnt * 4 + 127) & ~(size_t) 127;
+    u32 *xsm = (u32 *) ptr;
+    if (a.x_in_smem) ptr += ((size_t) a.cnt * CH * 4 + 127) & ~(size_t) 127;
+    unsigned char *stage0 = ptr;
+    const size_t stage_stride = (TriSmem<CH>::stage_bytes () + 127) & ~(size_t) 127;
+
+    const int tid = threadIdx.x;
+    const int NC = (blockDim.x >> 5) - 1;              // consumer warps (warp 0 produces)
+    const int cb = blockIdx.x, S = a.S, cnt = a.cnt, nU = a.nU, NS = a.stages;
     u32 *xg = a.out + (size_t) blockIdx.y * a.out_y_stride + (size_t) cb * cnt * CH;
     u32 *xs = a.x_in_smem ? xsm : xg;
 
-    for (int t = rg; t < cnt; t += RG)
+    if (tid == 0)
     {
-        xs[t * CH + ch] = 0;
-        if (ch == 0) { hist[t] = -1; a.pos[a.rows[t]] = t; }
+        for (int s = 0; s < NS; ++s) { mbar_init (&full[s], 1); mbar_init (&empty[s], NC); }
+        asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile ("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    __syncthreads ();
+    // all threads: clear x and the history, then scatter the source vector
     {
+        const int ch = tid % CH, rg = tid / CH, RG = blockDim.x / CH;
+        for (int t = rg; t < cnt; t += RG) { xs[t * CH + ch] = 0; if (ch == 0) hist[t] = -1; }
+        __syncthreads ();
         const u32 *src = a.src + (size_t) cb * a.src_total * CH;
         const int first = a.src_first + (int) (blockIdx.y * a.src_y_stride);
         for (int e = rg; e < a.src_cnt; e += RG)
@@ -387,57 +518,132 @@ __global__ void __launch_bounds__ (512) k_trisolve (TriArgs a)
             const int row = a.src_rows ? a.src_rows[e] : e;
             xs[a.pos[row] * CH + ch] = src[((size_t) first + (size_t) e * a.src_step) * CH + ch];
         }
+        __syncthreads ();
     }
-    __syncthreads ();
 
+    if (tid < 32)
+    {
+        // ---------------- producer warp ----------------
+        const int lane = tid;
+        int chunk = 0;
+        for (int u0 = 0; u0 < nU; u0 += 32)
+        {
+            StepInfo si;
+            si.lbase = nullptr; si.j = 0; si.len = 0; si.cbstride = 0; si.slot_off = 0;
+            if (u0 + lane < nU) si = a.steps[u0 + lane];
+            const int lim = min (32, nU - u0);
+            for (int i = 0; i < lim; ++i)
+            {
+                const u32 *lbase = (const u32 *) __shfl_sync (0xffffffffu, (unsigned long long) si.lbase, i);
+                const int j = __shfl_sync (0xffffffffu, si.j, i);
+                const int len = __shfl_sync (0xffffffffu, si.len, i);
+                const int cbs = __shfl_sync (0xffffffffu, si.cbstride, i);
+                const int soff = __shfl_sync (0xffffffffu, si.slot_off, i);
+                for (int m0 = 0; m0 < len; m0 += TRI_ROWS, ++chunk)
+                {
+                    const int st = chunk % NS;
+                    const u32 round = (u32) (chunk / NS);
+                    if (lane == 0)
+                    {
+                        mbar_wait (&empty[st], (round & 1) ^ 1);      // stage drained by the consumers
+                        unsigned char *sb = stage0 + (size_t) st * stage_stride;
+                        u32 *Lbuf = (u32 *) sb;
+                        int32_t *Sbuf = (int32_t *) (sb + (size_t) TRI_ROWS * CH * 4);
+                        u32 *Cbuf = (u32 *) (sb + (size_t) TRI_ROWS * CH * 4 + (size_t) TRI_ROWS * 4);
+                        StageMeta *meta = (StageMeta *) (Cbuf + 3 * CH);
+                        const int nrows = min (TRI_ROWS, len - m0);
+                        const int npad = (nrows + 3) & ~3;
+                        const bool first = (m0 == 0);
+                        meta->j = j; meta->nrows = nrows; meta->first = first; meta->last = (m0 + TRI_ROWS >= len);
+                        u32 bytes = (u32) nrows * CH * 4 + (u32) npad * 4;
+                        if (first) bytes += (j >= 1 ? 3 : 2) * CH * 4;
+                        mbar_expect_tx (&full[st], bytes);
+                        bulk_g2s (Lbuf, lbase + (size_t) cb * cbs + (size_t) m0 * CH, (u32) nrows * CH * 4, &full[st]);
+                        bulk_g2s (Sbuf, a.slots + soff + m0, (u32) npad * 4, &full[st]);
+                        if (first)
+                        {
+                            bulk_g2s (Cbuf, a.rho + (size_t) j * S + (size_t) cb * CH, CH * 4, &full[st]);
+                            bulk_g2s (Cbuf + CH, a.ratio + (size_t) j * S + (size_t) cb * CH, CH * 4, &full[st]);
+                            if (j >= 1)
+                                bulk_g2s (Cbuf + 2 * CH, a.invrho + (size_t) (j - 1) * S + (size_t) cb * CH, CH * 4, &full[st]);
+                        }
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumer warps ----------------
+    const int ctid = tid - 32, nthr = NC * 32;
+    const int ch = ctid % CH, rg = ctid / CH, RG = nthr / CH;
+    const int c = cb * CH + ch;
+    const u32 p = a.p[c], ni = a.ninv[c];
     u32 pend_val = 0; int pend_slot = -1;
+    int chunk = 0;
     for (int u = 0; u < nU; ++u)
     {
         if (pend_slot >= 0) { xs[pend_slot * CH + ch] = pend_val; pend_slot = -1; }
-        const int j = a.upos[u];
-        const ColDesc d = a.desc[j];
-        u32 xj = xs[u * CH + ch];
-        const int hj = hist[u];
-        if (hj < j - 1)
-        {   // history update of the finished U entry: level hj+1 -> level j
-            xj = mont_mul (xj, a.rho[(size_t) (j - 1) * S + c], p, ni);
-            if (hj >= 0) xj = mont_mul (xj, a.invrho[(size_t) hj * S + c], p, ni);
-            if (rg == 0) { pend_slot = u; pend_val = xj; }
-        }
-        const u32 y = (j >= 1) ? mont_mul (xj, a.invrho[(size_t) (j - 1) * S + c], p, ni) : xj;
-        const u32 negy = y ? p - y : 0u;
-        const u32 rj = a.ratio[(size_t) j * S + c];
-        const u32 rhoj = a.rho[(size_t) j * S + c];
-        const u32 *Lb = d.base + (size_t) cb * d.cnt * CH;
-        const int len = d.cnt - d.nU;
-        const int iters = (len + RG - 1) / RG;
-#pragma unroll 2
-        for (int it = 0; it < iters; ++it)
+        u32 negy = 0, rj = 0, rhoj = 0;
+        int j = 0;
+        for (;; ++chunk)
         {
-            const int m = d.nU + it * RG + rg;
-            const bool act = (m < d.cnt) && (m != d.pivslot);
-            int t = 0, h = 0;
-            if (act)
+            const int st = chunk % NS;
+            const u32 round = (u32) (chunk / NS);
+            mbar_wait (&full[st], round & 1);
+            const unsigned char *sb = stage0 + (size_t) st * stage_stride;
+            const u32 *Lbuf = (const u32 *) sb;
+            const int32_t *Sbuf = (const int32_t *) (sb + (size_t) TRI_ROWS * CH * 4);
+            const u32 *Cbuf = (const u32 *) (sb + (size_t) TRI_ROWS * CH * 4 + (size_t) TRI_ROWS * 4);
+            const StageMeta meta = *(const StageMeta *) (Cbuf + 3 * CH);
+            if (meta.first)
             {
-                t = a.pos[d.rows[m]];
-                const u32 l = Lb[(size_t) m * CH + ch];
-                h = hist[t];
-                u32 f = rj;
-                if (h != j - 1)
-                {
-                    f = rhoj;
-                    if (h >= 0) f = mont_mul (f, a.invrho[(size_t) h * S + c], p, ni);
+                j = meta.j;
+                u32 xj = xs[u * CH + ch];
+                const int hj = hist[u];
+                if (hj < j - 1)
+                {   // history update of the finished U entry: level hj+1 -> level j
+                    xj = mont_mul (xj, a.rho[(size_t) (j - 1) * S + c], p, ni);
+                    if (hj >= 0) xj = mont_mul (xj, a.invrho[(size_t) hj * S + c], p, ni);
+                    if (rg == 0) { pend_slot = u; pend_val = xj; }
                 }
-                const u32 xv = xs[t * CH + ch];
-                xs[t * CH + ch] = mont_redc ((u64) xv * f + (u64) l * negy, p, ni);
+                const u32 y = (j >= 1) ? mont_mul (xj, Cbuf[2 * CH + ch], p, ni) : xj;
+                negy = y ? p - y : 0u;
+                rhoj = Cbuf[ch];
+                rj = Cbuf[CH + ch];
+            }
+            const int nrows = meta.nrows;
+            const int iters = (nrows + RG - 1) / RG;
+#pragma unroll 4
+            for (int it = 0; it < iters; ++it)
+            {
+                const int r = it * RG + rg;
+                const int t = (r < nrows) ? Sbuf[r] : -1;
+                int h = 0;
+                if (t >= 0)
+                {
+                    const u32 l = Lbuf[r * CH + ch];
+                    h = hist[t];
+                    u32 f = rj;
+                    if (h != j - 1)
+                    {
+                        f = rhoj;
+                        if (h >= 0) f = mont_mul (f, a.invrho[(size_t) h * S + c], p, ni);
+                    }
+                    const u32 xv = xs[t * CH + ch];
+                    xs[t * CH + ch] = mont_redc ((u64) xv * f + (u64) l * negy, p, ni);
+                }
+                __syncwarp ();
+                if (t >= 0 && ch == 0) hist[t] = j;
             }
             __syncwarp ();
-            if (act && ch == 0) hist[t] = j;
+            if ((ctid & 31) == 0) mbar_arrive (&empty[st]);
+            if (meta.last) { ++chunk; break; }
         }
-        __syncthreads ();
+        consumer_bar (nthr);       // every update of this step is visible before the next x_j is read
     }
     if (pend_slot >= 0) xs[pend_slot * CH + ch] = pend_val;
-    __syncthreads ();
+    consumer_bar (nthr);
     // candidate rows: bring to level k; then publish the column
     for (int t = rg; t < cnt; t += RG)
     {
@@ -597,6 +803,184 @@ __global__ void __launch_bounds__ (128) k_garner (GarnerArgs a)
         if (nzm) { top = t0 + 31 - __clz (nzm); break; }
     }
     // zero-pad the digit row up to the next multiple of 4 (vector loads in later passes)
+    for (int t = s + lane; t < ((s + 3) & ~3); t += 32) dg[t] = 0;
+    if (lane == 0) { a.topd[e] = top; a.sign[e] = top < 0 ? 0 : (neg ? -1 : 1); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_garner_tiled: same result as k_garner, organised like a blocked triangular solve so that the
+// table C is read once per E entries and the long dependency chain is one CTA-wide step per 32
+// digits.  A CTA of W warps reconstructs E entries.  Digit block b (positions 32b..32b+31) is owned
+// by warp b mod W, which keeps the running sums  T[e] = sum_u d_e[u] C[u][t]  of its blocks in
+// registers.  Per block: the owner finishes its 32 digits (in-warp shuffles), publishes them, and
+// all warps add their contribution to the blocks they still own (right-looking).  Digits of
+// earlier tiles (s > 32*W*BPW) are applied first, left-looking, from global memory.
+// ------------------------------------------------------------------------------------------------
+template <int E, int BPW>
+__global__ void __launch_bounds__ (512) k_garner_tiled (GarnerArgs a)
+{
+    __shared__ __align__ (16) u32 dcur[2][E][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, W = blockDim.x >> 5;
+    const int s = a.s, S = a.S, CH = a.CH;
+    const int B = (s + 31) >> 5;
+    const unsigned full = 0xffffffffu;
+    const int g0 = blockIdx.x * E;
+    int ent[E];                         // entry indices (clamped; invalid ones recompute the last)
+#pragma unroll
+    for (int e = 0; e < E; ++e) ent[e] = a.e0 + min (g0 + e, a.ne - 1);
+
+    for (int tb0 = 0; tb0 < B; tb0 += W * BPW)
+    {
+        u64 acc[E][BPW];
+        u32 pt[BPW], nit[BPW];
+        int tpos[BPW];
+#pragma unroll
+        for (int i = 0; i < BPW; ++i)
+        {
+            const int t = 32 * (tb0 + w + i * W) + lane;
+            tpos[i] = t < s ? t : s - 1;
+            pt[i] = a.p[tpos[i]]; nit[i] = a.ninv[tpos[i]];
+#pragma unroll
+            for (int e = 0; e < E; ++e) acc[e][i] = 0;
+        }
+        // (1) digits of the previous tiles
+        for (int u = 0; u < tb0 * 32; u += 4)
+        {
+            uint4 d4[E];
+#pragma unroll
+            for (int e = 0; e < E; ++e) d4[e] = *reinterpret_cast<const uint4 *> (a.dig + (size_t) ent[e] * a.dstride + u);
+#pragma unroll
+            for (int i = 0; i < BPW; ++i)
+            {
+                const u32 *Cc = a.C + (size_t) u * S + tpos[i];
+                const u32 c0 = Cc[0], c1 = Cc[S], c2 = Cc[2 * (size_t) S], c3 = Cc[3 * (size_t) S];
+#pragma unroll
+                for (int e = 0; e < E; ++e)
+                {
+                    lazy_mac (acc[e][i], d4[e].x, c0, pt[i]); lazy_mac (acc[e][i], d4[e].y, c1, pt[i]);
+                    lazy_mac (acc[e][i], d4[e].z, c2, pt[i]); lazy_mac (acc[e][i], d4[e].w, c3, pt[i]);
+                }
+            }
+        }
+        // (2) the blocks of this tile, in order
+#pragma unroll
+        for (int li = 0; li < BPW; ++li)
+        {
+            for (int ow = 0; ow < W; ++ow)
+            {
+                const int b = tb0 + li * W + ow;
+                if (b >= B) break;                       // uniform across the CTA
+                const int buf = b & 1;
+                if (w == ow)
+                {   // finish the 32 digits of block b for the E entries
+                    const int t = 32 * b + lane;
+                    const bool valid = t < s;
+                    const int tt = tpos[li];
+                    const u32 p = pt[li], ni = nit[li];
+                    const u32 ib = a.invB[tt];
+                    u32 v[E], mine[E];
+                    u64 T[E];
+#pragma unroll
+                    for (int e = 0; e < E; ++e)
+                    {
+                        v[e] = mont_redc (a.base[((size_t) (tt / CH) * a.cnt + ent[e]) * CH + (tt % CH)], p, ni);
+                        T[e] = acc[e][li]; mine[e] = 0;
+                    }
+                    const u32 *Ccol = a.C + tt;
+                    for (int i = 0; i < 32; ++i)
+                    {
+                        const u32 cc = (lane > i) ? Ccol[(size_t) (32 * b + i) * S] : 0u;
+#pragma unroll
+                        for (int e = 0; e < E; ++e)
+                        {
+                            u32 di = 0;
+                            if (lane == i)
+                            {
+                                const u32 r = lazy_redc (T[e], p, ni);
+                                const u32 diff = v[e] >= r ? v[e] - r : v[e] + p - r;
+                                di = mont_mul (diff, ib, p, ni);
+                                mine[e] = di;
+                            }
+                            di = __shfl_sync (full, di, i);
+                            if (lane > i) lazy_mac (T[e], di, cc, p);
+                        }
+                    }
+#pragma unroll
+                    for (int e = 0; e < E; ++e)
+                    {
+                        if (valid && g0 + e < a.ne) a.dig[(size_t) ent[e] * a.dstride + t] = mine[e];
+                        dcur[buf][e][lane] = valid ? mine[e] : 0u;
+                    }
+                }
+                __syncthreads ();
+                // every warp: add block b's digits to the blocks it still owns
+                for (int q = 0; q < 32; q += 4)
+                {
+                    uint4 d4[E];
+#pragma unroll
+                    for (int e = 0; e < E; ++e) d4[e] = *reinterpret_cast<const uint4 *> (&dcur[buf][e][q]);
+#pragma unroll
+                    for (int i = 0; i < BPW; ++i)
+                    {
+                        // local block i is block tb0 + w + i*W; it is later than b iff i > li or (i == li and w > ow)
+                        if (i > li || (i == li && w > ow))
+                        {
+                            const u32 *Cc = a.C + (size_t) (32 * b + q) * S + tpos[i];
+                            const u32 c0 = Cc[0], c1 = Cc[S], c2 = Cc[2 * (size_t) S], c3 = Cc[3 * (size_t) S];
+#pragma unroll
+                            for (int e = 0; e < E; ++e)
+                            {
+                                lazy_mac (acc[e][i], d4[e].x, c0, pt[i]); lazy_mac (acc[e][i], d4[e].y, c1, pt[i]);
+                                lazy_mac (acc[e][i], d4[e].z, c2, pt[i]); lazy_mac (acc[e][i], d4[e].w, c3, pt[i]);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads ();
+    }
+    __syncthreads ();
+    // sign, magnitude digits and top digit: one warp per entry
+    if (w >= E || g0 + w >= a.ne) return;
+    const int e = a.e0 + g0 + w;
+    u32 *dg = a.dig + (size_t) e * a.dstride;
+    bool neg = false;
+    for (int t0 = ((s - 1) / 32) * 32; t0 >= 0; t0 -= 32)
+    {
+        const int t = t0 + lane;
+        u32 d = 0, h = 0;
+        if (t < s) { d = dg[t]; h = (a.p[t] - 1) >> 1; }
+        const unsigned ne = __ballot_sync (full, d != h);
+        if (ne)
+        {
+            const int top = 31 - __clz (ne);
+            neg = __shfl_sync (full, (int) (d > h), top) != 0;
+            break;
+        }
+    }
+    if (neg)
+    {
+        for (int t = lane; t < s; t += 32) dg[t] = a.p[t] - 1 - dg[t];
+        __syncwarp ();
+        if (lane == 0)
+        {
+            for (int t = 0; t < s; ++t)
+            {
+                u32 d = dg[t] + 1;
+                if (d == a.p[t]) dg[t] = 0; else { dg[t] = d; break; }
+            }
+        }
+        __syncwarp ();
+    }
+    int top = -1;
+    for (int t0 = ((s - 1) / 32) * 32; t0 >= 0; t0 -= 32)
+    {
+        const int t = t0 + lane;
+        const u32 d = (t < s) ? dg[t] : 0u;
+        const unsigned nzm = __ballot_sync (full, d != 0);
+        if (nzm) { top = t0 + 31 - __clz (nzm); break; }
+    }
     for (int t = s + lane; t < ((s + 3) & ~3); t += 32) dg[t] = 0;
     if (lane == 0) { a.topd[e] = top; a.sign[e] = top < 0 ? 0 : (neg ? -1 : 1); }
 }
@@ -795,6 +1179,7 @@ extern "C" void slipcu_factor_free (slipcu_factor *F)
     cudaFree (F->desc); cudaFree (F->pos); cudaFree (F->bad);
     cudaFree (F->dig); cudaFree (F->topd); cudaFree (F->d_info);
     cudaFree (F->tmp_limbs); cudaFree (F->tmp_nl);
+    cudaFree (F->slots); cudaFree (F->steps);
     if (F->h_packet) cudaFreeHost (F->h_packet);
     if (F->h_info) cudaFreeHost (F->h_info);
     if (F->ev) cudaEventDestroy (F->ev);
@@ -843,9 +1228,12 @@ static int session_common_init (slipcu_factor *F, int n, int channels)
     CH = env_int ("SLIP_B200_CH", CH);
     if (CH != 8 && CH != 16 && CH != 32) CH = 16;
     F->CH = CH;
-    F->threads = env_int ("SLIP_B200_THREADS", CH == 8 ? 256 : 512);
-    if (F->threads % 32 || F->threads < 32 || F->threads > 512) F->threads = 256;
+    F->threads = env_int ("SLIP_B200_THREADS", 288);       // one producer warp + consumer warps
+    if (F->threads % 32 || F->threads < 64 || F->threads > 544 || ((F->threads - 32) % CH)) F->threads = 288;
+    F->stages = env_int ("SLIP_B200_STAGES", 4);
+    if (F->stages < 2 || F->stages > TRI_MAX_STAGES) F->stages = 4;
     F->x_global = env_int ("SLIP_B200_X_GLOBAL", 0);
+    F->garner_mode = env_int ("SLIP_B200_GARNER", 1);
     int smem_optin = 0;
     cudaDeviceGetAttribute (&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, F->device);
     F->smem_limit = (size_t) smem_optin;
@@ -865,7 +1253,7 @@ static int session_common_init (slipcu_factor *F, int n, int channels)
     CU (cudaMalloc (&F->d_info, sizeof (slipcu_pivot_info)));
     CU (cudaMemset (F->bad, 0, sizeof (int32_t)));
     CU (cudaMemset (F->pos, 0, (size_t) n * sizeof (int32_t)));
-    CU (cudaHostAlloc (&F->h_packet, (size_t) 2 * n * sizeof (int32_t), cudaHostAllocDefault));
+    CU (cudaHostAlloc (&F->h_packet, ((size_t) 3 * n + 8) * sizeof (int32_t), cudaHostAllocDefault));
     CU (cudaHostAlloc (&F->h_info, sizeof (slipcu_pivot_info), cudaHostAllocDefault));
     F->cols.resize (n);
     return SLIPCU_OK;
@@ -917,12 +1305,70 @@ static cudaError_t launch_tri (const TriArgs &a, dim3 grid, int threads, size_t 
     k_trisolve<CH><<<grid, threads, smem, st>>> (a);
     return cudaGetLastError ();
 }
+static size_t tri_smem_bytes (int CH, int cnt, int stages, bool x_in_smem)
+{
+    if (CH == 8) return TriSmem<8>::total (cnt, stages, x_in_smem);
+    if (CH == 16) return TriSmem<16>::total (cnt, stages, x_in_smem);
+    return TriSmem<32>::total (cnt, stages, x_in_smem);
+}
 static cudaError_t launch_tri_any (int CH, const TriArgs &a, dim3 grid, int threads, size_t smem, cudaStream_t st)
 {
     g_launches++; g_tri_launches++;
     if (CH == 8) return launch_tri<8> (a, grid, threads, smem, st);
     if (CH == 16) return launch_tri<16> (a, grid, threads, smem, st);
     return launch_tri<32> (a, grid, threads, smem, st);
+}
+
+// symbolic pre-pass on the device: pos[], the slot lists and the step table of a column whose
+// pattern (rows), step positions (upos) and slot-list offsets (uoff, nU+1 entries) are on the device
+static int prepare_steps (slipcu_factor *F, int cnt, int nU, const int32_t *rows, const int32_t *upos,
+                          const int32_t *uoff, int total)
+{
+    if ((size_t) total > F->slots_cap)
+    {
+        CU (cudaStreamSynchronize (F->st));
+        cudaFree (F->slots); F->slots = nullptr;
+        size_t want = std::max ((size_t) total, F->slots_cap * 2);
+        CU (cudaMalloc (&F->slots, want * sizeof (int32_t)));
+        F->slots_cap = want;
+    }
+    if ((size_t) nU > F->steps_cap)
+    {
+        CU (cudaStreamSynchronize (F->st));
+        cudaFree (F->steps); F->steps = nullptr;
+        size_t want = std::max ((size_t) nU, std::max<size_t> (F->steps_cap * 2, 256));
+        CU (cudaMalloc (&F->steps, want * sizeof (StepInfo)));
+        F->steps_cap = want;
+    }
+    k_setpos<<<(cnt + 255) / 256, 256, 0, F->st>>> (cnt, rows, F->pos);
+    g_launches++;
+    CU (cudaGetLastError ());
+    if (debug_check ("k_setpos", F->st)) return fail (SLIPCU_CUDA_ERROR, "k_setpos", "debug");
+    if (nU > 0 && total > 0)
+    {
+        k_slots<<<(total + 255) / 256, 256, 0, F->st>>> (nU, total, F->CH, upos, uoff, F->desc, F->pos, F->slots, F->steps);
+        g_launches++;
+        CU (cudaGetLastError ());
+        if (debug_check ("k_slots", F->st)) return fail (SLIPCU_CUDA_ERROR, "k_slots", "debug");
+    }
+    return SLIPCU_OK;
+}
+
+// fills the launch geometry of a triangular solve; returns the dynamic shared memory size
+static int tri_geometry (slipcu_factor *F, TriArgs &a, size_t *smem)
+{
+    a.stages = F->stages;
+    a.x_in_smem = !F->x_global;
+    size_t need = tri_smem_bytes (F->CH, a.cnt, a.stages, a.x_in_smem);
+    while (need + 1024 > F->smem_limit && a.stages > 2) { a.stages--; need = tri_smem_bytes (F->CH, a.cnt, a.stages, a.x_in_smem); }
+    if (need + 1024 > F->smem_limit && a.x_in_smem)
+    {   // pattern too long for shared memory: x stays in the (L2-resident) output region
+        a.x_in_smem = 0; a.stages = F->stages;
+        need = tri_smem_bytes (F->CH, a.cnt, a.stages, false);
+    }
+    if (need + 1024 > F->smem_limit) return fail (SLIPCU_BAD_INPUT, "tri_geometry", "pattern too large for the shared history vector");
+    *smem = need;
+    return SLIPCU_OK;
 }
 
 static int check_channels (slipcu_factor *F);
@@ -955,9 +1401,19 @@ static int run_garner (slipcu_factor *F, const u32 *base, int region_cnt, int e0
     g.base = base; g.dig = F->dig; g.dstride = (size_t) F->S + 4; g.topd = F->topd; g.sign = sign;
     g.p = T.p; g.ninv = T.ninv; g.C = T.C; g.invB = T.invB;
     ScopedTimer tm (F, &g_recon_ms);
-    k_garner<<<(ne + 3) / 4, 128, 0, F->st>>> (g);
+    if (F->garner_mode == 0 || s < 64)
+        k_garner<<<(ne + 3) / 4, 128, 0, F->st>>> (g);
+    else
+    {
+        // pick the CTA width so that one tile covers s when possible (W warps x 5 blocks x 32 digits)
+        const int blocks = (s + 31) / 32;
+        int W = (blocks + 4) / 5;
+        W = std::max (4, std::min (16, W));      // >= E warps: the epilogue uses one warp per entry
+        k_garner_tiled<4, 5><<<(ne + 3) / 4, W * 32, 0, F->st>>> (g);
+    }
     g_launches++;
     CU (cudaGetLastError ());
+    if (debug_check ("k_garner", F->st)) return fail (SLIPCU_CUDA_ERROR, "k_garner", "debug");
     g_recon_mac += (double) ne * ((double) s * s * 0.5);
     return SLIPCU_OK;
 }
@@ -975,6 +1431,7 @@ static int run_limbs (slipcu_factor *F, int e0, int ne, int out0, int stride, in
     k_limbs<<<(ne + 3) / 4, 128, 0, F->st>>> (l);
     g_launches++;
     CU (cudaGetLastError ());
+    if (debug_check ("k_limbs", F->st)) return fail (SLIPCU_CUDA_ERROR, "k_limbs", "debug");
     g_recon_mac += (double) ne * ((double) s * s * 0.5);
     return SLIPCU_OK;
 }
@@ -1008,32 +1465,45 @@ extern "C" int slipcu_factor_column (slipcu_factor *F, int k, int col, int cnt, 
     hc.nU = nU;
     int rc = alloc_column (F, hc, cnt, s);
     if (rc) return rc;
-    hc.rows = (int32_t *) F->ints.alloc ((size_t) (cnt + nU) * sizeof (int32_t));
-    if (!hc.rows) return fail (SLIPCU_OUT_OF_MEMORY, "slipcu_factor_column", "device memory exhausted");
     rc = ensure_digits (F, (size_t) cnt);
     if (rc) return rc;
+    // packet: pattern rows, pivot positions of the U part, slot-list offsets (padded to 4)
     memcpy (F->h_packet, rows, (size_t) cnt * sizeof (int32_t));
     if (nU) memcpy (F->h_packet + cnt, upos, (size_t) nU * sizeof (int32_t));
-    CU (cudaMemcpyAsync (hc.rows, F->h_packet, (size_t) (cnt + nU) * sizeof (int32_t),
+    int32_t *uoff = F->h_packet + cnt + nU;
+    int64_t total = 0;
+    for (int u = 0; u < nU; ++u)
+    {
+        const HostCol &lj = F->cols[upos[u]];
+        uoff[u] = (int32_t) total;
+        total += ((lj.cnt - lj.nU) + 3) & ~3;
+        if (total > INT32_MAX) return fail (SLIPCU_BAD_INPUT, "slipcu_factor_column", "column has too many updates");
+    }
+    uoff[nU] = (int32_t) total;
+    hc.rows = (int32_t *) F->ints.alloc ((size_t) (cnt + 2 * nU + 1) * sizeof (int32_t));
+    if (!hc.rows) return fail (SLIPCU_OUT_OF_MEMORY, "slipcu_factor_column", "device memory exhausted");
+    CU (cudaMemcpyAsync (hc.rows, F->h_packet, (size_t) (cnt + 2 * nU + 1) * sizeof (int32_t),
                          cudaMemcpyHostToDevice, F->st));
+    g_h2d_bytes += (double) (cnt + 2 * nU + 1) * sizeof (int32_t);
+    rc = prepare_steps (F, cnt, nU, hc.rows, hc.rows + cnt, hc.rows + cnt + nU, (int) total);
+    if (rc) return rc;
 
     TriArgs a;
     a.k = k; a.S = S; a.cnt = cnt; a.nU = nU;
-    a.rows = hc.rows; a.upos = hc.rows + cnt;
+    a.rows = hc.rows; a.steps = F->steps; a.slots = F->slots;
     a.src = F->dA; a.src_total = F->nz; a.src_first = F->hAp[col]; a.src_step = 1;
     a.src_cnt = F->hAp[col + 1] - F->hAp[col]; a.src_rows = F->dAi + F->hAp[col];
     a.src_y_stride = 0;
     a.out = hc.base; a.out_y_stride = 0;
-    a.desc = F->desc; a.rho = F->rho; a.invrho = F->invrho; a.ratio = F->ratio;
+    a.rho = F->rho; a.invrho = F->invrho; a.ratio = F->ratio;
     a.p = T.p; a.ninv = T.ninv; a.pos = F->pos;
-    size_t smem = (((size_t) cnt * sizeof (int32_t) + 15) & ~(size_t) 15);
-    const size_t xbytes = (size_t) cnt * CH * sizeof (u32);
-    a.x_in_smem = (smem + xbytes + 1024 <= F->smem_limit) && !F->x_global;
-    if (a.x_in_smem) smem += xbytes;
-    if (smem > F->smem_limit) return fail (SLIPCU_BAD_INPUT, "slipcu_factor_column", "pattern too large for shared history");
+    size_t smem = 0;
+    rc = tri_geometry (F, a, &smem);
+    if (rc) return rc;
     {
         ScopedTimer tm (F, &g_tri_ms);
         CU (launch_tri_any (CH, a, dim3 (S / CH, 1), F->threads, smem, F->st));
+        if (debug_check ("k_trisolve(column)", F->st)) return fail (SLIPCU_CUDA_ERROR, "k_trisolve", "debug");
     }
     {   // algorithmic work of this launch
         double upd = 0;
@@ -1050,6 +1520,7 @@ extern "C" int slipcu_factor_column (slipcu_factor *F, int k, int col, int cnt, 
                                         hc.sign, F->bad, F->d_info);
     g_launches++;
     CU (cudaGetLastError ());
+    if (debug_check ("k_pivot_scan", F->st)) return fail (SLIPCU_CUDA_ERROR, "k_pivot_scan", "debug");
     CU (cudaMemcpyAsync (F->h_info, F->d_info, sizeof (slipcu_pivot_info), cudaMemcpyDeviceToHost, F->st));
     CU (cudaEventRecord (F->ev, F->st));
     if (F->keep_positional)
@@ -1087,7 +1558,8 @@ extern "C" int slipcu_factor_fetch_entry (slipcu_factor *F, int k, int slot, u32
             return fail (SLIPCU_BAD_INPUT, "slipcu_factor_fetch_entry", "entry no longer reconstructible");
         if (!F->tmp_limbs || F->tmp_stride < hc.stride)
         {
-            cudaFree (F->tmp_limbs); cudaFree (F->tmp_nl); F->tmp_limbs = nullptr; F->tmp_nl = nullptr;
+            cudaFree (F->tmp_limbs); cudaFree (F->tmp_nl);
+            F->tmp_limbs = nullptr; F->tmp_nl = nullptr;
             CU (cudaMalloc (&F->tmp_limbs, (size_t) (F->S + 2) * sizeof (u32)));
             CU (cudaMalloc (&F->tmp_nl, sizeof (int32_t)));
             F->tmp_stride = F->S + 2;
@@ -1114,6 +1586,7 @@ extern "C" int slipcu_factor_set_pivot (slipcu_factor *F, int k, int slot)
                                                            F->invrho, F->ratio, T.p, T.ninv, T.one, F->bad);
     g_launches++;
     CU (cudaGetLastError ());
+    if (debug_check ("k_pivot_commit", F->st)) return fail (SLIPCU_CUDA_ERROR, "k_pivot_commit", "debug");
     return SLIPCU_OK;
 }
 
@@ -1250,7 +1723,7 @@ extern "C" int slipcu_solve (slipcu_factor *F, int nrhs, const u32 *blimbs, cons
     if (top_digit_max) *top_digit_max = -1;
     std::vector<int32_t> row_at (n), ident (n);
     for (int r = 0; r < n; ++r) { row_at[pinv[r]] = r; ident[r] = r; }
-    int32_t *dpinv = nullptr;
+    int32_t *dpinv = nullptr, *duoff = nullptr;
     const size_t nl = (size_t) boff[total];
 #define CUG(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail (e_ == cudaErrorMemoryAllocation ? SLIPCU_OUT_OF_MEMORY : SLIPCU_CUDA_ERROR, #call, cudaGetErrorString (e_)); goto done; } } while (0)
     CUG (cudaMalloc (&dl, std::max<size_t> (nl, 1) * sizeof (u32)));
@@ -1282,6 +1755,18 @@ extern "C" int slipcu_solve (slipcu_factor *F, int nrhs, const u32 *blimbs, cons
         g_launches++;
         CUG (cudaGetLastError ());
     }
+    {   // symbolic pre-pass of the forward substitution: every column of L is one step
+        std::vector<int32_t> uoff (n + 1);
+        int64_t tot = 0;
+        for (int k = 0; k < n; ++k) { uoff[k] = (int32_t) tot; tot += ((F->cols[k].cnt - F->cols[k].nU) + 3) & ~3; }
+        uoff[n] = (int32_t) tot;
+        if (tot > INT32_MAX) { rc = fail (SLIPCU_BAD_INPUT, "slipcu_solve", "L has too many entries"); goto done; }
+        CUG (cudaMalloc (&duoff, (size_t) (n + 1) * sizeof (int32_t)));
+        CUG (cudaMemcpyAsync (duoff, uoff.data (), (size_t) (n + 1) * sizeof (int32_t), cudaMemcpyHostToDevice, F->st));
+        CUG (cudaStreamSynchronize (F->st));
+        rc = prepare_steps (F, n, n, F->rows_are_positions ? dident : drow_at, dident, duoff, (int) tot);
+        if (rc) goto done;
+    }
     for (int r0 = 0; r0 < nrhs; r0 += batch)
     {
         const int nb = std::min (batch, nrhs - r0);
@@ -1289,27 +1774,28 @@ extern "C" int slipcu_solve (slipcu_factor *F, int nrhs, const u32 *blimbs, cons
         a.k = n; a.S = S; a.cnt = n; a.nU = n;
         // slots are positions.  Resident sessions store original rows (slot of row r = pinv[r]);
         // uploaded sessions store positions (identity map), b rows are then routed through pinv.
-        a.rows = F->rows_are_positions ? dident : drow_at; a.upos = dident;
+        a.rows = F->rows_are_positions ? dident : drow_at;
+        a.steps = F->steps; a.slots = F->slots;
         a.src = dB; a.src_total = total; a.src_first = r0; a.src_step = nrhs; a.src_cnt = n;
         a.src_rows = F->rows_are_positions ? dpinv : nullptr;
         a.src_y_stride = 1;
         a.out = dz; a.out_y_stride = (size_t) n * S;
-        a.desc = F->desc; a.rho = F->rho; a.invrho = F->invrho; a.ratio = F->ratio;
+        a.rho = F->rho; a.invrho = F->invrho; a.ratio = F->ratio;
         a.p = T.p; a.ninv = T.ninv; a.pos = F->pos;
-        size_t smem = (((size_t) n * sizeof (int32_t) + 15) & ~(size_t) 15);
-        const size_t xbytes = (size_t) n * CH * sizeof (u32);
-        a.x_in_smem = (smem + xbytes + 1024 <= F->smem_limit) && !F->x_global;
-        if (a.x_in_smem) smem += xbytes;
-        if (smem > F->smem_limit) { rc = fail (SLIPCU_BAD_INPUT, "slipcu_solve", "n too large for shared history"); goto done; }
+        size_t smem = 0;
+        rc = tri_geometry (F, a, &smem);
+        if (rc) goto done;
         CUG (launch_tri_any (CH, a, dim3 (S / CH, nb), F->threads, smem, F->st));
+        if (debug_check ("k_trisolve(forward)", F->st)) { rc = fail (SLIPCU_CUDA_ERROR, "k_trisolve(forward)", "debug"); goto done; }
         BackArgs b;
         b.n = n; b.S = S; b.z = dz; b.z_y_stride = (size_t) n * S;
         b.desc = F->desc; b.rho = F->rho; b.invrho = F->invrho; b.p = T.p; b.ninv = T.ninv; b.pos = F->pos;
         g_launches++;
-        if (CH == 8) k_backsub<8><<<dim3 (S / CH, nb), F->threads, 0, F->st>>> (b);
-        else if (CH == 16) k_backsub<16><<<dim3 (S / CH, nb), F->threads, 0, F->st>>> (b);
-        else k_backsub<32><<<dim3 (S / CH, nb), F->threads, 0, F->st>>> (b);
+        if (CH == 8) k_backsub<8><<<dim3 (S / CH, nb), 256, 0, F->st>>> (b);
+        else if (CH == 16) k_backsub<16><<<dim3 (S / CH, nb), 256, 0, F->st>>> (b);
+        else k_backsub<32><<<dim3 (S / CH, nb), 256, 0, F->st>>> (b);
         CUG (cudaGetLastError ());
+        if (debug_check ("k_backsub", F->st)) { rc = fail (SLIPCU_CUDA_ERROR, "k_backsub", "debug"); goto done; }
         for (int r = 0; r < nb; ++r)
         {
             HostCol hc;
@@ -1331,7 +1817,7 @@ extern "C" int slipcu_solve (slipcu_factor *F, int nrhs, const u32 *blimbs, cons
 done:
     cudaStreamSynchronize (F->st);
     cudaFree (dl); cudaFree (doff); cudaFree (dsg); cudaFree (dB); cudaFree (dz); cudaFree (dlimbs);
-    cudaFree (drow_at); cudaFree (dident); cudaFree (dpinv); cudaFree (dnl); cudaFree (dsign);
+    cudaFree (drow_at); cudaFree (dident); cudaFree (dpinv); cudaFree (duoff); cudaFree (dnl); cudaFree (dsign);
     if (h_limbs) cudaFreeHost (h_limbs);
     if (h_nl) cudaFreeHost (h_nl);
     if (h_sign) cudaFreeHost (h_sign);

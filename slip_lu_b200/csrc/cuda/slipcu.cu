@@ -305,7 +305,7 @@ struct slipcu_factor
     cudaEvent_t ev = nullptr, ev0 = nullptr, ev1 = nullptr;
     int32_t *dAp = nullptr, *dAi = nullptr;
     u32 *dA = nullptr;                       // residues of A, [S/CH][nz][CH]
-    u32 *rho = nullptr, *invrho = nullptr, *ratio = nullptr;    // [n][S]
+    u32 *rho = nullptr, *invrho = nullptr;    // [n][S]
     ColDesc *desc = nullptr;                 // [n]
     int32_t *pos = nullptr;                  // [n]
     int32_t *bad = nullptr;                  // device flag
@@ -397,7 +397,8 @@ struct StepInfo           // one elimination step of a column: eliminate with co
     int32_t len;          // entries in the L part of column j (the pivot row included)
     int32_t cbstride;     // words between channel blocks of column j
     int32_t slot_off;     // offset of this step's slot list (multiple of 4)
-    int32_t pad[2];
+    int32_t chunk0;       // index of the step's first pipeline chunk (TRI_ROWS rows per chunk)
+    int32_t pad;
 };
 
 __global__ void k_setpos (int cnt, const int32_t *rows, int32_t *pos)
@@ -407,7 +408,8 @@ __global__ void k_setpos (int cnt, const int32_t *rows, int32_t *pos)
 }
 
 __global__ void k_slots (int nU, int total, int CH, const int32_t *upos, const int32_t *uoff,
-                         const ColDesc *desc, const int32_t *pos, int32_t *slots, StepInfo *steps)
+                         const int32_t *uchunk, const ColDesc *desc, const int32_t *pos, int32_t *slots,
+                         StepInfo *steps)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
@@ -422,18 +424,25 @@ __global__ void k_slots (int nU, int total, int CH, const int32_t *upos, const i
     {
         StepInfo si;
         si.lbase = d.base + (size_t) d.nU * CH; si.j = upos[u]; si.len = len; si.cbstride = d.cnt * CH;
-        si.slot_off = uoff[u]; si.pad[0] = si.pad[1] = 0;
+        si.slot_off = uoff[u]; si.chunk0 = uchunk[u]; si.pad = 0;
         steps[u] = si;
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // k_trisolve: sparse REF triangular solve of one column (or of one dense right-hand side).
-// One CTA per block of CH channels; channels are independent.  Warp 0 is the producer: it streams,
-// for every elimination step, the CH-wide rows of the L column, the slot list and the step's pivot
-// constants into a ring of shared-memory stages with TMA bulk copies (mbarrier completion).  The
-// consumer warps hold x (CH residues per pattern slot) and the symbolic history in shared memory
-// and apply   x_t <- x_t * f - l * (x_j / rho_{j-1})   per channel with one Montgomery reduction.
+// One CTA per block of CH channels; channels are independent.  One producer warp per pipeline
+// stage streams, for every elimination step, the CH-wide rows of the L column, the slot list and
+// the step's pivot constant into shared memory with TMA bulk copies (mbarrier completion).
+//
+// The consumer warps hold the vector in shared memory in NORMALISED form  w_t = x_t / rho_{h_t}
+// (h_t = last elimination step applied to x_t, rho_{-1} = 1).  In that form the REF update
+//     x_t <- (rho_j * rho_{j-1}/rho_{h_t} * x_t - l_tj * x_j) / rho_{j-1}
+// of slip_REF_triangular_solve.c:150-232, including every history update, collapses to
+//     w_t <- w_t - l_tj * yhat_j ,   yhat_j = w_j / rho_j
+// because division by a pivot is a multiplication by its inverse modulo the channel prime: the
+// history vector of the reference is not needed at all.  The true REF values are restored when
+// the column is published:  U(j,k) = w_j * rho_{j-1},  L(t,k) = w_t * rho_{k-1}.
 // Slots 0..nU-1 of the pattern are rows that are already pivotal (in pivot order); slots
 // nU..cnt-1 are the candidate rows.
 // ------------------------------------------------------------------------------------------------
@@ -454,9 +463,10 @@ struct TriArgs
     size_t src_y_stride;     // added to src_first per blockIdx.y (multiple right-hand sides)
     u32 *out;                // [S/CH][cnt][CH] result region (+ blockIdx.y * out_y_stride words)
     size_t out_y_stride;
-    const u32 *rho, *invrho, *ratio, *p, *ninv;
+    const u32 *rho, *invrho, *p, *ninv;      // [n][S] pivots and their inverses (Montgomery form)
     const int32_t *pos;      // [n] row -> slot
     int x_in_smem;
+    int nchunks;             // total pipeline chunks of this launch
 };
 
 struct StageMeta { int32_t j, nrows, first, last; };
@@ -467,38 +477,61 @@ struct TriSmem
     // byte offsets inside the dynamic shared memory block
     static __host__ __device__ size_t stage_bytes ()
     {
-        return (size_t) TRI_ROWS * CH * 4 + (size_t) TRI_ROWS * 4 + 3 * CH * 4 + 32;   // L rows, slots, constants, meta
+        return (size_t) TRI_ROWS * CH * 4 + (size_t) TRI_ROWS * 4 + CH * 4 + 32;   // L rows, slots, 1/rho_j, meta
     }
     static __host__ __device__ size_t header_bytes () { return 2 * TRI_MAX_STAGES * sizeof (uint64_t); }
     static __host__ __device__ size_t total (int cnt, int stages, bool x_in_smem)
     {
         size_t b = header_bytes ();
-        b += ((size_t) cnt * 4 + 127) & ~(size_t) 127;                        // history
         if (x_in_smem) b += ((size_t) cnt * CH * 4 + 127) & ~(size_t) 127;     // x
         b += (size_t) stages * ((stage_bytes () + 127) & ~(size_t) 127);
         return b;
     }
 };
 
-template <int CH>
-__global__ void __launch_bounds__ (544) k_trisolve (TriArgs a)
+__device__ __forceinline__ uint4 mont_mul4 (const uint4 a, const uint4 b, const uint4 p, const uint4 ni)
+{
+    return make_uint4 (mont_mul (a.x, b.x, p.x, ni.x), mont_mul (a.y, b.y, p.y, ni.y),
+                       mont_mul (a.z, b.z, p.z, ni.z), mont_mul (a.w, b.w, p.w, ni.w));
+}
+// x*f + l*ny reduced, four channels at a time
+__device__ __forceinline__ uint4 ref_update4 (const uint4 x, const uint4 f, const uint4 l, const uint4 ny,
+                                              const uint4 p, const uint4 ni)
+{
+    return make_uint4 (mont_redc ((u64) x.x * f.x + (u64) l.x * ny.x, p.x, ni.x),
+                       mont_redc ((u64) x.y * f.y + (u64) l.y * ny.y, p.y, ni.y),
+                       mont_redc ((u64) x.z * f.z + (u64) l.z * ny.z, p.z, ni.z),
+                       mont_redc ((u64) x.w * f.w + (u64) l.w * ny.w, p.w, ni.w));
+}
+// w + l*ny  (ny = -yhat): one Montgomery product and a modular add per channel
+__device__ __forceinline__ u32 add_mod (u32 a, u32 b, u32 p) { u32 r = a + b; return r >= p ? r - p : r; }
+__device__ __forceinline__ uint4 sub_mul4 (const uint4 w, const uint4 l, const uint4 ny, const uint4 p, const uint4 ni)
+{
+    return make_uint4 (add_mod (w.x, mont_mul (l.x, ny.x, p.x, ni.x), p.x), add_mod (w.y, mont_mul (l.y, ny.y, p.y, ni.y), p.y),
+                       add_mod (w.z, mont_mul (l.z, ny.z, p.z, ni.z), p.z), add_mod (w.w, mont_mul (l.w, ny.w, p.w, ni.w), p.w));
+}
+__device__ __forceinline__ uint4 neg4 (const uint4 y, const uint4 p)
+{
+    return make_uint4 (y.x ? p.x - y.x : 0u, y.y ? p.y - y.y : 0u, y.z ? p.z - y.z : 0u, y.w ? p.w - y.w : 0u);
+}
+
+template <int CH, bool XS>
+__global__ void __launch_bounds__ (768) k_trisolve (TriArgs a)
 {
     extern __shared__ __align__ (128) unsigned char smem_raw[];
     uint64_t *full = (uint64_t *) smem_raw;
     uint64_t *empty = full + TRI_MAX_STAGES;
     unsigned char *ptr = smem_raw + TriSmem<CH>::header_bytes ();
-    int32_t *hist = (int32_t *) ptr;
-    ptr += ((size_t) a.cnt * 4 + 127) & ~(size_t) 127;
     u32 *xsm = (u32 *) ptr;
-    if (a.x_in_smem) ptr += ((size_t) a.cnt * CH * 4 + 127) & ~(size_t) 127;
+    if (XS) ptr += ((size_t) a.cnt * CH * 4 + 127) & ~(size_t) 127;
     unsigned char *stage0 = ptr;
     const size_t stage_stride = (TriSmem<CH>::stage_bytes () + 127) & ~(size_t) 127;
 
     const int tid = threadIdx.x;
-    const int NC = (blockDim.x >> 5) - 1;              // consumer warps (warp 0 produces)
+    const int NC = (blockDim.x >> 5) - a.stages;       // consumer warps (one producer warp per stage)
     const int cb = blockIdx.x, S = a.S, cnt = a.cnt, nU = a.nU, NS = a.stages;
     u32 *xg = a.out + (size_t) blockIdx.y * a.out_y_stride + (size_t) cb * cnt * CH;
-    u32 *xs = a.x_in_smem ? xsm : xg;
+    u32 *xs = XS ? xsm : xg;
 
     if (tid == 0)
     {
@@ -506,86 +539,71 @@ __global__ void __launch_bounds__ (544) k_trisolve (TriArgs a)
         asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile ("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    // all threads: clear x and the history, then scatter the source vector
+    // all threads: clear the vector, then scatter the source
     {
-        const int ch = tid % CH, rg = tid / CH, RG = blockDim.x / CH;
-        for (int t = rg; t < cnt; t += RG) { xs[t * CH + ch] = 0; if (ch == 0) hist[t] = -1; }
+        for (int i = tid; i < cnt * CH; i += blockDim.x) xs[i] = 0;
         __syncthreads ();
         const u32 *src = a.src + (size_t) cb * a.src_total * CH;
         const int first = a.src_first + (int) (blockIdx.y * a.src_y_stride);
-        for (int e = rg; e < a.src_cnt; e += RG)
+        for (int i = tid; i < a.src_cnt * CH; i += blockDim.x)
         {
+            const int e = i / CH, ch = i % CH;
             const int row = a.src_rows ? a.src_rows[e] : e;
             xs[a.pos[row] * CH + ch] = src[((size_t) first + (size_t) e * a.src_step) * CH + ch];
         }
         __syncthreads ();
     }
 
-    if (tid < 32)
+    if (tid < 32 * NS)
     {
-        // ---------------- producer warp ----------------
-        const int lane = tid;
-        int chunk = 0;
-        for (int u0 = 0; u0 < nU; u0 += 32)
+        // ---------------- producer warps: warp w feeds stage w ----------------
+        if ((tid & 31) != 0 || a.nchunks == 0) return;
+        const int st = tid >> 5;
+        unsigned char *sb = stage0 + (size_t) st * stage_stride;
+        u32 *Lbuf = (u32 *) sb;
+        int32_t *Sbuf = (int32_t *) (sb + (size_t) TRI_ROWS * CH * 4);
+        u32 *Cbuf = (u32 *) (sb + (size_t) TRI_ROWS * CH * 4 + (size_t) TRI_ROWS * 4);
+        StageMeta *meta = (StageMeta *) (Cbuf + CH);
+        int u = 0;
+        StepInfo si = a.steps[0];
+        StepInfo guess = a.steps[min (st, nU - 1)];       // most steps are a single chunk
+        int ug = min (st, nU - 1);
+        for (int c = st; c < a.nchunks; c += NS)
         {
-            StepInfo si;
-            si.lbase = nullptr; si.j = 0; si.len = 0; si.cbstride = 0; si.slot_off = 0;
-            if (u0 + lane < nU) si = a.steps[u0 + lane];
-            const int lim = min (32, nU - u0);
-            for (int i = 0; i < lim; ++i)
-            {
-                const u32 *lbase = (const u32 *) __shfl_sync (0xffffffffu, (unsigned long long) si.lbase, i);
-                const int j = __shfl_sync (0xffffffffu, si.j, i);
-                const int len = __shfl_sync (0xffffffffu, si.len, i);
-                const int cbs = __shfl_sync (0xffffffffu, si.cbstride, i);
-                const int soff = __shfl_sync (0xffffffffu, si.slot_off, i);
-                for (int m0 = 0; m0 < len; m0 += TRI_ROWS, ++chunk)
-                {
-                    const int st = chunk % NS;
-                    const u32 round = (u32) (chunk / NS);
-                    if (lane == 0)
-                    {
-                        mbar_wait (&empty[st], (round & 1) ^ 1);      // stage drained by the consumers
-                        unsigned char *sb = stage0 + (size_t) st * stage_stride;
-                        u32 *Lbuf = (u32 *) sb;
-                        int32_t *Sbuf = (int32_t *) (sb + (size_t) TRI_ROWS * CH * 4);
-                        u32 *Cbuf = (u32 *) (sb + (size_t) TRI_ROWS * CH * 4 + (size_t) TRI_ROWS * 4);
-                        StageMeta *meta = (StageMeta *) (Cbuf + 3 * CH);
-                        const int nrows = min (TRI_ROWS, len - m0);
-                        const int npad = (nrows + 3) & ~3;
-                        const bool first = (m0 == 0);
-                        meta->j = j; meta->nrows = nrows; meta->first = first; meta->last = (m0 + TRI_ROWS >= len);
-                        u32 bytes = (u32) nrows * CH * 4 + (u32) npad * 4;
-                        if (first) bytes += (j >= 1 ? 3 : 2) * CH * 4;
-                        mbar_expect_tx (&full[st], bytes);
-                        bulk_g2s (Lbuf, lbase + (size_t) cb * cbs + (size_t) m0 * CH, (u32) nrows * CH * 4, &full[st]);
-                        bulk_g2s (Sbuf, a.slots + soff + m0, (u32) npad * 4, &full[st]);
-                        if (first)
-                        {
-                            bulk_g2s (Cbuf, a.rho + (size_t) j * S + (size_t) cb * CH, CH * 4, &full[st]);
-                            bulk_g2s (Cbuf + CH, a.ratio + (size_t) j * S + (size_t) cb * CH, CH * 4, &full[st]);
-                            if (j >= 1)
-                                bulk_g2s (Cbuf + 2 * CH, a.invrho + (size_t) (j - 1) * S + (size_t) cb * CH, CH * 4, &full[st]);
-                        }
-                    }
-                }
-            }
+            // the step that owns chunk c (steps are visited in order; chunk0 is increasing)
+            if (guess.chunk0 == c) { u = ug; si = guess; }
+            else while (u + 1 < nU && a.steps[u + 1].chunk0 <= c) { ++u; si = a.steps[u]; }
+            ug = min (u + NS, nU - 1);
+            guess = a.steps[ug];                          // in flight while this lane waits below
+            const int m0 = (c - si.chunk0) * TRI_ROWS;
+            const int nrows = min (TRI_ROWS, si.len - m0);
+            const int npad = (nrows + 3) & ~3;
+            const bool first = (m0 == 0);
+            const u32 round = (u32) (c / NS);
+            mbar_wait (&empty[st], (round & 1) ^ 1);          // stage drained by the consumers
+            meta->j = si.j; meta->nrows = nrows; meta->first = first; meta->last = (m0 + TRI_ROWS >= si.len);
+            u32 bytes = (u32) nrows * CH * 4 + (u32) npad * 4;
+            if (first) bytes += CH * 4;
+            mbar_expect_tx (&full[st], bytes);
+            bulk_g2s (Lbuf, si.lbase + (size_t) cb * si.cbstride + (size_t) m0 * CH, (u32) nrows * CH * 4, &full[st]);
+            bulk_g2s (Sbuf, a.slots + si.slot_off + m0, (u32) npad * 4, &full[st]);
+            if (first)
+                bulk_g2s (Cbuf, a.invrho + (size_t) si.j * S + (size_t) cb * CH, CH * 4, &full[st]);
         }
         return;
     }
 
-    // ---------------- consumer warps ----------------
-    const int ctid = tid - 32, nthr = NC * 32;
-    const int ch = ctid % CH, rg = ctid / CH, RG = nthr / CH;
-    const int c = cb * CH + ch;
-    const u32 p = a.p[c], ni = a.ninv[c];
-    u32 pend_val = 0; int pend_slot = -1;
+    // ---------------- consumer warps: each thread owns 4 channels of a row ----------------
+    constexpr int TPR = CH / 4;                        // threads per row
+    const int ctid = tid - 32 * NS, nthr = NC * 32;
+    const int q4 = (ctid % TPR) * 4, rg = ctid / TPR, RG = nthr / TPR;
+    const int c0 = cb * CH + q4;
+    const uint4 p4 = *reinterpret_cast<const uint4 *> (a.p + c0);
+    const uint4 ni4 = *reinterpret_cast<const uint4 *> (a.ninv + c0);
     int chunk = 0;
     for (int u = 0; u < nU; ++u)
     {
-        if (pend_slot >= 0) { xs[pend_slot * CH + ch] = pend_val; pend_slot = -1; }
-        u32 negy = 0, rj = 0, rhoj = 0;
-        int j = 0;
+        uint4 negy = make_uint4 (0, 0, 0, 0);
         for (;; ++chunk)
         {
             const int st = chunk % NS;
@@ -595,22 +613,11 @@ __global__ void __launch_bounds__ (544) k_trisolve (TriArgs a)
             const u32 *Lbuf = (const u32 *) sb;
             const int32_t *Sbuf = (const int32_t *) (sb + (size_t) TRI_ROWS * CH * 4);
             const u32 *Cbuf = (const u32 *) (sb + (size_t) TRI_ROWS * CH * 4 + (size_t) TRI_ROWS * 4);
-            const StageMeta meta = *(const StageMeta *) (Cbuf + 3 * CH);
+            const StageMeta meta = *(const StageMeta *) (Cbuf + CH);
             if (meta.first)
-            {
-                j = meta.j;
-                u32 xj = xs[u * CH + ch];
-                const int hj = hist[u];
-                if (hj < j - 1)
-                {   // history update of the finished U entry: level hj+1 -> level j
-                    xj = mont_mul (xj, a.rho[(size_t) (j - 1) * S + c], p, ni);
-                    if (hj >= 0) xj = mont_mul (xj, a.invrho[(size_t) hj * S + c], p, ni);
-                    if (rg == 0) { pend_slot = u; pend_val = xj; }
-                }
-                const u32 y = (j >= 1) ? mont_mul (xj, Cbuf[2 * CH + ch], p, ni) : xj;
-                negy = y ? p - y : 0u;
-                rhoj = Cbuf[ch];
-                rj = Cbuf[CH + ch];
+            {   // yhat_j = w_j / rho_j
+                const uint4 wj = *reinterpret_cast<const uint4 *> (xs + u * CH + q4);
+                negy = neg4 (mont_mul4 (wj, *reinterpret_cast<const uint4 *> (Cbuf + q4), p4, ni4), p4);
             }
             const int nrows = meta.nrows;
             const int iters = (nrows + RG - 1) / RG;
@@ -619,45 +626,26 @@ __global__ void __launch_bounds__ (544) k_trisolve (TriArgs a)
             {
                 const int r = it * RG + rg;
                 const int t = (r < nrows) ? Sbuf[r] : -1;
-                int h = 0;
                 if (t >= 0)
                 {
-                    const u32 l = Lbuf[r * CH + ch];
-                    h = hist[t];
-                    u32 f = rj;
-                    if (h != j - 1)
-                    {
-                        f = rhoj;
-                        if (h >= 0) f = mont_mul (f, a.invrho[(size_t) h * S + c], p, ni);
-                    }
-                    const u32 xv = xs[t * CH + ch];
-                    xs[t * CH + ch] = mont_redc ((u64) xv * f + (u64) l * negy, p, ni);
+                    const uint4 l = *reinterpret_cast<const uint4 *> (Lbuf + r * CH + q4);
+                    uint4 *xp = reinterpret_cast<uint4 *> (xs + t * CH + q4);
+                    *xp = sub_mul4 (*xp, l, negy, p4, ni4);
                 }
-                __syncwarp ();
-                if (t >= 0 && ch == 0) hist[t] = j;
             }
             __syncwarp ();
             if ((ctid & 31) == 0) mbar_arrive (&empty[st]);
             if (meta.last) { ++chunk; break; }
         }
-        consumer_bar (nthr);       // every update of this step is visible before the next x_j is read
+        consumer_bar (nthr);       // every update of this step is visible before the next w_j is read
     }
-    if (pend_slot >= 0) xs[pend_slot * CH + ch] = pend_val;
-    consumer_bar (nthr);
-    // candidate rows: bring to level k; then publish the column
+    // publish the column as true REF values: U(j,k) = w_j rho_{j-1}, candidates = w_t rho_{k-1}
     for (int t = rg; t < cnt; t += RG)
     {
-        u32 v = xs[t * CH + ch];
-        if (t >= nU)
-        {
-            const int h = hist[t];
-            if (h < a.k - 1)
-            {
-                v = mont_mul (v, a.rho[(size_t) (a.k - 1) * S + c], p, ni);
-                if (h >= 0) v = mont_mul (v, a.invrho[(size_t) h * S + c], p, ni);
-            }
-        }
-        xg[t * CH + ch] = v;
+        uint4 v = *reinterpret_cast<const uint4 *> (xs + t * CH + q4);
+        const int lvl = (t < nU) ? a.steps[t].j : a.k;           // level the entry is brought to
+        if (lvl >= 1) v = mont_mul4 (v, *reinterpret_cast<const uint4 *> (a.rho + (size_t) (lvl - 1) * S + c0), p4, ni4);
+        *reinterpret_cast<uint4 *> (xg + t * CH + q4) = v;
     }
 }
 
@@ -1133,7 +1121,7 @@ __global__ void __launch_bounds__ (256) k_pivot_scan (int cnt, int nU, int mode,
 // k_pivot_commit: rho_k, rho_k^-1, rho_k / rho_{k-1} in every channel; column descriptor
 // ------------------------------------------------------------------------------------------------
 __global__ void k_pivot_commit (int k, int S, int CH, int slot, ColDesc d, ColDesc *desc,
-                                u32 *rho, u32 *invrho, u32 *ratio,
+                                u32 *rho, u32 *invrho,
                                 const u32 *p, const u32 *ninv, const u32 *one, int32_t *bad)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1142,10 +1130,8 @@ __global__ void k_pivot_commit (int k, int S, int CH, int slot, ColDesc d, ColDe
     const u32 pc = p[c], ni = ninv[c];
     const u32 v = d.base[((size_t) (c / CH) * d.cnt + slot) * CH + (c % CH)];
     if (v == 0) atomicCAS (bad, 0, c + 1);
-    const u32 inv = mont_pow (v, pc - 2, one[c], pc, ni);
     rho[(size_t) k * S + c] = v;
-    invrho[(size_t) k * S + c] = inv;
-    ratio[(size_t) k * S + c] = k >= 1 ? mont_mul (v, invrho[(size_t) (k - 1) * S + c], pc, ni) : v;
+    invrho[(size_t) k * S + c] = mont_pow (v, pc - 2, one[c], pc, ni);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1175,7 +1161,7 @@ extern "C" void slipcu_factor_free (slipcu_factor *F)
     cudaSetDevice (F->device);
     if (F->st) cudaStreamSynchronize (F->st);
     cudaFree (F->dAp); cudaFree (F->dAi); cudaFree (F->dA);
-    cudaFree (F->rho); cudaFree (F->invrho); cudaFree (F->ratio);
+    cudaFree (F->rho); cudaFree (F->invrho);
     cudaFree (F->desc); cudaFree (F->pos); cudaFree (F->bad);
     cudaFree (F->dig); cudaFree (F->topd); cudaFree (F->d_info);
     cudaFree (F->tmp_limbs); cudaFree (F->tmp_nl);
@@ -1228,8 +1214,8 @@ static int session_common_init (slipcu_factor *F, int n, int channels)
     CH = env_int ("SLIP_B200_CH", CH);
     if (CH != 8 && CH != 16 && CH != 32) CH = 16;
     F->CH = CH;
-    F->threads = env_int ("SLIP_B200_THREADS", 288);       // one producer warp + consumer warps
-    if (F->threads % 32 || F->threads < 64 || F->threads > 544 || ((F->threads - 32) % CH)) F->threads = 288;
+    F->threads = env_int ("SLIP_B200_THREADS", 256);       // consumer threads (one producer warp per stage is added)
+    if (F->threads % 32 || F->threads < 32 || F->threads > 512) F->threads = 256;
     F->stages = env_int ("SLIP_B200_STAGES", 4);
     if (F->stages < 2 || F->stages > TRI_MAX_STAGES) F->stages = 4;
     F->x_global = env_int ("SLIP_B200_X_GLOBAL", 0);
@@ -1237,23 +1223,25 @@ static int session_common_init (slipcu_factor *F, int n, int channels)
     int smem_optin = 0;
     cudaDeviceGetAttribute (&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, F->device);
     F->smem_limit = (size_t) smem_optin;
-    CU (cudaFuncSetAttribute (k_trisolve<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
-    CU (cudaFuncSetAttribute (k_trisolve<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
-    CU (cudaFuncSetAttribute (k_trisolve<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
+    CU (cudaFuncSetAttribute (k_trisolve<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
+    CU (cudaFuncSetAttribute (k_trisolve<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
+    CU (cudaFuncSetAttribute (k_trisolve<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
+    CU (cudaFuncSetAttribute (k_trisolve<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
+    CU (cudaFuncSetAttribute (k_trisolve<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
+    CU (cudaFuncSetAttribute (k_trisolve<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
 
     CU (cudaStreamCreateWithFlags (&F->st, cudaStreamNonBlocking));
     CU (cudaEventCreateWithFlags (&F->ev, cudaEventDisableTiming));
     CU (cudaEventCreate (&F->ev0)); CU (cudaEventCreate (&F->ev1));
     CU (cudaMalloc (&F->rho, (size_t) n * S * sizeof (u32)));
     CU (cudaMalloc (&F->invrho, (size_t) n * S * sizeof (u32)));
-    CU (cudaMalloc (&F->ratio, (size_t) n * S * sizeof (u32)));
     CU (cudaMalloc (&F->desc, (size_t) n * sizeof (ColDesc)));
     CU (cudaMalloc (&F->pos, (size_t) n * sizeof (int32_t)));
     CU (cudaMalloc (&F->bad, sizeof (int32_t)));
     CU (cudaMalloc (&F->d_info, sizeof (slipcu_pivot_info)));
     CU (cudaMemset (F->bad, 0, sizeof (int32_t)));
     CU (cudaMemset (F->pos, 0, (size_t) n * sizeof (int32_t)));
-    CU (cudaHostAlloc (&F->h_packet, ((size_t) 3 * n + 8) * sizeof (int32_t), cudaHostAllocDefault));
+    CU (cudaHostAlloc (&F->h_packet, ((size_t) 4 * n + 8) * sizeof (int32_t), cudaHostAllocDefault));
     CU (cudaHostAlloc (&F->h_info, sizeof (slipcu_pivot_info), cudaHostAllocDefault));
     F->cols.resize (n);
     return SLIPCU_OK;
@@ -1302,7 +1290,8 @@ extern "C" int slipcu_factor_begin (slipcu_factor **out, int n, int nz, const in
 template <int CH>
 static cudaError_t launch_tri (const TriArgs &a, dim3 grid, int threads, size_t smem, cudaStream_t st)
 {
-    k_trisolve<CH><<<grid, threads, smem, st>>> (a);
+    if (a.x_in_smem) k_trisolve<CH, true><<<grid, threads, smem, st>>> (a);
+    else k_trisolve<CH, false><<<grid, threads, smem, st>>> (a);
     return cudaGetLastError ();
 }
 static size_t tri_smem_bytes (int CH, int cnt, int stages, bool x_in_smem)
@@ -1322,7 +1311,7 @@ static cudaError_t launch_tri_any (int CH, const TriArgs &a, dim3 grid, int thre
 // symbolic pre-pass on the device: pos[], the slot lists and the step table of a column whose
 // pattern (rows), step positions (upos) and slot-list offsets (uoff, nU+1 entries) are on the device
 static int prepare_steps (slipcu_factor *F, int cnt, int nU, const int32_t *rows, const int32_t *upos,
-                          const int32_t *uoff, int total)
+                          const int32_t *uoff, const int32_t *uchunk, int total)
 {
     if ((size_t) total > F->slots_cap)
     {
@@ -1346,7 +1335,7 @@ static int prepare_steps (slipcu_factor *F, int cnt, int nU, const int32_t *rows
     if (debug_check ("k_setpos", F->st)) return fail (SLIPCU_CUDA_ERROR, "k_setpos", "debug");
     if (nU > 0 && total > 0)
     {
-        k_slots<<<(total + 255) / 256, 256, 0, F->st>>> (nU, total, F->CH, upos, uoff, F->desc, F->pos, F->slots, F->steps);
+        k_slots<<<(total + 255) / 256, 256, 0, F->st>>> (nU, total, F->CH, upos, uoff, uchunk, F->desc, F->pos, F->slots, F->steps);
         g_launches++;
         CU (cudaGetLastError ());
         if (debug_check ("k_slots", F->st)) return fail (SLIPCU_CUDA_ERROR, "k_slots", "debug");
@@ -1366,7 +1355,7 @@ static int tri_geometry (slipcu_factor *F, TriArgs &a, size_t *smem)
         a.x_in_smem = 0; a.stages = F->stages;
         need = tri_smem_bytes (F->CH, a.cnt, a.stages, false);
     }
-    if (need + 1024 > F->smem_limit) return fail (SLIPCU_BAD_INPUT, "tri_geometry", "pattern too large for the shared history vector");
+    if (need + 1024 > F->smem_limit) return fail (SLIPCU_BAD_INPUT, "tri_geometry", "pattern too large for shared memory");
     *smem = need;
     return SLIPCU_OK;
 }
@@ -1471,21 +1460,24 @@ extern "C" int slipcu_factor_column (slipcu_factor *F, int k, int col, int cnt, 
     memcpy (F->h_packet, rows, (size_t) cnt * sizeof (int32_t));
     if (nU) memcpy (F->h_packet + cnt, upos, (size_t) nU * sizeof (int32_t));
     int32_t *uoff = F->h_packet + cnt + nU;
-    int64_t total = 0;
+    int32_t *uchunk = uoff + nU + 1;
+    int64_t total = 0, nchunks = 0;
     for (int u = 0; u < nU; ++u)
     {
         const HostCol &lj = F->cols[upos[u]];
-        uoff[u] = (int32_t) total;
-        total += ((lj.cnt - lj.nU) + 3) & ~3;
+        const int len = lj.cnt - lj.nU;
+        uoff[u] = (int32_t) total; uchunk[u] = (int32_t) nchunks;
+        total += (len + 3) & ~3;
+        nchunks += (len + TRI_ROWS - 1) / TRI_ROWS;
         if (total > INT32_MAX) return fail (SLIPCU_BAD_INPUT, "slipcu_factor_column", "column has too many updates");
     }
-    uoff[nU] = (int32_t) total;
-    hc.rows = (int32_t *) F->ints.alloc ((size_t) (cnt + 2 * nU + 1) * sizeof (int32_t));
+    uoff[nU] = (int32_t) total; uchunk[nU] = (int32_t) nchunks;
+    const size_t pk_ints = (size_t) cnt + 3 * (size_t) nU + 2;
+    hc.rows = (int32_t *) F->ints.alloc (pk_ints * sizeof (int32_t));
     if (!hc.rows) return fail (SLIPCU_OUT_OF_MEMORY, "slipcu_factor_column", "device memory exhausted");
-    CU (cudaMemcpyAsync (hc.rows, F->h_packet, (size_t) (cnt + 2 * nU + 1) * sizeof (int32_t),
-                         cudaMemcpyHostToDevice, F->st));
-    g_h2d_bytes += (double) (cnt + 2 * nU + 1) * sizeof (int32_t);
-    rc = prepare_steps (F, cnt, nU, hc.rows, hc.rows + cnt, hc.rows + cnt + nU, (int) total);
+    CU (cudaMemcpyAsync (hc.rows, F->h_packet, pk_ints * sizeof (int32_t), cudaMemcpyHostToDevice, F->st));
+    g_h2d_bytes += (double) pk_ints * sizeof (int32_t);
+    rc = prepare_steps (F, cnt, nU, hc.rows, hc.rows + cnt, hc.rows + cnt + nU, hc.rows + cnt + 2 * nU + 1, (int) total);
     if (rc) return rc;
 
     TriArgs a;
@@ -1495,14 +1487,15 @@ extern "C" int slipcu_factor_column (slipcu_factor *F, int k, int col, int cnt, 
     a.src_cnt = F->hAp[col + 1] - F->hAp[col]; a.src_rows = F->dAi + F->hAp[col];
     a.src_y_stride = 0;
     a.out = hc.base; a.out_y_stride = 0;
-    a.rho = F->rho; a.invrho = F->invrho; a.ratio = F->ratio;
+    a.rho = F->rho; a.invrho = F->invrho;
     a.p = T.p; a.ninv = T.ninv; a.pos = F->pos;
+    a.nchunks = (int) nchunks;
     size_t smem = 0;
     rc = tri_geometry (F, a, &smem);
     if (rc) return rc;
     {
         ScopedTimer tm (F, &g_tri_ms);
-        CU (launch_tri_any (CH, a, dim3 (S / CH, 1), F->threads, smem, F->st));
+        CU (launch_tri_any (CH, a, dim3 (S / CH, 1), F->threads + 32 * a.stages, smem, F->st));
         if (debug_check ("k_trisolve(column)", F->st)) return fail (SLIPCU_CUDA_ERROR, "k_trisolve", "debug");
     }
     {   // algorithmic work of this launch
@@ -1583,7 +1576,7 @@ extern "C" int slipcu_factor_set_pivot (slipcu_factor *F, int k, int slot)
     ColDesc d;
     d.base = hc.base; d.rows = hc.rows; d.cnt = hc.cnt; d.nU = hc.nU; d.pivslot = slot; d.pad = 0;
     k_pivot_commit<<<(F->S + 255) / 256, 256, 0, F->st>>> (k, F->S, F->CH, slot, d, F->desc, F->rho,
-                                                           F->invrho, F->ratio, T.p, T.ninv, T.one, F->bad);
+                                                           F->invrho, T.p, T.ninv, T.one, F->bad);
     g_launches++;
     CU (cudaGetLastError ());
     if (debug_check ("k_pivot_commit", F->st)) return fail (SLIPCU_CUDA_ERROR, "k_pivot_commit", "debug");
@@ -1723,7 +1716,7 @@ extern "C" int slipcu_solve (slipcu_factor *F, int nrhs, const u32 *blimbs, cons
     if (top_digit_max) *top_digit_max = -1;
     std::vector<int32_t> row_at (n), ident (n);
     for (int r = 0; r < n; ++r) { row_at[pinv[r]] = r; ident[r] = r; }
-    int32_t *dpinv = nullptr, *duoff = nullptr;
+    int32_t *dpinv = nullptr, *duoff = nullptr; int fwd_chunks = 0;
     const size_t nl = (size_t) boff[total];
 #define CUG(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail (e_ == cudaErrorMemoryAllocation ? SLIPCU_OUT_OF_MEMORY : SLIPCU_CUDA_ERROR, #call, cudaGetErrorString (e_)); goto done; } } while (0)
     CUG (cudaMalloc (&dl, std::max<size_t> (nl, 1) * sizeof (u32)));
@@ -1756,15 +1749,21 @@ extern "C" int slipcu_solve (slipcu_factor *F, int nrhs, const u32 *blimbs, cons
         CUG (cudaGetLastError ());
     }
     {   // symbolic pre-pass of the forward substitution: every column of L is one step
-        std::vector<int32_t> uoff (n + 1);
-        int64_t tot = 0;
-        for (int k = 0; k < n; ++k) { uoff[k] = (int32_t) tot; tot += ((F->cols[k].cnt - F->cols[k].nU) + 3) & ~3; }
-        uoff[n] = (int32_t) tot;
+        std::vector<int32_t> uoff (2 * (size_t) n + 2);
+        int64_t tot = 0, nch = 0;
+        for (int k = 0; k < n; ++k)
+        {
+            const int len = F->cols[k].cnt - F->cols[k].nU;
+            uoff[k] = (int32_t) tot; uoff[n + 1 + k] = (int32_t) nch;
+            tot += (len + 3) & ~3; nch += (len + TRI_ROWS - 1) / TRI_ROWS;
+        }
+        uoff[n] = (int32_t) tot; uoff[2 * n + 1] = (int32_t) nch;
+        fwd_chunks = (int) nch;
         if (tot > INT32_MAX) { rc = fail (SLIPCU_BAD_INPUT, "slipcu_solve", "L has too many entries"); goto done; }
-        CUG (cudaMalloc (&duoff, (size_t) (n + 1) * sizeof (int32_t)));
-        CUG (cudaMemcpyAsync (duoff, uoff.data (), (size_t) (n + 1) * sizeof (int32_t), cudaMemcpyHostToDevice, F->st));
+        CUG (cudaMalloc (&duoff, (2 * (size_t) n + 2) * sizeof (int32_t)));
+        CUG (cudaMemcpyAsync (duoff, uoff.data (), (2 * (size_t) n + 2) * sizeof (int32_t), cudaMemcpyHostToDevice, F->st));
         CUG (cudaStreamSynchronize (F->st));
-        rc = prepare_steps (F, n, n, F->rows_are_positions ? dident : drow_at, dident, duoff, (int) tot);
+        rc = prepare_steps (F, n, n, F->rows_are_positions ? dident : drow_at, dident, duoff, duoff + n + 1, (int) tot);
         if (rc) goto done;
     }
     for (int r0 = 0; r0 < nrhs; r0 += batch)
@@ -1780,12 +1779,13 @@ extern "C" int slipcu_solve (slipcu_factor *F, int nrhs, const u32 *blimbs, cons
         a.src_rows = F->rows_are_positions ? dpinv : nullptr;
         a.src_y_stride = 1;
         a.out = dz; a.out_y_stride = (size_t) n * S;
-        a.rho = F->rho; a.invrho = F->invrho; a.ratio = F->ratio;
+        a.rho = F->rho; a.invrho = F->invrho;
         a.p = T.p; a.ninv = T.ninv; a.pos = F->pos;
+        a.nchunks = fwd_chunks;
         size_t smem = 0;
         rc = tri_geometry (F, a, &smem);
         if (rc) goto done;
-        CUG (launch_tri_any (CH, a, dim3 (S / CH, nb), F->threads, smem, F->st));
+        CUG (launch_tri_any (CH, a, dim3 (S / CH, nb), F->threads + 32 * a.stages, smem, F->st));
         if (debug_check ("k_trisolve(forward)", F->st)) { rc = fail (SLIPCU_CUDA_ERROR, "k_trisolve(forward)", "debug"); goto done; }
         BackArgs b;
         b.n = n; b.S = S; b.z = dz; b.z_y_stride = (size_t) n * S;

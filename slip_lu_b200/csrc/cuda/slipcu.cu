@@ -128,11 +128,27 @@ static std::vector<u32> g_primes;          // descending from 2^31 - 1, retired 
 static u32 g_next_candidate = 0x7fffffffu;
 static std::shared_ptr<Tables> g_tables;
 
-static bool is_prime_u32 (u32 x)
+static u32 powmod_u32 (u32 b, u32 e, u32 m)
 {
+    u64 r = 1, x = b % m;
+    while (e) { if (e & 1) r = r * x % m; x = x * x % m; e >>= 1; }
+    return (u32) r;
+}
+static bool is_prime_u32 (u32 x)
+{   // deterministic Miller-Rabin for 32-bit integers (bases 2, 3, 5, 7)
     if (x < 2) return false;
-    if ((x & 1) == 0) return x == 2;
-    for (u32 d = 3; (u64) d * d <= x; d += 2) if (x % d == 0) return false;
+    for (u32 q : {2u, 3u, 5u, 7u, 11u, 13u, 17u, 19u, 23u, 29u, 31u, 37u})
+        if (x % q == 0) return x == q;
+    u32 d = x - 1; int r = 0;
+    while ((d & 1) == 0) { d >>= 1; ++r; }
+    for (u32 a : {2u, 3u, 5u, 7u})
+    {
+        u32 y = powmod_u32 (a, d, x);
+        if (y == 1 || y == x - 1) continue;
+        bool comp = true;
+        for (int i = 1; i < r && comp; ++i) { y = (u32) ((u64) y * y % x); if (y == x - 1) comp = false; }
+        if (comp) return false;
+    }
     return true;
 }
 static void extend_primes (size_t count)
@@ -323,7 +339,7 @@ struct slipcu_factor
     int32_t *slots = nullptr; size_t slots_cap = 0;      // slot lists of the current column
     StepInfo *steps = nullptr; size_t steps_cap = 0;
     int stages = 4;
-    int garner_mode = 1;
+    int garner_mode = 2;
     slipcu_factor () : resid ((size_t) 512 << 20), ints ((size_t) 16 << 20), limbs ((size_t) 256 << 20) {}
 };
 
@@ -874,10 +890,15 @@ __global__ void __launch_bounds__ (512) k_garner_tiled (GarnerArgs a)
                         v[e] = mont_redc (a.base[((size_t) (tt / CH) * a.cnt + ent[e]) * CH + (tt % CH)], p, ni);
                         T[e] = acc[e][li]; mine[e] = 0;
                     }
-                    const u32 *Ccol = a.C + tt;
+                    // the 32x32 diagonal block of C for this lane's column, loaded up front so that
+                    // the serial 32-step elimination below runs out of registers
+                    const u32 *Ccol = a.C + tt + (size_t) (32 * b) * S;
+                    u32 cc[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) cc[i] = Ccol[(size_t) i * S];
+#pragma unroll
                     for (int i = 0; i < 32; ++i)
                     {
-                        const u32 cc = (lane > i) ? Ccol[(size_t) (32 * b + i) * S] : 0u;
 #pragma unroll
                         for (int e = 0; e < E; ++e)
                         {
@@ -890,7 +911,7 @@ __global__ void __launch_bounds__ (512) k_garner_tiled (GarnerArgs a)
                                 mine[e] = di;
                             }
                             di = __shfl_sync (full, di, i);
-                            if (lane > i) lazy_mac (T[e], di, cc, p);
+                            if (lane > i) lazy_mac (T[e], di, cc[i], p);
                         }
                     }
 #pragma unroll
@@ -902,6 +923,7 @@ __global__ void __launch_bounds__ (512) k_garner_tiled (GarnerArgs a)
                 }
                 __syncthreads ();
                 // every warp: add block b's digits to the blocks it still owns
+#pragma unroll 2
                 for (int q = 0; q < 32; q += 4)
                 {
                     uint4 d4[E];
@@ -927,6 +949,190 @@ __global__ void __launch_bounds__ (512) k_garner_tiled (GarnerArgs a)
             }
         }
         __syncthreads ();
+    }
+    __syncthreads ();
+    // sign, magnitude digits and top digit: one warp per entry
+    if (w >= E || g0 + w >= a.ne) return;
+    const int e = a.e0 + g0 + w;
+    u32 *dg = a.dig + (size_t) e * a.dstride;
+    bool neg = false;
+    for (int t0 = ((s - 1) / 32) * 32; t0 >= 0; t0 -= 32)
+    {
+        const int t = t0 + lane;
+        u32 d = 0, h = 0;
+        if (t < s) { d = dg[t]; h = (a.p[t] - 1) >> 1; }
+        const unsigned ne = __ballot_sync (full, d != h);
+        if (ne)
+        {
+            const int top = 31 - __clz (ne);
+            neg = __shfl_sync (full, (int) (d > h), top) != 0;
+            break;
+        }
+    }
+    if (neg)
+    {
+        for (int t = lane; t < s; t += 32) dg[t] = a.p[t] - 1 - dg[t];
+        __syncwarp ();
+        if (lane == 0)
+        {
+            for (int t = 0; t < s; ++t)
+            {
+                u32 d = dg[t] + 1;
+                if (d == a.p[t]) dg[t] = 0; else { dg[t] = d; break; }
+            }
+        }
+        __syncwarp ();
+    }
+    int top = -1;
+    for (int t0 = ((s - 1) / 32) * 32; t0 >= 0; t0 -= 32)
+    {
+        const int t = t0 + lane;
+        const u32 d = (t < s) ? dg[t] : 0u;
+        const unsigned nzm = __ballot_sync (full, d != 0);
+        if (nzm) { top = t0 + 31 - __clz (nzm); break; }
+    }
+    for (int t = s + lane; t < ((s + 3) & ~3); t += 32) dg[t] = 0;
+    if (lane == 0) { a.topd[e] = top; a.sign[e] = top < 0 ? 0 : (neg ? -1 : 1); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_garner_flow: the tiled reconstruction as a dataflow inside the CTA (no CTA-wide barriers).
+// Block b (32 digits) is owned by warp b mod W.  A warp walks the blocks in order; when it reaches
+// a block it owns it finishes its 32 digits and raises ready[b]; otherwise it waits for ready[b].
+// Either way it then adds block b's digits to the later blocks it owns, NEAREST FIRST, and if that
+// nearest block is b+1 it finishes and publishes it before touching the others: the serial chain
+// (finish b -> apply to b+1 -> finish b+1 ...) never waits for the bulk of the updates, which the
+// other warps carry out behind it.  Requires all digit blocks to fit one tile (B <= W*BPW).
+// ------------------------------------------------------------------------------------------------
+template <int E, int BPW>
+__global__ void __launch_bounds__ (384) k_garner_flow (GarnerArgs a)
+{
+    extern __shared__ __align__ (16) unsigned char gsm[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, W = blockDim.x >> 5;
+    const int s = a.s, S = a.S, CH = a.CH;
+    const int B = (s + 31) >> 5;
+    u32 *digs = (u32 *) gsm;                               // [B][E][32]
+    volatile int *ready = (volatile int *) (digs + (size_t) B * E * 32);
+    const unsigned full = 0xffffffffu;
+    const int g0 = blockIdx.x * E;
+    int ent[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) ent[e] = a.e0 + min (g0 + e, a.ne - 1);
+    for (int b = threadIdx.x; b < B; b += blockDim.x) ready[b] = 0;
+    __syncthreads ();
+
+    u64 acc[BPW][E];
+    u32 pt[BPW], nit[BPW];
+    int tpos[BPW];
+#pragma unroll
+    for (int i = 0; i < BPW; ++i)
+    {
+        const int t = 32 * (w + i * W) + lane;
+        tpos[i] = t < s ? t : s - 1;
+        pt[i] = a.p[tpos[i]]; nit[i] = a.ninv[tpos[i]];
+#pragma unroll
+        for (int e = 0; e < E; ++e) acc[i][e] = 0;
+    }
+
+    u32 *ccs = (u32 *) (ready + B) + (size_t) w * 1024;          // this warp's 32x32 block of C
+    // add the digits of block b to one owned block
+    auto apply = [&] (int b, u64 (&T)[E], u32 p, int tt)
+    {
+        const u32 *Cc = a.C + (size_t) (32 * b) * S + tt;
+        const u32 *db = digs + (size_t) b * E * 32;
+#pragma unroll 2
+        for (int q = 0; q < 32; q += 4)
+        {
+            const u32 c0 = Cc[(size_t) q * S], c1 = Cc[(size_t) (q + 1) * S];
+            const u32 c2 = Cc[(size_t) (q + 2) * S], c3 = Cc[(size_t) (q + 3) * S];
+#pragma unroll
+            for (int e = 0; e < E; ++e)
+            {
+                const uint4 d4 = *reinterpret_cast<const uint4 *> (db + e * 32 + q);
+                lazy_mac (T[e], d4.x, c0, p); lazy_mac (T[e], d4.y, c1, p);
+                lazy_mac (T[e], d4.z, c2, p); lazy_mac (T[e], d4.w, c3, p);
+            }
+        }
+    };
+
+    for (int b = -1; b < B - 1 || b < 0; ++b)
+    {
+        if (b >= 0)
+        {
+            if (b % W != w) { while (ready[b] == 0) { } }
+            __threadfence_block ();
+            __syncwarp ();
+        }
+        // the block that continues the chain, b+1, first -- if it is mine
+        u64 T[E];
+        u32 fp = 0, fni = 0; int ftt = 0; bool mine_next = false;
+#pragma unroll
+        for (int i = 0; i < BPW; ++i)
+        {
+            const int bo = w + i * W;
+            if (bo == b + 1 && bo < B)
+            {
+                if (b >= 0) apply (b, acc[i], pt[i], tpos[i]);
+#pragma unroll
+                for (int e = 0; e < E; ++e) T[e] = acc[i][e];
+                fp = pt[i]; fni = nit[i]; ftt = tpos[i]; mine_next = true;
+            }
+        }
+        if (mine_next)
+        {   // finish the 32 digits of block b+1 for the E entries and publish them
+            const int bo = b + 1;
+            const int t = 32 * bo + lane;
+            const bool valid = t < s;
+            const u32 ib = a.invB[ftt];
+            u32 v[E], mine[E];
+#pragma unroll
+            for (int e = 0; e < E; ++e)
+            {
+                v[e] = mont_redc (a.base[((size_t) (ftt / CH) * a.cnt + ent[e]) * CH + (ftt % CH)], fp, fni);
+                mine[e] = 0;
+            }
+            const u32 *Ccol = a.C + ftt + (size_t) (32 * bo) * S;
+#pragma unroll 8
+            for (int i = 0; i < 32; ++i) ccs[i * 32 + lane] = Ccol[(size_t) i * S];
+            __syncwarp ();
+            for (int i = 0; i < 32; ++i)
+            {
+                const u32 cci = ccs[i * 32 + lane];
+#pragma unroll
+                for (int e = 0; e < E; ++e)
+                {
+                    u32 di = 0;
+                    if (lane == i)
+                    {
+                        const u32 r = lazy_redc (T[e], fp, fni);
+                        const u32 diff = v[e] >= r ? v[e] - r : v[e] + fp - r;
+                        di = mont_mul (diff, ib, fp, fni);
+                        mine[e] = di;
+                    }
+                    di = __shfl_sync (full, di, i);
+                    if (lane > i) lazy_mac (T[e], di, cci, fp);
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < E; ++e)
+            {
+                if (valid && g0 + e < a.ne) a.dig[(size_t) ent[e] * a.dstride + t] = mine[e];
+                digs[((size_t) bo * E + e) * 32 + lane] = valid ? mine[e] : 0u;
+            }
+            __threadfence_block ();
+            __syncwarp ();
+            if (lane == 0) ready[bo] = 1;
+        }
+        // then the rest of my later blocks
+        if (b >= 0)
+        {
+#pragma unroll
+            for (int i = 0; i < BPW; ++i)
+            {
+                const int bo = w + i * W;
+                if (bo > b + 1 && bo < B) apply (b, acc[i], pt[i], tpos[i]);
+            }
+        }
     }
     __syncthreads ();
     // sign, magnitude digits and top digit: one warp per entry
@@ -1219,7 +1425,8 @@ static int session_common_init (slipcu_factor *F, int n, int channels)
     F->stages = env_int ("SLIP_B200_STAGES", 4);
     if (F->stages < 2 || F->stages > TRI_MAX_STAGES) F->stages = 4;
     F->x_global = env_int ("SLIP_B200_X_GLOBAL", 0);
-    F->garner_mode = env_int ("SLIP_B200_GARNER", 1);
+    F->garner_mode = env_int ("SLIP_B200_GARNER", 2);
+    CU (cudaFuncSetAttribute (k_garner_flow<4, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     int smem_optin = 0;
     cudaDeviceGetAttribute (&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, F->device);
     F->smem_limit = (size_t) smem_optin;
@@ -1398,7 +1605,12 @@ static int run_garner (slipcu_factor *F, const u32 *base, int region_cnt, int e0
         const int blocks = (s + 31) / 32;
         int W = (blocks + 4) / 5;
         W = std::max (4, std::min (16, W));      // >= E warps: the epilogue uses one warp per entry
-        k_garner_tiled<4, 5><<<(ne + 3) / 4, W * 32, 0, F->st>>> (g);
+        const int Wf = std::max (4, (blocks + 5) / 6);          // dataflow variant: 6 blocks per warp
+        const size_t fsm = (size_t) blocks * 4 * 32 * sizeof (u32) + (size_t) blocks * sizeof (int) + (size_t) Wf * 4096 + 16;
+        if (F->garner_mode == 2 && Wf <= 12 && fsm <= 160 * 1024)
+            k_garner_flow<4, 6><<<(ne + 3) / 4, Wf * 32, fsm, F->st>>> (g);
+        else
+            k_garner_tiled<4, 5><<<(ne + 3) / 4, W * 32, 0, F->st>>> (g);
     }
     g_launches++;
     CU (cudaGetLastError ());

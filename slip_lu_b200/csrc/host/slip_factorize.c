@@ -10,7 +10,15 @@
  * The only arithmetic left on the host is the rational tolerance comparison of
  * SLIP_TOL_SMALLEST / SLIP_TOL_LARGEST on two already-reconstructed integers, done with the very
  * GMP call the reference uses (slip_get_pivot.c:94-143) so that its outcome is reproduced. */
+#include <time.h>
 #include "slip_internal.h"
+
+static double now_s (void)
+{
+    struct timespec t ;
+    clock_gettime (CLOCK_MONOTONIC, &t) ;
+    return (double) t.tv_sec + 1e-9 * (double) t.tv_nsec ;
+}
 
 /* ---- host copy of the patterns of the finished columns ---- */
 typedef struct
@@ -199,6 +207,8 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
     if (nz <= 0) return SLIP_INCORRECT_INPUT ;
     const int scheme = (int) option->pivot ;
     SLIP_info status = SLIP_OK ;
+    const int timing = getenv ("SLIP_B200_TIMING") != NULL ;
+    double t_sym = 0, t_dev = 0, t_piv = 0, t_begin = 0, t0 = now_s (), tt ;
     slip_limbs Al = {0} ;
     pattern_store P = {0} ;
     slipcu_factor *dev = NULL ;
@@ -235,8 +245,10 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
     {
         int retry = 0 ;
         SLIP_TRY (patterns_init (&P, n, (int64_t) S->lnz + S->unz)) ;
+        tt = now_s () ;
         SLIP_TRY (slip_from_device_status (slipcu_factor_begin (&dev, n, nz, A->p, A->i, Al.limbs, Al.off,
             Al.sign, channels, want_host_factors))) ;
+        t_begin += now_s () - tt ;
         const int S_dev = slipcu_factor_channels (dev) ;
         for (int32_t r = 0 ; r < n ; r++) { pinv [r] = r ; row_at [r] = r ; mark [r] = 0 ; }
         double cum_bits = 0 ;
@@ -246,6 +258,7 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
             cum_bits += colbits [col] ;
             int s_k = slip_channels_for_bits (cum_bits) ;
             if (s_k > S_dev) s_k = S_dev ;
+            tt = now_s () ;
             const int32_t cnt = column_pattern (A, col, k, &P, pinv, row_at, mark, stack, pat) ;
             int32_t nU = 0, diag_slot = -1 ;
             for (int32_t t = 0 ; t < cnt ; t++)
@@ -256,7 +269,9 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
             }
             if (cnt == nU) { status = SLIP_SINGULAR ; goto cleanup ; }    /* no candidate row at all */
             slipcu_pivot_info info ;
+            t_sym += now_s () - tt ; tt = now_s () ;
             int rc = slipcu_factor_column (dev, k, col, cnt, nU, pat, upos, s_k, scheme, diag_slot, &info) ;
+            t_dev += now_s () - tt ; tt = now_s () ;
             if (rc == SLIPCU_BAD_PRIME) { retry = 1 ; break ; }
             SLIP_TRY (slip_from_device_status (rc)) ;
             int32_t slot = -1 ;
@@ -271,6 +286,7 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
             memcpy (P.rows + P.used, pat, (size_t) cnt * sizeof (int32_t)) ;
             P.used += cnt ;
             P.ptr [k + 1] = P.used ; P.nU [k] = nU ; P.piv [k] = slot ;
+            t_piv += now_s () - tt ;
             if (k == n - 1)
             {   /* det = rho[n-1], kept with the resident factors for the rational solve */
                 res = (slip_resident *) SLIP_calloc (1, sizeof (slip_resident)) ;
@@ -304,6 +320,9 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
         }
     }
 
+    if (timing)
+        fprintf (stderr, "slip_lu_b200 timing: setup %.3fs (device begin %.3fs) symbolic %.3fs device columns %.3fs pivot/commit %.3fs total-so-far %.3fs\n",
+            0.0, t_begin, t_sym, t_dev, t_piv, now_s () - t0) ;
     if (want_host_factors)
     {
         int64_t lnz = 0, unz = 0 ;

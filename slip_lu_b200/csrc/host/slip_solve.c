@@ -5,7 +5,15 @@
  * SLIP_scale_x.c, SLIP_check_solution.c, SLIP_get_double_soln.c.  The substitutions run on the
  * GPU against the resident factors; the host turns the integer numerators det*x_i into canonical
  * rationals (the mpq_div of slip_array_div.c) and applies the permutation and the scale. */
+#include <time.h>
 #include "slip_internal.h"
+
+static double now_s (void)
+{
+    struct timespec t ;
+    clock_gettime (CLOCK_MONOTONIC, &t) ;
+    return (double) t.tv_sec + 1e-9 * (double) t.tv_nsec ;
+}
 
 /* ---- numerators det*x_i streamed from the device: x[i][c] = num / det, canonical ---- */
 typedef struct
@@ -203,8 +211,11 @@ static SLIP_info solve_exact (mpq_t **x, SLIP_sparse *A, SLIP_LU_analysis *S, SL
     const int32_t n = A->n ;
     int32_t *pinv = (int32_t *) SLIP_malloc ((size_t) n * sizeof (int32_t)) ;
     if (!pinv) return SLIP_OUT_OF_MEMORY ;
+    double t0 = now_s () ;
     SLIP_TRY (slip_factorize_driver (NULL, NULL, A, S, NULL, pinv, option, 0, &r, slip_dense_max_column_bits (b))) ;
+    double t1 = now_s () ;
     SLIP_TRY (slip_solve_resident (x, b, r, pinv)) ;
+    if (getenv ("SLIP_B200_TIMING")) fprintf (stderr, "slip_lu_b200 timing: factor %.3fs solve %.3fs\n", t1 - t0, now_s () - t1) ;
     SLIP_TRY (SLIP_permute_x (x, n, b->n, S)) ;
     SLIP_TRY (SLIP_scale_x (x, A, b)) ;
 cleanup:

@@ -191,6 +191,10 @@ SLIP_info SLIP_spok (SLIP_sparse *A, SLIP_options *option) ;
 const char *SLIP_B200_last_error (void) ;
 int SLIP_B200_device_count (void) ;
 int SLIP_B200_set_device (int device) ;
+/* work and timing of the calling thread's last factorization: n, nnz(L), nnz(U), channels, REF
+ * entry updates, schoolbook-equivalent 32-bit limb multiplies, seconds (symbolic, device, set-up,
+ * total).  Returns the number of values written. */
+int SLIP_B200_last_stats (double *out, int cap) ;
 
 #ifdef __cplusplus
 }

@@ -132,6 +132,9 @@ typedef struct
     double   trisolve_modmul;     /* 32-bit limb (modular) multiplies: 4 per entry update */
     double   recon_ms;            /* garner + to_limbs */
     double   recon_mac;           /* 32x32 multiply-accumulates in reconstruction */
+    double   h2d_bytes, d2h_bytes;/* bytes this library copied host->device / device->host */
+    double   device_ms;           /* CUDA-event time from "A resident in HBM" to "solution numerators
+                                     reconstructed in HBM", accumulated over slipcu_solve calls */
 } slipcu_counters;
 void slipcu_get_counters (slipcu_counters *out);
 void slipcu_reset_counters (void);

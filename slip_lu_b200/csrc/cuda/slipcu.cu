@@ -60,7 +60,7 @@ static int debug_check (const char *what, cudaStream_t st)
 extern "C" const char *slipcu_last_error (void) { return g_err.c_str (); }
 
 static std::atomic<uint64_t> g_launches{0}, g_tri_launches{0};
-static double g_h2d_bytes = 0;
+static double g_h2d_bytes = 0, g_d2h_bytes = 0, g_device_ms = 0;
 static double g_tri_ms = 0, g_tri_bytes = 0, g_tri_modmul = 0, g_recon_ms = 0, g_recon_mac = 0;
 static int g_profiling = 0;
 
@@ -319,6 +319,7 @@ struct slipcu_factor
     std::shared_ptr<Tables> tab;
     cudaStream_t st = nullptr;
     cudaEvent_t ev = nullptr, ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_end = nullptr;      // A resident ... solution numerators on device
     int32_t *dAp = nullptr, *dAi = nullptr;
     u32 *dA = nullptr;                       // residues of A, [S/CH][nz][CH]
     u32 *rho = nullptr, *invrho = nullptr;    // [n][S]
@@ -1377,6 +1378,8 @@ extern "C" void slipcu_factor_free (slipcu_factor *F)
     if (F->ev) cudaEventDestroy (F->ev);
     if (F->ev0) cudaEventDestroy (F->ev0);
     if (F->ev1) cudaEventDestroy (F->ev1);
+    if (F->ev_start) cudaEventDestroy (F->ev_start);
+    if (F->ev_end) cudaEventDestroy (F->ev_end);
     if (F->st) cudaStreamDestroy (F->st);
     delete F;
 }
@@ -1440,6 +1443,7 @@ static int session_common_init (slipcu_factor *F, int n, int channels)
     CU (cudaStreamCreateWithFlags (&F->st, cudaStreamNonBlocking));
     CU (cudaEventCreateWithFlags (&F->ev, cudaEventDisableTiming));
     CU (cudaEventCreate (&F->ev0)); CU (cudaEventCreate (&F->ev1));
+    CU (cudaEventCreate (&F->ev_start)); CU (cudaEventCreate (&F->ev_end));
     CU (cudaMalloc (&F->rho, (size_t) n * S * sizeof (u32)));
     CU (cudaMalloc (&F->invrho, (size_t) n * S * sizeof (u32)));
     CU (cudaMalloc (&F->desc, (size_t) n * sizeof (ColDesc)));
@@ -1490,7 +1494,9 @@ extern "C" int slipcu_factor_begin (slipcu_factor **out, int n, int nz, const in
         CU (cudaGetLastError ());
         CU (cudaStreamSynchronize (F->st));
         cudaFree (dl); cudaFree (doff); cudaFree (dsg);
+        g_h2d_bytes += (double) nl * 4 + (double) (nz + 1) * 8 + (double) nz * 5 + (double) (n + 1) * 4;
     }
+    CU (cudaEventRecord (F->ev_start, F->st));
     return SLIPCU_OK;
 }
 
@@ -1734,6 +1740,7 @@ extern "C" int slipcu_factor_column (slipcu_factor *F, int k, int col, int cnt, 
         if (rc) return rc;
     }
     CU (cudaEventSynchronize (F->ev));
+    g_d2h_bytes += sizeof (slipcu_pivot_info);
     *info = *F->h_info;
     F->cur = k;
     if (info->bad_channel) return fail (SLIPCU_BAD_PRIME, "slipcu_factor_column", "channel prime divides a pivot");
@@ -1776,6 +1783,7 @@ extern "C" int slipcu_factor_fetch_entry (slipcu_factor *F, int k, int slot, u32
     }
     CU (cudaMemcpyAsync (sign, hc.sign + slot, 1, cudaMemcpyDeviceToHost, F->st));
     CU (cudaStreamSynchronize (F->st));
+    g_d2h_bytes += (double) hc.stride * 4 + 5;
     return SLIPCU_OK;
 }
 
@@ -1859,6 +1867,7 @@ static int stream_column (slipcu_factor *F, int k, const HostCol &hc, slipcu_col
     CU (cudaMemcpyAsync (h_nl, hc.nl, (size_t) hc.cnt * sizeof (int32_t), cudaMemcpyDeviceToHost, F->st));
     CU (cudaMemcpyAsync (h_sign, hc.sign, (size_t) hc.cnt, cudaMemcpyDeviceToHost, F->st));
     CU (cudaStreamSynchronize (F->st));
+    g_d2h_bytes += (double) hc.cnt * hc.stride * 4 + (double) hc.cnt * 5;
     int rc = sink (user, k, hc.cnt, hc.stride, h_limbs, h_nl, h_sign);
     if (rc) return fail (rc, "column sink", "host sink failed");
     return SLIPCU_OK;
@@ -1951,6 +1960,7 @@ extern "C" int slipcu_solve (slipcu_factor *F, int nrhs, const u32 *blimbs, cons
     CUG (cudaMemcpyAsync (drow_at, row_at.data (), (size_t) n * sizeof (int32_t), cudaMemcpyHostToDevice, F->st));
     CUG (cudaMemcpyAsync (dident, ident.data (), (size_t) n * sizeof (int32_t), cudaMemcpyHostToDevice, F->st));
     CUG (cudaMemcpyAsync (dpinv, pinv, (size_t) n * sizeof (int32_t), cudaMemcpyHostToDevice, F->st));
+    g_h2d_bytes += (double) nl * 4 + (double) (total + 1) * 8 + (double) total + 3.0 * n * 4;
     rc = ensure_digits (F, (size_t) n);
     if (rc) goto done;
     {
@@ -2016,6 +2026,7 @@ extern "C" int slipcu_solve (slipcu_factor *F, int nrhs, const u32 *blimbs, cons
             if (rc) goto done;
             rc = run_limbs (F, 0, n, 0, stride, s, dlimbs, dnl);
             if (rc) goto done;
+            CUG (cudaEventRecord (F->ev_end, F->st));
             if (top_digit_max)
             {   // highest mixed-radix digit in use: lets the caller verify an estimated bound
                 CUG (cudaMemcpyAsync (h_nl, F->topd, (size_t) n * sizeof (int32_t), cudaMemcpyDeviceToHost, F->st));
@@ -2028,6 +2039,11 @@ extern "C" int slipcu_solve (slipcu_factor *F, int nrhs, const u32 *blimbs, cons
     }
 done:
     cudaStreamSynchronize (F->st);
+    if (rc == SLIPCU_OK && !F->rows_are_positions)
+    {   // device-side job time: A resident -> solution numerators reconstructed on the device
+        float ms = 0;
+        if (cudaEventElapsedTime (&ms, F->ev_start, F->ev_end) == cudaSuccess) g_device_ms += ms; else cudaGetLastError ();
+    }
     cudaFree (dl); cudaFree (doff); cudaFree (dsg); cudaFree (dB); cudaFree (dz); cudaFree (dlimbs);
     cudaFree (drow_at); cudaFree (dident); cudaFree (dpinv); cudaFree (duoff); cudaFree (dnl); cudaFree (dsign);
     if (h_limbs) cudaFreeHost (h_limbs);
@@ -2046,10 +2062,12 @@ extern "C" void slipcu_get_counters (slipcu_counters *o)
     o->launches = g_launches.load (); o->trisolve_launches = g_tri_launches.load ();
     o->trisolve_ms = g_tri_ms; o->trisolve_bytes = g_tri_bytes; o->trisolve_modmul = g_tri_modmul;
     o->recon_ms = g_recon_ms; o->recon_mac = g_recon_mac;
+    o->h2d_bytes = g_h2d_bytes; o->d2h_bytes = g_d2h_bytes; o->device_ms = g_device_ms;
 }
 extern "C" void slipcu_reset_counters (void)
 {
     g_launches = 0; g_tri_launches = 0;
     g_tri_ms = g_tri_bytes = g_tri_modmul = g_recon_ms = g_recon_mac = 0;
+    g_h2d_bytes = g_d2h_bytes = g_device_ms = 0;
 }
 extern "C" void slipcu_set_profiling (int enabled) { g_profiling = enabled; }

@@ -209,6 +209,8 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
     SLIP_info status = SLIP_OK ;
     const int timing = getenv ("SLIP_B200_TIMING") != NULL ;
     double t_sym = 0, t_dev = 0, t_piv = 0, t_begin = 0, t0 = now_s (), tt ;
+    double work_updates = 0, work_limbmul = 0 ;
+    double *cumbits_at = (double *) SLIP_calloc ((size_t) n, sizeof (double)) ;
     slip_limbs Al = {0} ;
     pattern_store P = {0} ;
     slipcu_factor *dev = NULL ;
@@ -219,7 +221,7 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
     int32_t *stack = (int32_t *) SLIP_malloc ((size_t) n * sizeof (int32_t)) ;
     int32_t *pat = (int32_t *) SLIP_malloc ((size_t) n * sizeof (int32_t)) ;
     int32_t *upos = (int32_t *) SLIP_malloc ((size_t) n * sizeof (int32_t)) ;
-    if (!colbits || !row_at || !mark || !stack || !pat || !upos) { status = SLIP_OUT_OF_MEMORY ; goto cleanup ; }
+    if (!colbits || !row_at || !mark || !stack || !pat || !upos || !cumbits_at) { status = SLIP_OUT_OF_MEMORY ; goto cleanup ; }
 
     for (int32_t a = 0 ; a < nz ; a++)
         if (A->i [a] < 0 || A->i [a] >= n) { status = SLIP_INCORRECT_INPUT ; goto cleanup ; }
@@ -252,6 +254,7 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
         const int S_dev = slipcu_factor_channels (dev) ;
         for (int32_t r = 0 ; r < n ; r++) { pinv [r] = r ; row_at [r] = r ; mark [r] = 0 ; }
         double cum_bits = 0 ;
+        work_updates = 0 ; work_limbmul = 0 ;
         for (int32_t k = 0 ; k < n ; k++)
         {
             const int32_t col = S->q [k] ;
@@ -282,6 +285,14 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
                 pinv [prow] = k ; pinv [displaced] = oldpos ;
             }
             SLIP_TRY (slip_from_device_status (slipcu_factor_set_pivot (dev, k, slot))) ;
+            for (int32_t u = 0 ; u < nU ; u++)
+            {   /* work model: every L entry below the pivot of column upos[u] is updated once */
+                const int32_t j = upos [u] ;
+                const double len = (double) (P.ptr [j + 1] - P.ptr [j]) - P.nU [j] - 1 ;
+                const double w = ceil (cumbits_at [j] / 32.0) ;
+                work_updates += len ; work_limbmul += 3.0 * len * w * w ;
+            }
+            cumbits_at [k] = cum_bits ;
             SLIP_TRY (patterns_reserve (&P, cnt)) ;
             memcpy (P.rows + P.used, pat, (size_t) cnt * sizeof (int32_t)) ;
             P.used += cnt ;
@@ -320,6 +331,15 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
         }
     }
 
+    {
+        double lnz = 0, unz = 0 ;
+        for (int32_t k = 0 ; k < n ; k++) { lnz += (double) (P.ptr [k + 1] - P.ptr [k]) - P.nU [k] ; unz += P.nU [k] + 1 ; }
+        slip_last_stats.n = n ; slip_last_stats.nnz_L = lnz ; slip_last_stats.nnz_U = unz ;
+        slip_last_stats.channels = slipcu_factor_channels (dev) ;
+        slip_last_stats.updates = work_updates ; slip_last_stats.limb_mul_equiv = work_limbmul ;
+        slip_last_stats.t_symbolic = t_sym ; slip_last_stats.t_device = t_dev ; slip_last_stats.t_begin = t_begin ;
+        slip_last_stats.t_factor_total = now_s () - t0 ;
+    }
     if (timing)
         fprintf (stderr, "slip_lu_b200 timing: setup %.3fs (device begin %.3fs) symbolic %.3fs device columns %.3fs pivot/commit %.3fs total-so-far %.3fs\n",
             0.0, t_begin, t_sym, t_dev, t_piv, now_s () - t0) ;
@@ -372,7 +392,7 @@ cleanup:
     slip_limbs_free (&Al) ;
     patterns_free (&P) ;
     SLIP_free (colbits) ; SLIP_free (row_at) ; SLIP_free (mark) ; SLIP_free (stack) ;
-    SLIP_free (pat) ; SLIP_free (upos) ;
+    SLIP_free (pat) ; SLIP_free (upos) ; SLIP_free (cumbits_at) ;
     return status ;
 }
 

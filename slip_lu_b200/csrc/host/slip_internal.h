@@ -33,6 +33,16 @@ int64_t slip_mpz_words (mpz_srcptr z) ;
 void slip_mpz_from_words (mpz_ptr z, const uint32_t *limbs, int32_t n32, int sign) ;
 
 SLIP_info slip_from_device_status (int rc) ;
+
+/* statistics of the last factorization of this thread (see SLIP_B200_last_stats) */
+typedef struct
+{
+    double n, nnz_L, nnz_U, channels ;
+    double updates ;           /* REF entry updates (one per L entry per elimination step) */
+    double limb_mul_equiv ;    /* schoolbook-equivalent 32-bit limb multiplies of those updates */
+    double t_symbolic, t_device, t_begin, t_factor_total ;
+} slip_b200_stats ;
+extern __thread slip_b200_stats slip_last_stats ;
 void slip_set_error (const char *msg) ;
 
 /* sizing: upper bound of log2 ||A(:,j)||_2 for every column, and of a dense matrix' columns */

@@ -65,3 +65,18 @@ SLIP_info slip_from_device_status (int rc)
             return SLIP_INCORRECT ;
     }
 }
+
+__thread slip_b200_stats slip_last_stats ;
+
+/* out[0..] = n, nnz(L), nnz(U), channels, updates, limb_mul_equiv, t_symbolic, t_device, t_begin,
+ * t_factor_total of the last factorization run by the calling thread; returns the count written */
+int SLIP_B200_last_stats (double *out, int cap)
+{
+    const double v [10] = { slip_last_stats.n, slip_last_stats.nnz_L, slip_last_stats.nnz_U,
+        slip_last_stats.channels, slip_last_stats.updates, slip_last_stats.limb_mul_equiv,
+        slip_last_stats.t_symbolic, slip_last_stats.t_device, slip_last_stats.t_begin,
+        slip_last_stats.t_factor_total } ;
+    int k = 0 ;
+    for ( ; k < 10 && k < cap ; k++) out [k] = v [k] ;
+    return k ;
+}

@@ -8,9 +8,10 @@
  * SLIP_LU_factorize / SLIP_LU_solve / SLIP_solve_* runs on an NVIDIA B200 (sm_100a); the
  * library has no CPU path for it and returns an error if no device is present.
  *
- * Not (yet) provided: the mpfr_t/mpq_t input builders and SLIP_solve_mpfr (ref:442-463,
- * 511-532, 575-592, 899-907), and this fork's experimental
- * SLIP_LU_analyze_and_factorize{,1} (ref:866-886).  See DESIGN.md "scope".
+ * Not (yet) provided: the mpfr_t input builders and SLIP_solve_mpfr / SLIP_get_mpfr_soln
+ * (ref:454-463, 523-532, 585-592, 899-907, 975-982), the SLIP_mpz_ / SLIP_mpq_ / SLIP_mpfr_ GMP wrappers
+ * (ref:1023-1156), and this fork's experimental SLIP_LU_analyze_and_factorize{,1}
+ * (ref:866-886).  See DESIGN.md "scope".
  */
 #ifndef SLIP_Include
 #define SLIP_Include

@@ -306,6 +306,7 @@ struct ColDesc            // one finished column, as the kernels see it
 };
 
 struct StepInfo;
+struct ChunkInfo;
 
 struct HostCol
 {
@@ -339,7 +340,8 @@ struct slipcu_factor
     u32 *tmp_limbs = nullptr; int32_t *tmp_nl = nullptr; int tmp_stride = 0;
     int32_t *slots = nullptr; size_t slots_cap = 0;      // slot lists of the current column
     StepInfo *steps = nullptr; size_t steps_cap = 0;
-    int stages = 4;
+    ChunkInfo *chunks = nullptr; size_t chunks_cap = 0;
+    int stages = 4, stages_forced = 0, sms = 148;
     int garner_mode = 2;
     slipcu_factor () : resid ((size_t) 512 << 20), ints ((size_t) 16 << 20), limbs ((size_t) 256 << 20) {}
 };
@@ -407,6 +409,9 @@ __device__ __forceinline__ void consumer_bar (int nthreads)
 // symbolic pre-pass of a column: row -> slot map, then for every elimination step the list of
 // target slots (one per entry of the L column used), shared by all channel blocks.
 // ------------------------------------------------------------------------------------------------
+#define TRI_ROWS 512          // rows per pipeline chunk
+#define TRI_MAX_STAGES 8
+
 struct StepInfo           // one elimination step of a column: eliminate with column j of L
 {
     const u32 *lbase;     // first L-part residue of column j for channel block 0
@@ -418,6 +423,16 @@ struct StepInfo           // one elimination step of a column: eliminate with co
     int32_t pad;
 };
 
+struct ChunkInfo          // one pipeline chunk (<= TRI_ROWS rows of one step), ready for the producer
+{
+    const u32 *lsrc;      // first L residue of the chunk for channel block 0
+    int32_t cbstride;     // words between channel blocks
+    int32_t slot_off;     // offset of the chunk's slot list
+    int32_t j;            // pivot position of the step
+    int32_t nrows;
+    int32_t first, last;  // first / last chunk of its step
+};
+
 __global__ void k_setpos (int cnt, const int32_t *rows, int32_t *pos)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -426,7 +441,7 @@ __global__ void k_setpos (int cnt, const int32_t *rows, int32_t *pos)
 
 __global__ void k_slots (int nU, int total, int CH, const int32_t *upos, const int32_t *uoff,
                          const int32_t *uchunk, const ColDesc *desc, const int32_t *pos, int32_t *slots,
-                         StepInfo *steps)
+                         StepInfo *steps, ChunkInfo *chunks)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
@@ -443,6 +458,14 @@ __global__ void k_slots (int nU, int total, int CH, const int32_t *upos, const i
         si.lbase = d.base + (size_t) d.nU * CH; si.j = upos[u]; si.len = len; si.cbstride = d.cnt * CH;
         si.slot_off = uoff[u]; si.chunk0 = uchunk[u]; si.pad = 0;
         steps[u] = si;
+    }
+    if (r < len && (r % TRI_ROWS) == 0)
+    {
+        ChunkInfo ci;
+        ci.lsrc = d.base + (size_t) (d.nU + r) * CH; ci.cbstride = d.cnt * CH;
+        ci.slot_off = uoff[u] + r; ci.j = upos[u];
+        ci.nrows = min (TRI_ROWS, len - r); ci.first = (r == 0); ci.last = (r + TRI_ROWS >= len);
+        chunks[uchunk[u] + r / TRI_ROWS] = ci;
     }
 }
 
@@ -463,8 +486,6 @@ __global__ void k_slots (int nU, int total, int CH, const int32_t *upos, const i
 // Slots 0..nU-1 of the pattern are rows that are already pivotal (in pivot order); slots
 // nU..cnt-1 are the candidate rows.
 // ------------------------------------------------------------------------------------------------
-#define TRI_ROWS 256          // rows per pipeline stage
-#define TRI_MAX_STAGES 8
 
 struct TriArgs
 {
@@ -473,6 +494,7 @@ struct TriArgs
     int stages;              // pipeline depth
     const int32_t *rows;     // [cnt] original row of each slot
     const StepInfo *steps;   // [nU]
+    const ChunkInfo *chunks; // [nchunks]
     const int32_t *slots;    // slot lists
     // source vector to scatter: src_cnt entries, entry e at residue index src_first + e*src_step,
     // going to the slot of row src_rows[e] (or row e when src_rows == nullptr)
@@ -488,6 +510,8 @@ struct TriArgs
 
 struct StageMeta { int32_t j, nrows, first, last; };
 
+#define TRI_BUFS 3            // shared-memory chunk buffers: two chunks in flight while one is consumed
+
 template <int CH>
 struct TriSmem
 {
@@ -496,32 +520,29 @@ struct TriSmem
     {
         return (size_t) TRI_ROWS * CH * 4 + (size_t) TRI_ROWS * 4 + CH * 4 + 32;   // L rows, slots, 1/rho_j, meta
     }
-    static __host__ __device__ size_t header_bytes () { return 2 * TRI_MAX_STAGES * sizeof (uint64_t); }
     static __host__ __device__ size_t total (int cnt, int stages, bool x_in_smem)
     {
-        size_t b = header_bytes ();
+        size_t b = 0;
         if (x_in_smem) b += ((size_t) cnt * CH * 4 + 127) & ~(size_t) 127;     // x
         b += (size_t) stages * ((stage_bytes () + 127) & ~(size_t) 127);
         return b;
     }
 };
 
+__device__ __forceinline__ void cp_async16 (void *dst, const void *src)
+{
+    asm volatile ("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32 (dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit () { asm volatile ("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait () { asm volatile ("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+// w + l*ny  (ny = -yhat): one Montgomery product and a modular add per channel
+__device__ __forceinline__ u32 add_mod (u32 a, u32 b, u32 p) { u32 r = a + b; return r >= p ? r - p : r; }
 __device__ __forceinline__ uint4 mont_mul4 (const uint4 a, const uint4 b, const uint4 p, const uint4 ni)
 {
     return make_uint4 (mont_mul (a.x, b.x, p.x, ni.x), mont_mul (a.y, b.y, p.y, ni.y),
                        mont_mul (a.z, b.z, p.z, ni.z), mont_mul (a.w, b.w, p.w, ni.w));
 }
-// x*f + l*ny reduced, four channels at a time
-__device__ __forceinline__ uint4 ref_update4 (const uint4 x, const uint4 f, const uint4 l, const uint4 ny,
-                                              const uint4 p, const uint4 ni)
-{
-    return make_uint4 (mont_redc ((u64) x.x * f.x + (u64) l.x * ny.x, p.x, ni.x),
-                       mont_redc ((u64) x.y * f.y + (u64) l.y * ny.y, p.y, ni.y),
-                       mont_redc ((u64) x.z * f.z + (u64) l.z * ny.z, p.z, ni.z),
-                       mont_redc ((u64) x.w * f.w + (u64) l.w * ny.w, p.w, ni.w));
-}
-// w + l*ny  (ny = -yhat): one Montgomery product and a modular add per channel
-__device__ __forceinline__ u32 add_mod (u32 a, u32 b, u32 p) { u32 r = a + b; return r >= p ? r - p : r; }
 __device__ __forceinline__ uint4 sub_mul4 (const uint4 w, const uint4 l, const uint4 ny, const uint4 p, const uint4 ni)
 {
     return make_uint4 (add_mod (w.x, mont_mul (l.x, ny.x, p.x, ni.x), p.x), add_mod (w.y, mont_mul (l.y, ny.y, p.y, ni.y), p.y),
@@ -532,130 +553,119 @@ __device__ __forceinline__ uint4 neg4 (const uint4 y, const uint4 p)
     return make_uint4 (y.x ? p.x - y.x : 0u, y.y ? p.y - y.y : 0u, y.z ? p.z - y.z : 0u, y.w ? p.w - y.w : 0u);
 }
 
+// All threads of the CTA are consumers; every thread also copies its share of the chunk that is
+// two positions ahead in the work list with 16-byte cp.async (LDGSTS): TRI_BUFS-1 chunks are in
+// flight per CTA while one is consumed.  (A TMA bulk-copy producer was measured first: with three
+// small bulk copies per elimination step the copy engine, not HBM, set the pace -- about 1.1 us
+// per step regardless of pipeline depth; see profiles/.)  One __syncthreads per chunk both
+// publishes the landed chunk and orders the previous chunk's updates before the next yhat.
 template <int CH, bool XS>
-__global__ void __launch_bounds__ (768) k_trisolve (TriArgs a)
+__global__ void __launch_bounds__ (256, 2) k_trisolve (TriArgs a)
 {
     extern __shared__ __align__ (128) unsigned char smem_raw[];
-    uint64_t *full = (uint64_t *) smem_raw;
-    uint64_t *empty = full + TRI_MAX_STAGES;
-    unsigned char *ptr = smem_raw + TriSmem<CH>::header_bytes ();
+    unsigned char *ptr = smem_raw;
     u32 *xsm = (u32 *) ptr;
     if (XS) ptr += ((size_t) a.cnt * CH * 4 + 127) & ~(size_t) 127;
     unsigned char *stage0 = ptr;
     const size_t stage_stride = (TriSmem<CH>::stage_bytes () + 127) & ~(size_t) 127;
 
-    const int tid = threadIdx.x;
-    const int NC = (blockDim.x >> 5) - a.stages;       // consumer warps (one producer warp per stage)
-    const int cb = blockIdx.x, S = a.S, cnt = a.cnt, nU = a.nU, NS = a.stages;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int cb = blockIdx.x, S = a.S, cnt = a.cnt, nU = a.nU, nchunks = a.nchunks;
     u32 *xg = a.out + (size_t) blockIdx.y * a.out_y_stride + (size_t) cb * cnt * CH;
     u32 *xs = XS ? xsm : xg;
 
-    if (tid == 0)
+    // issue the copies of chunk c into buffer c % TRI_BUFS (this thread's share)
+    auto issue = [&] (int c, const ChunkInfo &ci)
     {
-        for (int s = 0; s < NS; ++s) { mbar_init (&full[s], 1); mbar_init (&empty[s], NC); }
-        asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile ("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    // all threads: clear the vector, then scatter the source
+        unsigned char *sb = stage0 + (size_t) (c % TRI_BUFS) * stage_stride;
+        u32 *Lbuf = (u32 *) sb;
+        int32_t *Sbuf = (int32_t *) (sb + (size_t) TRI_ROWS * CH * 4);
+        u32 *Cbuf = (u32 *) (sb + (size_t) TRI_ROWS * CH * 4 + (size_t) TRI_ROWS * 4);
+        const u32 *lsrc = ci.lsrc + (size_t) cb * ci.cbstride;
+        const int lp = ci.nrows * (CH / 4);                        // 16-byte pieces of L rows
+        for (int i = tid; i < lp; i += nthr) cp_async16 (Lbuf + 4 * i, lsrc + 4 * i);
+        const int sp = (ci.nrows + 3) >> 2;
+        const int32_t *ssrc = a.slots + ci.slot_off;
+        for (int i = tid; i < sp; i += nthr) cp_async16 (Sbuf + 4 * i, ssrc + 4 * i);
+        if (ci.first && tid < CH / 4)
+            cp_async16 (Cbuf + 4 * tid, a.invrho + (size_t) ci.j * S + (size_t) cb * CH + 4 * tid);
+        if (tid == 0)
+        {
+            StageMeta *meta = (StageMeta *) (Cbuf + CH);
+            meta->j = ci.j; meta->nrows = ci.nrows; meta->first = ci.first; meta->last = ci.last;
+        }
+    };
+
+    // prologue: the first chunks are requested while the vector is initialised
+    for (int c = 0; c < TRI_BUFS - 1; ++c) { if (c < nchunks) issue (c, a.chunks[c]); cp_async_commit (); }
+    // descriptor of the next chunk to request, fetched one iteration ahead of its use
+    ChunkInfo pre;
+    pre.lsrc = nullptr; pre.cbstride = 0; pre.slot_off = 0; pre.j = 0; pre.nrows = 0; pre.first = 0; pre.last = 0;
+    if (TRI_BUFS - 1 < nchunks) pre = a.chunks[TRI_BUFS - 1];
     {
-        for (int i = tid; i < cnt * CH; i += blockDim.x) xs[i] = 0;
+        for (int i = tid; i < cnt * CH; i += nthr) xs[i] = 0;
         __syncthreads ();
         const u32 *src = a.src + (size_t) cb * a.src_total * CH;
         const int first = a.src_first + (int) (blockIdx.y * a.src_y_stride);
-        for (int i = tid; i < a.src_cnt * CH; i += blockDim.x)
+        for (int i = tid; i < a.src_cnt * CH; i += nthr)
         {
             const int e = i / CH, ch = i % CH;
             const int row = a.src_rows ? a.src_rows[e] : e;
             xs[a.pos[row] * CH + ch] = src[((size_t) first + (size_t) e * a.src_step) * CH + ch];
         }
-        __syncthreads ();
     }
 
-    if (tid < 32 * NS)
-    {
-        // ---------------- producer warps: warp w feeds stage w ----------------
-        if ((tid & 31) != 0 || a.nchunks == 0) return;
-        const int st = tid >> 5;
-        unsigned char *sb = stage0 + (size_t) st * stage_stride;
-        u32 *Lbuf = (u32 *) sb;
-        int32_t *Sbuf = (int32_t *) (sb + (size_t) TRI_ROWS * CH * 4);
-        u32 *Cbuf = (u32 *) (sb + (size_t) TRI_ROWS * CH * 4 + (size_t) TRI_ROWS * 4);
-        StageMeta *meta = (StageMeta *) (Cbuf + CH);
-        int u = 0;
-        StepInfo si = a.steps[0];
-        StepInfo guess = a.steps[min (st, nU - 1)];       // most steps are a single chunk
-        int ug = min (st, nU - 1);
-        for (int c = st; c < a.nchunks; c += NS)
-        {
-            // the step that owns chunk c (steps are visited in order; chunk0 is increasing)
-            if (guess.chunk0 == c) { u = ug; si = guess; }
-            else while (u + 1 < nU && a.steps[u + 1].chunk0 <= c) { ++u; si = a.steps[u]; }
-            ug = min (u + NS, nU - 1);
-            guess = a.steps[ug];                          // in flight while this lane waits below
-            const int m0 = (c - si.chunk0) * TRI_ROWS;
-            const int nrows = min (TRI_ROWS, si.len - m0);
-            const int npad = (nrows + 3) & ~3;
-            const bool first = (m0 == 0);
-            const u32 round = (u32) (c / NS);
-            mbar_wait (&empty[st], (round & 1) ^ 1);          // stage drained by the consumers
-            meta->j = si.j; meta->nrows = nrows; meta->first = first; meta->last = (m0 + TRI_ROWS >= si.len);
-            u32 bytes = (u32) nrows * CH * 4 + (u32) npad * 4;
-            if (first) bytes += CH * 4;
-            mbar_expect_tx (&full[st], bytes);
-            bulk_g2s (Lbuf, si.lbase + (size_t) cb * si.cbstride + (size_t) m0 * CH, (u32) nrows * CH * 4, &full[st]);
-            bulk_g2s (Sbuf, a.slots + si.slot_off + m0, (u32) npad * 4, &full[st]);
-            if (first)
-                bulk_g2s (Cbuf, a.invrho + (size_t) si.j * S + (size_t) cb * CH, CH * 4, &full[st]);
-        }
-        return;
-    }
-
-    // ---------------- consumer warps: each thread owns 4 channels of a row ----------------
-    constexpr int TPR = CH / 4;                        // threads per row
-    const int ctid = tid - 32 * NS, nthr = NC * 32;
-    const int q4 = (ctid % TPR) * 4, rg = ctid / TPR, RG = nthr / TPR;
+    constexpr int TPR = CH / 4;                        // threads per row, 4 channels each
+    const int q4 = (tid % TPR) * 4, rg = tid / TPR, RG = nthr / TPR;
     const int c0 = cb * CH + q4;
     const uint4 p4 = *reinterpret_cast<const uint4 *> (a.p + c0);
     const uint4 ni4 = *reinterpret_cast<const uint4 *> (a.ninv + c0);
-    int chunk = 0;
-    for (int u = 0; u < nU; ++u)
+    uint4 negy = make_uint4 (0, 0, 0, 0);
+    int u = 0;                                         // elimination step of the current chunk
+    for (int c = 0; c < nchunks; ++c)
     {
-        uint4 negy = make_uint4 (0, 0, 0, 0);
-        for (;; ++chunk)
-        {
-            const int st = chunk % NS;
-            const u32 round = (u32) (chunk / NS);
-            mbar_wait (&full[st], round & 1);
-            const unsigned char *sb = stage0 + (size_t) st * stage_stride;
-            const u32 *Lbuf = (const u32 *) sb;
-            const int32_t *Sbuf = (const int32_t *) (sb + (size_t) TRI_ROWS * CH * 4);
-            const u32 *Cbuf = (const u32 *) (sb + (size_t) TRI_ROWS * CH * 4 + (size_t) TRI_ROWS * 4);
-            const StageMeta meta = *(const StageMeta *) (Cbuf + CH);
-            if (meta.first)
-            {   // yhat_j = w_j / rho_j
-                const uint4 wj = *reinterpret_cast<const uint4 *> (xs + u * CH + q4);
-                negy = neg4 (mont_mul4 (wj, *reinterpret_cast<const uint4 *> (Cbuf + q4), p4, ni4), p4);
-            }
-            const int nrows = meta.nrows;
-            const int iters = (nrows + RG - 1) / RG;
-#pragma unroll 4
-            for (int it = 0; it < iters; ++it)
-            {
-                const int r = it * RG + rg;
-                const int t = (r < nrows) ? Sbuf[r] : -1;
-                if (t >= 0)
-                {
-                    const uint4 l = *reinterpret_cast<const uint4 *> (Lbuf + r * CH + q4);
-                    uint4 *xp = reinterpret_cast<uint4 *> (xs + t * CH + q4);
-                    *xp = sub_mul4 (*xp, l, negy, p4, ni4);
-                }
-            }
-            __syncwarp ();
-            if ((ctid & 31) == 0) mbar_arrive (&empty[st]);
-            if (meta.last) { ++chunk; break; }
+        cp_async_wait<TRI_BUFS - 2> ();                // this thread's copies of chunk c have landed
+        __syncthreads ();                              // ... and everyone's; chunk c-1 is fully applied
+        if (c + TRI_BUFS - 1 < nchunks) issue (c + TRI_BUFS - 1, pre);     // reuses the buffer of chunk c-1
+        cp_async_commit ();
+        if (c + TRI_BUFS < nchunks) pre = a.chunks[c + TRI_BUFS];
+        const unsigned char *sb = stage0 + (size_t) (c % TRI_BUFS) * stage_stride;
+        const u32 *Lbuf = (const u32 *) sb;
+        const int32_t *Sbuf = (const int32_t *) (sb + (size_t) TRI_ROWS * CH * 4);
+        const u32 *Cbuf = (const u32 *) (sb + (size_t) TRI_ROWS * CH * 4 + (size_t) TRI_ROWS * 4);
+        const StageMeta meta = *(const StageMeta *) (Cbuf + CH);
+        if (meta.first)
+        {   // yhat_j = w_j / rho_j
+            const uint4 wj = *reinterpret_cast<const uint4 *> (xs + u * CH + q4);
+            negy = neg4 (mont_mul4 (wj, *reinterpret_cast<const uint4 *> (Cbuf + q4), p4, ni4), p4);
         }
-        consumer_bar (nthr);       // every update of this step is visible before the next w_j is read
+        const int nrows = meta.nrows;
+        // rows of one step hit distinct slots: four rows per thread are loaded, updated and stored
+        // together so that their latencies overlap
+        for (int r0 = rg; r0 < nrows; r0 += 4 * RG)
+        {
+            int t[4]; uint4 l[4], w[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+            {
+                const int r = r0 + k * RG;
+                t[k] = (r < nrows) ? Sbuf[r] : -1;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (t[k] >= 0)
+                {
+                    l[k] = *reinterpret_cast<const uint4 *> (Lbuf + (r0 + k * RG) * CH + q4);
+                    w[k] = *reinterpret_cast<const uint4 *> (xs + t[k] * CH + q4);
+                }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (t[k] >= 0)
+                    *reinterpret_cast<uint4 *> (xs + t[k] * CH + q4) = sub_mul4 (w[k], l[k], negy, p4, ni4);
+        }
+        if (meta.last) ++u;
     }
+    __syncthreads ();
     // publish the column as true REF values: U(j,k) = w_j rho_{j-1}, candidates = w_t rho_{k-1}
     for (int t = rg; t < cnt; t += RG)
     {
@@ -1372,7 +1382,7 @@ extern "C" void slipcu_factor_free (slipcu_factor *F)
     cudaFree (F->desc); cudaFree (F->pos); cudaFree (F->bad);
     cudaFree (F->dig); cudaFree (F->topd); cudaFree (F->d_info);
     cudaFree (F->tmp_limbs); cudaFree (F->tmp_nl);
-    cudaFree (F->slots); cudaFree (F->steps);
+    cudaFree (F->slots); cudaFree (F->steps); cudaFree (F->chunks);
     if (F->h_packet) cudaFreeHost (F->h_packet);
     if (F->h_info) cudaFreeHost (F->h_info);
     if (F->ev) cudaEventDestroy (F->ev);
@@ -1424,9 +1434,11 @@ static int session_common_init (slipcu_factor *F, int n, int channels)
     if (CH != 8 && CH != 16 && CH != 32) CH = 16;
     F->CH = CH;
     F->threads = env_int ("SLIP_B200_THREADS", 256);       // consumer threads (one producer warp per stage is added)
-    if (F->threads % 32 || F->threads < 32 || F->threads > 512) F->threads = 256;
-    F->stages = env_int ("SLIP_B200_STAGES", 4);
-    if (F->stages < 2 || F->stages > TRI_MAX_STAGES) F->stages = 4;
+    if (F->threads % 32 || F->threads < 32 || F->threads > 256) F->threads = 256;
+    F->stages = env_int ("SLIP_B200_STAGES", 0);
+    F->stages_forced = (F->stages >= 2 && F->stages <= TRI_MAX_STAGES);
+    if (!F->stages_forced) F->stages = 4;
+    F->sms = sms;
     F->x_global = env_int ("SLIP_B200_X_GLOBAL", 0);
     F->garner_mode = env_int ("SLIP_B200_GARNER", 2);
     CU (cudaFuncSetAttribute (k_garner_flow<4, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
@@ -1524,8 +1536,16 @@ static cudaError_t launch_tri_any (int CH, const TriArgs &a, dim3 grid, int thre
 // symbolic pre-pass on the device: pos[], the slot lists and the step table of a column whose
 // pattern (rows), step positions (upos) and slot-list offsets (uoff, nU+1 entries) are on the device
 static int prepare_steps (slipcu_factor *F, int cnt, int nU, const int32_t *rows, const int32_t *upos,
-                          const int32_t *uoff, const int32_t *uchunk, int total)
+                          const int32_t *uoff, const int32_t *uchunk, int total, int nchunks)
 {
+    if ((size_t) nchunks > F->chunks_cap)
+    {
+        CU (cudaStreamSynchronize (F->st));
+        cudaFree (F->chunks); F->chunks = nullptr;
+        size_t want = std::max ((size_t) nchunks, std::max<size_t> (F->chunks_cap * 2, 1024));
+        CU (cudaMalloc (&F->chunks, want * sizeof (ChunkInfo)));
+        F->chunks_cap = want;
+    }
     if ((size_t) total > F->slots_cap)
     {
         CU (cudaStreamSynchronize (F->st));
@@ -1548,7 +1568,7 @@ static int prepare_steps (slipcu_factor *F, int cnt, int nU, const int32_t *rows
     if (debug_check ("k_setpos", F->st)) return fail (SLIPCU_CUDA_ERROR, "k_setpos", "debug");
     if (nU > 0 && total > 0)
     {
-        k_slots<<<(total + 255) / 256, 256, 0, F->st>>> (nU, total, F->CH, upos, uoff, uchunk, F->desc, F->pos, F->slots, F->steps);
+        k_slots<<<(total + 255) / 256, 256, 0, F->st>>> (nU, total, F->CH, upos, uoff, uchunk, F->desc, F->pos, F->slots, F->steps, F->chunks);
         g_launches++;
         CU (cudaGetLastError ());
         if (debug_check ("k_slots", F->st)) return fail (SLIPCU_CUDA_ERROR, "k_slots", "debug");
@@ -1559,14 +1579,13 @@ static int prepare_steps (slipcu_factor *F, int cnt, int nU, const int32_t *rows
 // fills the launch geometry of a triangular solve; returns the dynamic shared memory size
 static int tri_geometry (slipcu_factor *F, TriArgs &a, size_t *smem)
 {
-    a.stages = F->stages;
     a.x_in_smem = !F->x_global;
-    size_t need = tri_smem_bytes (F->CH, a.cnt, a.stages, a.x_in_smem);
-    while (need + 1024 > F->smem_limit && a.stages > 2) { a.stages--; need = tri_smem_bytes (F->CH, a.cnt, a.stages, a.x_in_smem); }
+    a.stages = TRI_BUFS;
+    size_t need = tri_smem_bytes (F->CH, a.cnt, TRI_BUFS, a.x_in_smem);
     if (need + 1024 > F->smem_limit && a.x_in_smem)
     {   // pattern too long for shared memory: x stays in the (L2-resident) output region
-        a.x_in_smem = 0; a.stages = F->stages;
-        need = tri_smem_bytes (F->CH, a.cnt, a.stages, false);
+        a.x_in_smem = 0;
+        need = tri_smem_bytes (F->CH, a.cnt, TRI_BUFS, false);
     }
     if (need + 1024 > F->smem_limit) return fail (SLIPCU_BAD_INPUT, "tri_geometry", "pattern too large for shared memory");
     *smem = need;
@@ -1695,12 +1714,12 @@ extern "C" int slipcu_factor_column (slipcu_factor *F, int k, int col, int cnt, 
     if (!hc.rows) return fail (SLIPCU_OUT_OF_MEMORY, "slipcu_factor_column", "device memory exhausted");
     CU (cudaMemcpyAsync (hc.rows, F->h_packet, pk_ints * sizeof (int32_t), cudaMemcpyHostToDevice, F->st));
     g_h2d_bytes += (double) pk_ints * sizeof (int32_t);
-    rc = prepare_steps (F, cnt, nU, hc.rows, hc.rows + cnt, hc.rows + cnt + nU, hc.rows + cnt + 2 * nU + 1, (int) total);
+    rc = prepare_steps (F, cnt, nU, hc.rows, hc.rows + cnt, hc.rows + cnt + nU, hc.rows + cnt + 2 * nU + 1, (int) total, (int) nchunks);
     if (rc) return rc;
 
     TriArgs a;
     a.k = k; a.S = S; a.cnt = cnt; a.nU = nU;
-    a.rows = hc.rows; a.steps = F->steps; a.slots = F->slots;
+    a.rows = hc.rows; a.steps = F->steps; a.chunks = F->chunks; a.slots = F->slots;
     a.src = F->dA; a.src_total = F->nz; a.src_first = F->hAp[col]; a.src_step = 1;
     a.src_cnt = F->hAp[col + 1] - F->hAp[col]; a.src_rows = F->dAi + F->hAp[col];
     a.src_y_stride = 0;
@@ -1713,7 +1732,7 @@ extern "C" int slipcu_factor_column (slipcu_factor *F, int k, int col, int cnt, 
     if (rc) return rc;
     {
         ScopedTimer tm (F, &g_tri_ms);
-        CU (launch_tri_any (CH, a, dim3 (S / CH, 1), F->threads + 32 * a.stages, smem, F->st));
+        CU (launch_tri_any (CH, a, dim3 (S / CH, 1), F->threads, smem, F->st));
         if (debug_check ("k_trisolve(column)", F->st)) return fail (SLIPCU_CUDA_ERROR, "k_trisolve", "debug");
     }
     {   // algorithmic work of this launch
@@ -1985,7 +2004,7 @@ extern "C" int slipcu_solve (slipcu_factor *F, int nrhs, const u32 *blimbs, cons
         CUG (cudaMalloc (&duoff, (2 * (size_t) n + 2) * sizeof (int32_t)));
         CUG (cudaMemcpyAsync (duoff, uoff.data (), (2 * (size_t) n + 2) * sizeof (int32_t), cudaMemcpyHostToDevice, F->st));
         CUG (cudaStreamSynchronize (F->st));
-        rc = prepare_steps (F, n, n, F->rows_are_positions ? dident : drow_at, dident, duoff, duoff + n + 1, (int) tot);
+        rc = prepare_steps (F, n, n, F->rows_are_positions ? dident : drow_at, dident, duoff, duoff + n + 1, (int) tot, (int) nch);
         if (rc) goto done;
     }
     for (int r0 = 0; r0 < nrhs; r0 += batch)
@@ -1996,7 +2015,7 @@ extern "C" int slipcu_solve (slipcu_factor *F, int nrhs, const u32 *blimbs, cons
         // slots are positions.  Resident sessions store original rows (slot of row r = pinv[r]);
         // uploaded sessions store positions (identity map), b rows are then routed through pinv.
         a.rows = F->rows_are_positions ? dident : drow_at;
-        a.steps = F->steps; a.slots = F->slots;
+        a.steps = F->steps; a.chunks = F->chunks; a.slots = F->slots;
         a.src = dB; a.src_total = total; a.src_first = r0; a.src_step = nrhs; a.src_cnt = n;
         a.src_rows = F->rows_are_positions ? dpinv : nullptr;
         a.src_y_stride = 1;
@@ -2007,7 +2026,7 @@ extern "C" int slipcu_solve (slipcu_factor *F, int nrhs, const u32 *blimbs, cons
         size_t smem = 0;
         rc = tri_geometry (F, a, &smem);
         if (rc) goto done;
-        CUG (launch_tri_any (CH, a, dim3 (S / CH, nb), F->threads + 32 * a.stages, smem, F->st));
+        CUG (launch_tri_any (CH, a, dim3 (S / CH, nb), F->threads, smem, F->st));
         if (debug_check ("k_trisolve(forward)", F->st)) { rc = fail (SLIPCU_CUDA_ERROR, "k_trisolve(forward)", "debug"); goto done; }
         BackArgs b;
         b.n = n; b.S = S; b.z = dz; b.z_y_stride = (size_t) n * S;

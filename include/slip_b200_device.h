@@ -135,6 +135,7 @@ typedef struct
     double   h2d_bytes, d2h_bytes;/* bytes this library copied host->device / device->host */
     double   device_ms;           /* CUDA-event time from "A resident in HBM" to "solution numerators
                                      reconstructed in HBM", accumulated over slipcu_solve calls */
+    double   other_ms;            /* symbolic pre-pass + pivot scan kernels (profiling mode) */
 } slipcu_counters;
 void slipcu_get_counters (slipcu_counters *out);
 void slipcu_reset_counters (void);

@@ -60,9 +60,12 @@ static int debug_check (const char *what, cudaStream_t st)
 extern "C" const char *slipcu_last_error (void) { return g_err.c_str (); }
 
 static std::atomic<uint64_t> g_launches{0}, g_tri_launches{0};
-static double g_h2d_bytes = 0, g_d2h_bytes = 0, g_device_ms = 0;
+static double g_h2d_bytes = 0, g_d2h_bytes = 0, g_device_ms = 0, g_other_ms = 0;
 static double g_tri_ms = 0, g_tri_bytes = 0, g_tri_modmul = 0, g_recon_ms = 0, g_recon_mac = 0;
 static int g_profiling = 0;
+static double g_hw[8] = {0,0,0,0,0,0,0,0};     // host wall-clock per section of slipcu_factor_column (debug)
+#include <chrono>
+static inline double wall_s () { return std::chrono::duration<double> (std::chrono::steady_clock::now ().time_since_epoch ()).count (); }
 
 // ------------------------------------------------------------------------------------------------
 // Montgomery arithmetic modulo a prime p < 2^31, R = 2^32
@@ -269,6 +272,60 @@ extern "C" int slipcu_retire_channel (int channel)
 }
 
 // ------------------------------------------------------------------------------------------------
+// process-wide cache of device allocations.  cudaMalloc costs tens of milliseconds per call on a
+// 180 GB part, and a factorization session needs dozens of large blocks; sessions come and go
+// (one per SLIP_solve_* call), so freed blocks are kept and handed to the next session instead of
+// going back to the driver.  Blocks are rounded to power-of-two sizes >= 1 MB.
+// ------------------------------------------------------------------------------------------------
+#include <map>
+static std::mutex g_pool_mutex;
+static std::multimap<size_t, void *> g_pool_free;          // size -> block
+static std::map<void *, size_t> g_pool_size;               // every live or cached block
+static size_t g_pool_cached = 0;
+
+static size_t pool_round (size_t bytes)
+{
+    size_t r = (size_t) 1 << 20;
+    while (r < bytes) r <<= 1;
+    return r;
+}
+static void pool_trim_locked ()
+{
+    for (auto &kv : g_pool_free) { cudaFree (kv.second); g_pool_size.erase (kv.second); }
+    g_pool_free.clear (); g_pool_cached = 0;
+}
+static cudaError_t pool_alloc (void **out, size_t bytes)
+{
+    const size_t want = pool_round (std::max<size_t> (bytes, 1));
+    std::lock_guard<std::mutex> lk (g_pool_mutex);
+    auto it = g_pool_free.find (want);
+    if (it != g_pool_free.end ())
+    {
+        *out = it->second; g_pool_cached -= want; g_pool_free.erase (it);
+        return cudaSuccess;
+    }
+    cudaError_t e = cudaMalloc (out, want);
+    if (e != cudaSuccess)
+    {   // memory pressure: give the cached blocks back and try once more
+        cudaGetLastError ();
+        pool_trim_locked ();
+        e = cudaMalloc (out, want);
+    }
+    if (e == cudaSuccess) g_pool_size[*out] = want;
+    return e;
+}
+static void pool_free (void *ptr)
+{
+    if (!ptr) return;
+    std::lock_guard<std::mutex> lk (g_pool_mutex);
+    auto it = g_pool_size.find (ptr);
+    if (it == g_pool_size.end ()) { cudaFree (ptr); return; }
+    g_pool_free.insert ({it->second, ptr});
+    g_pool_cached += it->second;
+}
+template <typename T> static cudaError_t pool_alloc_t (T **out, size_t bytes) { return pool_alloc ((void **) out, bytes); }
+
+// ------------------------------------------------------------------------------------------------
 // device memory arena (bump allocation in large chunks; columns never straddle a chunk)
 // ------------------------------------------------------------------------------------------------
 struct Arena
@@ -283,13 +340,13 @@ struct Arena
         {
             size_t cb = std::max (chunk_bytes, bytes);
             char *ptr = nullptr;
-            if (cudaMalloc (&ptr, cb) != cudaSuccess) { cudaGetLastError (); return nullptr; }
+            if (pool_alloc ((void **) &ptr, cb) != cudaSuccess) { cudaGetLastError (); return nullptr; }
             chunks.push_back ({ptr, cb}); cur = ptr; left = cb; total += cb;
         }
         void *r = cur; cur += bytes; left -= bytes;
         return r;
     }
-    ~Arena () { for (auto &c : chunks) cudaFree (c.first); }
+    ~Arena () { for (auto &c : chunks) pool_free (c.first); }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -344,6 +401,24 @@ struct slipcu_factor
     int stages = 4, stages_forced = 0, sms = 148;
     int garner_mode = 2;
     slipcu_factor () : resid ((size_t) 512 << 20), ints ((size_t) 16 << 20), limbs ((size_t) 256 << 20) {}
+};
+
+// timing helper for the optional profiling mode
+struct ScopedTimer
+{
+    slipcu_factor *F; double *acc;
+    ScopedTimer (slipcu_factor *F_, double *acc_) : F (F_), acc (acc_)
+    {
+        if (g_profiling) cudaEventRecord (F->ev0, F->st);
+    }
+    ~ScopedTimer ()
+    {
+        if (!g_profiling) return;
+        cudaEventRecord (F->ev1, F->st);
+        cudaEventSynchronize (F->ev1);
+        float ms = 0; cudaEventElapsedTime (&ms, F->ev0, F->ev1);
+        *acc += ms;
+    }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -1375,14 +1450,18 @@ static int env_int (const char *name, int dflt)
 extern "C" void slipcu_factor_free (slipcu_factor *F)
 {
     if (!F) return;
+    if (getenv ("SLIP_B200_TIMING"))
+        fprintf (stderr, "slipcu host wall: alloc %.3f packet+prepass %.3f trisolve-launch %.3f garner-launch %.3f scan-launch %.3f wait %.3f\n",
+                 g_hw[0], g_hw[1], g_hw[2], g_hw[3], g_hw[4], g_hw[5]);
+    for (double &v : g_hw) v = 0;
     cudaSetDevice (F->device);
     if (F->st) cudaStreamSynchronize (F->st);
-    cudaFree (F->dAp); cudaFree (F->dAi); cudaFree (F->dA);
-    cudaFree (F->rho); cudaFree (F->invrho);
-    cudaFree (F->desc); cudaFree (F->pos); cudaFree (F->bad);
-    cudaFree (F->dig); cudaFree (F->topd); cudaFree (F->d_info);
-    cudaFree (F->tmp_limbs); cudaFree (F->tmp_nl);
-    cudaFree (F->slots); cudaFree (F->steps); cudaFree (F->chunks);
+    pool_free (F->dAp); pool_free (F->dAi); pool_free (F->dA);
+    pool_free (F->rho); pool_free (F->invrho);
+    pool_free (F->desc); pool_free (F->pos); pool_free (F->bad);
+    pool_free (F->dig); pool_free (F->topd); pool_free (F->d_info);
+    pool_free (F->tmp_limbs); pool_free (F->tmp_nl);
+    pool_free (F->slots); pool_free (F->steps); pool_free (F->chunks);
     if (F->h_packet) cudaFreeHost (F->h_packet);
     if (F->h_info) cudaFreeHost (F->h_info);
     if (F->ev) cudaEventDestroy (F->ev);
@@ -1402,9 +1481,9 @@ static int ensure_digits (slipcu_factor *F, size_t rows)
     size_t want = std::max (rows, F->dig_rows * 2);
     want = std::min<size_t> (std::max<size_t> (want, 64), std::max<size_t> (rows, (size_t) F->n));
     CU (cudaStreamSynchronize (F->st));
-    cudaFree (F->dig); cudaFree (F->topd); F->dig = nullptr; F->topd = nullptr; F->dig_rows = 0;
-    CU (cudaMalloc (&F->dig, want * (size_t) (F->S + 4) * sizeof (u32)));
-    CU (cudaMalloc (&F->topd, want * sizeof (int32_t)));
+    pool_free (F->dig); pool_free (F->topd); F->dig = nullptr; F->topd = nullptr; F->dig_rows = 0;
+    CU (pool_alloc_t (&F->dig, want * (size_t) (F->S + 4) * sizeof (u32)));
+    CU (pool_alloc_t (&F->topd, want * sizeof (int32_t)));
     F->dig_rows = want;
     return SLIPCU_OK;
 }
@@ -1456,12 +1535,12 @@ static int session_common_init (slipcu_factor *F, int n, int channels)
     CU (cudaEventCreateWithFlags (&F->ev, cudaEventDisableTiming));
     CU (cudaEventCreate (&F->ev0)); CU (cudaEventCreate (&F->ev1));
     CU (cudaEventCreate (&F->ev_start)); CU (cudaEventCreate (&F->ev_end));
-    CU (cudaMalloc (&F->rho, (size_t) n * S * sizeof (u32)));
-    CU (cudaMalloc (&F->invrho, (size_t) n * S * sizeof (u32)));
-    CU (cudaMalloc (&F->desc, (size_t) n * sizeof (ColDesc)));
-    CU (cudaMalloc (&F->pos, (size_t) n * sizeof (int32_t)));
-    CU (cudaMalloc (&F->bad, sizeof (int32_t)));
-    CU (cudaMalloc (&F->d_info, sizeof (slipcu_pivot_info)));
+    CU (pool_alloc_t (&F->rho, (size_t) n * S * sizeof (u32)));
+    CU (pool_alloc_t (&F->invrho, (size_t) n * S * sizeof (u32)));
+    CU (pool_alloc_t (&F->desc, (size_t) n * sizeof (ColDesc)));
+    CU (pool_alloc_t (&F->pos, (size_t) n * sizeof (int32_t)));
+    CU (pool_alloc_t (&F->bad, sizeof (int32_t)));
+    CU (pool_alloc_t (&F->d_info, sizeof (slipcu_pivot_info)));
     CU (cudaMemset (F->bad, 0, sizeof (int32_t)));
     CU (cudaMemset (F->pos, 0, (size_t) n * sizeof (int32_t)));
     CU (cudaHostAlloc (&F->h_packet, ((size_t) 4 * n + 8) * sizeof (int32_t), cudaHostAllocDefault));
@@ -1483,9 +1562,9 @@ extern "C" int slipcu_factor_begin (slipcu_factor **out, int n, int nz, const in
     F->nz = nz;
     F->keep_positional = keep_positional ? 1 : 0;
     const int S = F->S, CH = F->CH;
-    CU (cudaMalloc (&F->dAp, (size_t) (n + 1) * sizeof (int32_t)));
-    CU (cudaMalloc (&F->dAi, (size_t) nz * sizeof (int32_t)));
-    CU (cudaMalloc (&F->dA, (size_t) nz * S * sizeof (u32)));
+    CU (pool_alloc_t (&F->dAp, (size_t) (n + 1) * sizeof (int32_t)));
+    CU (pool_alloc_t (&F->dAi, (size_t) nz * sizeof (int32_t)));
+    CU (pool_alloc_t (&F->dA, (size_t) nz * S * sizeof (u32)));
     F->hAp.assign (Ap, Ap + n + 1);
     CU (cudaMemcpy (F->dAp, Ap, (size_t) (n + 1) * sizeof (int32_t), cudaMemcpyHostToDevice));
     CU (cudaMemcpy (F->dAi, Ai, (size_t) nz * sizeof (int32_t), cudaMemcpyHostToDevice));
@@ -1493,9 +1572,9 @@ extern "C" int slipcu_factor_begin (slipcu_factor **out, int n, int nz, const in
     {
         u32 *dl = nullptr; int64_t *doff = nullptr; int8_t *dsg = nullptr;
         const size_t nl = (size_t) Aoff[nz];
-        CU (cudaMalloc (&dl, std::max<size_t> (nl, 1) * sizeof (u32)));
-        CU (cudaMalloc (&doff, (size_t) (nz + 1) * sizeof (int64_t)));
-        CU (cudaMalloc (&dsg, (size_t) nz));
+        CU (pool_alloc_t (&dl, std::max<size_t> (nl, 1) * sizeof (u32)));
+        CU (pool_alloc_t (&doff, (size_t) (nz + 1) * sizeof (int64_t)));
+        CU (pool_alloc_t (&dsg, (size_t) nz));
         CU (cudaMemcpy (dl, Alimbs, nl * sizeof (u32), cudaMemcpyHostToDevice));
         CU (cudaMemcpy (doff, Aoff, (size_t) (nz + 1) * sizeof (int64_t), cudaMemcpyHostToDevice));
         CU (cudaMemcpy (dsg, Asign, (size_t) nz, cudaMemcpyHostToDevice));
@@ -1505,7 +1584,7 @@ extern "C" int slipcu_factor_begin (slipcu_factor **out, int n, int nz, const in
         g_launches++;
         CU (cudaGetLastError ());
         CU (cudaStreamSynchronize (F->st));
-        cudaFree (dl); cudaFree (doff); cudaFree (dsg);
+        pool_free (dl); pool_free (doff); pool_free (dsg);
         g_h2d_bytes += (double) nl * 4 + (double) (nz + 1) * 8 + (double) nz * 5 + (double) (n + 1) * 4;
     }
     CU (cudaEventRecord (F->ev_start, F->st));
@@ -1541,27 +1620,28 @@ static int prepare_steps (slipcu_factor *F, int cnt, int nU, const int32_t *rows
     if ((size_t) nchunks > F->chunks_cap)
     {
         CU (cudaStreamSynchronize (F->st));
-        cudaFree (F->chunks); F->chunks = nullptr;
+        pool_free (F->chunks); F->chunks = nullptr;
         size_t want = std::max ((size_t) nchunks, std::max<size_t> (F->chunks_cap * 2, 1024));
-        CU (cudaMalloc (&F->chunks, want * sizeof (ChunkInfo)));
+        CU (pool_alloc_t (&F->chunks, want * sizeof (ChunkInfo)));
         F->chunks_cap = want;
     }
     if ((size_t) total > F->slots_cap)
     {
         CU (cudaStreamSynchronize (F->st));
-        cudaFree (F->slots); F->slots = nullptr;
+        pool_free (F->slots); F->slots = nullptr;
         size_t want = std::max ((size_t) total, F->slots_cap * 2);
-        CU (cudaMalloc (&F->slots, want * sizeof (int32_t)));
+        CU (pool_alloc_t (&F->slots, want * sizeof (int32_t)));
         F->slots_cap = want;
     }
     if ((size_t) nU > F->steps_cap)
     {
         CU (cudaStreamSynchronize (F->st));
-        cudaFree (F->steps); F->steps = nullptr;
+        pool_free (F->steps); F->steps = nullptr;
         size_t want = std::max ((size_t) nU, std::max<size_t> (F->steps_cap * 2, 256));
-        CU (cudaMalloc (&F->steps, want * sizeof (StepInfo)));
+        CU (pool_alloc_t (&F->steps, want * sizeof (StepInfo)));
         F->steps_cap = want;
     }
+    ScopedTimer tm_other (F, &g_other_ms);
     k_setpos<<<(cnt + 255) / 256, 256, 0, F->st>>> (cnt, rows, F->pos);
     g_launches++;
     CU (cudaGetLastError ());
@@ -1594,23 +1674,6 @@ static int tri_geometry (slipcu_factor *F, TriArgs &a, size_t *smem)
 
 static int check_channels (slipcu_factor *F);
 
-// timing helper for the optional profiling mode
-struct ScopedTimer
-{
-    slipcu_factor *F; double *acc;
-    ScopedTimer (slipcu_factor *F_, double *acc_) : F (F_), acc (acc_)
-    {
-        if (g_profiling) cudaEventRecord (F->ev0, F->st);
-    }
-    ~ScopedTimer ()
-    {
-        if (!g_profiling) return;
-        cudaEventRecord (F->ev1, F->st);
-        cudaEventSynchronize (F->ev1);
-        float ms = 0; cudaEventElapsedTime (&ms, F->ev0, F->ev1);
-        *acc += ms;
-    }
-};
 
 // mixed-radix digits + sign of entries e0..e0+ne-1 of a residue region (digit row = entry index)
 static int run_garner (slipcu_factor *F, const u32 *base, int region_cnt, int e0, int ne, int s, int8_t *sign)
@@ -1686,6 +1749,7 @@ extern "C" int slipcu_factor_column (slipcu_factor *F, int k, int col, int cnt, 
         return fail (SLIPCU_BAD_INPUT, "slipcu_factor_column", "bad argument");
     const Tables &T = *F->tab;
     const int S = F->S, CH = F->CH;
+    double tw = wall_s ();
     int s = std::min (std::max (recon_channels, 1), S);
     HostCol &hc = F->cols[k];
     hc.nU = nU;
@@ -1693,6 +1757,7 @@ extern "C" int slipcu_factor_column (slipcu_factor *F, int k, int col, int cnt, 
     if (rc) return rc;
     rc = ensure_digits (F, (size_t) cnt);
     if (rc) return rc;
+    g_hw[0] += wall_s () - tw; tw = wall_s ();
     // packet: pattern rows, pivot positions of the U part, slot-list offsets (padded to 4)
     memcpy (F->h_packet, rows, (size_t) cnt * sizeof (int32_t));
     if (nU) memcpy (F->h_packet + cnt, upos, (size_t) nU * sizeof (int32_t));
@@ -1717,6 +1782,7 @@ extern "C" int slipcu_factor_column (slipcu_factor *F, int k, int col, int cnt, 
     rc = prepare_steps (F, cnt, nU, hc.rows, hc.rows + cnt, hc.rows + cnt + nU, hc.rows + cnt + 2 * nU + 1, (int) total, (int) nchunks);
     if (rc) return rc;
 
+    g_hw[1] += wall_s () - tw; tw = wall_s ();
     TriArgs a;
     a.k = k; a.S = S; a.cnt = cnt; a.nU = nU;
     a.rows = hc.rows; a.steps = F->steps; a.chunks = F->chunks; a.slots = F->slots;
@@ -1735,6 +1801,7 @@ extern "C" int slipcu_factor_column (slipcu_factor *F, int k, int col, int cnt, 
         CU (launch_tri_any (CH, a, dim3 (S / CH, 1), F->threads, smem, F->st));
         if (debug_check ("k_trisolve(column)", F->st)) return fail (SLIPCU_CUDA_ERROR, "k_trisolve", "debug");
     }
+    g_hw[2] += wall_s () - tw; tw = wall_s ();
     {   // algorithmic work of this launch
         double upd = 0;
         for (int u = 0; u < nU; ++u) { const HostCol &lj = F->cols[upos[u]]; upd += (double) (lj.cnt - lj.nU - 1); }
@@ -1745,11 +1812,13 @@ extern "C" int slipcu_factor_column (slipcu_factor *F, int k, int col, int cnt, 
     const int e0 = F->keep_positional ? 0 : nU;
     rc = run_garner (F, hc.base, cnt, e0, cnt - e0, s, hc.sign);
     if (rc) return rc;
+    g_hw[3] += wall_s () - tw; tw = wall_s ();
     const int mode = (scheme == 2) ? 2 : ((scheme == 4 || scheme == 5) ? 1 : 0);
+    { ScopedTimer tm_scan (F, &g_other_ms);
     k_pivot_scan<<<1, 256, 0, F->st>>> (cnt, nU, mode, diag_slot, F->dig, (size_t) F->S + 4, F->topd,
                                         hc.sign, F->bad, F->d_info);
     g_launches++;
-    CU (cudaGetLastError ());
+    CU (cudaGetLastError ()); }
     if (debug_check ("k_pivot_scan", F->st)) return fail (SLIPCU_CUDA_ERROR, "k_pivot_scan", "debug");
     CU (cudaMemcpyAsync (F->h_info, F->d_info, sizeof (slipcu_pivot_info), cudaMemcpyDeviceToHost, F->st));
     CU (cudaEventRecord (F->ev, F->st));
@@ -1758,7 +1827,9 @@ extern "C" int slipcu_factor_column (slipcu_factor *F, int k, int col, int cnt, 
         rc = run_limbs (F, 0, cnt, 0, hc.stride, s, hc.limbs, hc.nl);
         if (rc) return rc;
     }
+    g_hw[4] += wall_s () - tw; tw = wall_s ();
     CU (cudaEventSynchronize (F->ev));
+    g_hw[5] += wall_s () - tw;
     g_d2h_bytes += sizeof (slipcu_pivot_info);
     *info = *F->h_info;
     F->cur = k;
@@ -1789,10 +1860,10 @@ extern "C" int slipcu_factor_fetch_entry (slipcu_factor *F, int k, int slot, u32
             return fail (SLIPCU_BAD_INPUT, "slipcu_factor_fetch_entry", "entry no longer reconstructible");
         if (!F->tmp_limbs || F->tmp_stride < hc.stride)
         {
-            cudaFree (F->tmp_limbs); cudaFree (F->tmp_nl);
+            pool_free (F->tmp_limbs); pool_free (F->tmp_nl);
             F->tmp_limbs = nullptr; F->tmp_nl = nullptr;
-            CU (cudaMalloc (&F->tmp_limbs, (size_t) (F->S + 2) * sizeof (u32)));
-            CU (cudaMalloc (&F->tmp_nl, sizeof (int32_t)));
+            CU (pool_alloc_t (&F->tmp_limbs, (size_t) (F->S + 2) * sizeof (u32)));
+            CU (pool_alloc_t (&F->tmp_nl, sizeof (int32_t)));
             F->tmp_stride = F->S + 2;
         }
         int rc = run_limbs (F, slot, 1, 0, hc.stride, hc.s, F->tmp_limbs, F->tmp_nl);
@@ -1846,9 +1917,9 @@ extern "C" int slipcu_factor_upload (slipcu_factor **out, int n, int channels, c
     for (int k = 0; k < n; ++k) total += (size_t) colcnt[k];
     u32 *dl = nullptr; int64_t *doff = nullptr; int8_t *dsg = nullptr; int32_t *drows = nullptr;
     const size_t nl = (size_t) off[total];
-    CU (cudaMalloc (&dl, std::max<size_t> (nl, 1) * sizeof (u32)));
-    CU (cudaMalloc (&doff, (total + 1) * sizeof (int64_t)));
-    CU (cudaMalloc (&dsg, total));
+    CU (pool_alloc_t (&dl, std::max<size_t> (nl, 1) * sizeof (u32)));
+    CU (pool_alloc_t (&doff, (total + 1) * sizeof (int64_t)));
+    CU (pool_alloc_t (&dsg, total));
     drows = (int32_t *) F->ints.alloc (total * sizeof (int32_t));
     if (!drows) return fail (SLIPCU_OUT_OF_MEMORY, "slipcu_factor_upload", "device memory exhausted");
     CU (cudaMemcpyAsync (dl, limbs, nl * sizeof (u32), cudaMemcpyHostToDevice, F->st));
@@ -1874,7 +1945,7 @@ extern "C" int slipcu_factor_upload (slipcu_factor **out, int n, int channels, c
         e += (size_t) cnt;
     }
     CU (cudaStreamSynchronize (F->st));
-    cudaFree (dl); cudaFree (doff); cudaFree (dsg);
+    pool_free (dl); pool_free (doff); pool_free (dsg);
     return check_channels (F);
 }
 
@@ -1959,17 +2030,17 @@ extern "C" int slipcu_solve (slipcu_factor *F, int nrhs, const u32 *blimbs, cons
     int32_t *dpinv = nullptr, *duoff = nullptr; int fwd_chunks = 0;
     const size_t nl = (size_t) boff[total];
 #define CUG(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail (e_ == cudaErrorMemoryAllocation ? SLIPCU_OUT_OF_MEMORY : SLIPCU_CUDA_ERROR, #call, cudaGetErrorString (e_)); goto done; } } while (0)
-    CUG (cudaMalloc (&dl, std::max<size_t> (nl, 1) * sizeof (u32)));
-    CUG (cudaMalloc (&doff, (size_t) (total + 1) * sizeof (int64_t)));
-    CUG (cudaMalloc (&dsg, (size_t) total));
-    CUG (cudaMalloc (&dB, (size_t) total * S * sizeof (u32)));
-    CUG (cudaMalloc (&dz, (size_t) batch * n * S * sizeof (u32)));
-    CUG (cudaMalloc (&dlimbs, (size_t) n * stride * sizeof (u32)));
-    CUG (cudaMalloc (&drow_at, (size_t) n * sizeof (int32_t)));
-    CUG (cudaMalloc (&dident, (size_t) n * sizeof (int32_t)));
-    CUG (cudaMalloc (&dpinv, (size_t) n * sizeof (int32_t)));
-    CUG (cudaMalloc (&dnl, (size_t) n * sizeof (int32_t)));
-    CUG (cudaMalloc (&dsign, (size_t) n));
+    CUG (pool_alloc_t (&dl, std::max<size_t> (nl, 1) * sizeof (u32)));
+    CUG (pool_alloc_t (&doff, (size_t) (total + 1) * sizeof (int64_t)));
+    CUG (pool_alloc_t (&dsg, (size_t) total));
+    CUG (pool_alloc_t (&dB, (size_t) total * S * sizeof (u32)));
+    CUG (pool_alloc_t (&dz, (size_t) batch * n * S * sizeof (u32)));
+    CUG (pool_alloc_t (&dlimbs, (size_t) n * stride * sizeof (u32)));
+    CUG (pool_alloc_t (&drow_at, (size_t) n * sizeof (int32_t)));
+    CUG (pool_alloc_t (&dident, (size_t) n * sizeof (int32_t)));
+    CUG (pool_alloc_t (&dpinv, (size_t) n * sizeof (int32_t)));
+    CUG (pool_alloc_t (&dnl, (size_t) n * sizeof (int32_t)));
+    CUG (pool_alloc_t (&dsign, (size_t) n));
     CUG (cudaHostAlloc (&h_limbs, (size_t) n * stride * sizeof (u32), cudaHostAllocDefault));
     CUG (cudaHostAlloc (&h_nl, (size_t) n * sizeof (int32_t), cudaHostAllocDefault));
     CUG (cudaHostAlloc (&h_sign, (size_t) n, cudaHostAllocDefault));
@@ -2001,7 +2072,7 @@ extern "C" int slipcu_solve (slipcu_factor *F, int nrhs, const u32 *blimbs, cons
         uoff[n] = (int32_t) tot; uoff[2 * n + 1] = (int32_t) nch;
         fwd_chunks = (int) nch;
         if (tot > INT32_MAX) { rc = fail (SLIPCU_BAD_INPUT, "slipcu_solve", "L has too many entries"); goto done; }
-        CUG (cudaMalloc (&duoff, (2 * (size_t) n + 2) * sizeof (int32_t)));
+        CUG (pool_alloc_t (&duoff, (2 * (size_t) n + 2) * sizeof (int32_t)));
         CUG (cudaMemcpyAsync (duoff, uoff.data (), (2 * (size_t) n + 2) * sizeof (int32_t), cudaMemcpyHostToDevice, F->st));
         CUG (cudaStreamSynchronize (F->st));
         rc = prepare_steps (F, n, n, F->rows_are_positions ? dident : drow_at, dident, duoff, duoff + n + 1, (int) tot, (int) nch);
@@ -2063,8 +2134,8 @@ done:
         float ms = 0;
         if (cudaEventElapsedTime (&ms, F->ev_start, F->ev_end) == cudaSuccess) g_device_ms += ms; else cudaGetLastError ();
     }
-    cudaFree (dl); cudaFree (doff); cudaFree (dsg); cudaFree (dB); cudaFree (dz); cudaFree (dlimbs);
-    cudaFree (drow_at); cudaFree (dident); cudaFree (dpinv); cudaFree (duoff); cudaFree (dnl); cudaFree (dsign);
+    pool_free (dl); pool_free (doff); pool_free (dsg); pool_free (dB); pool_free (dz); pool_free (dlimbs);
+    pool_free (drow_at); pool_free (dident); pool_free (dpinv); pool_free (duoff); pool_free (dnl); pool_free (dsign);
     if (h_limbs) cudaFreeHost (h_limbs);
     if (h_nl) cudaFreeHost (h_nl);
     if (h_sign) cudaFreeHost (h_sign);
@@ -2081,12 +2152,12 @@ extern "C" void slipcu_get_counters (slipcu_counters *o)
     o->launches = g_launches.load (); o->trisolve_launches = g_tri_launches.load ();
     o->trisolve_ms = g_tri_ms; o->trisolve_bytes = g_tri_bytes; o->trisolve_modmul = g_tri_modmul;
     o->recon_ms = g_recon_ms; o->recon_mac = g_recon_mac;
-    o->h2d_bytes = g_h2d_bytes; o->d2h_bytes = g_d2h_bytes; o->device_ms = g_device_ms;
+    o->h2d_bytes = g_h2d_bytes; o->d2h_bytes = g_d2h_bytes; o->device_ms = g_device_ms; o->other_ms = g_other_ms;
 }
 extern "C" void slipcu_reset_counters (void)
 {
     g_launches = 0; g_tri_launches = 0;
     g_tri_ms = g_tri_bytes = g_tri_modmul = g_recon_ms = g_recon_mac = 0;
-    g_h2d_bytes = g_d2h_bytes = g_device_ms = 0;
+    g_h2d_bytes = g_d2h_bytes = g_device_ms = g_other_ms = 0;
 }
 extern "C" void slipcu_set_profiling (int enabled) { g_profiling = enabled; }

@@ -16,7 +16,8 @@ from slip_lu_b200 import capi, synth  # noqa: E402
 class Counters(C.Structure):
     _fields_ = [("launches", C.c_uint64), ("trisolve_launches", C.c_uint64), ("trisolve_ms", C.c_double),
                 ("trisolve_bytes", C.c_double), ("trisolve_modmul", C.c_double), ("recon_ms", C.c_double),
-                ("recon_mac", C.c_double)]
+                ("recon_mac", C.c_double), ("h2d_bytes", C.c_double), ("d2h_bytes", C.c_double),
+                ("device_ms", C.c_double), ("other_ms", C.c_double)]
 
 
 def main():
@@ -46,7 +47,7 @@ def main():
         print(f"n={n} analyze {ta:.3f}s factor+solve {dt:.3f}s check={ok} nnz={nnz} launches={c.launches} "
               f"tri_ms={c.trisolve_ms:.1f} tri_GB={c.trisolve_bytes/1e9:.2f} "
               f"tri_GBps={(c.trisolve_bytes/1e9)/(c.trisolve_ms/1e3) if c.trisolve_ms else 0:.0f} "
-              f"recon_ms={c.recon_ms:.1f} recon_Gmac={c.recon_mac/1e9:.1f}", flush=True)
+              f"recon_ms={c.recon_ms:.1f} recon_Gmac={c.recon_mac/1e9:.1f} other_ms={c.other_ms:.1f}", flush=True)
         if host_factors:
             lib.free_sparse(L); lib.free_sparse(U)
 

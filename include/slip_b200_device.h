@@ -73,6 +73,13 @@ int slipcu_factor_column (slipcu_factor *F, int k, int col, int cnt, int nU,
                           const int32_t *rows, const int32_t *upos, int recon_channels,
                           int scheme, int diag_slot, slipcu_pivot_info *info);
 
+/* the same in two halves, so that the host can prepare the next column's symbolic pattern while
+ * the GPU works: _launch enqueues everything and returns, _wait blocks for the scan result. */
+int slipcu_factor_column_launch (slipcu_factor *F, int k, int col, int cnt, int nU,
+                                 const int32_t *rows, const int32_t *upos, int recon_channels,
+                                 int scheme, int diag_slot);
+int slipcu_factor_column_wait (slipcu_factor *F, slipcu_pivot_info *info);
+
 /* one reconstructed entry of the current column (used only for the rational tolerance test of
  * SLIP_TOL_SMALLEST / SLIP_TOL_LARGEST, slip_get_pivot.c:94-143).  limbs must hold stride words. */
 int slipcu_factor_fetch_entry (slipcu_factor *F, int k, int slot, uint32_t *limbs,

@@ -87,6 +87,7 @@ __host__ __device__ __forceinline__ u32 mont_pow (u32 a_m, u32 e, u32 one_m, u32
     while (e) { if (e & 1) r = mont_mul (r, a_m, p, ninv); a_m = mont_mul (a_m, a_m, p, ninv); e >>= 1; }
     return r;
 }
+__host__ __device__ __forceinline__ u32 add_mod (u32 a, u32 b, u32 p) { u32 r = a + b; return r >= p ? r - p : r; }
 __host__ __device__ __forceinline__ u32 reduce_word (u32 w, u32 p)
 {   // w < 2^32 < 4p  (p > 2^30)
     if (w >= p) w -= p;
@@ -612,7 +613,6 @@ __device__ __forceinline__ void cp_async_commit () { asm volatile ("cp.async.com
 template <int N> __device__ __forceinline__ void cp_async_wait () { asm volatile ("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
 // w + l*ny  (ny = -yhat): one Montgomery product and a modular add per channel
-__device__ __forceinline__ u32 add_mod (u32 a, u32 b, u32 p) { u32 r = a + b; return r >= p ? r - p : r; }
 __device__ __forceinline__ uint4 mont_mul4 (const uint4 a, const uint4 b, const uint4 p, const uint4 ni)
 {
     return make_uint4 (mont_mul (a.x, b.x, p.x, ni.x), mont_mul (a.y, b.y, p.y, ni.y),
@@ -1126,17 +1126,22 @@ __global__ void __launch_bounds__ (384) k_garner_flow (GarnerArgs a)
     {
         const u32 *Cc = a.C + (size_t) (32 * b) * S + tt;
         const u32 *db = digs + (size_t) b * E * 32;
-#pragma unroll 2
-        for (int q = 0; q < 32; q += 4)
-        {
-            const u32 c0 = Cc[(size_t) q * S], c1 = Cc[(size_t) (q + 1) * S];
-            const u32 c2 = Cc[(size_t) (q + 2) * S], c3 = Cc[(size_t) (q + 3) * S];
 #pragma unroll
-            for (int e = 0; e < E; ++e)
+        for (int q = 0; q < 32; q += 16)
+        {
+            u32 c[16];
+#pragma unroll
+            for (int r = 0; r < 16; ++r) c[r] = Cc[(size_t) (q + r) * S];      // 16 loads in flight
+#pragma unroll
+            for (int r = 0; r < 16; r += 4)
             {
-                const uint4 d4 = *reinterpret_cast<const uint4 *> (db + e * 32 + q);
-                lazy_mac (T[e], d4.x, c0, p); lazy_mac (T[e], d4.y, c1, p);
-                lazy_mac (T[e], d4.z, c2, p); lazy_mac (T[e], d4.w, c3, p);
+#pragma unroll
+                for (int e = 0; e < E; ++e)
+                {
+                    const uint4 d4 = *reinterpret_cast<const uint4 *> (db + e * 32 + q + r);
+                    lazy_mac (T[e], d4.x, c[r], p); lazy_mac (T[e], d4.y, c[r + 1], p);
+                    lazy_mac (T[e], d4.z, c[r + 2], p); lazy_mac (T[e], d4.w, c[r + 3], p);
+                }
             }
         }
     };
@@ -1695,7 +1700,8 @@ static int run_garner (slipcu_factor *F, const u32 *base, int region_cnt, int e0
         W = std::max (4, std::min (16, W));      // >= E warps: the epilogue uses one warp per entry
         const int Wf = std::max (4, (blocks + 5) / 6);          // dataflow variant: 6 blocks per warp
         const size_t fsm = (size_t) blocks * 4 * 32 * sizeof (u32) + (size_t) blocks * sizeof (int) + (size_t) Wf * 4096 + 16;
-        if (F->garner_mode == 2 && Wf <= 12 && fsm <= 160 * 1024)
+        if (false) { }
+        else if (F->garner_mode >= 2 && Wf <= 12 && fsm <= 160 * 1024)
             k_garner_flow<4, 6><<<(ne + 3) / 4, Wf * 32, fsm, F->st>>> (g);
         else
             k_garner_tiled<4, 5><<<(ne + 3) / 4, W * 32, 0, F->st>>> (g);
@@ -1741,11 +1747,11 @@ static int alloc_column (slipcu_factor *F, HostCol &hc, int cnt, int s)
     return SLIPCU_OK;
 }
 
-extern "C" int slipcu_factor_column (slipcu_factor *F, int k, int col, int cnt, int nU,
-                                     const int32_t *rows, const int32_t *upos, int recon_channels,
-                                     int scheme, int diag_slot, slipcu_pivot_info *info)
+extern "C" int slipcu_factor_column_launch (slipcu_factor *F, int k, int col, int cnt, int nU,
+                                            const int32_t *rows, const int32_t *upos, int recon_channels,
+                                            int scheme, int diag_slot)
 {
-    if (!F || k < 0 || k >= F->n || cnt <= 0 || cnt > F->n || nU < 0 || nU >= cnt || !rows || !info)
+    if (!F || k < 0 || k >= F->n || cnt <= 0 || cnt > F->n || nU < 0 || nU >= cnt || !rows)
         return fail (SLIPCU_BAD_INPUT, "slipcu_factor_column", "bad argument");
     const Tables &T = *F->tab;
     const int S = F->S, CH = F->CH;
@@ -1827,14 +1833,30 @@ extern "C" int slipcu_factor_column (slipcu_factor *F, int k, int col, int cnt, 
         rc = run_limbs (F, 0, cnt, 0, hc.stride, s, hc.limbs, hc.nl);
         if (rc) return rc;
     }
-    g_hw[4] += wall_s () - tw; tw = wall_s ();
+    g_hw[4] += wall_s () - tw;
+    F->cur = k;
+    return SLIPCU_OK;
+}
+
+extern "C" int slipcu_factor_column_wait (slipcu_factor *F, slipcu_pivot_info *info)
+{
+    if (!F || !info || F->cur < 0) return fail (SLIPCU_BAD_INPUT, "slipcu_factor_column_wait", "bad argument");
+    double tw = wall_s ();
     CU (cudaEventSynchronize (F->ev));
     g_hw[5] += wall_s () - tw;
     g_d2h_bytes += sizeof (slipcu_pivot_info);
     *info = *F->h_info;
-    F->cur = k;
     if (info->bad_channel) return fail (SLIPCU_BAD_PRIME, "slipcu_factor_column", "channel prime divides a pivot");
     return SLIPCU_OK;
+}
+
+extern "C" int slipcu_factor_column (slipcu_factor *F, int k, int col, int cnt, int nU,
+                                     const int32_t *rows, const int32_t *upos, int recon_channels,
+                                     int scheme, int diag_slot, slipcu_pivot_info *info)
+{
+    int rc = slipcu_factor_column_launch (F, k, col, cnt, nU, rows, upos, recon_channels, scheme, diag_slot);
+    if (rc) return rc;
+    return slipcu_factor_column_wait (F, info);
 }
 
 extern "C" int slipcu_factor_column_stride (slipcu_factor *F, int k)

@@ -59,19 +59,14 @@ static SLIP_info patterns_reserve (pattern_store *P, int64_t extra)
     return SLIP_OK ;
 }
 
-static int cmp_i32 (const void *a, const void *b)
-{
-    int32_t x = *(const int32_t *) a, y = *(const int32_t *) b ;
-    return (x > y) - (x < y) ;
-}
-
-/* pattern of column k: rows reachable from the rows of A(:,col) through the finished columns of
- * L, written to out[] sorted by current position.  Returns the count. */
-static int32_t column_pattern (const SLIP_sparse *A, int32_t col, int32_t k, const pattern_store *P,
-    const int32_t *pinv, const int32_t *row_at, int32_t *mark, int32_t *stack, int32_t *out)
+/* Rows reachable from the rows of A(:,col) through the finished columns 0..klim-1 of L, unordered.
+ * With klim = k this is the pattern of column k (slip_reach.c / slip_dfs.c).  With klim = k-1 it is
+ * the part of that pattern that does not depend on the pivot of column k-1, which is what the host
+ * computes while the GPU is still working on column k-1.  mark[r] == stamp flags membership. */
+static int32_t reach_unordered (const SLIP_sparse *A, int32_t col, int32_t klim, const pattern_store *P,
+    const int32_t *pinv, int32_t *mark, int32_t stamp, int32_t *stack, int32_t *out)
 {
     int32_t cnt = 0 ;
-    const int32_t stamp = k + 1 ;
     for (int32_t a = A->p [col] ; a < A->p [col + 1] ; a++)
     {
         int32_t r0 = A->i [a] ;
@@ -82,8 +77,8 @@ static int32_t column_pattern (const SLIP_sparse *A, int32_t col, int32_t k, con
         {
             const int32_t r = stack [--sp] ;
             const int32_t pos = pinv [r] ;
-            out [cnt++] = pos ;
-            if (pos < k)
+            out [cnt++] = r ;
+            if (pos < klim)
             {   /* row r is the pivot of column pos: follow the L part of that column */
                 const int32_t *rows = P->rows + P->ptr [pos] ;
                 const int32_t len = (int32_t) (P->ptr [pos + 1] - P->ptr [pos]) ;
@@ -95,9 +90,24 @@ static int32_t column_pattern (const SLIP_sparse *A, int32_t col, int32_t k, con
             }
         }
     }
-    qsort (out, (size_t) cnt, sizeof (int32_t), cmp_i32) ;
-    for (int32_t t = 0 ; t < cnt ; t++) out [t] = row_at [out [t]] ;
     return cnt ;
+}
+
+/* order a pattern by current row position (slip_sort_xi.c): positions are a permutation, so a
+ * flag per position and one sweep replace the sort */
+static void order_by_position (int32_t n, int32_t cnt, int32_t *pat, const int32_t *pinv,
+    const int32_t *row_at, int32_t *posflag, int32_t stamp)
+{
+    int32_t lo = n, hi = -1 ;
+    for (int32_t t = 0 ; t < cnt ; t++)
+    {
+        const int32_t pos = pinv [pat [t]] ;
+        posflag [pos] = stamp ;
+        if (pos < lo) lo = pos ;
+        if (pos > hi) hi = pos ;
+    }
+    int32_t w = 0 ;
+    for (int32_t pos = lo ; pos <= hi ; pos++) if (posflag [pos] == stamp) pat [w++] = row_at [pos] ;
 }
 
 /* ---- the rational tolerance test on two reconstructed entries ---- */
@@ -221,7 +231,9 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
     int32_t *stack = (int32_t *) SLIP_malloc ((size_t) n * sizeof (int32_t)) ;
     int32_t *pat = (int32_t *) SLIP_malloc ((size_t) n * sizeof (int32_t)) ;
     int32_t *upos = (int32_t *) SLIP_malloc ((size_t) n * sizeof (int32_t)) ;
-    if (!colbits || !row_at || !mark || !stack || !pat || !upos || !cumbits_at) { status = SLIP_OUT_OF_MEMORY ; goto cleanup ; }
+    int32_t *npat = (int32_t *) SLIP_malloc ((size_t) n * sizeof (int32_t)) ;
+    int32_t *posflag = (int32_t *) SLIP_calloc ((size_t) n, sizeof (int32_t)) ;
+    if (!colbits || !row_at || !mark || !stack || !pat || !upos || !cumbits_at || !npat || !posflag) { status = SLIP_OUT_OF_MEMORY ; goto cleanup ; }
 
     for (int32_t a = 0 ; a < nz ; a++)
         if (A->i [a] < 0 || A->i [a] >= n) { status = SLIP_INCORRECT_INPUT ; goto cleanup ; }
@@ -252,17 +264,20 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
             Al.sign, channels, want_host_factors))) ;
         t_begin += now_s () - tt ;
         const int S_dev = slipcu_factor_channels (dev) ;
-        for (int32_t r = 0 ; r < n ; r++) { pinv [r] = r ; row_at [r] = r ; mark [r] = 0 ; }
+        for (int32_t r = 0 ; r < n ; r++) { pinv [r] = r ; row_at [r] = r ; mark [r] = 0 ; posflag [r] = 0 ; }
         double cum_bits = 0 ;
         work_updates = 0 ; work_limbmul = 0 ;
+        /* pattern of column 0; afterwards the pattern of column k+1 is prepared (up to the effect
+           of pivot k) while the GPU works on column k */
+        int32_t cnt = reach_unordered (A, S->q [0], 0, &P, pinv, mark, 1, stack, pat) ;
         for (int32_t k = 0 ; k < n ; k++)
         {
             const int32_t col = S->q [k] ;
+            tt = now_s () ;
             cum_bits += colbits [col] ;
             int s_k = slip_channels_for_bits (cum_bits) ;
             if (s_k > S_dev) s_k = S_dev ;
-            tt = now_s () ;
-            const int32_t cnt = column_pattern (A, col, k, &P, pinv, row_at, mark, stack, pat) ;
+            order_by_position (n, cnt, pat, pinv, row_at, posflag, k + 1) ;
             int32_t nU = 0, diag_slot = -1 ;
             for (int32_t t = 0 ; t < cnt ; t++)
             {
@@ -271,16 +286,25 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
                 else if (pat [t] == col) diag_slot = t ;
             }
             if (cnt == nU) { status = SLIP_SINGULAR ; goto cleanup ; }    /* no candidate row at all */
-            slipcu_pivot_info info ;
             t_sym += now_s () - tt ; tt = now_s () ;
-            int rc = slipcu_factor_column (dev, k, col, cnt, nU, pat, upos, s_k, scheme, diag_slot, &info) ;
-            t_dev += now_s () - tt ; tt = now_s () ;
+            int rc = slipcu_factor_column_launch (dev, k, col, cnt, nU, pat, upos, s_k, scheme, diag_slot) ;
             if (rc == SLIPCU_BAD_PRIME) { retry = 1 ; break ; }
             SLIP_TRY (slip_from_device_status (rc)) ;
+            t_dev += now_s () - tt ; tt = now_s () ;
+            /* while the GPU works: the part of the next pattern that does not depend on pivot k */
+            int32_t ncnt = 0 ;
+            if (k + 1 < n) ncnt = reach_unordered (A, S->q [k + 1], k, &P, pinv, mark, k + 2, stack, npat) ;
+            t_sym += now_s () - tt ; tt = now_s () ;
+            slipcu_pivot_info info ;
+            rc = slipcu_factor_column_wait (dev, &info) ;
+            if (rc == SLIPCU_BAD_PRIME) { retry = 1 ; break ; }
+            SLIP_TRY (slip_from_device_status (rc)) ;
+            t_dev += now_s () - tt ; tt = now_s () ;
             int32_t slot = -1 ;
             SLIP_TRY (decide_pivot (dev, k, scheme, option->tol, diag_slot, &info, &slot)) ;
+            const int32_t prow = pat [slot] ;
             {   /* move the pivot row to position k (slip_get_pivot.c:152-172) */
-                const int32_t prow = pat [slot], oldpos = pinv [prow], displaced = row_at [k] ;
+                const int32_t oldpos = pinv [prow], displaced = row_at [k] ;
                 row_at [k] = prow ; row_at [oldpos] = displaced ;
                 pinv [prow] = k ; pinv [displaced] = oldpos ;
             }
@@ -297,7 +321,6 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
             memcpy (P.rows + P.used, pat, (size_t) cnt * sizeof (int32_t)) ;
             P.used += cnt ;
             P.ptr [k + 1] = P.used ; P.nU [k] = nU ; P.piv [k] = slot ;
-            t_piv += now_s () - tt ;
             if (k == n - 1)
             {   /* det = rho[n-1], kept with the resident factors for the rational solve */
                 res = (slip_resident *) SLIP_calloc (1, sizeof (slip_resident)) ;
@@ -312,6 +335,18 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
                 SLIP_free (w) ;
                 SLIP_TRY (slip_from_device_status (rc)) ;
             }
+            else if (mark [prow] == k + 2)
+            {   /* the new pivot row is in the next pattern: its column of L (the candidate rows of
+                   column k, none of them pivotal yet) joins it */
+                for (int32_t t = nU ; t < cnt ; t++)
+                {
+                    const int32_t rr = pat [t] ;
+                    if (mark [rr] != k + 2) { mark [rr] = k + 2 ; npat [ncnt++] = rr ; }
+                }
+            }
+            { int32_t *sw = pat ; pat = npat ; npat = sw ; }
+            cnt = ncnt ;
+            t_piv += now_s () - tt ;
         }
         if (!retry)
         {   /* the last pivot is only checked against the channel primes here */
@@ -392,7 +427,7 @@ cleanup:
     slip_limbs_free (&Al) ;
     patterns_free (&P) ;
     SLIP_free (colbits) ; SLIP_free (row_at) ; SLIP_free (mark) ; SLIP_free (stack) ;
-    SLIP_free (pat) ; SLIP_free (upos) ; SLIP_free (cumbits_at) ;
+    SLIP_free (pat) ; SLIP_free (upos) ; SLIP_free (cumbits_at) ; SLIP_free (npat) ; SLIP_free (posflag) ;
     return status ;
 }
 

@@ -138,3 +138,75 @@ def test_bench_scale_properties(gpu):
     assert gpu.mpq_mat_to_py(x1, n, 2) == gpu.mpq_mat_to_py(x2, n, 2)
     assert gpu.dll.SLIP_check_solution(A, x2, B) == 0
     print(f"n=400 factor+solve (with host factors) {t1 - t0:.2f}s, nnz(L)={Lp[-1]}, det bits={abs(rh[-1]).bit_length()}")
+
+
+def test_many_right_hand_sides(gpu, oracle):
+    """configs[3] family: one factorization, many right-hand sides (batched by the solve kernels)."""
+    n, cp, ri, vals, b = synth.random_sparse(48, 5, 24, seed=41, nrhs=37, rhs_bits=40)
+    q = cases.colamd_like_order(n, cp, ri)
+    want = cases.run_oracle(oracle, n, cp, ri, vals, b, q)
+    got = cases.run_library(gpu, n, cp, ri, vals, b, q)
+    cases.assert_same_factorization(got, want, "37 rhs")
+    # the same through SLIP_solve_mpq with a tiny batch budget (forces several batches)
+    os.environ["SLIP_B200_SOLVE_BATCH_MB"] = "1"
+    try:
+        o = gpu.default_options(order=capi.SLIP_NO_ORDERING)
+        A = gpu.sparse_from_csc(n, cp, ri, vals); B = gpu.dense_from_rows(b)
+        S = gpu.analyze(A, o, q=q)
+        x = gpu.solve_mpq(A, S, B, o)
+        got2 = gpu.mpq_mat_to_py(x, n, 37)
+    finally:
+        del os.environ["SLIP_B200_SOLVE_BATCH_MB"]
+    want2 = [None] * n
+    for i in range(n):
+        want2[q[i]] = want["x"][i]
+    assert got2 == want2
+
+
+def test_batch_of_independent_systems(gpu, oracle):
+    """configs[4] family: a batch of LP-basis style systems, solved through the sharding helper
+    (world size 1 here; the partitioning itself is covered on CPU with gloo)."""
+    from slip_lu_b200.sharding import solve_batch_sharded
+    systems = [synth.lp_basis(120, seed=s, nrhs=1) for s in range(12)]
+    got = solve_batch_sharded(gpu, systems, 1, 0,
+                              options=lambda: gpu.default_options(order=capi.SLIP_NO_ORDERING))
+    for g, x in got:
+        n, cp, ri, vals, b = systems[g]
+        f = oracle.factorize(n, cp, ri, vals, list(range(n)))
+        assert x == oracle.solve(f, b), f"system {g}"
+
+
+def test_laplacian_pattern_64bit(gpu, oracle):
+    """configs[2] family at a size the oracle still reaches: 16x16 grid, 64-bit entries."""
+    n, cp, ri, vals, b = synth.laplacian_2d(16, 64, seed=6, nrhs=1)
+    q = cases.colamd_like_order(n, cp, ri)
+    want = cases.run_oracle(oracle, n, cp, ri, vals, b, q)
+    got = cases.run_library(gpu, n, cp, ri, vals, b, q)
+    cases.assert_same_factorization(got, want, "lap256")
+    assert abs(got["rhos"][-1]).bit_length() > 15000
+
+
+def test_double_input_end_to_end(gpu, oracle):
+    """double input -> integer system (SLIP_build_*_double) -> SLIP_solve_double, against the
+    oracle run on the same integer system and scaled back."""
+    from fractions import Fraction
+    (sysd, dvals) = synth.decimal_scaled(40, 4, 5, seed=13, nrhs=2)
+    n, cp, ri, _, b = sysd
+    o = gpu.default_options(order=capi.SLIP_NO_ORDERING)
+    A = gpu.dll.SLIP_create_sparse()
+    nz = len(dvals)
+    assert gpu.dll.SLIP_build_sparse_ccf_double(A, (C.c_int32 * (n + 1))(*cp), (C.c_int32 * nz)(*ri),
+                                                (C.c_double * nz)(*dvals), n, nz, o) == 0
+    _, _, ivals = gpu.sparse_to_py(A)
+    sa = Fraction(*capi.mpq_to_pair(A.contents.scale))
+    B = gpu.dense_from_rows(b)
+    S = gpu.analyze(A, o)
+    xd = gpu.dll.SLIP_create_double_mat(n, 2)
+    assert gpu.dll.SLIP_solve_double(xd, A, S, B, o) == 0
+    f = oracle.factorize(n, cp, ri, ivals, list(range(n)))
+    want = oracle.solve(f, b)
+    for i in range(n):
+        for c in range(2):
+            exact = Fraction(*want[i][c]) * sa           # x of the original (double) system
+            # mpq_get_d truncates where float() rounds: allow one unit in the last place
+            assert abs(xd[i][c] - float(exact)) <= abs(float(exact)) * 2.0 ** -51, (i, c)

@@ -210,3 +210,21 @@ def test_double_input_end_to_end(gpu, oracle):
             exact = Fraction(*want[i][c]) * sa           # x of the original (double) system
             # mpq_get_d truncates where float() rounds: allow one unit in the last place
             assert abs(xd[i][c] - float(exact)) <= abs(float(exact)) * 2.0 ** -51, (i, c)
+
+
+def test_channel_prime_dividing_a_pivot_is_retired(gpu, oracle):
+    """The first channel prime is 2^31-1.  A matrix whose first pivot IS that prime makes the pivot
+    vanish in channel 0; the factorization must notice, retire the prime and still be exact."""
+    p0 = 2 ** 31 - 1
+    n, cp, ri, vals = 3, [0, 2, 4, 6], [0, 1, 1, 2, 0, 2], [p0, 3, 5, 7, 11, 13]
+    b = [[1], [2], [3]]
+    q = [0, 1, 2]
+    want = cases.run_oracle(oracle, n, cp, ri, vals, b, q, capi.SLIP_LARGEST, 1.0)
+    assert want["rhos"][0] == p0
+    got = cases.run_library(gpu, n, cp, ri, vals, b, q, capi.SLIP_LARGEST)
+    cases.assert_same_factorization(got, want, "pivot equal to a channel prime")
+    # and the library keeps working afterwards (tables rebuilt without the retired prime)
+    n, cp, ri, vals, b = synth.random_sparse(30, 4, 20, seed=77, nrhs=1)
+    q = cases.colamd_like_order(n, cp, ri)
+    cases.assert_same_factorization(cases.run_library(gpu, n, cp, ri, vals, b, q),
+                                    cases.run_oracle(oracle, n, cp, ri, vals, b, q), "after retirement")

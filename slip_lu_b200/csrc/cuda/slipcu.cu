@@ -1813,6 +1813,14 @@ extern "C" int slipcu_factor_column_launch (slipcu_factor *F, int k, int col, in
         for (int u = 0; u < nU; ++u) { const HostCol &lj = F->cols[upos[u]]; upd += (double) (lj.cnt - lj.nU - 1); }
         g_tri_bytes += (upd + (double) cnt) * (double) S * 4.0;
         g_tri_modmul += upd * (double) S * 4.0;
+        if (const char *tf = getenv ("SLIP_B200_TRACE_FILE"))
+        {   // per-launch algorithmic bytes, to set beside an ncu capture of the same launch
+            if (FILE *fp = fopen (tf, "a"))
+            {
+                fprintf (fp, "%d %d %d %.0f %.0f\n", k, cnt, nU, upd, (upd + (double) cnt) * (double) S * 4.0);
+                fclose (fp);
+            }
+        }
     }
     // exact values: candidates always (pivot scan); the U part only if the factors go to the host
     const int e0 = F->keep_positional ? 0 : nU;

@@ -70,12 +70,16 @@ static inline double wall_s () { return std::chrono::duration<double> (std::chro
 // ------------------------------------------------------------------------------------------------
 // Montgomery arithmetic modulo a prime p < 2^31, R = 2^32
 // ------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ u32 csub (u32 r, u32 p)
+{   // r in [0, 2p) -> [0, p): r - p wraps above r exactly when r < p
+    const u32 d = r - p;
+    return d < r ? d : r;
+}
 __host__ __device__ __forceinline__ u32 mont_redc (u64 T, u32 p, u32 ninv)
 {   // requires T < p * 2^32; returns T / R mod p in [0, p)
     u32 m = (u32) T * ninv;
     u64 t = T + (u64) m * p;
-    u32 r = (u32) (t >> 32);
-    return r >= p ? r - p : r;
+    return csub ((u32) (t >> 32), p);
 }
 __host__ __device__ __forceinline__ u32 mont_mul (u32 a, u32 b, u32 p, u32 ninv)
 {
@@ -87,7 +91,7 @@ __host__ __device__ __forceinline__ u32 mont_pow (u32 a_m, u32 e, u32 one_m, u32
     while (e) { if (e & 1) r = mont_mul (r, a_m, p, ninv); a_m = mont_mul (a_m, a_m, p, ninv); e >>= 1; }
     return r;
 }
-__host__ __device__ __forceinline__ u32 add_mod (u32 a, u32 b, u32 p) { u32 r = a + b; return r >= p ? r - p : r; }
+__host__ __device__ __forceinline__ u32 add_mod (u32 a, u32 b, u32 p) { return csub (a + b, p); }
 __host__ __device__ __forceinline__ u32 reduce_word (u32 w, u32 p)
 {   // w < 2^32 < 4p  (p > 2^30)
     if (w >= p) w -= p;

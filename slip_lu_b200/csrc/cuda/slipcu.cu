@@ -1187,25 +1187,33 @@ __global__ void __launch_bounds__ (384) k_garner_flow (GarnerArgs a)
                 mine[e] = 0;
             }
             const u32 *Ccol = a.C + ftt + (size_t) (32 * bo) * S;
+            // diagonal block of C, pre-multiplied by 1/B_t:  d_t = (v_t - sum)/B_t  then becomes a
+            // running value q_t that loses d_i * (C[i][t]/B_t) per finished digit -- one Montgomery
+            // product per step on the serial chain instead of two
 #pragma unroll 8
-            for (int i = 0; i < 32; ++i) ccs[i * 32 + lane] = Ccol[(size_t) i * S];
+            for (int i = 0; i < 32; ++i) ccs[i * 32 + lane] = mont_mul (Ccol[(size_t) i * S], ib, fp, fni);
             __syncwarp ();
+            u32 qv[E];
+#pragma unroll
+            for (int e = 0; e < E; ++e)
+            {
+                const u32 r = lazy_redc (T[e], fp, fni);
+                const u32 diff = v[e] >= r ? v[e] - r : v[e] + fp - r;
+                qv[e] = mont_mul (diff, ib, fp, fni);
+            }
             for (int i = 0; i < 32; ++i)
             {
                 const u32 cci = ccs[i * 32 + lane];
 #pragma unroll
                 for (int e = 0; e < E; ++e)
                 {
-                    u32 di = 0;
-                    if (lane == i)
+                    const u32 di = __shfl_sync (full, qv[e], i);
+                    if (lane == i) mine[e] = di;
+                    if (lane > i)
                     {
-                        const u32 r = lazy_redc (T[e], fp, fni);
-                        const u32 diff = v[e] >= r ? v[e] - r : v[e] + fp - r;
-                        di = mont_mul (diff, ib, fp, fni);
-                        mine[e] = di;
+                        const u32 sub = mont_mul (di, cci, fp, fni);
+                        qv[e] = qv[e] >= sub ? qv[e] - sub : qv[e] + fp - sub;
                     }
-                    di = __shfl_sync (full, di, i);
-                    if (lane > i) lazy_mac (T[e], di, cci, fp);
                 }
             }
 #pragma unroll

@@ -289,6 +289,14 @@ def main():
     except Exception:
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
     achieved = (c.trisolve_bytes / 1e9) / (c.trisolve_ms / 1e3) if c.trisolve_ms > 0 else 0.0
+    # DRAM traffic per launch: the ratio measured by one `ncu --set full` capture of this kernel
+    # (profiles/r01_trisolve_ncu_full.json) applied to the live average algorithmic bytes per launch
+    traffic = None
+    try:
+        cap = json.load(open(os.path.join(ROOT, "profiles", "r01_trisolve_ncu_full.json")))
+        traffic = cap["traffic_over_algorithmic"] * c.trisolve_bytes / max(1, c.trisolve_launches)
+    except Exception:
+        pass
     out = {
         "metric": "limb_mul_ops_per_s", "value": W_total / t_dev, "unit": "limb-mul/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -305,7 +313,8 @@ def main():
                     "limb_mul_equiv": limbmul, "exact_check": "A x = b verified in rational arithmetic"},
         "roofline": {"bound": "hbm", "kernel": "k_trisolve", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak if peak else None, "peak_source": peak_src,
-                     "launches": int(c.trisolve_launches), "traffic": None,
+                     "launches": int(c.trisolve_launches), "traffic": traffic,
+                     "algorithmic_bytes_per_launch": c.trisolve_bytes / max(1, c.trisolve_launches),
                      "modmul_per_s": c.trisolve_modmul / (c.trisolve_ms / 1e3) if c.trisolve_ms > 0 else None,
                      "kernel_share_of_step": (c.trisolve_ms / 1e3) / (t_dev) if t_dev > 0 else None},
         "reconstruction": {"kernel": "k_garner_flow", "ms": c.recon_ms / args.steps,

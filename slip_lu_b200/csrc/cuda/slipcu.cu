@@ -403,7 +403,7 @@ struct slipcu_factor
     int32_t *slots = nullptr; size_t slots_cap = 0;      // slot lists of the current column
     StepInfo *steps = nullptr; size_t steps_cap = 0;
     ChunkInfo *chunks = nullptr; size_t chunks_cap = 0;
-    int stages = 4, stages_forced = 0, sms = 148;
+    int sms = 148;
     int garner_mode = 2;
     slipcu_factor () : resid ((size_t) 512 << 20), ints ((size_t) 16 << 20), limbs ((size_t) 256 << 20) {}
 };
@@ -453,44 +453,15 @@ __global__ void k_residues (int count, int CH, const u32 *limbs, const int64_t *
 }
 
 // ------------------------------------------------------------------------------------------------
-// TMA bulk copy + mbarrier primitives (sm_90+; SASS: UBLKCP / SYNCS)
+// shared-memory address helper for the cp.async (LDGSTS) copies
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ u32 smem_u32 (const void *p) { return (u32) __cvta_generic_to_shared (p); }
-__device__ __forceinline__ void mbar_init (uint64_t *b, u32 cnt)
-{
-    asm volatile ("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32 (b)), "r"(cnt));
-}
-__device__ __forceinline__ void mbar_expect_tx (uint64_t *b, u32 bytes)
-{
-    asm volatile ("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32 (b)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive (uint64_t *b)
-{
-    asm volatile ("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32 (b)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait (uint64_t *b, u32 parity)
-{
-    asm volatile ("{\n .reg .pred p;\n WAIT_%=:\n"
-                  " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-                  " @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}"
-                  :: "r"(smem_u32 (b)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s (void *dst, const void *src, u32 bytes, uint64_t *b)
-{
-    asm volatile ("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                  :: "r"(smem_u32 (dst)), "l"(src), "r"(bytes), "r"(smem_u32 (b)) : "memory");
-}
-__device__ __forceinline__ void consumer_bar (int nthreads)
-{
-    asm volatile ("bar.sync 1, %0;" :: "r"(nthreads) : "memory");
-}
 
 // ------------------------------------------------------------------------------------------------
 // symbolic pre-pass of a column: row -> slot map, then for every elimination step the list of
 // target slots (one per entry of the L column used), shared by all channel blocks.
 // ------------------------------------------------------------------------------------------------
 #define TRI_ROWS 512          // rows per pipeline chunk
-#define TRI_MAX_STAGES 8
 
 struct StepInfo           // one elimination step of a column: eliminate with column j of L
 {
@@ -571,7 +542,7 @@ struct TriArgs
 {
     int k;                   // level the L part is brought to (column index; n for a rhs)
     int S, cnt, nU;
-    int stages;              // pipeline depth
+    int stages;              // chunk buffers (TRI_BUFS)
     const int32_t *rows;     // [cnt] original row of each slot
     const StepInfo *steps;   // [nU]
     const ChunkInfo *chunks; // [nchunks]
@@ -1531,9 +1502,6 @@ static int session_common_init (slipcu_factor *F, int n, int channels)
     F->CH = CH;
     F->threads = env_int ("SLIP_B200_THREADS", 256);       // consumer threads (one producer warp per stage is added)
     if (F->threads % 32 || F->threads < 32 || F->threads > 256) F->threads = 256;
-    F->stages = env_int ("SLIP_B200_STAGES", 0);
-    F->stages_forced = (F->stages >= 2 && F->stages <= TRI_MAX_STAGES);
-    if (!F->stages_forced) F->stages = 4;
     F->sms = sms;
     F->x_global = env_int ("SLIP_B200_X_GLOBAL", 0);
     F->garner_mode = env_int ("SLIP_B200_GARNER", 2);

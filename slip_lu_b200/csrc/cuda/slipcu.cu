@@ -207,7 +207,7 @@ static int build_tables (int S, std::shared_ptr<Tables> &out)
     }
     // prefix products as limb strings: row t = p_0 .. p_{t-1}  (t limbs at most)
     T->LB = S + 1;
-    std::vector<u32> B ((size_t) S * T->LB, 0u);
+    std::vector<u32> B ((size_t) (S + 4) * T->LB, 0u);      // 4 spare zero rows: k_limbs reads rows in fours
     {
         std::vector<u32> cur (T->LB, 0u);
         cur[0] = 1; int len = 1;
@@ -229,7 +229,7 @@ static int build_tables (int S, std::shared_ptr<Tables> &out)
     CU (cudaMalloc (&T->one, S * sizeof (u32)));
     CU (cudaMalloc (&T->invB, S * sizeof (u32)));
     CU (cudaMalloc (&T->C, (size_t) S * S * sizeof (u32)));
-    CU (cudaMalloc (&T->Bpos, (size_t) S * T->LB * sizeof (u32)));
+    CU (cudaMalloc (&T->Bpos, (size_t) (S + 4) * T->LB * sizeof (u32)));
     CU (cudaMemcpy (T->p, T->hp.data (), S * sizeof (u32), cudaMemcpyHostToDevice));
     CU (cudaMemcpy (T->ninv, ninv.data (), S * sizeof (u32), cudaMemcpyHostToDevice));
     CU (cudaMemcpy (T->r2, r2.data (), S * sizeof (u32), cudaMemcpyHostToDevice));
@@ -1275,70 +1275,86 @@ struct LimbArgs
     u32 *limbs; int32_t *nl;
 };
 
+// E entries per warp share every load of the table Bpos (the same idea as in the Garner kernels)
+template <int E>
 __global__ void __launch_bounds__ (128) k_limbs (LimbArgs a)
 {
     const int lane = threadIdx.x & 31;
     const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (w >= a.ne) return;
-    const int e = a.e0 + w;
-    const int eo = a.out0 + w;
+    if (w * E >= a.ne) return;
     const unsigned full = 0xffffffffu;
-    const int top = a.topd[e];
-    u32 *out = a.limbs + (size_t) eo * a.stride;
-    const u32 *dg = a.dig + (size_t) e * a.dstride;
-    if (top < 0)
+    int ent[E], eo[E], top[E];
+    const u32 *dg[E];
+    int maxtop = -1;
+#pragma unroll
+    for (int i = 0; i < E; ++i)
     {
-        for (int l = lane; l < a.stride; l += 32) out[l] = 0;
-        if (lane == 0) a.nl[eo] = 0;
-        return;
+        const int k = min (w * E + i, a.ne - 1);          // surplus lanes of the last group redo the last entry
+        ent[i] = a.e0 + k; eo[i] = a.out0 + k;
+        top[i] = a.topd[ent[i]];
+        dg[i] = a.dig + (size_t) ent[i] * a.dstride;
+        maxtop = max (maxtop, top[i]);
     }
-    u32 in_a1 = 0, in_a2 = 0, in_b2 = 0;   // spill of the previous chunk: a1[31], a2[31], a2[30]
-    u32 carry_in = 0;
-    int nl = 0;
+    u32 in_a1[E], in_a2[E], in_b2[E], carry_in[E];
+    int nl[E];
+#pragma unroll
+    for (int i = 0; i < E; ++i) { in_a1[i] = in_a2[i] = in_b2[i] = carry_in[i] = 0; nl[i] = 0; }
     for (int l0 = 0; l0 < a.stride; l0 += 32)
     {
         const int l = l0 + lane;
         const int lr = l < a.LB ? l : a.LB - 1;      // lanes past the row read a zero column
-        u32 a0 = 0, a1 = 0, a2 = 0;
-        // B_t has no limb l for t < l (p_i < 2^32); digits above `top` are zero
-        int t = l0 & ~3;
-        for (; t + 3 <= top; t += 4)
+        u32 a0[E], a1[E], a2[E];
+#pragma unroll
+        for (int i = 0; i < E; ++i) a0[i] = a1[i] = a2[i] = 0;
+        // B_t has no limb l for t < l (p_i < 2^32); digits above an entry's top digit are zero and
+        // the digit rows are zero-padded to a multiple of four
+        for (int t = l0 & ~3; t <= maxtop; t += 4)
         {
-            const uint4 d4 = *reinterpret_cast<const uint4 *> (dg + t);
             const u32 *Bp = a.Bpos + (size_t) t * a.LB + lr;
-            mac96 (a0, a1, a2, d4.x, Bp[0]);
-            mac96 (a0, a1, a2, d4.y, Bp[a.LB]);
-            mac96 (a0, a1, a2, d4.z, Bp[2 * (size_t) a.LB]);
-            mac96 (a0, a1, a2, d4.w, Bp[3 * (size_t) a.LB]);
+            const u32 b0 = Bp[0], b1 = Bp[a.LB], b2 = Bp[2 * (size_t) a.LB], b3 = Bp[3 * (size_t) a.LB];
+#pragma unroll
+            for (int i = 0; i < E; ++i)
+            {
+                const uint4 d4 = *reinterpret_cast<const uint4 *> (dg[i] + t);
+                mac96 (a0[i], a1[i], a2[i], d4.x, b0);
+                mac96 (a0[i], a1[i], a2[i], d4.y, b1);
+                mac96 (a0[i], a1[i], a2[i], d4.z, b2);
+                mac96 (a0[i], a1[i], a2[i], d4.w, b3);
+            }
         }
-        for (; t <= top; ++t) mac96 (a0, a1, a2, dg[t], a.Bpos[(size_t) t * a.LB + lr]);
-        // column sum for limb l: a0[l] + a1[l-1] + a2[l-2]
-        u32 p1 = __shfl_up_sync (full, a1, 1), p2 = __shfl_up_sync (full, a2, 2);
-        if (lane == 0) { p1 = in_a1; p2 = in_b2; }
-        if (lane == 1) { p2 = in_a2; }
-        const u64 sum = (u64) a0 + p1 + p2;
-        // carries are < 4: iterate the ripple until it settles
-        u32 cin = (lane == 0) ? carry_in : 0u, cout;
-        for (;;)
+#pragma unroll
+        for (int i = 0; i < E; ++i)
         {
+            // column sum for limb l: a0[l] + a1[l-1] + a2[l-2]
+            u32 p1 = __shfl_up_sync (full, a1[i], 1), p2 = __shfl_up_sync (full, a2[i], 2);
+            if (lane == 0) { p1 = in_a1[i]; p2 = in_b2[i]; }
+            if (lane == 1) { p2 = in_a2[i]; }
+            const u64 sum = (u64) a0[i] + p1 + p2;
+            // carries are < 4: iterate the ripple until it settles
+            u32 cin = (lane == 0) ? carry_in[i] : 0u, cout;
+            for (;;)
+            {
+                cout = (u32) ((sum + cin) >> 32);
+                u32 nin = __shfl_up_sync (full, cout, 1);
+                if (lane == 0) nin = carry_in[i];
+                const bool changed = nin != cin;
+                cin = nin;
+                if (!__any_sync (full, changed)) break;
+            }
+            const u32 limb = (u32) (sum + cin);
             cout = (u32) ((sum + cin) >> 32);
-            u32 nin = __shfl_up_sync (full, cout, 1);
-            if (lane == 0) nin = carry_in;
-            const bool changed = nin != cin;
-            cin = nin;
-            if (!__any_sync (full, changed)) break;
+            if (l < a.stride && w * E + i < a.ne) a.limbs[(size_t) eo[i] * a.stride + l] = limb;
+            const unsigned nzm = __ballot_sync (full, limb != 0 && l < a.stride);
+            if (nzm) nl[i] = l0 + 32 - __clz (nzm);
+            carry_in[i] = __shfl_sync (full, cout, 31);
+            in_a1[i] = __shfl_sync (full, a1[i], 31);
+            in_a2[i] = __shfl_sync (full, a2[i], 31);
+            in_b2[i] = __shfl_sync (full, a2[i], 30);
         }
-        const u32 limb = (u32) (sum + cin);
-        cout = (u32) ((sum + cin) >> 32);
-        if (l < a.stride) out[l] = limb;
-        const unsigned nzm = __ballot_sync (full, limb != 0 && l < a.stride);
-        if (nzm) nl = l0 + 32 - __clz (nzm);
-        carry_in = __shfl_sync (full, cout, 31);
-        in_a1 = __shfl_sync (full, a1, 31);
-        in_a2 = __shfl_sync (full, a2, 31);
-        in_b2 = __shfl_sync (full, a2, 30);
     }
-    if (lane == 0) a.nl[eo] = nl;
+#pragma unroll
+    for (int i = 0; i < E; ++i)
+        if (lane == 0 && w * E + i < a.ne) a.nl[eo[i]] = top[i] < 0 ? 0 : nl[i];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1703,7 +1719,8 @@ static int run_limbs (slipcu_factor *F, int e0, int ne, int out0, int stride, in
     l.dig = F->dig; l.dstride = (size_t) F->S + 4; l.topd = F->topd; l.Bpos = T.Bpos;
     l.limbs = limbs; l.nl = nl;
     ScopedTimer tm (F, &g_recon_ms);
-    k_limbs<<<(ne + 3) / 4, 128, 0, F->st>>> (l);
+    if (ne >= 64) k_limbs<4><<<((ne + 3) / 4 + 3) / 4, 128, 0, F->st>>> (l);
+    else k_limbs<1><<<(ne + 3) / 4, 128, 0, F->st>>> (l);
     g_launches++;
     CU (cudaGetLastError ());
     if (debug_check ("k_limbs", F->st)) return fail (SLIPCU_CUDA_ERROR, "k_limbs", "debug");

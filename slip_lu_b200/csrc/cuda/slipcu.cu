@@ -369,6 +369,7 @@ struct ColDesc            // one finished column, as the kernels see it
 
 struct StepInfo;
 struct ChunkInfo;
+struct TimedRange;
 
 struct HostCol
 {
@@ -399,6 +400,7 @@ struct slipcu_factor
     slipcu_pivot_info *d_info = nullptr;
     size_t smem_limit = 0;
     int keep_positional = 1, rows_are_positions = 0, x_global = 0, cur = -1;
+    std::vector<struct TimedRange> ranges;      // profiling: event pairs not yet read
     u32 *tmp_limbs = nullptr; int32_t *tmp_nl = nullptr; int tmp_stride = 0;
     int32_t *slots = nullptr; size_t slots_cap = 0;      // slot lists of the current column
     StepInfo *steps = nullptr; size_t steps_cap = 0;
@@ -408,23 +410,50 @@ struct slipcu_factor
     slipcu_factor () : resid ((size_t) 512 << 20), ints ((size_t) 16 << 20), limbs ((size_t) 256 << 20) {}
 };
 
-// timing helper for the optional profiling mode
+// timing helper for the optional profiling mode: CUDA events on the session's stream around a
+// launch.  Nothing blocks: the event pairs are queued and read after the next stream
+// synchronisation (flush_timers), so profiling does not disturb the overlap of host and device.
+struct TimedRange { cudaEvent_t a, b; double *acc; };
+static std::vector<cudaEvent_t> g_event_pool;
+static std::mutex g_event_mutex;
+static cudaEvent_t take_event ()
+{
+    {
+        std::lock_guard<std::mutex> lk (g_event_mutex);
+        if (!g_event_pool.empty ()) { cudaEvent_t e = g_event_pool.back (); g_event_pool.pop_back (); return e; }
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate (&e);
+    return e;
+}
 struct ScopedTimer
 {
-    slipcu_factor *F; double *acc;
+    slipcu_factor *F; double *acc; cudaEvent_t a = nullptr;
     ScopedTimer (slipcu_factor *F_, double *acc_) : F (F_), acc (acc_)
     {
-        if (g_profiling) cudaEventRecord (F->ev0, F->st);
+        if (g_profiling) { a = take_event (); cudaEventRecord (a, F->st); }
     }
     ~ScopedTimer ()
     {
-        if (!g_profiling) return;
-        cudaEventRecord (F->ev1, F->st);
-        cudaEventSynchronize (F->ev1);
-        float ms = 0; cudaEventElapsedTime (&ms, F->ev0, F->ev1);
-        *acc += ms;
+        if (!a) return;
+        cudaEvent_t b = take_event ();
+        cudaEventRecord (b, F->st);
+        F->ranges.push_back ({a, b, acc});
     }
 };
+// call after the stream has been synchronised
+static void flush_timers (slipcu_factor *F)
+{
+    if (F->ranges.empty ()) return;
+    std::lock_guard<std::mutex> lk (g_event_mutex);
+    for (auto &r : F->ranges)
+    {
+        float ms = 0;
+        if (cudaEventElapsedTime (&ms, r.a, r.b) == cudaSuccess) *r.acc += ms; else cudaGetLastError ();
+        g_event_pool.push_back (r.a); g_event_pool.push_back (r.b);
+    }
+    F->ranges.clear ();
+}
 
 // ------------------------------------------------------------------------------------------------
 // k_residues: positional limb strings -> Montgomery residues, channel-blocked
@@ -1460,6 +1489,7 @@ extern "C" void slipcu_factor_free (slipcu_factor *F)
     for (double &v : g_hw) v = 0;
     cudaSetDevice (F->device);
     if (F->st) cudaStreamSynchronize (F->st);
+    flush_timers (F);
     pool_free (F->dAp); pool_free (F->dAi); pool_free (F->dA);
     pool_free (F->rho); pool_free (F->invrho);
     pool_free (F->desc); pool_free (F->pos); pool_free (F->bad);
@@ -2156,6 +2186,7 @@ extern "C" int slipcu_solve (slipcu_factor *F, int nrhs, const u32 *blimbs, cons
     }
 done:
     cudaStreamSynchronize (F->st);
+    flush_timers (F);
     if (rc == SLIPCU_OK && !F->rows_are_positions)
     {   // device-side job time: A resident -> solution numerators reconstructed on the device
         float ms = 0;

@@ -228,3 +228,31 @@ def test_channel_prime_dividing_a_pivot_is_retired(gpu, oracle):
     q = cases.colamd_like_order(n, cp, ri)
     cases.assert_same_factorization(cases.run_library(gpu, n, cp, ri, vals, b, q),
                                     cases.run_oracle(oracle, n, cp, ri, vals, b, q), "after retirement")
+
+
+@pytest.mark.parametrize("env", [{"SLIP_B200_CH": "16"}, {"SLIP_B200_CH": "32"}, {"SLIP_B200_X_GLOBAL": "1"},
+                                 {"SLIP_B200_CH": "32", "SLIP_B200_X_GLOBAL": "1"}, {"SLIP_B200_GARNER": "1"},
+                                 {"SLIP_B200_GARNER": "0"}, {"SLIP_B200_THREADS": "128"}])
+def test_kernel_variants_agree(gpu, oracle, env):
+    """The kernel configurations that large problems select automatically (wider channel blocks,
+    work vector in global memory when the pattern outgrows shared memory, the other Garner
+    kernels) are forced here on a small case and must give the same bits."""
+    n, cp, ri, vals, b = synth.random_sparse(72, 6, 40, seed=17, nrhs=2)
+    q = cases.colamd_like_order(n, cp, ri)
+    want = cases.run_oracle(oracle, n, cp, ri, vals, b, q)
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        got = cases.run_library(gpu, n, cp, ri, vals, b, q)
+        o = gpu.default_options(order=capi.SLIP_NO_ORDERING)
+        A = gpu.sparse_from_csc(n, cp, ri, vals); B = gpu.dense_from_rows(b)
+        S = gpu.analyze(A, o, q=q)
+        x = gpu.solve_mpq(A, S, B, o)
+        assert gpu.dll.SLIP_check_solution(A, x, B) == 0
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    cases.assert_same_factorization(got, want, str(env))

@@ -25,7 +25,8 @@ def main():
     sizes = [int(a) for a in sys.argv[1:] if a.isdigit()] or [200, 400, 800]
     prof = "--prof" in sys.argv
     host_factors = "--factors" in sys.argv
-    for n in sizes:
+    rep = 2 if "--repeat" in sys.argv else 1
+    for n in [m for m in sizes for _ in range(rep)]:
         n, cp, ri, vals, b = synth.random_sparse(n, 10, 32, seed=1)
         o = lib.default_options()
         A = lib.sparse_from_csc(n, cp, ri, vals)

@@ -35,19 +35,32 @@ def gather_objects(obj, world: int, rank: int):
     return out
 
 
-def solve_batch_sharded(lib, systems, world: int, rank: int, options=None):
-    """Solve the shard of `systems` (each (n, colptr, rowidx, values, b_rows)) owned by this rank with
-    SLIP_LU_analyze + SLIP_solve_mpq; returns [(global_index, solution)] for the shard."""
-    lo, hi = shard_range(len(systems), world, rank)
-    out = []
-    for g in range(lo, hi):
-        n, cp, ri, vals, b = systems[g]
-        o = options() if options else lib.default_options()
-        A = lib.sparse_from_csc(n, cp, ri, vals)
-        B = lib.dense_from_rows(b)
-        S = lib.analyze(A, o)
+def _solve_one(lib, system, options):
+    n, cp, ri, vals, b = system
+    o = options() if options else lib.default_options()
+    A = lib.sparse_from_csc(n, cp, ri, vals)
+    B = lib.dense_from_rows(b)
+    S = lib.analyze(A, o)
+    try:
         x = lib.solve_mpq(A, S, B, o)
-        out.append((g, lib.mpq_mat_to_py(x, n, len(b[0]))))
-        lib.free_mpq_mat(x, n, len(b[0])); lib.free_analysis(S); lib.free_dense(B); lib.free_sparse(A)
-        lib.free_options(o)
+        out = lib.mpq_mat_to_py(x, n, len(b[0]))
+        lib.free_mpq_mat(x, n, len(b[0]))
+    finally:
+        lib.free_analysis(S); lib.free_dense(B); lib.free_sparse(A); lib.free_options(o)
     return out
+
+
+def solve_batch_sharded(lib, systems, world: int, rank: int, options=None, threads: int = 1):
+    """Solve the shard of `systems` (each (n, colptr, rowidx, values, b_rows)) owned by this rank with
+    SLIP_LU_analyze + SLIP_solve_mpq; returns [(global_index, solution)] for the shard.
+
+    Small systems leave most of a B200 idle (a column is a handful of short launches), so with
+    threads > 1 several systems of the shard are in flight at once: every factorization session has
+    its own CUDA stream, and the ctypes calls release the GIL."""
+    lo, hi = shard_range(len(systems), world, rank)
+    if threads <= 1:
+        return [(g, _solve_one(lib, systems[g], options)) for g in range(lo, hi)]
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=threads) as pool:
+        futs = [(g, pool.submit(_solve_one, lib, systems[g], options)) for g in range(lo, hi)]
+        return [(g, f.result()) for g, f in futs]

@@ -170,6 +170,10 @@ def test_batch_of_independent_systems(gpu, oracle):
     systems = [synth.lp_basis(120, seed=s, nrhs=1) for s in range(12)]
     got = solve_batch_sharded(gpu, systems, 1, 0,
                               options=lambda: gpu.default_options(order=capi.SLIP_NO_ORDERING))
+    # several systems in flight at once (one CUDA stream per session, host threads)
+    got_mt = solve_batch_sharded(gpu, systems, 1, 0, threads=4,
+                                 options=lambda: gpu.default_options(order=capi.SLIP_NO_ORDERING))
+    assert got_mt == got
     for g, x in got:
         n, cp, ri, vals, b = systems[g]
         f = oracle.factorize(n, cp, ri, vals, list(range(n)))

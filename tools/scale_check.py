@@ -42,3 +42,18 @@ if "batch" in which:
             continue                      # exactly singular random basis
         assert lib.dll.SLIP_check_solution(A, x, B) == 0
     print(f"configs[4]-style: 32 systems n=500 in {time.time() - t:.2f}s ({(time.time() - t) / 32 * 1e3:.1f} ms each)", flush=True)
+if "threads" in which:
+    from slip_lu_b200.sharding import solve_batch_sharded
+    systems = []
+    seed = 100
+    while len(systems) < 64:
+        sm = synth.lp_basis(500, seed=seed, nrhs=1); seed += 1
+        try:
+            solve_batch_sharded(lib, [sm], 1, 0)
+            systems.append(sm)
+        except capi.SlipError:
+            pass
+    for th in (1, 4, 8, 16):
+        t = time.time()
+        solve_batch_sharded(lib, systems, 1, 0, threads=th)
+        print(f"64 systems n=500, {th} host threads: {(time.time() - t) / 64 * 1e3:.1f} ms per system", flush=True)

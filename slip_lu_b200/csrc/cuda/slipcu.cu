@@ -490,7 +490,20 @@ __device__ __forceinline__ u32 smem_u32 (const void *p) { return (u32) __cvta_ge
 // symbolic pre-pass of a column: row -> slot map, then for every elimination step the list of
 // target slots (one per entry of the L column used), shared by all channel blocks.
 // ------------------------------------------------------------------------------------------------
-#define TRI_ROWS 512          // rows per pipeline chunk
+#define TRI_THREADS 256       // threads of a k_trisolve CTA
+#define TRI_BUFS 3            // shared-memory chunk buffers: two chunks in flight while one is consumed
+#define TRI_RING 8            // chunk descriptors kept in shared memory
+
+// Every thread of k_trisolve owns 4 channels, so CH/4 threads share a row and a CTA covers
+// TRI_THREADS/(CH/4) rows at a time; a pipeline chunk is four such row groups (16 KB of L).
+static __host__ __device__ inline int tri_row_groups (int CH) { return TRI_THREADS / (CH / 4); }
+static __host__ __device__ inline int tri_chunk_rows (int CH) { return 4 * tri_row_groups (CH); }
+// entries of the slot list of a step with len rows: full chunks, then 4 entries per thread in use
+static __host__ __device__ inline int tri_slot_extent (int len, int CH)
+{
+    const int R = tri_chunk_rows (CH), RG = tri_row_groups (CH), rem = len % R;
+    return (len / R) * R + 4 * (rem < RG ? rem : RG);
+}
 
 struct StepInfo           // one elimination step of a column: eliminate with column j of L
 {
@@ -499,18 +512,18 @@ struct StepInfo           // one elimination step of a column: eliminate with co
     int32_t len;          // entries in the L part of column j (the pivot row included)
     int32_t cbstride;     // words between channel blocks of column j
     int32_t slot_off;     // offset of this step's slot list (multiple of 4)
-    int32_t chunk0;       // index of the step's first pipeline chunk (TRI_ROWS rows per chunk)
+    int32_t chunk0;       // index of the step's first pipeline chunk
     int32_t pad;
 };
 
-struct ChunkInfo          // one pipeline chunk (<= TRI_ROWS rows of one step), ready for the producer
+struct __align__ (16) ChunkInfo   // one pipeline chunk (rows of one step); 32 bytes, read as two 16-byte words
 {
     const u32 *lsrc;      // first L residue of the chunk for channel block 0
     int32_t cbstride;     // words between channel blocks
     int32_t slot_off;     // offset of the chunk's slot list
     int32_t j;            // pivot position of the step
-    int32_t nrows;
-    int32_t first, last;  // first / last chunk of its step
+    int32_t meta;         // rows | first chunk of its step << 16 | last chunk << 17
+    int32_t pad0, pad1;
 };
 
 __global__ void k_setpos (int cnt, const int32_t *rows, int32_t *pos)
@@ -519,7 +532,12 @@ __global__ void k_setpos (int cnt, const int32_t *rows, int32_t *pos)
     if (t < cnt) pos[rows[t]] = t;
 }
 
-__global__ void k_slots (int nU, int total, int CH, const int32_t *upos, const int32_t *uoff,
+// Slot lists.  For each chunk the list is stored in the order the consumer threads read it: entry
+// 4*g + q is the target of chunk row g + q*RG (g = row group of the thread), so that one 16-byte
+// load gives a thread its four targets.  A target is the BYTE offset of the slot's row in the work
+// vector; rows without a target (past the end of the chunk, or the pivot row itself) point at the
+// spare row `cnt` of the vector, which absorbs their updates.
+__global__ void k_slots (int nU, int total, int CH, int cnt, const int32_t *upos, const int32_t *uoff,
                          const int32_t *uchunk, const ColDesc *desc, const int32_t *pos, int32_t *slots,
                          StepInfo *steps, ChunkInfo *chunks)
 {
@@ -527,35 +545,39 @@ __global__ void k_slots (int nU, int total, int CH, const int32_t *upos, const i
     if (i >= total) return;
     int lo = 0, hi = nU - 1;                      // last u with uoff[u] <= i
     while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (uoff[mid] <= i) lo = mid; else hi = mid - 1; }
-    const int u = lo, r = i - uoff[u];
+    const int u = lo, o = i - uoff[u];
+    const int R = tri_chunk_rows (CH), RG = tri_row_groups (CH);
     const ColDesc d = desc[upos[u]];
     const int len = d.cnt - d.nU;
+    const int ci = o / R, q = o % R;              // chunk of the step, entry inside the chunk
+    const int r = ci * R + (q & 3) * RG + (q >> 2);
     const int m = d.nU + r;
-    slots[i] = (r < len && m != d.pivslot) ? pos[d.rows[m]] : -1;
-    if (r == 0)
+    const int rowbytes = CH * 4;
+    slots[i] = (r < len && m != d.pivslot) ? pos[d.rows[m]] * rowbytes : cnt * rowbytes;
+    if (o == 0)
     {
         StepInfo si;
         si.lbase = d.base + (size_t) d.nU * CH; si.j = upos[u]; si.len = len; si.cbstride = d.cnt * CH;
         si.slot_off = uoff[u]; si.chunk0 = uchunk[u]; si.pad = 0;
         steps[u] = si;
     }
-    if (r < len && (r % TRI_ROWS) == 0)
+    if (q == 0)
     {
-        ChunkInfo ci;
-        ci.lsrc = d.base + (size_t) (d.nU + r) * CH; ci.cbstride = d.cnt * CH;
-        ci.slot_off = uoff[u] + r; ci.j = upos[u];
-        ci.nrows = min (TRI_ROWS, len - r); ci.first = (r == 0); ci.last = (r + TRI_ROWS >= len);
-        chunks[uchunk[u] + r / TRI_ROWS] = ci;
+        ChunkInfo c;
+        const int r0 = ci * R;
+        c.lsrc = d.base + (size_t) (d.nU + r0) * CH; c.cbstride = d.cnt * CH;
+        c.slot_off = uoff[u] + r0; c.j = upos[u];
+        c.meta = min (R, len - r0) | ((r0 == 0) << 16) | ((r0 + R >= len) << 17);
+        c.pad0 = 0; c.pad1 = 0;
+        chunks[uchunk[u] + ci] = c;
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // k_trisolve: sparse REF triangular solve of one column (or of one dense right-hand side).
-// One CTA per block of CH channels; channels are independent.  One producer warp per pipeline
-// stage streams, for every elimination step, the CH-wide rows of the L column, the slot list and
-// the step's pivot constant into shared memory with TMA bulk copies (mbarrier completion).
+// One CTA per block of CH channels; channels are independent.
 //
-// The consumer warps hold the vector in shared memory in NORMALISED form  w_t = x_t / rho_{h_t}
+// The vector is held in shared memory in NORMALISED form  w_t = x_t / rho_{h_t}
 // (h_t = last elimination step applied to x_t, rho_{-1} = 1).  In that form the REF update
 //     x_t <- (rho_j * rho_{j-1}/rho_{h_t} * x_t - l_tj * x_j) / rho_{j-1}
 // of slip_REF_triangular_solve.c:150-232, including every history update, collapses to
@@ -564,14 +586,13 @@ __global__ void k_slots (int nU, int total, int CH, const int32_t *upos, const i
 // history vector of the reference is not needed at all.  The true REF values are restored when
 // the column is published:  U(j,k) = w_j * rho_{j-1},  L(t,k) = w_t * rho_{k-1}.
 // Slots 0..nU-1 of the pattern are rows that are already pivotal (in pivot order); slots
-// nU..cnt-1 are the candidate rows.
+// nU..cnt-1 are the candidate rows; row cnt is a spare that absorbs updates without a target.
 // ------------------------------------------------------------------------------------------------
 
 struct TriArgs
 {
     int k;                   // level the L part is brought to (column index; n for a rhs)
     int S, cnt, nU;
-    int stages;              // chunk buffers (TRI_BUFS)
     const int32_t *rows;     // [cnt] original row of each slot
     const StepInfo *steps;   // [nU]
     const ChunkInfo *chunks; // [nchunks]
@@ -588,33 +609,44 @@ struct TriArgs
     int nchunks;             // total pipeline chunks of this launch
 };
 
-struct StageMeta { int32_t j, nrows, first, last; };
-
-#define TRI_BUFS 3            // shared-memory chunk buffers: two chunks in flight while one is consumed
-
 template <int CH>
 struct TriSmem
 {
-    // byte offsets inside the dynamic shared memory block
-    static __host__ __device__ size_t stage_bytes ()
+    static constexpr int RG = TRI_THREADS / (CH / 4);            // row groups
+    static constexpr int R = 4 * RG;                             // rows per chunk
+    static constexpr int L_BYTES = R * CH * 4;                   // 16 KB
+    static constexpr int S_BYTES = R * 4;
+    static constexpr int STAGE = (L_BYTES + S_BYTES + CH * 4 + 127) & ~127;   // L rows, targets, 1/rho_j
+    static constexpr int RING_BYTES = TRI_RING * (int) sizeof (ChunkInfo);
+    static __host__ __device__ size_t x_bytes (int cnt) { return ((size_t) (cnt + 1) * CH * 4 + 127) & ~(size_t) 127; }
+    static __host__ __device__ size_t total (int cnt, bool x_in_smem)
     {
-        return (size_t) TRI_ROWS * CH * 4 + (size_t) TRI_ROWS * 4 + CH * 4 + 32;   // L rows, slots, 1/rho_j, meta
-    }
-    static __host__ __device__ size_t total (int cnt, int stages, bool x_in_smem)
-    {
-        size_t b = 0;
-        if (x_in_smem) b += ((size_t) cnt * CH * 4 + 127) & ~(size_t) 127;     // x
-        b += (size_t) stages * ((stage_bytes () + 127) & ~(size_t) 127);
-        return b;
+        return (x_in_smem ? x_bytes (cnt) : (size_t) 0) + RING_BYTES + (size_t) TRI_BUFS * STAGE;
     }
 };
 
-__device__ __forceinline__ void cp_async16 (void *dst, const void *src)
+__device__ __forceinline__ void cp_async16 (u32 dst_smem, const void *src)
 {
-    asm volatile ("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32 (dst)), "l"(src) : "memory");
+    asm volatile ("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst_smem), "l"(src) : "memory");
+}
+template <int OFF> __device__ __forceinline__ void cp_async16_off (u32 dst_smem, const void *src)
+{   // same displacement on both sides, folded into the instruction
+    asm volatile ("cp.async.cg.shared.global [%0+%2], [%1+%2], 16;" :: "r"(dst_smem), "l"(src), "n"(OFF) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit () { asm volatile ("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait () { asm volatile ("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+__device__ __forceinline__ uint4 lds128 (u32 addr)
+{
+    uint4 v;
+    asm volatile ("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint2 lds64 (u32 addr)
+{
+    uint2 v;
+    asm volatile ("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
 
 // w + l*ny  (ny = -yhat): one Montgomery product and a modular add per channel
 __device__ __forceinline__ uint4 mont_mul4 (const uint4 a, const uint4 b, const uint4 p, const uint4 ni)
@@ -634,59 +666,68 @@ __device__ __forceinline__ uint4 neg4 (const uint4 y, const uint4 p)
 
 // All threads of the CTA are consumers; every thread also copies its share of the chunk that is
 // two positions ahead in the work list with 16-byte cp.async (LDGSTS): TRI_BUFS-1 chunks are in
-// flight per CTA while one is consumed.  (A TMA bulk-copy producer was measured first: with three
-// small bulk copies per elimination step the copy engine, not HBM, set the pace -- about 1.1 us
-// per step regardless of pipeline depth; see profiles/.)  One __syncthreads per chunk both
-// publishes the landed chunk and orders the previous chunk's updates before the next yhat.
+// flight per CTA while one is consumed.  The chunk descriptors travel through a small ring in
+// shared memory, requested four chunks ahead in the same copy groups, so that the loop has no
+// global load of its own.  (A TMA bulk-copy producer was measured first: with three small bulk
+// copies per elimination step the copy engine, not HBM, set the pace -- about 1.1 us per step
+// regardless of pipeline depth; see profiles/.)  One __syncthreads per chunk both publishes the
+// landed chunk and orders the previous chunk's updates before the next yhat.
 template <int CH, bool XS>
-__global__ void __launch_bounds__ (256, 2) k_trisolve (TriArgs a)
+__global__ void __launch_bounds__ (TRI_THREADS, 2) k_trisolve (TriArgs a)
 {
+    typedef TriSmem<CH> SM;
+    constexpr int NT = TRI_THREADS, TPR = CH / 4, RG = SM::RG;
     extern __shared__ __align__ (128) unsigned char smem_raw[];
-    unsigned char *ptr = smem_raw;
-    u32 *xsm = (u32 *) ptr;
-    if (XS) ptr += ((size_t) a.cnt * CH * 4 + 127) & ~(size_t) 127;
-    unsigned char *stage0 = ptr;
-    const size_t stage_stride = (TriSmem<CH>::stage_bytes () + 127) & ~(size_t) 127;
-
-    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int tid = threadIdx.x;
     const int cb = blockIdx.x, S = a.S, cnt = a.cnt, nU = a.nU, nchunks = a.nchunks;
     u32 *xg = a.out + (size_t) blockIdx.y * a.out_y_stride + (size_t) cb * cnt * CH;
-    u32 *xs = XS ? xsm : xg;
+    u32 *xs = XS ? (u32 *) smem_raw : xg;
+    const u32 smem0 = smem_u32 (smem_raw);
+    const u32 ring = smem0 + (XS ? (u32) SM::x_bytes (cnt) : 0u);
+    const u32 stage0 = ring + SM::RING_BYTES;
+    const u32 spare = (u32) cnt * CH * 4;              // byte offset of the spare row
 
-    // issue the copies of chunk c into buffer c % TRI_BUFS (this thread's share)
-    auto issue = [&] (int c, const ChunkInfo &ci)
+    // request descriptor X (two threads, 16 bytes each)
+    auto fetch_desc = [&] (int X, int half)
     {
-        unsigned char *sb = stage0 + (size_t) (c % TRI_BUFS) * stage_stride;
-        u32 *Lbuf = (u32 *) sb;
-        int32_t *Sbuf = (int32_t *) (sb + (size_t) TRI_ROWS * CH * 4);
-        u32 *Cbuf = (u32 *) (sb + (size_t) TRI_ROWS * CH * 4 + (size_t) TRI_ROWS * 4);
-        const u32 *lsrc = ci.lsrc + (size_t) cb * ci.cbstride;
-        const int lp = ci.nrows * (CH / 4);                        // 16-byte pieces of L rows
-        for (int i = tid; i < lp; i += nthr) cp_async16 (Lbuf + 4 * i, lsrc + 4 * i);
-        const int sp = (ci.nrows + 3) >> 2;
-        const int32_t *ssrc = a.slots + ci.slot_off;
-        for (int i = tid; i < sp; i += nthr) cp_async16 (Sbuf + 4 * i, ssrc + 4 * i);
-        if (ci.first && tid < CH / 4)
-            cp_async16 (Cbuf + 4 * tid, a.invrho + (size_t) ci.j * S + (size_t) cb * CH + 4 * tid);
-        if (tid == 0)
-        {
-            StageMeta *meta = (StageMeta *) (Cbuf + CH);
-            meta->j = ci.j; meta->nrows = ci.nrows; meta->first = ci.first; meta->last = ci.last;
-        }
+        cp_async16 (ring + (u32) (X % TRI_RING) * (u32) sizeof (ChunkInfo) + half * 16,
+                    (const unsigned char *) (a.chunks + X) + half * 16);
+    };
+    // issue this thread's share of the copies of the chunk whose descriptor sits in ring slot rs
+    auto issue = [&] (int rs, u32 sb)
+    {
+        const u32 da = ring + (u32) rs * (u32) sizeof (ChunkInfo);
+        const uint4 d0 = lds128 (da);                  // lsrc (lo, hi), cbstride, slot_off
+        const uint2 d1 = lds64 (da + 16);              // j, meta
+        const int nrows = (int) (d1.y & 0xffffu);
+        const unsigned char *lsrc = (const unsigned char *) (((unsigned long long) d0.y << 32) | d0.x)
+                                  + ((size_t) cb * d0.z) * 4 + (size_t) tid * 16;
+        const u32 ldst = sb + (u32) tid * 16;
+        const int lp = nrows * TPR;                    // 16-byte pieces of L rows, at most 4 per thread
+        if (tid < lp) cp_async16_off<0> (ldst, lsrc);
+        if (tid + NT < lp) cp_async16_off<NT * 16> (ldst, lsrc);
+        if (tid + 2 * NT < lp) cp_async16_off<2 * NT * 16> (ldst, lsrc);
+        if (tid + 3 * NT < lp) cp_async16_off<3 * NT * 16> (ldst, lsrc);
+        if (tid < min (nrows, RG))                     // one 16-byte group of targets per row group in use
+            cp_async16 (sb + SM::L_BYTES + (u32) tid * 16, a.slots + (size_t) d0.w + (size_t) tid * 4);
+        if ((d1.y & 0x10000u) && tid < TPR)
+            cp_async16 (sb + SM::L_BYTES + SM::S_BYTES + (u32) tid * 16,
+                        a.invrho + (size_t) d1.x * S + (size_t) cb * CH + 4 * tid);
     };
 
-    // prologue: the first chunks are requested while the vector is initialised
-    for (int c = 0; c < TRI_BUFS - 1; ++c) { if (c < nchunks) issue (c, a.chunks[c]); cp_async_commit (); }
-    // descriptor of the next chunk to request, fetched one iteration ahead of its use
-    ChunkInfo pre;
-    pre.lsrc = nullptr; pre.cbstride = 0; pre.slot_off = 0; pre.j = 0; pre.nrows = 0; pre.first = 0; pre.last = 0;
-    if (TRI_BUFS - 1 < nchunks) pre = a.chunks[TRI_BUFS - 1];
+    // prologue: the first descriptors, then the first chunks, are requested while the vector is initialised
+    if (tid < 8 && (tid >> 1) < nchunks) fetch_desc (tid >> 1, tid & 1);
+    cp_async_commit ();
+    cp_async_wait<0> ();
+    __syncthreads ();
+    for (int c = 0; c < TRI_BUFS - 1; ++c) { if (c < nchunks) issue (c, stage0 + (u32) c * SM::STAGE); cp_async_commit (); }
     {
-        for (int i = tid; i < cnt * CH; i += nthr) xs[i] = 0;
+        const int words = (XS ? cnt + 1 : cnt) * CH;
+        for (int i = tid; i < words; i += NT) xs[i] = 0;
         __syncthreads ();
         const u32 *src = a.src + (size_t) cb * a.src_total * CH;
         const int first = a.src_first + (int) (blockIdx.y * a.src_y_stride);
-        for (int i = tid; i < a.src_cnt * CH; i += nthr)
+        for (int i = tid; i < a.src_cnt * CH; i += NT)
         {
             const int e = i / CH, ch = i % CH;
             const int row = a.src_rows ? a.src_rows[e] : e;
@@ -694,55 +735,50 @@ __global__ void __launch_bounds__ (256, 2) k_trisolve (TriArgs a)
         }
     }
 
-    constexpr int TPR = CH / 4;                        // threads per row, 4 channels each
-    const int q4 = (tid % TPR) * 4, rg = tid / TPR, RG = nthr / TPR;
+    const int q4 = (tid % TPR) * 4, rg = tid / TPR;
     const int c0 = cb * CH + q4;
     const uint4 p4 = *reinterpret_cast<const uint4 *> (a.p + c0);
     const uint4 ni4 = *reinterpret_cast<const uint4 *> (a.ninv + c0);
+    unsigned char *xb = (unsigned char *) xs + q4 * 4;             // this thread's channels of row 0
     uint4 negy = make_uint4 (0, 0, 0, 0);
     int u = 0;                                         // elimination step of the current chunk
+    int bc = 0, bi = TRI_BUFS - 1;                     // buffers of the chunk consumed / requested
     for (int c = 0; c < nchunks; ++c)
     {
         cp_async_wait<TRI_BUFS - 2> ();                // this thread's copies of chunk c have landed
         __syncthreads ();                              // ... and everyone's; chunk c-1 is fully applied
-        if (c + TRI_BUFS - 1 < nchunks) issue (c + TRI_BUFS - 1, pre);     // reuses the buffer of chunk c-1
+        if (c + TRI_BUFS - 1 < nchunks) issue ((c + TRI_BUFS - 1) % TRI_RING, stage0 + (u32) bi * SM::STAGE);
+        if (tid < 2 && c + 4 < nchunks) fetch_desc (c + 4, tid);
         cp_async_commit ();
-        if (c + TRI_BUFS < nchunks) pre = a.chunks[c + TRI_BUFS];
-        const unsigned char *sb = stage0 + (size_t) (c % TRI_BUFS) * stage_stride;
-        const u32 *Lbuf = (const u32 *) sb;
-        const int32_t *Sbuf = (const int32_t *) (sb + (size_t) TRI_ROWS * CH * 4);
-        const u32 *Cbuf = (const u32 *) (sb + (size_t) TRI_ROWS * CH * 4 + (size_t) TRI_ROWS * 4);
-        const StageMeta meta = *(const StageMeta *) (Cbuf + CH);
-        if (meta.first)
+        const u32 sb = stage0 + (u32) bc * SM::STAGE;
+        const u32 meta = lds64 (ring + (u32) (c % TRI_RING) * (u32) sizeof (ChunkInfo) + 16).y;
+        if (meta & 0x10000u)
         {   // yhat_j = w_j / rho_j
-            const uint4 wj = *reinterpret_cast<const uint4 *> (xs + u * CH + q4);
-            negy = neg4 (mont_mul4 (wj, *reinterpret_cast<const uint4 *> (Cbuf + q4), p4, ni4), p4);
+            const uint4 wj = *reinterpret_cast<const uint4 *> (xb + (size_t) u * CH * 4);
+            negy = neg4 (mont_mul4 (wj, lds128 (sb + SM::L_BYTES + SM::S_BYTES + q4 * 4), p4, ni4), p4);
         }
-        const int nrows = meta.nrows;
-        // rows of one step hit distinct slots: four rows per thread are loaded, updated and stored
-        // together so that their latencies overlap
-        for (int r0 = rg; r0 < nrows; r0 += 4 * RG)
+        // rows of one step hit distinct slots: the four rows of a thread are loaded, updated and
+        // stored together so that their latencies overlap
+        if (rg < (int) (meta & 0xffffu))
         {
-            int t[4]; uint4 l[4], w[4];
+            const uint4 tq = lds128 (sb + SM::L_BYTES + (u32) rg * 16);
+            const u32 t[4] = { tq.x, tq.y, tq.z, tq.w };
+            const u32 lrow = sb + (u32) rg * (CH * 4) + q4 * 4;
+            uint4 l[4], w[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
+            for (int q = 0; q < 4; ++q)
             {
-                const int r = r0 + k * RG;
-                t[k] = (r < nrows) ? Sbuf[r] : -1;
+                l[q] = lds128 (lrow + q * RG * CH * 4);
+                if (XS || t[q] != spare) w[q] = *reinterpret_cast<const uint4 *> (xb + t[q]);
             }
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (t[k] >= 0)
-                {
-                    l[k] = *reinterpret_cast<const uint4 *> (Lbuf + (r0 + k * RG) * CH + q4);
-                    w[k] = *reinterpret_cast<const uint4 *> (xs + t[k] * CH + q4);
-                }
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (t[k] >= 0)
-                    *reinterpret_cast<uint4 *> (xs + t[k] * CH + q4) = sub_mul4 (w[k], l[k], negy, p4, ni4);
+            for (int q = 0; q < 4; ++q)
+                if (XS || t[q] != spare)
+                    *reinterpret_cast<uint4 *> (xb + t[q]) = sub_mul4 (w[q], l[q], negy, p4, ni4);
         }
-        if (meta.last) ++u;
+        if (meta & 0x20000u) ++u;
+        bc = (bc == TRI_BUFS - 1) ? 0 : bc + 1;
+        bi = (bi == TRI_BUFS - 1) ? 0 : bi + 1;
     }
     __syncthreads ();
     // publish the column as true REF values: U(j,k) = w_j rho_{j-1}, candidates = w_t rho_{k-1}
@@ -1546,8 +1582,7 @@ static int session_common_init (slipcu_factor *F, int n, int channels)
     CH = env_int ("SLIP_B200_CH", CH);
     if (CH != 8 && CH != 16 && CH != 32) CH = 16;
     F->CH = CH;
-    F->threads = env_int ("SLIP_B200_THREADS", 256);       // consumer threads (one producer warp per stage is added)
-    if (F->threads % 32 || F->threads < 32 || F->threads > 256) F->threads = 256;
+    F->threads = TRI_THREADS;
     F->sms = sms;
     F->x_global = env_int ("SLIP_B200_X_GLOBAL", 0);
     F->garner_mode = env_int ("SLIP_B200_GARNER", 2);
@@ -1561,6 +1596,14 @@ static int session_common_init (slipcu_factor *F, int n, int channels)
     CU (cudaFuncSetAttribute (k_trisolve<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
     CU (cudaFuncSetAttribute (k_trisolve<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
     CU (cudaFuncSetAttribute (k_trisolve<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
+    if (env_int ("SLIP_B200_CARVEOUT", 1))
+    {   // ask for the full shared-memory carve-out so that two CTAs stay resident per SM
+        const int mx = (int) cudaSharedmemCarveoutMaxShared;
+        cudaFuncSetAttribute (k_trisolve<8, true>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        cudaFuncSetAttribute (k_trisolve<16, true>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        cudaFuncSetAttribute (k_trisolve<32, true>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        cudaGetLastError ();
+    }
 
     CU (cudaStreamCreateWithFlags (&F->st, cudaStreamNonBlocking));
     CU (cudaEventCreateWithFlags (&F->ev, cudaEventDisableTiming));
@@ -1629,11 +1672,11 @@ static cudaError_t launch_tri (const TriArgs &a, dim3 grid, int threads, size_t 
     else k_trisolve<CH, false><<<grid, threads, smem, st>>> (a);
     return cudaGetLastError ();
 }
-static size_t tri_smem_bytes (int CH, int cnt, int stages, bool x_in_smem)
+static size_t tri_smem_bytes (int CH, int cnt, bool x_in_smem)
 {
-    if (CH == 8) return TriSmem<8>::total (cnt, stages, x_in_smem);
-    if (CH == 16) return TriSmem<16>::total (cnt, stages, x_in_smem);
-    return TriSmem<32>::total (cnt, stages, x_in_smem);
+    if (CH == 8) return TriSmem<8>::total (cnt, x_in_smem);
+    if (CH == 16) return TriSmem<16>::total (cnt, x_in_smem);
+    return TriSmem<32>::total (cnt, x_in_smem);
 }
 static cudaError_t launch_tri_any (int CH, const TriArgs &a, dim3 grid, int threads, size_t smem, cudaStream_t st)
 {
@@ -1679,7 +1722,7 @@ static int prepare_steps (slipcu_factor *F, int cnt, int nU, const int32_t *rows
     if (debug_check ("k_setpos", F->st)) return fail (SLIPCU_CUDA_ERROR, "k_setpos", "debug");
     if (nU > 0 && total > 0)
     {
-        k_slots<<<(total + 255) / 256, 256, 0, F->st>>> (nU, total, F->CH, upos, uoff, uchunk, F->desc, F->pos, F->slots, F->steps, F->chunks);
+        k_slots<<<(total + 255) / 256, 256, 0, F->st>>> (nU, total, F->CH, cnt, upos, uoff, uchunk, F->desc, F->pos, F->slots, F->steps, F->chunks);
         g_launches++;
         CU (cudaGetLastError ());
         if (debug_check ("k_slots", F->st)) return fail (SLIPCU_CUDA_ERROR, "k_slots", "debug");
@@ -1691,12 +1734,11 @@ static int prepare_steps (slipcu_factor *F, int cnt, int nU, const int32_t *rows
 static int tri_geometry (slipcu_factor *F, TriArgs &a, size_t *smem)
 {
     a.x_in_smem = !F->x_global;
-    a.stages = TRI_BUFS;
-    size_t need = tri_smem_bytes (F->CH, a.cnt, TRI_BUFS, a.x_in_smem);
+    size_t need = tri_smem_bytes (F->CH, a.cnt, a.x_in_smem);
     if (need + 1024 > F->smem_limit && a.x_in_smem)
     {   // pattern too long for shared memory: x stays in the (L2-resident) output region
         a.x_in_smem = 0;
-        need = tri_smem_bytes (F->CH, a.cnt, TRI_BUFS, false);
+        need = tri_smem_bytes (F->CH, a.cnt, false);
     }
     if (need + 1024 > F->smem_limit) return fail (SLIPCU_BAD_INPUT, "tri_geometry", "pattern too large for shared memory");
     *smem = need;
@@ -1797,13 +1839,14 @@ extern "C" int slipcu_factor_column_launch (slipcu_factor *F, int k, int col, in
     int32_t *uoff = F->h_packet + cnt + nU;
     int32_t *uchunk = uoff + nU + 1;
     int64_t total = 0, nchunks = 0;
+    const int chunk_rows = tri_chunk_rows (CH);
     for (int u = 0; u < nU; ++u)
     {
         const HostCol &lj = F->cols[upos[u]];
         const int len = lj.cnt - lj.nU;
         uoff[u] = (int32_t) total; uchunk[u] = (int32_t) nchunks;
-        total += (len + 3) & ~3;
-        nchunks += (len + TRI_ROWS - 1) / TRI_ROWS;
+        total += tri_slot_extent (len, CH);
+        nchunks += (len + chunk_rows - 1) / chunk_rows;
         if (total > INT32_MAX) return fail (SLIPCU_BAD_INPUT, "slipcu_factor_column", "column has too many updates");
     }
     uoff[nU] = (int32_t) total; uchunk[nU] = (int32_t) nchunks;
@@ -2124,7 +2167,7 @@ extern "C" int slipcu_solve (slipcu_factor *F, int nrhs, const u32 *blimbs, cons
         {
             const int len = F->cols[k].cnt - F->cols[k].nU;
             uoff[k] = (int32_t) tot; uoff[n + 1 + k] = (int32_t) nch;
-            tot += (len + 3) & ~3; nch += (len + TRI_ROWS - 1) / TRI_ROWS;
+            tot += tri_slot_extent (len, CH); nch += (len + tri_chunk_rows (CH) - 1) / tri_chunk_rows (CH);
         }
         uoff[n] = (int32_t) tot; uoff[2 * n + 1] = (int32_t) nch;
         fwd_chunks = (int) nch;

@@ -236,7 +236,7 @@ def test_channel_prime_dividing_a_pivot_is_retired(gpu, oracle):
 
 @pytest.mark.parametrize("env", [{"SLIP_B200_CH": "16"}, {"SLIP_B200_CH": "32"}, {"SLIP_B200_X_GLOBAL": "1"},
                                  {"SLIP_B200_CH": "32", "SLIP_B200_X_GLOBAL": "1"}, {"SLIP_B200_GARNER": "1"},
-                                 {"SLIP_B200_GARNER": "0"}, {"SLIP_B200_THREADS": "128"}])
+                                 {"SLIP_B200_GARNER": "0"}])
 def test_kernel_variants_agree(gpu, oracle, env):
     """The kernel configurations that large problems select automatically (wider channel blocks,
     work vector in global memory when the pattern outgrows shared memory, the other Garner

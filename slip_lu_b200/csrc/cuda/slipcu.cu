@@ -105,6 +105,14 @@ __device__ __forceinline__ void lazy_mac (u64 &T, u32 a, u32 b, u32 p)
     T += (u64) a * b;                       // < 2^63 + 2^62
     if (T >> 63) T -= ((u64) p << 32);      // p * 2^32 >= 2^62, keeps T < 2^63 and T mod p
 }
+// two products per range check: T < 2^63 and each product <= (p-1)^2 < 2^62, so the sum cannot
+// wrap; if it reaches 2^63, T - p*2^32 <= 2^63 - 1 + 2(p-1)^2 - p*2^32 < 2^63 because 2p < 2^32
+__device__ __forceinline__ void lazy_mac2 (u64 &T, u32 a0, u32 b0, u32 a1, u32 b1, u32 p)
+{
+    T += (u64) a0 * b0;
+    T += (u64) a1 * b1;
+    if (T >> 63) T -= ((u64) p << 32);
+}
 __device__ __forceinline__ u32 lazy_redc (u64 T, u32 p, u32 ninv)
 {
     u32 hi = reduce_word ((u32) (T >> 32), p);
@@ -379,7 +387,7 @@ struct HostCol
 
 struct slipcu_factor
 {
-    int n = 0, nz = 0, S = 0, CH = 16, threads = 512, device = 0;
+    int n = 0, nz = 0, S = 0, CH = 16, threads = 256, cpt = 4, device = 0;
     std::shared_ptr<Tables> tab;
     cudaStream_t st = nullptr;
     cudaEvent_t ev = nullptr, ev0 = nullptr, ev1 = nullptr;
@@ -490,7 +498,7 @@ __device__ __forceinline__ u32 smem_u32 (const void *p) { return (u32) __cvta_ge
 // symbolic pre-pass of a column: row -> slot map, then for every elimination step the list of
 // target slots (one per entry of the L column used), shared by all channel blocks.
 // ------------------------------------------------------------------------------------------------
-#define TRI_THREADS 256       // threads of a k_trisolve CTA
+#define TRI_THREADS 256       // threads of a k_trisolve CTA when a thread owns 4 channels
 #define TRI_BUFS 3            // shared-memory chunk buffers: two chunks in flight while one is consumed
 #define TRI_RING 8            // chunk descriptors kept in shared memory
 
@@ -648,20 +656,48 @@ __device__ __forceinline__ uint2 lds64 (u32 addr)
     return v;
 }
 
+// CPT (2 or 4) consecutive channels of one row, as one vector access
+template <int CPT> struct ChanVec { u32 v[CPT]; };
+template <int CPT> __device__ __forceinline__ ChanVec<CPT> ldv (const void *p)
+{
+    ChanVec<CPT> r;
+    if (CPT == 4) { const uint4 t = *reinterpret_cast<const uint4 *> (p); r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; }
+    else { const uint2 t = *reinterpret_cast<const uint2 *> (p); r.v[0] = t.x; r.v[1] = t.y; }
+    return r;
+}
+template <int CPT> __device__ __forceinline__ void stv (void *p, const ChanVec<CPT> &r)
+{
+    if (CPT == 4) *reinterpret_cast<uint4 *> (p) = make_uint4 (r.v[0], r.v[1], r.v[2], r.v[3]);
+    else *reinterpret_cast<uint2 *> (p) = make_uint2 (r.v[0], r.v[1]);
+}
+template <int CPT> __device__ __forceinline__ ChanVec<CPT> ldsv (u32 addr)
+{
+    ChanVec<CPT> r;
+    if (CPT == 4) { const uint4 t = lds128 (addr); r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; }
+    else { const uint2 t = lds64 (addr); r.v[0] = t.x; r.v[1] = t.y; }
+    return r;
+}
+template <int CPT> __device__ __forceinline__ ChanVec<CPT> mont_mulv (const ChanVec<CPT> &a, const ChanVec<CPT> &b, const ChanVec<CPT> &p, const ChanVec<CPT> &ni)
+{
+    ChanVec<CPT> r;
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) r.v[i] = mont_mul (a.v[i], b.v[i], p.v[i], ni.v[i]);
+    return r;
+}
 // w + l*ny  (ny = -yhat): one Montgomery product and a modular add per channel
-__device__ __forceinline__ uint4 mont_mul4 (const uint4 a, const uint4 b, const uint4 p, const uint4 ni)
+template <int CPT> __device__ __forceinline__ ChanVec<CPT> sub_mulv (const ChanVec<CPT> &w, const ChanVec<CPT> &l, const ChanVec<CPT> &ny, const ChanVec<CPT> &p, const ChanVec<CPT> &ni)
 {
-    return make_uint4 (mont_mul (a.x, b.x, p.x, ni.x), mont_mul (a.y, b.y, p.y, ni.y),
-                       mont_mul (a.z, b.z, p.z, ni.z), mont_mul (a.w, b.w, p.w, ni.w));
+    ChanVec<CPT> r;
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) r.v[i] = add_mod (w.v[i], mont_mul (l.v[i], ny.v[i], p.v[i], ni.v[i]), p.v[i]);
+    return r;
 }
-__device__ __forceinline__ uint4 sub_mul4 (const uint4 w, const uint4 l, const uint4 ny, const uint4 p, const uint4 ni)
+template <int CPT> __device__ __forceinline__ ChanVec<CPT> negv (const ChanVec<CPT> &y, const ChanVec<CPT> &p)
 {
-    return make_uint4 (add_mod (w.x, mont_mul (l.x, ny.x, p.x, ni.x), p.x), add_mod (w.y, mont_mul (l.y, ny.y, p.y, ni.y), p.y),
-                       add_mod (w.z, mont_mul (l.z, ny.z, p.z, ni.z), p.z), add_mod (w.w, mont_mul (l.w, ny.w, p.w, ni.w), p.w));
-}
-__device__ __forceinline__ uint4 neg4 (const uint4 y, const uint4 p)
-{
-    return make_uint4 (y.x ? p.x - y.x : 0u, y.y ? p.y - y.y : 0u, y.z ? p.z - y.z : 0u, y.w ? p.w - y.w : 0u);
+    ChanVec<CPT> r;
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) r.v[i] = y.v[i] ? p.v[i] - y.v[i] : 0u;
+    return r;
 }
 
 // All threads of the CTA are consumers; every thread also copies its share of the chunk that is
@@ -672,11 +708,14 @@ __device__ __forceinline__ uint4 neg4 (const uint4 y, const uint4 p)
 // copies per elimination step the copy engine, not HBM, set the pace -- about 1.1 us per step
 // regardless of pipeline depth; see profiles/.)  One __syncthreads per chunk both publishes the
 // landed chunk and orders the previous chunk's updates before the next yhat.
-template <int CH, bool XS>
-__global__ void __launch_bounds__ (TRI_THREADS, 2) k_trisolve (TriArgs a)
+// A thread owns CPT channels of a row: CPT = 4 gives 256-thread CTAs, CPT = 2 gives 512-thread CTAs
+// (twice the warps per SM for the same shared memory, at more instructions per element).
+template <int CH, bool XS, int CPT>
+__global__ void __launch_bounds__ (TRI_THREADS * 4 / CPT, 2) k_trisolve (TriArgs a)
 {
     typedef TriSmem<CH> SM;
-    constexpr int NT = TRI_THREADS, TPR = CH / 4, RG = SM::RG;
+    typedef ChanVec<CPT> V;
+    constexpr int NT = TRI_THREADS * 4 / CPT, TPR = CH / CPT, RG = SM::RG;
     extern __shared__ __align__ (128) unsigned char smem_raw[];
     const int tid = threadIdx.x;
     const int cb = blockIdx.x, S = a.S, cnt = a.cnt, nU = a.nU, nchunks = a.nchunks;
@@ -703,14 +742,17 @@ __global__ void __launch_bounds__ (TRI_THREADS, 2) k_trisolve (TriArgs a)
         const unsigned char *lsrc = (const unsigned char *) (((unsigned long long) d0.y << 32) | d0.x)
                                   + ((size_t) cb * d0.z) * 4 + (size_t) tid * 16;
         const u32 ldst = sb + (u32) tid * 16;
-        const int lp = nrows * TPR;                    // 16-byte pieces of L rows, at most 4 per thread
+        const int lp = nrows * (CH / 4);               // 16-byte pieces of L rows, at most CPT per thread
         if (tid < lp) cp_async16_off<0> (ldst, lsrc);
         if (tid + NT < lp) cp_async16_off<NT * 16> (ldst, lsrc);
-        if (tid + 2 * NT < lp) cp_async16_off<2 * NT * 16> (ldst, lsrc);
-        if (tid + 3 * NT < lp) cp_async16_off<3 * NT * 16> (ldst, lsrc);
+        if (CPT == 4)
+        {
+            if (tid + 2 * NT < lp) cp_async16_off<2 * NT * 16> (ldst, lsrc);
+            if (tid + 3 * NT < lp) cp_async16_off<3 * NT * 16> (ldst, lsrc);
+        }
         if (tid < min (nrows, RG))                     // one 16-byte group of targets per row group in use
             cp_async16 (sb + SM::L_BYTES + (u32) tid * 16, a.slots + (size_t) d0.w + (size_t) tid * 4);
-        if ((d1.y & 0x10000u) && tid < TPR)
+        if ((d1.y & 0x10000u) && tid < CH / 4)
             cp_async16 (sb + SM::L_BYTES + SM::S_BYTES + (u32) tid * 16,
                         a.invrho + (size_t) d1.x * S + (size_t) cb * CH + 4 * tid);
     };
@@ -735,12 +777,13 @@ __global__ void __launch_bounds__ (TRI_THREADS, 2) k_trisolve (TriArgs a)
         }
     }
 
-    const int q4 = (tid % TPR) * 4, rg = tid / TPR;
-    const int c0 = cb * CH + q4;
-    const uint4 p4 = *reinterpret_cast<const uint4 *> (a.p + c0);
-    const uint4 ni4 = *reinterpret_cast<const uint4 *> (a.ninv + c0);
-    unsigned char *xb = (unsigned char *) xs + q4 * 4;             // this thread's channels of row 0
-    uint4 negy = make_uint4 (0, 0, 0, 0);
+    const int qc = (tid % TPR) * CPT, rg = tid / TPR;  // first channel of this thread inside the block, row group
+    const int c0 = cb * CH + qc;
+    const V pv = ldv<CPT> (a.p + c0), niv = ldv<CPT> (a.ninv + c0);
+    unsigned char *xb = (unsigned char *) xs + qc * 4;             // this thread's channels of row 0
+    V negy;
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) negy.v[i] = 0;
     int u = 0;                                         // elimination step of the current chunk
     int bc = 0, bi = TRI_BUFS - 1;                     // buffers of the chunk consumed / requested
     for (int c = 0; c < nchunks; ++c)
@@ -754,8 +797,8 @@ __global__ void __launch_bounds__ (TRI_THREADS, 2) k_trisolve (TriArgs a)
         const u32 meta = lds64 (ring + (u32) (c % TRI_RING) * (u32) sizeof (ChunkInfo) + 16).y;
         if (meta & 0x10000u)
         {   // yhat_j = w_j / rho_j
-            const uint4 wj = *reinterpret_cast<const uint4 *> (xb + (size_t) u * CH * 4);
-            negy = neg4 (mont_mul4 (wj, lds128 (sb + SM::L_BYTES + SM::S_BYTES + q4 * 4), p4, ni4), p4);
+            const V wj = ldv<CPT> (xb + (size_t) u * CH * 4);
+            negy = negv<CPT> (mont_mulv<CPT> (wj, ldsv<CPT> (sb + SM::L_BYTES + SM::S_BYTES + qc * 4), pv, niv), pv);
         }
         // rows of one step hit distinct slots: the four rows of a thread are loaded, updated and
         // stored together so that their latencies overlap
@@ -763,18 +806,17 @@ __global__ void __launch_bounds__ (TRI_THREADS, 2) k_trisolve (TriArgs a)
         {
             const uint4 tq = lds128 (sb + SM::L_BYTES + (u32) rg * 16);
             const u32 t[4] = { tq.x, tq.y, tq.z, tq.w };
-            const u32 lrow = sb + (u32) rg * (CH * 4) + q4 * 4;
-            uint4 l[4], w[4];
+            const u32 lrow = sb + (u32) rg * (CH * 4) + qc * 4;
+            V l[4], w[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q)
             {
-                l[q] = lds128 (lrow + q * RG * CH * 4);
-                if (XS || t[q] != spare) w[q] = *reinterpret_cast<const uint4 *> (xb + t[q]);
+                l[q] = ldsv<CPT> (lrow + q * RG * CH * 4);
+                if (XS || t[q] != spare) w[q] = ldv<CPT> (xb + t[q]);
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-                if (XS || t[q] != spare)
-                    *reinterpret_cast<uint4 *> (xb + t[q]) = sub_mul4 (w[q], l[q], negy, p4, ni4);
+                if (XS || t[q] != spare) stv<CPT> (xb + t[q], sub_mulv<CPT> (w[q], l[q], negy, pv, niv));
         }
         if (meta & 0x20000u) ++u;
         bc = (bc == TRI_BUFS - 1) ? 0 : bc + 1;
@@ -784,10 +826,10 @@ __global__ void __launch_bounds__ (TRI_THREADS, 2) k_trisolve (TriArgs a)
     // publish the column as true REF values: U(j,k) = w_j rho_{j-1}, candidates = w_t rho_{k-1}
     for (int t = rg; t < cnt; t += RG)
     {
-        uint4 v = *reinterpret_cast<const uint4 *> (xs + t * CH + q4);
+        V v = ldv<CPT> (xs + t * CH + qc);
         const int lvl = (t < nU) ? a.steps[t].j : a.k;           // level the entry is brought to
-        if (lvl >= 1) v = mont_mul4 (v, *reinterpret_cast<const uint4 *> (a.rho + (size_t) (lvl - 1) * S + c0), p4, ni4);
-        *reinterpret_cast<uint4 *> (xg + t * CH + q4) = v;
+        if (lvl >= 1) v = mont_mulv<CPT> (v, ldv<CPT> (a.rho + (size_t) (lvl - 1) * S + c0), pv, niv);
+        stv<CPT> (xg + t * CH + qc, v);
     }
 }
 
@@ -1179,8 +1221,8 @@ __global__ void __launch_bounds__ (384) k_garner_flow (GarnerArgs a)
                 for (int e = 0; e < E; ++e)
                 {
                     const uint4 d4 = *reinterpret_cast<const uint4 *> (db + e * 32 + q + r);
-                    lazy_mac (T[e], d4.x, c[r], p); lazy_mac (T[e], d4.y, c[r + 1], p);
-                    lazy_mac (T[e], d4.z, c[r + 2], p); lazy_mac (T[e], d4.w, c[r + 3], p);
+                    lazy_mac2 (T[e], d4.x, c[r], d4.y, c[r + 1], p);
+                    lazy_mac2 (T[e], d4.z, c[r + 2], d4.w, c[r + 3], p);
                 }
             }
         }
@@ -1558,6 +1600,30 @@ static int ensure_digits (slipcu_factor *F, size_t rows)
     return SLIPCU_OK;
 }
 
+// opt the k_trisolve instances in to the full shared memory of the SM
+template <int CH, bool XS, int CPT> static cudaError_t tri_configure_one (int smem_optin)
+{
+    cudaError_t e = cudaFuncSetAttribute (k_trisolve<CH, XS, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute (k_trisolve<CH, XS, CPT>, cudaFuncAttributePreferredSharedMemoryCarveout, (int) cudaSharedmemCarveoutMaxShared);
+}
+template <int CPT> static cudaError_t tri_configure_cpt (int smem_optin)
+{
+    cudaError_t e;
+    if ((e = tri_configure_one<8, true, CPT> (smem_optin)) != cudaSuccess) return e;
+    if ((e = tri_configure_one<16, true, CPT> (smem_optin)) != cudaSuccess) return e;
+    if ((e = tri_configure_one<32, true, CPT> (smem_optin)) != cudaSuccess) return e;
+    if ((e = tri_configure_one<8, false, CPT> (smem_optin)) != cudaSuccess) return e;
+    if ((e = tri_configure_one<16, false, CPT> (smem_optin)) != cudaSuccess) return e;
+    return tri_configure_one<32, false, CPT> (smem_optin);
+}
+static int tri_configure (int smem_optin)
+{
+    CU (tri_configure_cpt<4> (smem_optin));
+    CU (tri_configure_cpt<2> (smem_optin));
+    return SLIPCU_OK;
+}
+
 // everything a session needs apart from the input matrix
 static int session_common_init (slipcu_factor *F, int n, int channels)
 {
@@ -1582,7 +1648,6 @@ static int session_common_init (slipcu_factor *F, int n, int channels)
     CH = env_int ("SLIP_B200_CH", CH);
     if (CH != 8 && CH != 16 && CH != 32) CH = 16;
     F->CH = CH;
-    F->threads = TRI_THREADS;
     F->sms = sms;
     F->x_global = env_int ("SLIP_B200_X_GLOBAL", 0);
     F->garner_mode = env_int ("SLIP_B200_GARNER", 2);
@@ -1590,20 +1655,11 @@ static int session_common_init (slipcu_factor *F, int n, int channels)
     int smem_optin = 0;
     cudaDeviceGetAttribute (&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, F->device);
     F->smem_limit = (size_t) smem_optin;
-    CU (cudaFuncSetAttribute (k_trisolve<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
-    CU (cudaFuncSetAttribute (k_trisolve<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
-    CU (cudaFuncSetAttribute (k_trisolve<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
-    CU (cudaFuncSetAttribute (k_trisolve<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
-    CU (cudaFuncSetAttribute (k_trisolve<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
-    CU (cudaFuncSetAttribute (k_trisolve<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
-    if (env_int ("SLIP_B200_CARVEOUT", 1))
-    {   // ask for the full shared-memory carve-out so that two CTAs stay resident per SM
-        const int mx = (int) cudaSharedmemCarveoutMaxShared;
-        cudaFuncSetAttribute (k_trisolve<8, true>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-        cudaFuncSetAttribute (k_trisolve<16, true>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-        cudaFuncSetAttribute (k_trisolve<32, true>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-        cudaGetLastError ();
-    }
+    F->cpt = env_int ("SLIP_B200_CPT", 4);             // channels per thread of k_trisolve: 4 or 2
+    if (F->cpt != 2 && F->cpt != 4) F->cpt = 4;
+    F->threads = TRI_THREADS * 4 / F->cpt;
+    rc = tri_configure (smem_optin);
+    if (rc) return rc;
 
     CU (cudaStreamCreateWithFlags (&F->st, cudaStreamNonBlocking));
     CU (cudaEventCreateWithFlags (&F->ev, cudaEventDisableTiming));
@@ -1665,11 +1721,11 @@ extern "C" int slipcu_factor_begin (slipcu_factor **out, int n, int nz, const in
     return SLIPCU_OK;
 }
 
-template <int CH>
-static cudaError_t launch_tri (const TriArgs &a, dim3 grid, int threads, size_t smem, cudaStream_t st)
+template <int CH, int CPT>
+static cudaError_t launch_tri (const TriArgs &a, dim3 grid, size_t smem, cudaStream_t st)
 {
-    if (a.x_in_smem) k_trisolve<CH, true><<<grid, threads, smem, st>>> (a);
-    else k_trisolve<CH, false><<<grid, threads, smem, st>>> (a);
+    if (a.x_in_smem) k_trisolve<CH, true, CPT><<<grid, TRI_THREADS * 4 / CPT, smem, st>>> (a);
+    else k_trisolve<CH, false, CPT><<<grid, TRI_THREADS * 4 / CPT, smem, st>>> (a);
     return cudaGetLastError ();
 }
 static size_t tri_smem_bytes (int CH, int cnt, bool x_in_smem)
@@ -1678,12 +1734,18 @@ static size_t tri_smem_bytes (int CH, int cnt, bool x_in_smem)
     if (CH == 16) return TriSmem<16>::total (cnt, x_in_smem);
     return TriSmem<32>::total (cnt, x_in_smem);
 }
-static cudaError_t launch_tri_any (int CH, const TriArgs &a, dim3 grid, int threads, size_t smem, cudaStream_t st)
+static cudaError_t launch_tri_any (int CH, int cpt, const TriArgs &a, dim3 grid, size_t smem, cudaStream_t st)
 {
     g_launches++; g_tri_launches++;
-    if (CH == 8) return launch_tri<8> (a, grid, threads, smem, st);
-    if (CH == 16) return launch_tri<16> (a, grid, threads, smem, st);
-    return launch_tri<32> (a, grid, threads, smem, st);
+    if (cpt == 2)
+    {
+        if (CH == 8) return launch_tri<8, 2> (a, grid, smem, st);
+        if (CH == 16) return launch_tri<16, 2> (a, grid, smem, st);
+        return launch_tri<32, 2> (a, grid, smem, st);
+    }
+    if (CH == 8) return launch_tri<8, 4> (a, grid, smem, st);
+    if (CH == 16) return launch_tri<16, 4> (a, grid, smem, st);
+    return launch_tri<32, 4> (a, grid, smem, st);
 }
 
 // symbolic pre-pass on the device: pos[], the slot lists and the step table of a column whose
@@ -1874,7 +1936,7 @@ extern "C" int slipcu_factor_column_launch (slipcu_factor *F, int k, int col, in
     if (rc) return rc;
     {
         ScopedTimer tm (F, &g_tri_ms);
-        CU (launch_tri_any (CH, a, dim3 (S / CH, 1), F->threads, smem, F->st));
+        CU (launch_tri_any (CH, F->cpt, a, dim3 (S / CH, 1), smem, F->st));
         if (debug_check ("k_trisolve(column)", F->st)) return fail (SLIPCU_CUDA_ERROR, "k_trisolve", "debug");
     }
     g_hw[2] += wall_s () - tw; tw = wall_s ();
@@ -2197,7 +2259,7 @@ extern "C" int slipcu_solve (slipcu_factor *F, int nrhs, const u32 *blimbs, cons
         size_t smem = 0;
         rc = tri_geometry (F, a, &smem);
         if (rc) goto done;
-        CUG (launch_tri_any (CH, a, dim3 (S / CH, nb), F->threads, smem, F->st));
+        CUG (launch_tri_any (CH, F->cpt, a, dim3 (S / CH, nb), smem, F->st));
         if (debug_check ("k_trisolve(forward)", F->st)) { rc = fail (SLIPCU_CUDA_ERROR, "k_trisolve(forward)", "debug"); goto done; }
         BackArgs b;
         b.n = n; b.S = S; b.z = dz; b.z_y_stride = (size_t) n * S;

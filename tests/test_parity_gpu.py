@@ -236,7 +236,8 @@ def test_channel_prime_dividing_a_pivot_is_retired(gpu, oracle):
 
 @pytest.mark.parametrize("env", [{"SLIP_B200_CH": "16"}, {"SLIP_B200_CH": "32"}, {"SLIP_B200_X_GLOBAL": "1"},
                                  {"SLIP_B200_CH": "32", "SLIP_B200_X_GLOBAL": "1"}, {"SLIP_B200_GARNER": "1"},
-                                 {"SLIP_B200_GARNER": "0"}])
+                                 {"SLIP_B200_GARNER": "0"}, {"SLIP_B200_CPT": "2"}, {"SLIP_B200_CPT": "4"},
+                                 {"SLIP_B200_CPT": "2", "SLIP_B200_CH": "32", "SLIP_B200_X_GLOBAL": "1"}])
 def test_kernel_variants_agree(gpu, oracle, env):
     """The kernel configurations that large problems select automatically (wider channel blocks,
     work vector in global memory when the pattern outgrows shared memory, the other Garner
@@ -260,3 +261,31 @@ def test_kernel_variants_agree(gpu, oracle, env):
             else:
                 os.environ[k] = v
     cases.assert_same_factorization(got, want, str(env))
+
+
+_MULTI_CHUNK = {}
+
+
+@pytest.mark.parametrize("cpt", ["4", "2"])
+def test_steps_spanning_several_chunks(gpu, oracle, cpt):
+    """With 32-channel blocks a pipeline chunk holds 128 rows, so the dense trailing columns of this
+    case are eliminated in several chunks per step (first/last-chunk flags, descriptor ring wrap)."""
+    n, cp, ri, vals, b = synth.random_sparse(300, 9, 24, seed=5, nrhs=1)
+    q = cases.colamd_like_order(n, cp, ri)
+    if "want" not in _MULTI_CHUNK:
+        _MULTI_CHUNK["want"] = cases.run_oracle(oracle, n, cp, ri, vals, b, q)
+    want = _MULTI_CHUNK["want"]
+    env = {"SLIP_B200_CH": "32", "SLIP_B200_CPT": cpt}
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        got = cases.run_library(gpu, n, cp, ri, vals, b, q)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    cases.assert_same_factorization(got, want, f"multi-chunk cpt={cpt}")
+    lp = want["L"][0]
+    assert max(lp[k + 1] - lp[k] for k in range(n)) > 128, "case too sparse to span two chunks"

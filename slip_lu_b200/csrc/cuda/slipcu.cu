@@ -387,7 +387,7 @@ struct HostCol
 
 struct slipcu_factor
 {
-    int n = 0, nz = 0, S = 0, CH = 16, threads = 256, cpt = 4, device = 0;
+    int n = 0, nz = 0, S = 0, CH = 16, threads = 256, cpt = 4, garner_e = 0, device = 0;
     std::shared_ptr<Tables> tab;
     cudaStream_t st = nullptr;
     cudaEvent_t ev = nullptr, ev0 = nullptr, ev1 = nullptr;
@@ -1173,7 +1173,7 @@ __global__ void __launch_bounds__ (512) k_garner_tiled (GarnerArgs a)
 // other warps carry out behind it.  Requires all digit blocks to fit one tile (B <= W*BPW).
 // ------------------------------------------------------------------------------------------------
 template <int E, int BPW>
-__global__ void __launch_bounds__ (384) k_garner_flow (GarnerArgs a)
+__global__ void __launch_bounds__ (384, 1) k_garner_flow (GarnerArgs a)
 {
     extern __shared__ __align__ (16) unsigned char gsm[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, W = blockDim.x >> 5;
@@ -1651,7 +1651,13 @@ static int session_common_init (slipcu_factor *F, int n, int channels)
     F->sms = sms;
     F->x_global = env_int ("SLIP_B200_X_GLOBAL", 0);
     F->garner_mode = env_int ("SLIP_B200_GARNER", 2);
+    CU (cudaFuncSetAttribute (k_garner_flow<1, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CU (cudaFuncSetAttribute (k_garner_flow<2, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CU (cudaFuncSetAttribute (k_garner_flow<3, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     CU (cudaFuncSetAttribute (k_garner_flow<4, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CU (cudaFuncSetAttribute (k_garner_flow<5, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CU (cudaFuncSetAttribute (k_garner_flow<6, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    F->garner_e = env_int ("SLIP_B200_GARNER_E", 0);       // 0: chosen per launch
     int smem_optin = 0;
     cudaDeviceGetAttribute (&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, F->device);
     F->smem_limit = (size_t) smem_optin;
@@ -1828,11 +1834,38 @@ static int run_garner (slipcu_factor *F, const u32 *base, int region_cnt, int e0
         const int blocks = (s + 31) / 32;
         int W = (blocks + 4) / 5;
         W = std::max (4, std::min (16, W));      // >= E warps: the epilogue uses one warp per entry
-        const int Wf = std::max (4, (blocks + 5) / 6);          // dataflow variant: 6 blocks per warp
-        const size_t fsm = (size_t) blocks * 4 * 32 * sizeof (u32) + (size_t) blocks * sizeof (int) + (size_t) Wf * 4096 + 16;
-        if (false) { }
-        else if (F->garner_mode >= 2 && Wf <= 12 && fsm <= 160 * 1024)
-            k_garner_flow<4, 6><<<(ne + 3) / 4, Wf * 32, fsm, F->st>>> (g);
+        const int Wf = std::max (6, (blocks + 5) / 6);          // dataflow variant: 6 blocks per warp
+        if (F->garner_mode >= 2 && Wf <= 12)
+        {
+            // A CTA reconstructs E entries; its run time grows with E (measured, relative, in
+            // garner_cost) and the grid runs in waves of one CTA per SM: take the E with the least
+            // waves x cost.  (Cutting a launch into pieces with different E was measured slower:
+            // separate launches do not overlap their tails.)
+            static const int garner_cost[7] = { 0, 180, 260, 345, 420, 518, 625 };
+            int E = 1;
+            if (F->garner_e) E = std::max (1, std::min (6, F->garner_e));
+            else
+            {
+                long bestc = -1;
+                for (int e = 1; e <= 6; ++e)
+                {
+                    const long waves = ((ne + e - 1) / e + F->sms - 1) / F->sms;
+                    const long c = waves * garner_cost[e];
+                    if (bestc < 0 || c < bestc) { bestc = c; E = e; }
+                }
+            }
+            const size_t fsm = (size_t) blocks * E * 32 * sizeof (u32) + (size_t) blocks * sizeof (int) + (size_t) Wf * 4096 + 16;
+            const int grid = (ne + E - 1) / E;
+            switch (E)
+            {
+                case 1: k_garner_flow<1, 6><<<grid, Wf * 32, fsm, F->st>>> (g); break;
+                case 2: k_garner_flow<2, 6><<<grid, Wf * 32, fsm, F->st>>> (g); break;
+                case 3: k_garner_flow<3, 6><<<grid, Wf * 32, fsm, F->st>>> (g); break;
+                case 4: k_garner_flow<4, 6><<<grid, Wf * 32, fsm, F->st>>> (g); break;
+                case 5: k_garner_flow<5, 6><<<grid, Wf * 32, fsm, F->st>>> (g); break;
+                default: k_garner_flow<6, 6><<<grid, Wf * 32, fsm, F->st>>> (g); break;
+            }
+        }
         else
             k_garner_tiled<4, 5><<<(ne + 3) / 4, W * 32, 0, F->st>>> (g);
     }

@@ -16,6 +16,12 @@ ROOT = os.path.dirname(HERE)
 INC = os.path.join(ROOT, "include")
 OUT = os.path.join(HERE, "libslip_lu_b200.so")
 BUILD = os.path.join(HERE, "csrc", "_build")
+# SuiteSparse COLAMD/AMD (third-party prerequisite of SLIP_LU_analyze, like GMP): a system
+# libcolamd/libamd is used when present; this image has none, so the packages are compiled from a
+# SuiteSparse source tree (the copy the reference distribution vendors) into _deps/.
+SUITESPARSE_SRC = os.environ.get("SLIP_B200_SUITESPARSE_SRC", "/root/reference")
+DEPS = os.path.join(HERE, "_deps")
+ORDERING_SO = os.path.join(DEPS, "libsuitesparse_ordering.so")
 
 
 def _have_system_gmp_header() -> bool:
@@ -37,7 +43,23 @@ def _stale(target: str, sources) -> bool:
     return any(os.path.getmtime(s) > t for s in sources)
 
 
+def build_ordering(force: bool = False) -> str | None:
+    """libsuitesparse_ordering.so = SuiteSparse COLAMD + AMD + SuiteSparse_config, unmodified, compiled
+    from SUITESPARSE_SRC where it lies (nothing is copied into the repository)."""
+    col = os.path.join(SUITESPARSE_SRC, "COLAMD", "Source", "colamd.c")
+    if not os.path.exists(col):
+        return ORDERING_SO if os.path.exists(ORDERING_SO) else None
+    src = [col, os.path.join(SUITESPARSE_SRC, "SuiteSparse_config", "SuiteSparse_config.c")]
+    src += sorted(glob.glob(os.path.join(SUITESPARSE_SRC, "AMD", "Source", "*.c")))
+    if force or _stale(ORDERING_SO, src):
+        os.makedirs(DEPS, exist_ok=True)
+        inc = ["-I" + os.path.join(SUITESPARSE_SRC, d) for d in ("SuiteSparse_config", "COLAMD/Include", "AMD/Include")]
+        subprocess.check_call(["gcc", "-O2", "-fPIC", "-w", "-shared"] + inc + ["-o", ORDERING_SO] + src + ["-lm"])
+    return ORDERING_SO
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    build_ordering(force)
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     os.makedirs(BUILD, exist_ok=True)
     headers = glob.glob(os.path.join(INC, "*.h")) + glob.glob(os.path.join(HERE, "csrc", "host", "*.h"))

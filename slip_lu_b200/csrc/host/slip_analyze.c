@@ -4,8 +4,10 @@
  * COLAMD and AMD are SuiteSparse packages (separate libraries, libcolamd / libamd; the reference
  * vendors copies of them).  They are host-side preprocessing outside the hot path, so this
  * library does not re-implement them: it calls `colamd` / `amd_order` from the SuiteSparse
- * libraries found at run time (SLIP_B200_ORDERING_LIB, or libcolamd.so / libamd.so on the loader
- * path).  SLIP_NO_ORDERING and a caller-supplied S->q need nothing. */
+ * libraries found at run time: SLIP_B200_ORDERING_LIB if set, else the build of SuiteSparse that
+ * slip_lu_b200/build.py places next to this library (_deps/libsuitesparse_ordering.so), else
+ * libcolamd.so / libamd.so on the loader path.  SLIP_NO_ORDERING and a caller-supplied S->q need
+ * nothing. */
 #define _GNU_SOURCE
 #include <dlfcn.h>
 #include "slip_internal.h"
@@ -19,6 +21,24 @@ static void *open_ordering_lib (const char *fallback1, const char *fallback2)
     const char *env = getenv ("SLIP_B200_ORDERING_LIB") ;
     void *h = NULL ;
     if (env && *env) h = dlopen (env, RTLD_NOW | RTLD_LOCAL) ;
+    if (!h)
+    {   /* <directory of this shared library>/_deps/libsuitesparse_ordering.so */
+        Dl_info me ;
+        if (dladdr ((void *) &SLIP_LU_analyze, &me) && me.dli_fname)
+        {
+            const char *slash = strrchr (me.dli_fname, '/') ;
+            size_t dir = slash ? (size_t) (slash - me.dli_fname) : 0 ;
+            static const char tail [] = "/_deps/libsuitesparse_ordering.so" ;
+            char *path = (char *) SLIP_malloc (dir + sizeof (tail) + 2) ;
+            if (path)
+            {
+                if (dir) memcpy (path, me.dli_fname, dir) ; else { path [0] = '.' ; dir = 1 ; }
+                memcpy (path + dir, tail, sizeof (tail)) ;
+                h = dlopen (path, RTLD_NOW | RTLD_LOCAL) ;
+                SLIP_free (path) ;
+            }
+        }
+    }
     if (!h) h = dlopen (fallback1, RTLD_NOW | RTLD_LOCAL) ;
     if (!h && fallback2) h = dlopen (fallback2, RTLD_NOW | RTLD_LOCAL) ;
     return h ;

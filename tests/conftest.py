@@ -7,11 +7,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-# COLAMD/AMD are SuiteSparse libraries the product loads at run time; in this image the only
-# build of them is inside the reference library compiled under oracle/_ref (checker side).
-_ref = os.path.join(ROOT, "oracle", "_ref", "libslip_ref.so")
-if os.path.exists(_ref):
-    os.environ.setdefault("SLIP_B200_ORDERING_LIB", _ref)
+
+
+def have_ordering_library() -> bool:
+    """COLAMD/AMD are SuiteSparse libraries the product loads at run time: its own build of them
+    (slip_lu_b200/_deps, made by slip_lu_b200/build.py) or whatever SLIP_B200_ORDERING_LIB names."""
+    from slip_lu_b200 import build as b
+    return bool(os.environ.get("SLIP_B200_ORDERING_LIB")) or os.path.exists(b.ORDERING_SO)
 
 
 def pytest_configure(config):

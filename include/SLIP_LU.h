@@ -8,10 +8,9 @@
  * SLIP_LU_factorize / SLIP_LU_solve / SLIP_solve_* runs on an NVIDIA B200 (sm_100a); the
  * library has no CPU path for it and returns an error if no device is present.
  *
- * Not (yet) provided: the mpfr_t input builders and SLIP_solve_mpfr / SLIP_get_mpfr_soln
- * (ref:454-463, 523-532, 585-592, 899-907, 975-982), the SLIP_mpz_ / SLIP_mpq_ / SLIP_mpfr_ GMP wrappers
- * (ref:1023-1156), and this fork's experimental SLIP_LU_analyze_and_factorize{,1}
- * (ref:866-886).  See DESIGN.md "scope".
+ * Not provided: the SLIP_mpz_ / SLIP_mpq_ / SLIP_mpfr_ GMP wrappers (ref:1023-1156; call GMP/MPFR
+ * directly) and this fork's experimental SLIP_LU_analyze_and_factorize{,1} (ref:866-886).  See
+ * DESIGN.md "scope".
  */
 #ifndef SLIP_Include
 #define SLIP_Include
@@ -142,11 +141,17 @@ SLIP_info SLIP_build_sparse_trip_int (SLIP_sparse *A_output, int32_t *I, int32_t
     int32_t n, int32_t nz) ;
 SLIP_info SLIP_build_sparse_trip_mpq (SLIP_sparse *A_output, int32_t *I, int32_t *J, mpq_t *x,
     int32_t n, int32_t nz) ;
+SLIP_info SLIP_build_sparse_ccf_mpfr (SLIP_sparse *A_output, int32_t *p, int32_t *I, mpfr_t *x,
+    int32_t n, int32_t nz, SLIP_options *option) ;                 /* ref:454-463 */
+SLIP_info SLIP_build_sparse_trip_mpfr (SLIP_sparse *A_output, int32_t *I, int32_t *J, mpfr_t *x,
+    int32_t n, int32_t nz, SLIP_options *option) ;                 /* ref:523-532 */
 SLIP_info SLIP_build_dense_mpz (SLIP_dense *A_output, mpz_t **b, int32_t m, int32_t n) ;
 SLIP_info SLIP_build_dense_double (SLIP_dense *A_output, double **b, int32_t m, int32_t n,
     SLIP_options *option) ;
 SLIP_info SLIP_build_dense_int (SLIP_dense *A_output, int32_t **b, int32_t m, int32_t n) ;
 SLIP_info SLIP_build_dense_mpq (SLIP_dense *A_output, mpq_t **b, int32_t m, int32_t n) ;
+SLIP_info SLIP_build_dense_mpfr (SLIP_dense *A_output, mpfr_t **b, int32_t m, int32_t n,
+    SLIP_options *option) ;                                        /* ref:585-592 */
 
 /* ---- 2D and 1D helper containers (ref:602-797) ---- */
 double **SLIP_create_double_mat (int32_t m, int32_t n) ;
@@ -157,6 +162,10 @@ mpq_t **SLIP_create_mpq_mat (int32_t m, int32_t n) ;
 void SLIP_delete_mpq_mat (mpq_t ***A, int32_t m, int32_t n) ;
 mpz_t **SLIP_create_mpz_mat (int32_t m, int32_t n) ;
 void SLIP_delete_mpz_mat (mpz_t ***A, int32_t m, int32_t n) ;
+mpfr_t **SLIP_create_mpfr_mat (int32_t m, int32_t n, SLIP_options *option) ;
+void SLIP_delete_mpfr_mat (mpfr_t ***A, int32_t m, int32_t n) ;
+mpfr_t *SLIP_create_mpfr_array (int32_t n, SLIP_options *option) ;
+void SLIP_delete_mpfr_array (mpfr_t **x, int32_t n) ;
 mpq_t *SLIP_create_mpq_array (int32_t n) ;
 void SLIP_delete_mpq_array (mpq_t **x, int32_t n) ;
 mpz_t *SLIP_create_mpz_array (int32_t n) ;
@@ -178,10 +187,14 @@ SLIP_info SLIP_solve_mpq (mpq_t **x_mpq, SLIP_sparse *A, SLIP_LU_analysis *S, SL
     SLIP_options *option) ;
 SLIP_info SLIP_solve_double (double **x_doub, SLIP_sparse *A, SLIP_LU_analysis *S, SLIP_dense *b,
     SLIP_options *option) ;
+SLIP_info SLIP_solve_mpfr (mpfr_t **x_mpfr, SLIP_sparse *A, SLIP_LU_analysis *S, SLIP_dense *b,
+    SLIP_options *option) ;                                        /* ref:899-907 */
 SLIP_info SLIP_permute_x (mpq_t **x, int32_t n, int32_t numRHS, SLIP_LU_analysis *S) ;
 SLIP_info SLIP_scale_x (mpq_t **x, SLIP_sparse *A, SLIP_dense *b) ;
 SLIP_info SLIP_check_solution (SLIP_sparse *A, mpq_t **x, SLIP_dense *b) ;
 SLIP_info SLIP_get_double_soln (double **x_doub, mpq_t **x_mpq, int32_t n, int32_t numRHS) ;
+SLIP_info SLIP_get_mpfr_soln (mpfr_t **x_mpfr, mpq_t **x_mpq, int32_t n, int32_t numRHS,
+    SLIP_options *option) ;                                        /* ref:975-982 */
 SLIP_info SLIP_spok (SLIP_sparse *A, SLIP_options *option) ;
 
 /* ---- extensions of this implementation (not in the reference header) ----

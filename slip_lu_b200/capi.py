@@ -33,6 +33,12 @@ class MpqStruct(C.Structure):
     _fields_ = [("_mp_num", MpzStruct), ("_mp_den", MpzStruct)]
 
 
+class MpfrStruct(C.Structure):
+    # __mpfr_struct of MPFR 4 (x86-64): precision, sign, exponent, limb pointer
+    _fields_ = [("_mpfr_prec", C.c_long), ("_mpfr_sign", C.c_int), ("_mpfr_exp", C.c_long),
+                ("_mpfr_d", C.c_void_p)]
+
+
 class SLIP_options(C.Structure):
     # reference: SLIP_LU/Include/SLIP_LU.h:212-223
     _fields_ = [("pivot", C.c_int), ("order", C.c_int), ("tol", C.c_double),
@@ -117,6 +123,51 @@ def gmp() -> _Gmp:
     return _gmp
 
 
+_mpfr = None
+
+
+def mpfr() -> C.CDLL:
+    """libmpfr with the few entry points the tests need (values in and out of mpfr_t)."""
+    global _mpfr
+    if _mpfr is None:
+        gmp()
+        for name in ("libmpfr.so.6", "libmpfr.so", ctypes.util.find_library("mpfr")):
+            if not name:
+                continue
+            try:
+                _mpfr = C.CDLL(name, mode=C.RTLD_GLOBAL)
+                break
+            except OSError:
+                continue
+        if _mpfr is None:
+            raise OSError("libmpfr not found")
+        F, Z = C.POINTER(MpfrStruct), C.POINTER(MpzStruct)
+        _mpfr.mpfr_set_str.restype, _mpfr.mpfr_set_str.argtypes = C.c_int, [F, C.c_char_p, C.c_int, C.c_int]
+        _mpfr.mpfr_get_z_2exp.restype, _mpfr.mpfr_get_z_2exp.argtypes = C.c_long, [Z, F]
+    return _mpfr
+
+
+def mpfr_set_decimal(x, text: str, rnd: int = 0) -> None:
+    """x (an initialised mpfr_t element) = the decimal string, rounded to x's precision."""
+    xp = x if isinstance(x, C.POINTER(MpfrStruct)) else C.pointer(x)
+    if mpfr().mpfr_set_str(xp, text.encode(), 10, rnd) != 0:
+        raise ValueError(f"bad mpfr literal {text!r}")
+
+
+def mpfr_to_pair(x) -> Tuple[int, int]:
+    """Exact value of a finite mpfr as (mantissa, exponent): mantissa * 2**exponent; zero is (0, 0)."""
+    xp = x if isinstance(x, C.POINTER(MpfrStruct)) else C.pointer(x)
+    g = gmp()
+    z = MpzStruct()
+    g.mpz_init(C.byref(z))
+    e = mpfr().mpfr_get_z_2exp(C.byref(z), xp)
+    m = mpz_to_int(z)
+    g.mpz_clear(C.byref(z))
+    while m and m % 2 == 0:          # normalise so that equal values compare equal
+        m //= 2; e += 1
+    return (m, e) if m else (0, 0)
+
+
 def mpz_to_int(z: MpzStruct) -> int:
     """Read a GMP integer's limbs directly (no library call)."""
     sz = z._mp_size
@@ -196,6 +247,20 @@ class SlipLib:
             "SLIP_solve_double": (C.c_int, [P(P(C.c_double)), P(SLIP_sparse), P(SLIP_LU_analysis),
                                            P(SLIP_dense), P(SLIP_options)]),
             "SLIP_check_solution": (C.c_int, [P(SLIP_sparse), P(P(MpqStruct)), P(SLIP_dense)]),
+            "SLIP_create_mpfr_array": (P(MpfrStruct), [C.c_int32, P(SLIP_options)]),
+            "SLIP_delete_mpfr_array": (None, [P(P(MpfrStruct)), C.c_int32]),
+            "SLIP_create_mpfr_mat": (P(P(MpfrStruct)), [C.c_int32, C.c_int32, P(SLIP_options)]),
+            "SLIP_delete_mpfr_mat": (None, [P(P(P(MpfrStruct))), C.c_int32, C.c_int32]),
+            "SLIP_build_sparse_ccf_mpfr": (C.c_int, [P(SLIP_sparse), P(C.c_int32), P(C.c_int32),
+                                                    P(MpfrStruct), C.c_int32, C.c_int32, P(SLIP_options)]),
+            "SLIP_build_sparse_trip_mpfr": (C.c_int, [P(SLIP_sparse), P(C.c_int32), P(C.c_int32),
+                                                     P(MpfrStruct), C.c_int32, C.c_int32, P(SLIP_options)]),
+            "SLIP_build_dense_mpfr": (C.c_int, [P(SLIP_dense), P(P(MpfrStruct)), C.c_int32, C.c_int32,
+                                               P(SLIP_options)]),
+            "SLIP_solve_mpfr": (C.c_int, [P(P(MpfrStruct)), P(SLIP_sparse), P(SLIP_LU_analysis),
+                                         P(SLIP_dense), P(SLIP_options)]),
+            "SLIP_get_mpfr_soln": (C.c_int, [P(P(MpfrStruct)), P(P(MpqStruct)), C.c_int32, C.c_int32,
+                                            P(SLIP_options)]),
             "SLIP_create_double_mat": (P(P(C.c_double)), [C.c_int32, C.c_int32]),
             "SLIP_delete_double_mat": (None, [P(P(P(C.c_double))), C.c_int32, C.c_int32]),
         }

@@ -132,6 +132,83 @@ SLIP_info slip_expand_double_mat (mpz_t **x_out, double **x, mpq_t scale, int32_
     return status ;
 }
 
+/* ---- mpfr -> integer: x_out = round (10^prec * x) / gcd, scale = 10^prec / gcd, with 10^prec
+ * itself rounded to option->prec bits as in slip_expand_mpfr_array.c / slip_expand_mpfr_mat.c
+ * (same MPFR calls, same row-major gcd scan that stops at 1 and divides from the first nonzero) ---- */
+static SLIP_info expand_mpfrs (mpz_t **slot, mpfr_t **src, int64_t count, mpq_t scale, SLIP_options *option)
+{
+    if (!option) return SLIP_INCORRECT_INPUT ;
+    mpfr_t ten, w ;
+    mpz_t g ;
+    mpfr_init2 (ten, (mpfr_prec_t) option->prec) ;
+    mpfr_init2 (w, (mpfr_prec_t) option->prec) ;
+    mpz_init (g) ;
+    mpfr_ui_pow_ui (ten, 10, (unsigned long) option->prec, option->SLIP_MPFR_ROUND) ;
+    for (int64_t k = 0 ; k < count ; k++)
+    {
+        mpfr_mul (w, *src [k], ten, option->SLIP_MPFR_ROUND) ;
+        mpfr_get_z (*slot [k], w, option->SLIP_MPFR_ROUND) ;
+    }
+    mpfr_get_z (g, ten, option->SLIP_MPFR_ROUND) ;
+    mpq_set_z (scale, g) ;
+    int64_t first = -1 ;
+    int reduced_to_one = 0 ;
+    for (int64_t k = 0 ; k < count && !reduced_to_one ; k++)
+    {
+        if (first < 0)
+        {
+            if (mpz_sgn (*slot [k]) != 0) { first = k ; mpz_set (g, *slot [k]) ; }
+        }
+        else
+        {
+            mpz_gcd (g, g, *slot [k]) ;
+            if (mpz_cmp_ui (g, 1) == 0) reduced_to_one = 1 ;
+        }
+    }
+    if (first < 0) mpq_set_ui (scale, 1, 1) ;          /* all zero */
+    else if (!reduced_to_one)
+    {
+        mpq_t t ;
+        mpq_init (t) ;
+        for (int64_t k = first ; k < count ; k++) mpz_divexact (*slot [k], *slot [k], g) ;
+        mpq_set_z (t, g) ;
+        mpq_div (scale, scale, t) ;
+        mpq_clear (t) ;
+    }
+    mpz_clear (g) ;
+    mpfr_clear (w) ; mpfr_clear (ten) ;
+    return SLIP_OK ;
+}
+
+SLIP_info slip_expand_mpfr_array (mpz_t *x_out, mpfr_t *x, mpq_t scale, int32_t n, SLIP_options *option)
+{
+    if (!x || !x_out || n <= 0) return SLIP_INCORRECT_INPUT ;
+    mpz_t **slot = (mpz_t **) SLIP_malloc ((size_t) n * sizeof (mpz_t *)) ;
+    mpfr_t **src = (mpfr_t **) SLIP_malloc ((size_t) n * sizeof (mpfr_t *)) ;
+    if (!slot || !src) { SLIP_free (slot) ; SLIP_free (src) ; return SLIP_OUT_OF_MEMORY ; }
+    for (int32_t k = 0 ; k < n ; k++) { slot [k] = &x_out [k] ; src [k] = &x [k] ; }
+    SLIP_info status = expand_mpfrs (slot, src, n, scale, option) ;
+    SLIP_free (slot) ; SLIP_free (src) ;
+    return status ;
+}
+
+SLIP_info slip_expand_mpfr_mat (mpz_t **x_out, mpfr_t **x, mpq_t scale, int32_t m, int32_t n, SLIP_options *option)
+{
+    const int64_t count = (int64_t) m * n ;
+    mpz_t **slot = (mpz_t **) SLIP_malloc ((size_t) count * sizeof (mpz_t *)) ;
+    mpfr_t **src = (mpfr_t **) SLIP_malloc ((size_t) count * sizeof (mpfr_t *)) ;
+    if (!slot || !src) { SLIP_free (slot) ; SLIP_free (src) ; return SLIP_OUT_OF_MEMORY ; }
+    for (int32_t i = 0 ; i < m ; i++)
+        for (int32_t j = 0 ; j < n ; j++)
+        {
+            slot [(int64_t) i * n + j] = &x_out [i][j] ;
+            src [(int64_t) i * n + j] = &x [i][j] ;
+        }
+    SLIP_info status = expand_mpfrs (slot, src, count, scale, option) ;
+    SLIP_free (slot) ; SLIP_free (src) ;
+    return status ;
+}
+
 /* ---- rationals -> integer: scale = lcm of denominators, x_out = scale * x ---- */
 static SLIP_info expand_rationals (mpz_t **slot, mpq_t **src, int64_t count, mpq_t scale)
 {
@@ -197,7 +274,7 @@ SLIP_info SLIP_build_sparse_trip_mpz (SLIP_sparse *A, int32_t *I, int32_t *J, mp
     return status ;
 }
 
-typedef enum { SRC_INT, SRC_DOUBLE, SRC_MPQ } src_kind ;
+typedef enum { SRC_INT, SRC_DOUBLE, SRC_MPQ, SRC_MPFR } src_kind ;
 
 static SLIP_info build_sparse_any (SLIP_sparse *A, int32_t *a, int32_t *b, void *x, int32_t n, int32_t nz,
     src_kind kind, int triplet, SLIP_options *option)
@@ -212,6 +289,7 @@ static SLIP_info build_sparse_any (SLIP_sparse *A, int32_t *a, int32_t *b, void 
         mpq_set_ui (A->scale, 1, 1) ;
     }
     else if (kind == SRC_DOUBLE) status = slip_expand_double_array (xi, (double *) x, A->scale, nz, option) ;
+    else if (kind == SRC_MPFR) status = slip_expand_mpfr_array (xi, (mpfr_t *) x, A->scale, nz, option) ;
     else status = slip_expand_mpq_array (xi, (mpq_t *) x, A->scale, nz) ;
     if (status == SLIP_OK)
         status = triplet ? slip_sparse_from_trip (A, a, b, xi, n, nz) : slip_sparse_from_ccf (A, a, b, xi, n, nz) ;
@@ -231,6 +309,11 @@ SLIP_info SLIP_build_sparse_trip_double (SLIP_sparse *A, int32_t *I, int32_t *J,
 { return build_sparse_any (A, I, J, x, n, nz, SRC_DOUBLE, 1, option) ; }
 SLIP_info SLIP_build_sparse_trip_mpq (SLIP_sparse *A, int32_t *I, int32_t *J, mpq_t *x, int32_t n, int32_t nz)
 { return build_sparse_any (A, I, J, x, n, nz, SRC_MPQ, 1, NULL) ; }
+
+SLIP_info SLIP_build_sparse_ccf_mpfr (SLIP_sparse *A, int32_t *p, int32_t *I, mpfr_t *x, int32_t n, int32_t nz, SLIP_options *option)
+{ return option ? build_sparse_any (A, p, I, x, n, nz, SRC_MPFR, 0, option) : SLIP_INCORRECT_INPUT ; }
+SLIP_info SLIP_build_sparse_trip_mpfr (SLIP_sparse *A, int32_t *I, int32_t *J, mpfr_t *x, int32_t n, int32_t nz, SLIP_options *option)
+{ return option ? build_sparse_any (A, I, J, x, n, nz, SRC_MPFR, 1, option) : SLIP_INCORRECT_INPUT ; }
 
 /* ---- dense builders ---- */
 static SLIP_info dense_alloc (SLIP_dense *A, int32_t m, int32_t n)
@@ -279,4 +362,12 @@ SLIP_info SLIP_build_dense_mpq (SLIP_dense *A, mpq_t **b, int32_t m, int32_t n)
     SLIP_info status = dense_alloc (A, m, n) ;
     if (status != SLIP_OK) return status ;
     return slip_expand_mpq_mat (A->x, b, A->scale, m, n) ;
+}
+
+SLIP_info SLIP_build_dense_mpfr (SLIP_dense *A, mpfr_t **b, int32_t m, int32_t n, SLIP_options *option)
+{
+    if (BAD_DENSE_ARGS (b, A) || !option) return SLIP_INCORRECT_INPUT ;
+    SLIP_info status = dense_alloc (A, m, n) ;
+    if (status != SLIP_OK) return status ;
+    return slip_expand_mpfr_mat (A->x, b, A->scale, m, n, option) ;
 }

@@ -77,6 +77,8 @@ SLIP_info slip_expand_double_array (mpz_t *x_out, double *x, mpq_t scale, int32_
 SLIP_info slip_expand_double_mat (mpz_t **x_out, double **x, mpq_t scale, int32_t m, int32_t n, SLIP_options *option) ;
 SLIP_info slip_expand_mpq_array (mpz_t *x_out, mpq_t *x, mpq_t scale, int32_t n) ;
 SLIP_info slip_expand_mpq_mat (mpz_t **x_out, mpq_t **x, mpq_t scale, int32_t m, int32_t n) ;
+SLIP_info slip_expand_mpfr_array (mpz_t *x_out, mpfr_t *x, mpq_t scale, int32_t n, SLIP_options *option) ;
+SLIP_info slip_expand_mpfr_mat (mpz_t **x_out, mpfr_t **x, mpq_t scale, int32_t m, int32_t n, SLIP_options *option) ;
 SLIP_info slip_sparse_from_ccf (SLIP_sparse *A, const int32_t *p, const int32_t *I, mpz_t *x, int32_t n, int32_t nz) ;
 SLIP_info slip_sparse_from_trip (SLIP_sparse *A, const int32_t *I, const int32_t *J, mpz_t *x, int32_t n, int32_t nz) ;
 

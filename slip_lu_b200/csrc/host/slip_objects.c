@@ -154,6 +154,47 @@ void SLIP_delete_mpq_mat (mpq_t ***A, int32_t m, int32_t n)
     *A = NULL ;
 }
 
+/* ---- mpfr containers at option->prec (SLIP_create_mpfr_array.c, SLIP_create_mpfr_mat.c,
+ * SLIP_delete_mpfr_array.c, SLIP_delete_mpfr_mat.c) ---- */
+mpfr_t *SLIP_create_mpfr_array (int32_t n, SLIP_options *option)
+{
+    if (n <= 0 || !option) return NULL ;
+    mpfr_t *x = (mpfr_t *) SLIP_calloc ((size_t) n, sizeof (mpfr_t)) ;
+    if (!x) return NULL ;
+    for (int32_t k = 0 ; k < n ; k++) mpfr_init2 (x [k], (mpfr_prec_t) option->prec) ;
+    return x ;
+}
+
+void SLIP_delete_mpfr_array (mpfr_t **x, int32_t n)
+{
+    if (!x || !*x) return ;
+    for (int32_t k = 0 ; k < n ; k++)
+        if ((*x) [k]->_mpfr_d) mpfr_clear ((*x) [k]) ;
+    SLIP_free (*x) ;
+    *x = NULL ;
+}
+
+mpfr_t **SLIP_create_mpfr_mat (int32_t m, int32_t n, SLIP_options *option)
+{
+    if (m <= 0 || n <= 0 || !option) return NULL ;
+    mpfr_t **A = (mpfr_t **) SLIP_calloc ((size_t) m, sizeof (mpfr_t *)) ;
+    if (!A) return NULL ;
+    for (int32_t i = 0 ; i < m ; i++)
+    {
+        A [i] = SLIP_create_mpfr_array (n, option) ;
+        if (!A [i]) { SLIP_delete_mpfr_mat (&A, m, n) ; return NULL ; }
+    }
+    return A ;
+}
+
+void SLIP_delete_mpfr_mat (mpfr_t ***A, int32_t m, int32_t n)
+{
+    if (!A || !*A) return ;
+    for (int32_t i = 0 ; i < m ; i++) SLIP_delete_mpfr_array (&(*A) [i], n) ;
+    SLIP_free (*A) ;
+    *A = NULL ;
+}
+
 double **SLIP_create_double_mat (int32_t m, int32_t n)
 {
     if (m <= 0 || n <= 0) return NULL ;

@@ -251,6 +251,30 @@ SLIP_info SLIP_solve_double (double **x_doub, SLIP_sparse *A, SLIP_LU_analysis *
     return status ;
 }
 
+/* SLIP_get_mpfr_soln.c:27-49: x_mpfr[i][j] = x_mpq[i][j] rounded per option->SLIP_MPFR_ROUND (the
+ * precision is the one x_mpfr was created with) */
+SLIP_info SLIP_get_mpfr_soln (mpfr_t **x_mpfr, mpq_t **x_mpq, int32_t n, int32_t numRHS, SLIP_options *option)
+{
+    if (!x_mpfr || !x_mpq || !option) return SLIP_INCORRECT_INPUT ;
+    for (int32_t i = 0 ; i < n ; i++)
+        for (int32_t j = 0 ; j < numRHS ; j++)
+            mpfr_set_q (x_mpfr [i][j], x_mpq [i][j], option->SLIP_MPFR_ROUND) ;
+    return SLIP_OK ;
+}
+
+/* SLIP_solve_mpfr.c:35-77: factor, solve, permute, scale, then round to mpfr */
+SLIP_info SLIP_solve_mpfr (mpfr_t **x_mpfr, SLIP_sparse *A, SLIP_LU_analysis *S, SLIP_dense *b, SLIP_options *option)
+{
+    if (!x_mpfr || !A || !A->p || !A->i || !A->x || !S || !S->q || !b || !b->x || !option)
+        return SLIP_INCORRECT_INPUT ;
+    mpq_t **x = SLIP_create_mpq_mat (A->n, b->n) ;
+    if (!x) return SLIP_OUT_OF_MEMORY ;
+    SLIP_info status = solve_exact (x, A, S, b, option) ;
+    if (status == SLIP_OK) status = SLIP_get_mpfr_soln (x_mpfr, x, A->n, b->n, option) ;
+    SLIP_delete_mpq_mat (&x, A->n, b->n) ;
+    return status ;
+}
+
 /* exact residual check A x == b in rational arithmetic, for the integer system (before scaling) */
 SLIP_info SLIP_check_solution (SLIP_sparse *A, mpq_t **x, SLIP_dense *b)
 {

@@ -107,6 +107,56 @@ def doubles_fixture(ref):
     print("double_builders ok")
 
 
+def mpfr_fixture(ref):
+    """What the reference's mpfr builders and SLIP_solve_mpfr produce (slip_expand_mpfr_array/_mat,
+    SLIP_get_mpfr_soln), at two precisions."""
+    import ctypes as C
+    doc = dict(name="mpfr_builders", cases=[])
+    literals = ["0.1", "-0.25", "3", "1e-3", "123456.789", "-7.5e-9", "0", "1.52587890625e-05"]
+    for prec in (128, 53):
+        o = ref.default_options()
+        o.contents.prec = prec
+        nz = len(literals)
+        x = ref.dll.SLIP_create_mpfr_array(nz, o)
+        for k, t in enumerate(literals):
+            capi.mpfr_set_decimal(x[k], t)
+        A = ref.dll.SLIP_create_sparse()
+        p = (C.c_int32 * (nz + 1))(*range(nz + 1)); i = (C.c_int32 * nz)(*range(nz))
+        assert ref.dll.SLIP_build_sparse_ccf_mpfr(A, p, i, x, nz, nz, o) == 0
+        _, _, ax = ref.sparse_to_py(A)
+        num, den = capi.mpq_to_pair(A.contents.scale)
+        # the same values as a 2 x 4 dense block, and one lone negative entry (sign of the "gcd")
+        M = ref.dll.SLIP_create_mpfr_mat(2, 4, o)
+        for r in range(2):
+            for c in range(4):
+                capi.mpfr_set_decimal(M[r][c], literals[4 * r + c])
+        D = ref.dll.SLIP_create_dense()
+        assert ref.dll.SLIP_build_dense_mpfr(D, M, 2, 4, o) == 0
+        dx = [[S(capi.mpz_to_int(D.contents.x[r][c])) for c in range(4)] for r in range(2)]
+        dnum, dden = capi.mpq_to_pair(D.contents.scale)
+        x1 = ref.dll.SLIP_create_mpfr_array(1, o)
+        capi.mpfr_set_decimal(x1[0], "-0.75")
+        A1 = ref.dll.SLIP_create_sparse()
+        assert ref.dll.SLIP_build_sparse_trip_mpfr(A1, (C.c_int32 * 1)(0), (C.c_int32 * 1)(0), x1, 1, 1, o) == 0
+        _, _, ax1 = ref.sparse_to_py(A1)
+        n1, d1 = capi.mpq_to_pair(A1.contents.scale)
+        # SLIP_solve_mpfr on a small integer system
+        n, cp, ri, vals, b = synth.random_sparse(24, 4, 20, seed=11, nrhs=2)
+        As = ref.sparse_from_csc(n, cp, ri, vals); Bs = ref.dense_from_rows(b)
+        o.contents.order = capi.SLIP_NO_ORDERING
+        Sy = ref.analyze(As, o)
+        X = ref.dll.SLIP_create_mpfr_mat(n, 2, o)
+        assert ref.dll.SLIP_solve_mpfr(X, As, Sy, Bs, o) == 0
+        sol = [[[S(v) for v in capi.mpfr_to_pair(X[r][c])] for c in range(2)] for r in range(n)]
+        doc["cases"].append(dict(prec=prec, literals=literals, ints=[S(v) for v in ax], scale=[S(num), S(den)],
+                                 dense_ints=dx, dense_scale=[S(dnum), S(dden)],
+                                 single_ints=[S(v) for v in ax1], single_scale=[S(n1), S(d1)],
+                                 solve=dict(n=n, nnz_per_col=4, bits=20, seed=11, nrhs=2, x=sol)))
+    with open(os.path.join(HERE, "mpfr_builders.json"), "w") as f:
+        json.dump(doc, f, separators=(",", ":"))
+    print("mpfr_builders ok")
+
+
 def main():
     ob.build()
     ref = capi.SlipLib(ob.REF_SO)
@@ -136,6 +186,7 @@ def main():
     fixture(ref, "decimal80_multirhs", *sysd, capi.SLIP_TOL_SMALLEST, capi.SLIP_COLAMD,
             note="configs[3] family (scaled decimals, several right-hand sides)")
     doubles_fixture(ref)
+    mpfr_fixture(ref)
 
 
 if __name__ == "__main__":

@@ -82,6 +82,68 @@ def test_double_builder_matches_reference_golden(product):
         product.free_sparse(A)
 
 
+def test_mpfr_builders_match_reference_golden(product):
+    """SLIP_build_sparse_{ccf,trip}_mpfr / SLIP_build_dense_mpfr (slip_expand_mpfr_array.c,
+    slip_expand_mpfr_mat.c): same integers and scale as the reference, at two precisions."""
+    g = cases.load_golden("mpfr_builders")
+    for case in g["cases"]:
+        o = product.default_options()
+        o.contents.prec = case["prec"]
+        lit = case["literals"]
+        nz = len(lit)
+        x = product.dll.SLIP_create_mpfr_array(nz, o)
+        for k, t in enumerate(lit):
+            capi.mpfr_set_decimal(x[k], t)
+        A = product.dll.SLIP_create_sparse()
+        rc = product.dll.SLIP_build_sparse_ccf_mpfr(A, (C.c_int32 * (nz + 1))(*range(nz + 1)),
+                                                    (C.c_int32 * nz)(*range(nz)), x, nz, nz, o)
+        assert rc == 0
+        assert product.sparse_to_py(A)[2] == [int(v) for v in case["ints"]], case["prec"]
+        assert capi.mpq_to_pair(A.contents.scale) == tuple(int(v) for v in case["scale"])
+        product.free_sparse(A)
+        M = product.dll.SLIP_create_mpfr_mat(2, 4, o)
+        for r in range(2):
+            for c in range(4):
+                capi.mpfr_set_decimal(M[r][c], lit[4 * r + c])
+        D = product.dll.SLIP_create_dense()
+        assert product.dll.SLIP_build_dense_mpfr(D, M, 2, 4, o) == 0
+        assert [[capi.mpz_to_int(D.contents.x[r][c]) for c in range(4)] for r in range(2)] == \
+            [[int(v) for v in row] for row in case["dense_ints"]]
+        assert capi.mpq_to_pair(D.contents.scale) == tuple(int(v) for v in case["dense_scale"])
+        product.free_dense(D)
+        x1 = product.dll.SLIP_create_mpfr_array(1, o)
+        capi.mpfr_set_decimal(x1[0], "-0.75")
+        A1 = product.dll.SLIP_create_sparse()
+        assert product.dll.SLIP_build_sparse_trip_mpfr(A1, (C.c_int32 * 1)(0), (C.c_int32 * 1)(0), x1, 1, 1, o) == 0
+        assert product.sparse_to_py(A1)[2] == [int(v) for v in case["single_ints"]]
+        assert capi.mpq_to_pair(A1.contents.scale) == tuple(int(v) for v in case["single_scale"])
+        product.free_sparse(A1)
+        Mp = C.pointer(M); product.dll.SLIP_delete_mpfr_mat(Mp, 2, 4)
+        xp = C.pointer(x); product.dll.SLIP_delete_mpfr_array(xp, nz)
+        xp1 = C.pointer(x1); product.dll.SLIP_delete_mpfr_array(xp1, 1)
+    # argument checks of the reference
+    o = product.default_options()
+    A = product.dll.SLIP_create_sparse()
+    assert product.dll.SLIP_build_sparse_ccf_mpfr(A, None, None, None, 3, 3, o) == capi.SLIP_INCORRECT_INPUT
+    product.free_sparse(A)
+
+
+def test_get_mpfr_soln_rounds_like_mpfr_set_q(product):
+    o = product.default_options()
+    o.contents.prec = 80
+    xq = product.dll.SLIP_create_mpq_mat(2, 1)
+    capi.int_to_mpz(xq[0][0]._mp_num, 1); capi.int_to_mpz(xq[0][0]._mp_den, 3)
+    capi.int_to_mpz(xq[1][0]._mp_num, -22); capi.int_to_mpz(xq[1][0]._mp_den, 7)
+    X = product.dll.SLIP_create_mpfr_mat(2, 1, o)
+    assert product.dll.SLIP_get_mpfr_soln(X, xq, 2, 1, o) == 0
+    from fractions import Fraction
+    for r, want in ((0, Fraction(1, 3)), (1, Fraction(-22, 7))):
+        m, e = capi.mpfr_to_pair(X[r][0])
+        got = Fraction(m) * (Fraction(2) ** e)
+        assert abs(got - want) <= abs(want) * Fraction(1, 2 ** 79) and abs(m).bit_length() <= 80
+    assert product.dll.SLIP_get_mpfr_soln(None, xq, 2, 1, o) == capi.SLIP_INCORRECT_INPUT
+
+
 def test_analyze_matches_golden_orderings(product):
     """SLIP_LU_analyze (COLAMD / AMD through the SuiteSparse library found at run time, and the
     nnz guesses) reproduces the reference's q."""

@@ -292,3 +292,21 @@ def test_steps_spanning_several_chunks(gpu, oracle, cpt):
     cases.assert_same_factorization(got, want, f"multi-chunk cpt={cpt}")
     lp = want["L"][0]
     assert max(lp[k + 1] - lp[k] for k in range(n)) > 128, "case too sparse to span two chunks"
+
+
+def test_solve_mpfr_matches_reference_golden(gpu):
+    """SLIP_solve_mpfr (SLIP_solve_mpfr.c): the exact solution rounded to option->prec bits, value for
+    value what the reference returned for the same system (fixture mpfr_builders.json)."""
+    g = cases.load_golden("mpfr_builders")
+    for case in g["cases"]:
+        sv = case["solve"]
+        n, cp, ri, vals, b = synth.random_sparse(sv["n"], sv["nnz_per_col"], sv["bits"], seed=sv["seed"], nrhs=sv["nrhs"])
+        o = gpu.default_options(order=capi.SLIP_NO_ORDERING)
+        o.contents.prec = case["prec"]
+        A = gpu.sparse_from_csc(n, cp, ri, vals); B = gpu.dense_from_rows(b)
+        S = gpu.analyze(A, o)
+        X = gpu.dll.SLIP_create_mpfr_mat(n, sv["nrhs"], o)
+        assert gpu.dll.SLIP_solve_mpfr(X, A, S, B, o) == 0
+        got = [[list(capi.mpfr_to_pair(X[r][c])) for c in range(sv["nrhs"])] for r in range(n)]
+        want = [[[int(v) for v in pair] for pair in row] for row in sv["x"]]
+        assert got == want, case["prec"]

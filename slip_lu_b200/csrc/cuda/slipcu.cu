@@ -1208,7 +1208,7 @@ __global__ void __launch_bounds__ (384, 1) k_garner_flow (GarnerArgs a)
     {
         const u32 *Cc = a.C + (size_t) (32 * b) * S + tt;
         const u32 *db = digs + (size_t) b * E * 32;
-#pragma unroll
+#pragma unroll 1
         for (int q = 0; q < 32; q += 16)
         {
             u32 c[16];
@@ -1232,7 +1232,7 @@ __global__ void __launch_bounds__ (384, 1) k_garner_flow (GarnerArgs a)
     {
         if (b >= 0)
         {
-            if (b % W != w) { while (ready[b] == 0) { } }
+            if (b % W != w) { while (ready[b] == 0) __nanosleep (40); }   // back off: a spinning warp steals issue slots
             __threadfence_block ();
             __syncwarp ();
         }
@@ -1279,6 +1279,7 @@ __global__ void __launch_bounds__ (384, 1) k_garner_flow (GarnerArgs a)
                 const u32 diff = v[e] >= r ? v[e] - r : v[e] + fp - r;
                 qv[e] = mont_mul (diff, ib, fp, fni);
             }
+#pragma unroll 2
             for (int i = 0; i < 32; ++i)
             {
                 const u32 cci = ccs[i * 32 + lane];

@@ -81,13 +81,13 @@ class ClockSampler:
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+    def __init__(self, gpu_index, period_ms=1000):
+        self.rows, self.proc, self.gpu, self.period_ms = [], None, gpu_index, period_ms
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", str(self.period_ms), "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
@@ -172,6 +172,8 @@ def main():
     ap.add_argument("--ref-n", type=int, default=240)
     ap.add_argument("--seed", type=int, default=20261018)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--clock-period-ms", type=int, default=1000, help="nvidia-smi sampling period during the timed region")
+    ap.add_argument("--no-kernel-timers", action="store_true", help="(diagnostic) no CUDA-event brackets around the kernels: roofline is then not measured")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -244,9 +246,9 @@ def main():
         S, x = step()
         lib.free_mpq_mat(x, n, 1); lib.free_analysis(S)
 
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, args.clock_period_ms)
     lib.dll.slipcu_reset_counters()
-    lib.dll.slipcu_set_profiling(1)           # CUDA-event bracket around every k_trisolve launch
+    lib.dll.slipcu_set_profiling(0 if args.no_kernel_timers else 1)   # CUDA-event bracket around every k_trisolve launch
     barrier()
     sampler.start()
     t0 = time.perf_counter()

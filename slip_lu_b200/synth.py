@@ -100,6 +100,22 @@ def decimal_scaled(n: int, nnz_per_col: int = 6, digits: int = 6, seed: int = 0,
     return (n, colptr, rowidx, values, _rhs(rng, n, nrhs, 20)), dvals
 
 
+def dense_head(n: int, head: int = 5, bits: int = 12, seed: int = 0, nrhs: int = 1) -> Csc:
+    """A few long columns at little total cost: column 0 is dense, columns 1..head-1 have an entry in
+    row 0 (so they fill in completely and are eliminated with columns of n, n-1, ... rows), the rest
+    is diagonal.  Used to put elimination steps of a chosen length through the chunked kernels."""
+    rng = random.Random(seed)
+    I, J, V = [], [], []
+    for r in range(n):
+        I.append(r); J.append(0); V.append(_val(rng, bits))
+    for k in range(1, n):
+        if k < head:
+            I.append(0); J.append(k); V.append(_val(rng, bits))
+        I.append(k); J.append(k); V.append(_val(rng, bits))
+    cp, ri, vals = triplets_to_csc(n, I, J, V)
+    return n, cp, ri, vals, _rhs(rng, n, nrhs, bits)
+
+
 def read_triplet_file(path: str):
     """Reader for the ExampleMats text format ("m n nz" then "i j value" lines, 0- or
     1-based decided from the first triplet like the reference demo reader,

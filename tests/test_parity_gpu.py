@@ -310,3 +310,14 @@ def test_solve_mpfr_matches_reference_golden(gpu):
         got = [[list(capi.mpfr_to_pair(X[r][c])) for c in range(sv["nrhs"])] for r in range(n)]
         want = [[[int(v) for v in pair] for pair in row] for row in sv["x"]]
         assert got == want, case["prec"]
+
+
+@pytest.mark.parametrize("n", [513, 1030])
+def test_long_steps_cross_chunk_boundaries(gpu, oracle, n):
+    """Elimination steps of n, n-1, ... rows with the default 8-channel blocks (512-row chunks): one
+    full chunk plus a one-row tail at n = 513, two full chunks plus a short tail at n = 1030."""
+    n, cp, ri, vals, b = synth.dense_head(n, head=5, bits=12, seed=n)
+    q = list(range(n))
+    want = cases.run_oracle(oracle, n, cp, ri, vals, b, q)
+    got = cases.run_library(gpu, n, cp, ri, vals, b, q)
+    cases.assert_same_factorization(got, want, f"dense head n={n}")

@@ -47,9 +47,16 @@ class Counters(C.Structure):
                 ("device_ms", C.c_double), ("other_ms", C.c_double)]
 
 
-def workload(n, seed):
+def workload(n, seed, rhs_seed=None):
+    """configs[1]: random sparse integer matrix; rhs_seed gives a rank its own right-hand side for the
+    same matrix, so that every GPU of a weak-scaling run has the same amount of work."""
+    import random
     from slip_lu_b200 import synth
-    return synth.random_sparse(n, 10, 32, seed=seed, nrhs=1)
+    n, cp, ri, vals, b = synth.random_sparse(n, 10, 32, seed=seed, nrhs=1)
+    if rhs_seed:
+        rng = random.Random(rhs_seed)
+        b = [[rng.getrandbits(32) - (1 << 31) or 1] for _ in range(n)]
+    return n, cp, ri, vals, b
 
 
 def work_model(n, cp, vals, q, Lp, Up, Ui):
@@ -180,10 +187,18 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        # torchrun pins OMP_NUM_THREADS=1 for multi-rank jobs; the host side of the interface (limb
+        # export, canonical rationals) is OpenMP-parallel: give every rank its share of the cores
+        try:
+            cores = len(os.sched_getaffinity(0))
+        except AttributeError:
+            cores = os.cpu_count() or 1
+        os.environ["OMP_NUM_THREADS"] = str(max(1, cores // world))
 
     config = {"workload": f"BASELINE configs[1]: synthetic random sparse integer matrix n={args.n}, 10 nnz/col, "
                           "32-bit entries, COLAMD order, 1 RHS, SLIP_TOL_SMALLEST pivoting (defaults)",
-              "per_gpu": "one independent system per GPU (different seed per rank), no data-path collective",
+              "per_gpu": "one independent system per GPU (the same matrix, a different right-hand side per rank: equal work per GPU), no data-path collective",
               "l2": "factor data streamed per column (>> 126 MB L2; ~10 GB of L residues at n=2000)"}
 
     if args.impl == "reference":
@@ -225,7 +240,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     lib.dll.SLIP_B200_last_stats.argtypes = [C.POINTER(C.c_double), C.c_int]
 
-    n, cp, ri, vals, b = workload(args.n, args.seed + rank)
+    n, cp, ri, vals, b = workload(args.n, args.seed, rhs_seed=rank)
     o = lib.default_options()
     A = lib.sparse_from_csc(n, cp, ri, vals)          # host mpz_t matrices: the interface's inputs
     B = lib.dense_from_rows(b)

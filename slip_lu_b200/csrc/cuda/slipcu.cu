@@ -398,8 +398,17 @@ struct slipcu_factor
     ColDesc *desc = nullptr;                 // [n]
     int32_t *pos = nullptr;                  // [n]
     int32_t *bad = nullptr;                  // device flag
-    u32 *dig = nullptr; size_t dig_rows = 0; // [dig_rows][S] digit scratch
+    u32 *dig = nullptr; size_t dig_rows = 0; // [dig_rows][S] digit scratch in use (= digbuf[i])
     int32_t *topd = nullptr;                 // [dig_rows]
+    // Sessions that keep positional factors reconstruct the U part and convert the whole column
+    // to limbs on a second stream, behind the pivot search and the next column's elimination:
+    // the digit scratch is then double-buffered and ev_side[i] guards the reuse of buffer i.
+    cudaStream_t st2 = nullptr, wst = nullptr;          // side stream; stream run_garner/run_limbs launch on
+    cudaEvent_t ev_tri = nullptr, ev_gl = nullptr, ev_side[2] = { nullptr, nullptr };
+    bool side_pending[2] = { false, false };
+    u32 *digbuf[2] = { nullptr, nullptr };
+    int32_t *topdbuf[2] = { nullptr, nullptr };
+    int overlap = 0, seq = 0;
     Arena resid, ints, limbs;
     std::vector<HostCol> cols;
     std::vector<int32_t> hAp;
@@ -439,13 +448,13 @@ struct ScopedTimer
     slipcu_factor *F; double *acc; cudaEvent_t a = nullptr;
     ScopedTimer (slipcu_factor *F_, double *acc_) : F (F_), acc (acc_)
     {
-        if (g_profiling) { a = take_event (); cudaEventRecord (a, F->st); }
+        if (g_profiling) { a = take_event (); cudaEventRecord (a, F->wst); }
     }
     ~ScopedTimer ()
     {
         if (!a) return;
         cudaEvent_t b = take_event ();
-        cudaEventRecord (b, F->st);
+        cudaEventRecord (b, F->wst);
         F->ranges.push_back ({a, b, acc});
     }
 };
@@ -454,13 +463,15 @@ static void flush_timers (slipcu_factor *F)
 {
     if (F->ranges.empty ()) return;
     std::lock_guard<std::mutex> lk (g_event_mutex);
+    std::vector<TimedRange> later;
     for (auto &r : F->ranges)
     {
+        if (cudaEventQuery (r.b) == cudaErrorNotReady) { later.push_back (r); continue; }   // side stream still busy
         float ms = 0;
         if (cudaEventElapsedTime (&ms, r.a, r.b) == cudaSuccess) *r.acc += ms; else cudaGetLastError ();
         g_event_pool.push_back (r.a); g_event_pool.push_back (r.b);
     }
-    F->ranges.clear ();
+    F->ranges.swap (later);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1568,11 +1579,13 @@ extern "C" void slipcu_factor_free (slipcu_factor *F)
     for (double &v : g_hw) v = 0;
     cudaSetDevice (F->device);
     if (F->st) cudaStreamSynchronize (F->st);
+    if (F->st2) cudaStreamSynchronize (F->st2);
     flush_timers (F);
     pool_free (F->dAp); pool_free (F->dAi); pool_free (F->dA);
     pool_free (F->rho); pool_free (F->invrho);
     pool_free (F->desc); pool_free (F->pos); pool_free (F->bad);
-    pool_free (F->dig); pool_free (F->topd); pool_free (F->d_info);
+    pool_free (F->digbuf[0]); pool_free (F->topdbuf[0]); pool_free (F->digbuf[1]); pool_free (F->topdbuf[1]);
+    pool_free (F->d_info);
     pool_free (F->tmp_limbs); pool_free (F->tmp_nl);
     pool_free (F->slots); pool_free (F->steps); pool_free (F->chunks);
     if (F->h_packet) cudaFreeHost (F->h_packet);
@@ -1582,6 +1595,11 @@ extern "C" void slipcu_factor_free (slipcu_factor *F)
     if (F->ev1) cudaEventDestroy (F->ev1);
     if (F->ev_start) cudaEventDestroy (F->ev_start);
     if (F->ev_end) cudaEventDestroy (F->ev_end);
+    if (F->ev_tri) cudaEventDestroy (F->ev_tri);
+    if (F->ev_gl) cudaEventDestroy (F->ev_gl);
+    if (F->ev_side[0]) cudaEventDestroy (F->ev_side[0]);
+    if (F->ev_side[1]) cudaEventDestroy (F->ev_side[1]);
+    if (F->st2) cudaStreamDestroy (F->st2);
     if (F->st) cudaStreamDestroy (F->st);
     delete F;
 }
@@ -1594,9 +1612,17 @@ static int ensure_digits (slipcu_factor *F, size_t rows)
     size_t want = std::max (rows, F->dig_rows * 2);
     want = std::min<size_t> (std::max<size_t> (want, 64), std::max<size_t> (rows, (size_t) F->n));
     CU (cudaStreamSynchronize (F->st));
-    pool_free (F->dig); pool_free (F->topd); F->dig = nullptr; F->topd = nullptr; F->dig_rows = 0;
-    CU (pool_alloc_t (&F->dig, want * (size_t) (F->S + 4) * sizeof (u32)));
-    CU (pool_alloc_t (&F->topd, want * sizeof (int32_t)));
+    if (F->st2) CU (cudaStreamSynchronize (F->st2));
+    F->side_pending[0] = F->side_pending[1] = false;
+    F->dig = nullptr; F->topd = nullptr; F->dig_rows = 0;
+    for (int i = 0; i < 2; ++i)
+    {
+        pool_free (F->digbuf[i]); pool_free (F->topdbuf[i]); F->digbuf[i] = nullptr; F->topdbuf[i] = nullptr;
+        if (i == 1 && !F->overlap) break;
+        CU (pool_alloc_t (&F->digbuf[i], want * (size_t) (F->S + 4) * sizeof (u32)));
+        CU (pool_alloc_t (&F->topdbuf[i], want * sizeof (int32_t)));
+    }
+    F->dig = F->digbuf[0]; F->topd = F->topdbuf[0];
     F->dig_rows = want;
     return SLIPCU_OK;
 }
@@ -1671,6 +1697,7 @@ static int session_common_init (slipcu_factor *F, int n, int channels)
     if (rc) return rc;
 
     CU (cudaStreamCreateWithFlags (&F->st, cudaStreamNonBlocking));
+    F->wst = F->st;
     CU (cudaEventCreateWithFlags (&F->ev, cudaEventDisableTiming));
     CU (cudaEventCreate (&F->ev0)); CU (cudaEventCreate (&F->ev1));
     CU (cudaEventCreate (&F->ev_start)); CU (cudaEventCreate (&F->ev_end));
@@ -1700,6 +1727,15 @@ extern "C" int slipcu_factor_begin (slipcu_factor **out, int n, int nz, const in
     if (rc) return rc;
     F->nz = nz;
     F->keep_positional = keep_positional ? 1 : 0;
+    if (F->keep_positional && env_int ("SLIP_B200_OVERLAP", 1))
+    {   // second stream for the positional reconstruction (see the session struct)
+        F->overlap = 1;
+        CU (cudaStreamCreateWithFlags (&F->st2, cudaStreamNonBlocking));
+        CU (cudaEventCreateWithFlags (&F->ev_tri, cudaEventDisableTiming));
+        CU (cudaEventCreateWithFlags (&F->ev_gl, cudaEventDisableTiming));
+        CU (cudaEventCreateWithFlags (&F->ev_side[0], cudaEventDisableTiming));
+        CU (cudaEventCreateWithFlags (&F->ev_side[1], cudaEventDisableTiming));
+    }
     const int S = F->S, CH = F->CH;
     CU (pool_alloc_t (&F->dAp, (size_t) (n + 1) * sizeof (int32_t)));
     CU (pool_alloc_t (&F->dAi, (size_t) nz * sizeof (int32_t)));
@@ -1830,7 +1866,7 @@ static int run_garner (slipcu_factor *F, const u32 *base, int region_cnt, int e0
     g.p = T.p; g.ninv = T.ninv; g.C = T.C; g.invB = T.invB;
     ScopedTimer tm (F, &g_recon_ms);
     if (F->garner_mode == 0 || s < 64)
-        k_garner<<<(ne + 3) / 4, 128, 0, F->st>>> (g);
+        k_garner<<<(ne + 3) / 4, 128, 0, F->wst>>> (g);
     else
     {
         // pick the CTA width so that one tile covers s when possible (W warps x 5 blocks x 32 digits)
@@ -1861,20 +1897,20 @@ static int run_garner (slipcu_factor *F, const u32 *base, int region_cnt, int e0
             const int grid = (ne + E - 1) / E;
             switch (E)
             {
-                case 1: k_garner_flow<1, 6><<<grid, Wf * 32, fsm, F->st>>> (g); break;
-                case 2: k_garner_flow<2, 6><<<grid, Wf * 32, fsm, F->st>>> (g); break;
-                case 3: k_garner_flow<3, 6><<<grid, Wf * 32, fsm, F->st>>> (g); break;
-                case 4: k_garner_flow<4, 6><<<grid, Wf * 32, fsm, F->st>>> (g); break;
-                case 5: k_garner_flow<5, 6><<<grid, Wf * 32, fsm, F->st>>> (g); break;
-                default: k_garner_flow<6, 6><<<grid, Wf * 32, fsm, F->st>>> (g); break;
+                case 1: k_garner_flow<1, 6><<<grid, Wf * 32, fsm, F->wst>>> (g); break;
+                case 2: k_garner_flow<2, 6><<<grid, Wf * 32, fsm, F->wst>>> (g); break;
+                case 3: k_garner_flow<3, 6><<<grid, Wf * 32, fsm, F->wst>>> (g); break;
+                case 4: k_garner_flow<4, 6><<<grid, Wf * 32, fsm, F->wst>>> (g); break;
+                case 5: k_garner_flow<5, 6><<<grid, Wf * 32, fsm, F->wst>>> (g); break;
+                default: k_garner_flow<6, 6><<<grid, Wf * 32, fsm, F->wst>>> (g); break;
             }
         }
         else
-            k_garner_tiled<4, 5><<<(ne + 3) / 4, W * 32, 0, F->st>>> (g);
+            k_garner_tiled<4, 5><<<(ne + 3) / 4, W * 32, 0, F->wst>>> (g);
     }
     g_launches++;
     CU (cudaGetLastError ());
-    if (debug_check ("k_garner", F->st)) return fail (SLIPCU_CUDA_ERROR, "k_garner", "debug");
+    if (debug_check ("k_garner", F->wst)) return fail (SLIPCU_CUDA_ERROR, "k_garner", "debug");
     g_recon_mac += (double) ne * ((double) s * s * 0.5);
     return SLIPCU_OK;
 }
@@ -1889,11 +1925,11 @@ static int run_limbs (slipcu_factor *F, int e0, int ne, int out0, int stride, in
     l.dig = F->dig; l.dstride = (size_t) F->S + 4; l.topd = F->topd; l.Bpos = T.Bpos;
     l.limbs = limbs; l.nl = nl;
     ScopedTimer tm (F, &g_recon_ms);
-    if (ne >= 64) k_limbs<4><<<((ne + 3) / 4 + 3) / 4, 128, 0, F->st>>> (l);
-    else k_limbs<1><<<(ne + 3) / 4, 128, 0, F->st>>> (l);
+    if (ne >= 64) k_limbs<4><<<((ne + 3) / 4 + 3) / 4, 128, 0, F->wst>>> (l);
+    else k_limbs<1><<<(ne + 3) / 4, 128, 0, F->wst>>> (l);
     g_launches++;
     CU (cudaGetLastError ());
-    if (debug_check ("k_limbs", F->st)) return fail (SLIPCU_CUDA_ERROR, "k_limbs", "debug");
+    if (debug_check ("k_limbs", F->wst)) return fail (SLIPCU_CUDA_ERROR, "k_limbs", "debug");
     g_recon_mac += (double) ne * ((double) s * s * 0.5);
     return SLIPCU_OK;
 }
@@ -1990,10 +2026,21 @@ extern "C" int slipcu_factor_column_launch (slipcu_factor *F, int k, int col, in
             }
         }
     }
-    // exact values: candidates always (pivot scan); the U part only if the factors go to the host
-    const int e0 = F->keep_positional ? 0 : nU;
+    // exact values: candidates always (pivot scan); the U part only if the factors go to the host,
+    // and then on the side stream, off the path to the pivot
+    const bool ov = F->keep_positional && F->overlap;
+    int bufi = 0;
+    if (ov)
+    {
+        CU (cudaEventRecord (F->ev_tri, F->st));
+        bufi = F->seq++ & 1;
+        F->dig = F->digbuf[bufi]; F->topd = F->topdbuf[bufi];
+        if (F->side_pending[bufi]) { CU (cudaStreamWaitEvent (F->st, F->ev_side[bufi], 0)); F->side_pending[bufi] = false; }
+    }
+    const int e0 = (F->keep_positional && !ov) ? 0 : nU;
     rc = run_garner (F, hc.base, cnt, e0, cnt - e0, s, hc.sign);
     if (rc) return rc;
+    if (ov) CU (cudaEventRecord (F->ev_gl, F->st));
     g_hw[3] += wall_s () - tw; tw = wall_s ();
     const int mode = (scheme == 2) ? 2 : ((scheme == 4 || scheme == 5) ? 1 : 0);
     { ScopedTimer tm_scan (F, &g_other_ms);
@@ -2004,7 +2051,22 @@ extern "C" int slipcu_factor_column_launch (slipcu_factor *F, int k, int col, in
     if (debug_check ("k_pivot_scan", F->st)) return fail (SLIPCU_CUDA_ERROR, "k_pivot_scan", "debug");
     CU (cudaMemcpyAsync (F->h_info, F->d_info, sizeof (slipcu_pivot_info), cudaMemcpyDeviceToHost, F->st));
     CU (cudaEventRecord (F->ev, F->st));
-    if (F->keep_positional)
+    if (ov)
+    {   // side stream: digits of the U part, then positional limbs of the whole column
+        F->wst = F->st2;
+        CU (cudaStreamWaitEvent (F->st2, F->ev_tri, 0));
+        rc = run_garner (F, hc.base, cnt, 0, nU, s, hc.sign);
+        if (rc == SLIPCU_OK)
+        {
+            cudaStreamWaitEvent (F->st2, F->ev_gl, 0);
+            rc = run_limbs (F, 0, cnt, 0, hc.stride, s, hc.limbs, hc.nl);
+        }
+        F->wst = F->st;
+        if (rc) return rc;
+        CU (cudaEventRecord (F->ev_side[bufi], F->st2));
+        F->side_pending[bufi] = true;
+    }
+    else if (F->keep_positional)
     {   // positional limbs of the whole column; overlaps the host's pivot decision
         rc = run_limbs (F, 0, cnt, 0, hc.stride, s, hc.limbs, hc.nl);
         if (rc) return rc;
@@ -2048,6 +2110,7 @@ extern "C" int slipcu_factor_fetch_entry (slipcu_factor *F, int k, int slot, u32
     if (slot < 0 || slot >= hc.cnt) return fail (SLIPCU_BAD_INPUT, "slipcu_factor_fetch_entry", "bad slot");
     if (F->keep_positional)
     {
+        if (F->st2) CU (cudaStreamSynchronize (F->st2));       // the column's limbs come from the side stream
         CU (cudaMemcpyAsync (limbs, hc.limbs + (size_t) slot * hc.stride, (size_t) hc.stride * sizeof (u32),
                              cudaMemcpyDeviceToHost, F->st));
         CU (cudaMemcpyAsync (nlimbs32, hc.nl + slot, sizeof (int32_t), cudaMemcpyDeviceToHost, F->st));
@@ -2165,6 +2228,7 @@ static int stream_column (slipcu_factor *F, int k, const HostCol &hc, slipcu_col
 static int check_channels (slipcu_factor *F)
 {
     int32_t bad = 0;
+    if (F->st2) CU (cudaStreamSynchronize (F->st2));
     CU (cudaMemcpyAsync (&bad, F->bad, sizeof (bad), cudaMemcpyDeviceToHost, F->st));
     CU (cudaStreamSynchronize (F->st));
     if (bad) return fail (SLIPCU_BAD_PRIME, "check_channels", "channel prime divides a pivot");

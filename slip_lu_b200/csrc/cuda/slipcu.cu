@@ -122,6 +122,8 @@ __device__ __forceinline__ u32 lazy_redc (u64 T, u32 p, u32 ninv)
 // ------------------------------------------------------------------------------------------------
 // channel primes and reconstruction tables (shared by all sessions, immutable once built)
 // ------------------------------------------------------------------------------------------------
+#define FRAC_WMAX 128          // words of the fixed-point reciprocals 1/p_i
+
 struct Tables
 {
     int S = 0;                 // channels covered
@@ -132,10 +134,13 @@ struct Tables
     u32 *invB = nullptr;       // [S]     (p_0..p_{t-1})^-1 mod p_t, Montgomery form
     u32 *Bpos = nullptr;       // [S][LB] limbs of p_0..p_{t-1}
     int LB = 0;
+    // approximate magnitudes (k_fraccrt): Minv[(s-1)*S + i] = (p_0..p_{s-1} / p_i)^-1 mod p_i in
+    // Montgomery form for i < s; Urec[i] = floor(2^(32*FRAC_WMAX) / p_i), most significant word first
+    u32 *Minv = nullptr, *Urec = nullptr;
     ~Tables ()
     {
         cudaFree (p); cudaFree (ninv); cudaFree (r2); cudaFree (one);
-        cudaFree (C); cudaFree (invB); cudaFree (Bpos);
+        cudaFree (C); cudaFree (invB); cudaFree (Bpos); cudaFree (Minv); cudaFree (Urec);
     }
 };
 
@@ -193,6 +198,21 @@ __global__ void k_build_tables (int S, const u32 *p, const u32 *ninv, const u32 
     invB[t] = mont_pow (acc, pt - 2, one[t], pt, ni);
 }
 
+// Minv: one thread per channel i walks the prefix lengths s = i+1 .. S
+__global__ void k_build_minv (int S, const u32 *p, const u32 *ninv, const u32 *r2, const u32 *one, u32 *Minv)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S) return;
+    const u32 pi = p[i], ni = ninv[i], rr = r2[i];
+    u32 prod = one[i];
+    for (int j = 0; j < i; ++j) prod = mont_mul (prod, mont_mul (reduce_word (p[j], pi), rr, pi, ni), pi, ni);
+    for (int s = i + 1; s <= S; ++s)
+    {
+        if (s > i + 1) prod = mont_mul (prod, mont_mul (reduce_word (p[s - 1], pi), rr, pi, ni), pi, ni);
+        Minv[(size_t) (s - 1) * S + i] = mont_pow (prod, pi - 2, one[i], pi, ni);
+    }
+}
+
 static int build_tables (int S, std::shared_ptr<Tables> &out)
 {
     auto T = std::make_shared<Tables> ();
@@ -247,6 +267,27 @@ static int build_tables (int S, std::shared_ptr<Tables> &out)
     k_build_tables<<<(S + 127) / 128, 128>>> (S, T->p, T->ninv, T->r2, T->one, T->C, T->invB);
     g_launches++;
     CU (cudaGetLastError ());
+    {   // tables of the approximate magnitude pass
+        std::vector<u32> U ((size_t) S * FRAC_WMAX);
+        for (int c = 0; c < S; ++c)
+        {   // long division of 2^(32*FRAC_WMAX) by p_c, one 32-bit word of the quotient per step
+            const u64 pc = T->hp[c];
+            u64 rem = 1;
+            for (int w = 0; w < FRAC_WMAX; ++w)
+            {
+                const u64 num = rem << 32;
+                U[(size_t) c * FRAC_WMAX + w] = (u32) (num / pc);
+                rem = num % pc;
+            }
+        }
+        CU (cudaMalloc (&T->Urec, U.size () * sizeof (u32)));
+        CU (cudaMemcpy (T->Urec, U.data (), U.size () * sizeof (u32), cudaMemcpyHostToDevice));
+        CU (cudaMalloc (&T->Minv, (size_t) S * S * sizeof (u32)));
+        CU (cudaMemset (T->Minv, 0, (size_t) S * S * sizeof (u32)));
+        k_build_minv<<<(S + 63) / 64, 64>>> (S, T->p, T->ninv, T->r2, T->one, T->Minv);
+        g_launches++;
+        CU (cudaGetLastError ());
+    }
     CU (cudaDeviceSynchronize ());
     out = T;
     return SLIPCU_OK;
@@ -409,6 +450,11 @@ struct slipcu_factor
     u32 *digbuf[2] = { nullptr, nullptr };
     int32_t *topdbuf[2] = { nullptr, nullptr };
     int overlap = 0, seq = 0;
+    // approximate pivot search (k_fraccrt) of sessions that do not keep positional factors
+    int frac = 0, fracW = 8, frac_col = -1;             // enabled, words for the next column, column searched that way
+    struct { int cnt, nU, s, mode, diag_slot, W; } fq = { 0, 0, 0, 0, 0, 0 };
+    struct FracKey *frackey = nullptr; size_t frac_rows = 0;
+    uint64_t frac_cols = 0, frac_retries = 0, frac_fallbacks = 0;
     Arena resid, ints, limbs;
     std::vector<HostCol> cols;
     std::vector<int32_t> hAp;
@@ -1477,6 +1523,267 @@ __global__ void __launch_bounds__ (128) k_limbs (LimbArgs a)
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_fraccrt / k_fracselect: pivot search without reconstructing the candidates.
+//
+// For X = x mod M (M = p_0..p_{s-1}, |x| < M/4) the Chinese remainder theorem gives
+//     X / M = frac ( sum_i c_i / p_i ),   c_i = x_i * (M/p_i)^-1 mod p_i .
+// With u_i = floor (2^(32W) / p_i) the W-word integer  F = sum_i c_i u_i  mod 2^(32W)  satisfies
+//     2^(32W) * frac(X/M)  in  [F, F + s*2^31)   (circularly),
+// so g = min (F, 2^(32W) - F) approximates 2^(32W) |x| / M within s*2^31 < 2^44 units: s*W
+// multiply-adds per entry instead of the s^2/2 of the mixed-radix reconstruction, and no serial
+// chain.  k_fracselect takes the extreme g and accepts it only if every other candidate differs
+// from it by far more than the error bound (first differing word at least five words above the
+// bottom, 96-bit window difference >= 2); otherwise -- ties, near ties, or too few words for the
+// size of the entries -- the caller adds words or falls back to the exact scan.  Zero entries are
+// recognised exactly (all residues zero).  The decision is therefore the exact one whenever it is
+// accepted, which is what keeps the factorization bit-identical to the reference.
+// ------------------------------------------------------------------------------------------------
+struct FracKey                          // approximate magnitude of one candidate
+{
+    int32_t lead;                       // leading zero words of g (W if none is set); -1: the entry is exactly zero
+    uint32_t k[4];                      // the four words of g from the leading one down (zero padded)
+    int32_t neg;                        // the entry is negative
+};
+
+struct FracArgs
+{
+    int cnt, e0, ne, s, CH, S, W;       // region rows, first entry, entries, channels, table stride, words
+    const u32 *base, *p, *ninv, *minv, *urec;
+    FracKey *key;                       // [ne]
+};
+
+#define FRAC_WARPS 8
+// One CTA per E entries; the channels are dealt to the 8 warps in chunks of 32, each warp keeps the
+// 96-bit column sums of its share (lane l owns word positions l, l+32, ...), warp e adds the
+// eight partial sums of entry e, ripples the carries and extracts the key.
+template <int E, int NW>
+__global__ void __launch_bounds__ (FRAC_WARPS * 32) k_fraccrt (FracArgs a)
+{
+    extern __shared__ u32 fsm[];                 // [FRAC_WARPS][E][NW*32][3] partial sums, then flags
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int g0 = blockIdx.x * E;
+    const unsigned full = 0xffffffffu;
+    const int s = a.s, W = a.W, CH = a.CH;
+    int ent[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) ent[e] = a.e0 + min (g0 + e, a.ne - 1);
+    u32 a0[E][NW], a1[E][NW], a2[E][NW];
+    bool nz[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+    {
+        nz[e] = false;
+#pragma unroll
+        for (int j = 0; j < NW; ++j) a0[e][j] = a1[e][j] = a2[e][j] = 0;
+    }
+    for (int i0 = w * 32; i0 < s; i0 += FRAC_WARPS * 32)
+    {
+        const int i = i0 + lane;
+        u32 c[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) c[e] = 0;
+        if (i < s)
+        {
+            const u32 pi = a.p[i], ni = a.ninv[i], mi = a.minv[i];
+#pragma unroll
+            for (int e = 0; e < E; ++e)
+            {
+                const u32 x = a.base[((size_t) (i / CH) * a.cnt + ent[e]) * CH + (i % CH)];
+                nz[e] = nz[e] || (x != 0);
+                c[e] = mont_redc (mont_mul (x, mi, pi, ni), pi, ni);        // standard form, < p_i
+            }
+        }
+        const int lim = min (32, s - i0);
+#pragma unroll 4
+        for (int j = 0; j < lim; ++j)
+        {
+            const u32 *ur = a.urec + (size_t) (i0 + j) * FRAC_WMAX;
+            u32 u[NW];
+#pragma unroll
+            for (int q = 0; q < NW; ++q)
+            {
+                const int l = lane + 32 * q;                  // word position, 0 = least significant
+                u[q] = (l < W) ? ur[W - 1 - l] : 0u;
+            }
+#pragma unroll
+            for (int e = 0; e < E; ++e)
+            {
+                const u32 cj = __shfl_sync (full, c[e], j);
+#pragma unroll
+                for (int q = 0; q < NW; ++q) mac96 (a0[e][q], a1[e][q], a2[e][q], cj, u[q]);
+            }
+        }
+    }
+    int *nzflag = (int *) (fsm + (size_t) FRAC_WARPS * E * NW * 32 * 3);       // [FRAC_WARPS][E]
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+    {
+#pragma unroll
+        for (int q = 0; q < NW; ++q)
+        {
+            u32 *d = fsm + (((size_t) (w * E + e) * NW + q) * 32 + lane) * 3;
+            d[0] = a0[e][q]; d[1] = a1[e][q]; d[2] = a2[e][q];
+        }
+        const bool any = __any_sync (full, nz[e]);
+        if (lane == 0) nzflag[w * E + e] = any ? 1 : 0;
+    }
+    __syncthreads ();
+    if (w >= E || g0 + w >= a.ne) return;
+    const int e = w;
+    bool nonzero = false;
+    for (int v = 0; v < FRAC_WARPS; ++v) nonzero = nonzero || nzflag[v * E + e];
+    u32 word[NW];
+    u32 in_a1 = 0, in_a2 = 0, in_b2 = 0, carry_in = 0;
+#pragma unroll
+    for (int q = 0; q < NW; ++q)
+    {
+        u64 T0 = 0, T1 = 0, T2 = 0;
+        for (int v = 0; v < FRAC_WARPS; ++v)
+        {
+            const u32 *d = fsm + (((size_t) (v * E + e) * NW + q) * 32 + lane) * 3;
+            T0 += d[0]; T1 += d[1]; T2 += d[2];
+        }
+        T1 += T0 >> 32; T2 += T1 >> 32;
+        const u32 b0 = (u32) T0, b1 = (u32) T1, b2 = (u32) T2;
+        u32 p1 = __shfl_up_sync (full, b1, 1), p2 = __shfl_up_sync (full, b2, 2);
+        if (lane == 0) { p1 = in_a1; p2 = in_b2; }
+        if (lane == 1) { p2 = in_a2; }
+        const u64 sum = (u64) b0 + p1 + p2;
+        u32 cin = (lane == 0) ? carry_in : 0u, cout;
+        for (;;)
+        {
+            cout = (u32) ((sum + cin) >> 32);
+            u32 nin = __shfl_up_sync (full, cout, 1);
+            if (lane == 0) nin = carry_in;
+            const bool changed = nin != cin;
+            cin = nin;
+            if (!__any_sync (full, changed)) break;
+        }
+        word[q] = (u32) (sum + cin);
+        cout = (u32) ((sum + cin) >> 32);
+        carry_in = __shfl_sync (full, cout, 31);
+        in_a1 = __shfl_sync (full, b1, 31);
+        in_a2 = __shfl_sync (full, b2, 31);
+        in_b2 = __shfl_sync (full, b2, 30);
+    }
+    // sign = top bit of the top word (position W-1); g = F or its complement (one unit off at most)
+    const int tp = W - 1;
+    u32 topw = 0;
+#pragma unroll
+    for (int q = 0; q < NW; ++q) { const u32 v = __shfl_sync (full, word[q], tp & 31); if (q == (tp >> 5)) topw = v; }
+    const bool neg = (topw >> 31) != 0;
+    int hp = -1;                                 // highest position with a nonzero word of g
+#pragma unroll
+    for (int q = 0; q < NW; ++q)
+    {
+        const int l = lane + 32 * q;
+        word[q] = (l < W) ? (neg ? ~word[q] : word[q]) : 0u;
+        const unsigned m = __ballot_sync (full, word[q] != 0);
+        if (m) hp = 32 * q + 31 - __clz (m);
+    }
+    u32 key[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+    {
+        const int pos = hp - j;
+        u32 val = 0;
+#pragma unroll
+        for (int q = 0; q < NW; ++q) { const u32 v = __shfl_sync (full, word[q], pos & 31); if (pos >= 0 && q == (pos >> 5)) val = v; }
+        key[j] = val;
+    }
+    if (lane == 0)
+    {
+        FracKey k;
+        k.lead = nonzero ? (hp < 0 ? W : W - 1 - hp) : -1;
+        k.k[0] = key[0]; k.k[1] = key[1]; k.k[2] = key[2]; k.k[3] = key[3];
+        k.neg = neg ? 1 : 0;
+        a.key[g0 + e] = k;
+    }
+}
+
+struct FracSel
+{
+    int ne, nU, mode, diag_slot, W;     // candidates (slots nU .. nU+ne-1), 0 smallest / 1 largest
+    const FracKey *key; const int32_t *bad;
+    slipcu_pivot_info *info;
+};
+// order of the approximate magnitudes: more leading zero words is smaller, then the key words
+__device__ __forceinline__ int frac_cmp (const FracKey &x, const FracKey &y)
+{
+    if (x.lead != y.lead) return x.lead > y.lead ? -1 : 1;
+    for (int j = 0; j < 4; ++j) if (x.k[j] != y.k[j]) return x.k[j] < y.k[j] ? -1 : 1;
+    return 0;
+}
+__device__ __forceinline__ int frac_better (const FracKey *key, int mode, int x, int y)
+{
+    if (x < 0) return y;
+    if (y < 0) return x;
+    int c = frac_cmp (key[x], key[y]);
+    if (mode == 1) c = -c;
+    if (c < 0) return x;
+    if (c > 0) return y;
+    return x < y ? x : y;
+}
+// |small| < |large| proven: the 96-bit windows at the leading word of `large`, five or more words
+// above the bottom where the error of the sums lives, differ by at least two units
+__device__ __forceinline__ bool frac_proven_less (const FracKey &small, const FracKey &large, int W)
+{
+    if (large.lead > W - 6 || small.lead < large.lead) return false;
+    const int d = small.lead - large.lead;
+    unsigned __int128 L = ((unsigned __int128) large.k[0] << 64) | ((unsigned __int128) large.k[1] << 32) | large.k[2];
+    unsigned __int128 S = 0;
+    if (d == 0) S = ((unsigned __int128) small.k[0] << 64) | ((unsigned __int128) small.k[1] << 32) | small.k[2];
+    else if (d == 1) S = ((unsigned __int128) small.k[0] << 32) | small.k[1];
+    else if (d == 2) S = small.k[0];
+    return L > S && L - S >= 2;
+}
+__global__ void __launch_bounds__ (256) k_fracselect (FracSel a)
+{
+    __shared__ int sbest[256];
+    __shared__ int s_uncertain;
+    if (threadIdx.x == 0) s_uncertain = 0;
+    int best = -1;
+    for (int r = threadIdx.x; r < a.ne; r += blockDim.x)
+        if (a.key[r].lead >= 0) best = frac_better (a.key, a.mode, best, r);
+    sbest[threadIdx.x] = best;
+    __syncthreads ();
+    for (int h = blockDim.x >> 1; h > 0; h >>= 1)
+    {
+        if ((int) threadIdx.x < h)
+            sbest[threadIdx.x] = frac_better (a.key, a.mode, sbest[threadIdx.x], sbest[threadIdx.x + h]);
+        __syncthreads ();
+    }
+    best = sbest[0];
+    if (best >= 0)
+    {
+        const FracKey kb = a.key[best];
+        for (int r = threadIdx.x; r < a.ne; r += blockDim.x)
+        {
+            if (r == best) continue;
+            const FracKey kr = a.key[r];
+            if (kr.lead < 0) continue;
+            const bool ok = (a.mode == 0) ? frac_proven_less (kb, kr, a.W) : frac_proven_less (kr, kb, a.W);
+            if (!ok) s_uncertain = 1;
+        }
+    }
+    __syncthreads ();
+    if (threadIdx.x == 0)
+    {
+        slipcu_pivot_info *info = a.info;
+        info->best_slot = best >= 0 ? a.nU + best : -1;
+        info->best_sign = best >= 0 ? (a.key[best].neg ? -1 : 1) : 0;
+        const int dr = a.diag_slot - a.nU;
+        const int de = (dr >= 0 && dr < a.ne && a.key[dr].lead >= 0) ? 1 : 0;
+        info->diag_eligible = de;
+        info->diag_vs_best = (de && best >= 0 && dr != best) ? (a.mode == 0 ? 1 : -1) : 0;
+        info->bad_channel = *a.bad;
+        info->reserved[0] = s_uncertain ? 0 : 1;      // 1: the choice is proven
+        info->reserved[1] = best >= 0 ? a.key[best].lead : 0;
+        info->reserved[2] = a.W;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_pivot_scan: exact nonzero / magnitude scan over the candidate slots (nU..cnt-1)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int cmp_mag (const u32 *dig, size_t ds, const int32_t *topd, int e1, int e2)
@@ -1585,7 +1892,10 @@ extern "C" void slipcu_factor_free (slipcu_factor *F)
     pool_free (F->rho); pool_free (F->invrho);
     pool_free (F->desc); pool_free (F->pos); pool_free (F->bad);
     pool_free (F->digbuf[0]); pool_free (F->topdbuf[0]); pool_free (F->digbuf[1]); pool_free (F->topdbuf[1]);
-    pool_free (F->d_info);
+    pool_free (F->d_info); pool_free (F->frackey);
+    if (getenv ("SLIP_B200_TIMING") && F->frac)
+        fprintf (stderr, "slipcu pivot search: %llu columns by approximate magnitudes, %llu word-count retries, %llu exact fallbacks\n",
+                 (unsigned long long) F->frac_cols, (unsigned long long) F->frac_retries, (unsigned long long) F->frac_fallbacks);
     pool_free (F->tmp_limbs); pool_free (F->tmp_nl);
     pool_free (F->slots); pool_free (F->steps); pool_free (F->chunks);
     if (F->h_packet) cudaFreeHost (F->h_packet);
@@ -1680,6 +1990,7 @@ static int session_common_init (slipcu_factor *F, int n, int channels)
     F->sms = sms;
     F->x_global = env_int ("SLIP_B200_X_GLOBAL", 0);
     F->garner_mode = env_int ("SLIP_B200_GARNER", 2);
+    F->frac = env_int ("SLIP_B200_FRAC", 1);
     CU (cudaFuncSetAttribute (k_garner_flow<1, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     CU (cudaFuncSetAttribute (k_garner_flow<2, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     CU (cudaFuncSetAttribute (k_garner_flow<3, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
@@ -1934,6 +2245,55 @@ static int run_limbs (slipcu_factor *F, int e0, int ne, int out0, int stride, in
     return SLIPCU_OK;
 }
 
+// approximate magnitudes of the candidates (slots nU .. cnt-1) with W words, then the selection
+static int run_frac (slipcu_factor *F, const HostCol &hc, int cnt, int nU, int s, int mode, int diag_slot, int W)
+{
+    const Tables &T = *F->tab;
+    const int ne = cnt - nU;
+    if ((size_t) ne > F->frac_rows)
+    {
+        CU (cudaStreamSynchronize (F->st));
+        pool_free (F->frackey); F->frackey = nullptr;
+        const size_t want = std::max<size_t> ((size_t) ne, std::min<size_t> ((size_t) F->n, std::max<size_t> (64, F->frac_rows * 2)));
+        CU (pool_alloc_t (&F->frackey, want * sizeof (FracKey)));
+        F->frac_rows = want;
+    }
+    FracArgs a;
+    a.cnt = cnt; a.e0 = nU; a.ne = ne; a.s = s; a.CH = F->CH; a.S = T.S; a.W = W;
+    a.base = hc.base; a.p = T.p; a.ninv = T.ninv; a.minv = T.Minv + (size_t) (s - 1) * T.S; a.urec = T.Urec;
+    a.key = F->frackey;
+    {
+        ScopedTimer tm (F, &g_recon_ms);
+        const int NW = (W + 31) / 32;
+        int E = ne >= 4 * F->sms ? 4 : (ne >= F->sms ? 2 : 1);            // entries per CTA (they share the table loads)
+        if (E == 4 && NW == 4) E = 2;                                     // keeps the partial sums within 48 KB
+        const int grid = (ne + E - 1) / E;
+        const size_t fsm = (size_t) FRAC_WARPS * E * NW * 32 * 3 * sizeof (u32) + (size_t) FRAC_WARPS * E * sizeof (int);
+#define FRAC_LAUNCH(EE, NN) k_fraccrt<EE, NN><<<grid, FRAC_WARPS * 32, fsm, F->st>>> (a)
+        if (E == 4) { if (NW == 1) FRAC_LAUNCH (4, 1); else if (NW == 2) FRAC_LAUNCH (4, 2); else if (NW == 3) FRAC_LAUNCH (4, 3); else FRAC_LAUNCH (4, 4); }
+        else if (E == 2) { if (NW == 1) FRAC_LAUNCH (2, 1); else if (NW == 2) FRAC_LAUNCH (2, 2); else if (NW == 3) FRAC_LAUNCH (2, 3); else FRAC_LAUNCH (2, 4); }
+        else { if (NW == 1) FRAC_LAUNCH (1, 1); else if (NW == 2) FRAC_LAUNCH (1, 2); else if (NW == 3) FRAC_LAUNCH (1, 3); else FRAC_LAUNCH (1, 4); }
+#undef FRAC_LAUNCH
+        g_launches++;
+        CU (cudaGetLastError ());
+        if (debug_check ("k_fraccrt", F->st)) return fail (SLIPCU_CUDA_ERROR, "k_fraccrt", "debug");
+        g_recon_mac += (double) ne * (double) s * (double) W;
+    }
+    FracSel q;
+    q.ne = ne; q.nU = nU; q.mode = mode; q.diag_slot = diag_slot; q.W = W;
+    q.key = F->frackey; q.bad = F->bad; q.info = F->d_info;
+    {
+        ScopedTimer tm (F, &g_other_ms);
+        k_fracselect<<<1, 256, 0, F->st>>> (q);
+        g_launches++;
+        CU (cudaGetLastError ());
+        if (debug_check ("k_fracselect", F->st)) return fail (SLIPCU_CUDA_ERROR, "k_fracselect", "debug");
+    }
+    F->fq.cnt = cnt; F->fq.nU = nU; F->fq.s = s; F->fq.mode = mode; F->fq.diag_slot = diag_slot; F->fq.W = W;
+    return SLIPCU_OK;
+}
+static int frac_word_cap (int s) { return std::min (FRAC_WMAX, s + 2); }
+
 static int alloc_column (slipcu_factor *F, HostCol &hc, int cnt, int s)
 {
     hc.cnt = cnt; hc.s = s;
@@ -1947,6 +2307,17 @@ static int alloc_column (slipcu_factor *F, HostCol &hc, int cnt, int s)
     }
     if (!hc.base || !hc.sign || (F->keep_positional && (!hc.limbs || !hc.nl)))
         return fail (SLIPCU_OUT_OF_MEMORY, "alloc_column", "device memory exhausted");
+    return SLIPCU_OK;
+}
+
+static int run_exact_scan (slipcu_factor *F, const HostCol &hc, int cnt, int nU, int mode, int diag_slot)
+{
+    ScopedTimer tm_scan (F, &g_other_ms);
+    k_pivot_scan<<<1, 256, 0, F->st>>> (cnt, nU, mode, diag_slot, F->dig, (size_t) F->S + 4, F->topd,
+                                        hc.sign, F->bad, F->d_info);
+    g_launches++;
+    CU (cudaGetLastError ());
+    if (debug_check ("k_pivot_scan", F->st)) return fail (SLIPCU_CUDA_ERROR, "k_pivot_scan", "debug");
     return SLIPCU_OK;
 }
 
@@ -2037,18 +2408,26 @@ extern "C" int slipcu_factor_column_launch (slipcu_factor *F, int k, int col, in
         F->dig = F->digbuf[bufi]; F->topd = F->topdbuf[bufi];
         if (F->side_pending[bufi]) { CU (cudaStreamWaitEvent (F->st, F->ev_side[bufi], 0)); F->side_pending[bufi] = false; }
     }
-    const int e0 = (F->keep_positional && !ov) ? 0 : nU;
-    rc = run_garner (F, hc.base, cnt, e0, cnt - e0, s, hc.sign);
-    if (rc) return rc;
-    if (ov) CU (cudaEventRecord (F->ev_gl, F->st));
-    g_hw[3] += wall_s () - tw; tw = wall_s ();
     const int mode = (scheme == 2) ? 2 : ((scheme == 4 || scheme == 5) ? 1 : 0);
-    { ScopedTimer tm_scan (F, &g_other_ms);
-    k_pivot_scan<<<1, 256, 0, F->st>>> (cnt, nU, mode, diag_slot, F->dig, (size_t) F->S + 4, F->topd,
-                                        hc.sign, F->bad, F->d_info);
-    g_launches++;
-    CU (cudaGetLastError ()); }
-    if (debug_check ("k_pivot_scan", F->st)) return fail (SLIPCU_CUDA_ERROR, "k_pivot_scan", "debug");
+    F->frac_col = -1;
+    if (F->frac && !F->keep_positional && mode != 2 && s >= 16)
+    {   // magnitudes only: no digits unless the choice turns out to be too close to call
+        const int W = std::min (std::max (F->fracW, 8), frac_word_cap (s));
+        rc = run_frac (F, hc, cnt, nU, s, mode, diag_slot, W);
+        if (rc) return rc;
+        F->frac_col = k;
+        g_hw[3] += wall_s () - tw; tw = wall_s ();
+    }
+    else
+    {
+        const int e0 = (F->keep_positional && !ov) ? 0 : nU;
+        rc = run_garner (F, hc.base, cnt, e0, cnt - e0, s, hc.sign);
+        if (rc) return rc;
+        if (ov) CU (cudaEventRecord (F->ev_gl, F->st));
+        g_hw[3] += wall_s () - tw; tw = wall_s ();
+        rc = run_exact_scan (F, hc, cnt, nU, mode, diag_slot);
+        if (rc) return rc;
+    }
     CU (cudaMemcpyAsync (F->h_info, F->d_info, sizeof (slipcu_pivot_info), cudaMemcpyDeviceToHost, F->st));
     CU (cudaEventRecord (F->ev, F->st));
     if (ov)
@@ -2081,9 +2460,42 @@ extern "C" int slipcu_factor_column_wait (slipcu_factor *F, slipcu_pivot_info *i
     if (!F || !info || F->cur < 0) return fail (SLIPCU_BAD_INPUT, "slipcu_factor_column_wait", "bad argument");
     double tw = wall_s ();
     CU (cudaEventSynchronize (F->ev));
-    g_hw[5] += wall_s () - tw;
     g_d2h_bytes += sizeof (slipcu_pivot_info);
     *info = *F->h_info;
+    if (F->frac_col == F->cur)
+    {   // approximate search: accept a proven choice, add words if the entries are smaller than
+        // the words resolve, otherwise (ties, near ties) run the exact scan
+        HostCol &hc = F->cols[F->cur];
+        const int cap = frac_word_cap (F->fq.s);
+        F->frac_cols++;
+        while (!info->reserved[0] && info->best_slot >= 0 && info->reserved[1] > F->fq.W - 10 && F->fq.W < cap)
+        {
+            const int W = std::min (cap, std::max (2 * F->fq.W, info->reserved[1] + 12));
+            F->frac_retries++;
+            int rc = run_frac (F, hc, F->fq.cnt, F->fq.nU, F->fq.s, F->fq.mode, F->fq.diag_slot, W);
+            if (rc) return rc;
+            CU (cudaMemcpyAsync (F->h_info, F->d_info, sizeof (slipcu_pivot_info), cudaMemcpyDeviceToHost, F->st));
+            CU (cudaStreamSynchronize (F->st));
+            g_d2h_bytes += sizeof (slipcu_pivot_info);
+            *info = *F->h_info;
+        }
+        if (!info->reserved[0])
+        {
+            F->frac_fallbacks++;
+            F->frac_col = -1;
+            int rc = run_garner (F, hc.base, F->fq.cnt, F->fq.nU, F->fq.cnt - F->fq.nU, F->fq.s, hc.sign);
+            if (rc == SLIPCU_OK) rc = run_exact_scan (F, hc, F->fq.cnt, F->fq.nU, F->fq.mode, F->fq.diag_slot);
+            if (rc) return rc;
+            CU (cudaMemcpyAsync (F->h_info, F->d_info, sizeof (slipcu_pivot_info), cudaMemcpyDeviceToHost, F->st));
+            CU (cudaStreamSynchronize (F->st));
+            g_d2h_bytes += sizeof (slipcu_pivot_info);
+            *info = *F->h_info;
+        }
+        else if (info->best_slot >= 0)
+            F->fracW = std::min (FRAC_WMAX, std::max (8, info->reserved[1] + 12));  // words for the next column
+        info->reserved[0] = info->reserved[1] = info->reserved[2] = 0;
+    }
+    g_hw[5] += wall_s () - tw;
     if (info->bad_channel) return fail (SLIPCU_BAD_PRIME, "slipcu_factor_column", "channel prime divides a pivot");
     return SLIPCU_OK;
 }
@@ -2126,6 +2538,11 @@ extern "C" int slipcu_factor_fetch_entry (slipcu_factor *F, int k, int slot, u32
             CU (pool_alloc_t (&F->tmp_limbs, (size_t) (F->S + 2) * sizeof (u32)));
             CU (pool_alloc_t (&F->tmp_nl, sizeof (int32_t)));
             F->tmp_stride = F->S + 2;
+        }
+        if (F->frac_col == k)
+        {   // the column was searched by approximate magnitudes: no digits yet for this entry
+            int rcg = run_garner (F, hc.base, hc.cnt, slot, 1, hc.s, hc.sign);
+            if (rcg) return rcg;
         }
         int rc = run_limbs (F, slot, 1, 0, hc.stride, hc.s, F->tmp_limbs, F->tmp_nl);
         if (rc) return rc;

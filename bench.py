@@ -334,7 +334,8 @@ def main():
                      "algorithmic_bytes_per_launch": c.trisolve_bytes / max(1, c.trisolve_launches),
                      "modmul_per_s": c.trisolve_modmul / (c.trisolve_ms / 1e3) if c.trisolve_ms > 0 else None,
                      "kernel_share_of_step": (c.trisolve_ms / 1e3) / (t_dev) if t_dev > 0 else None},
-        "reconstruction": {"kernel": "k_garner_flow", "ms": c.recon_ms / args.steps,
+        "reconstruction": {"kernel": "k_fraccrt (approximate magnitudes for the pivot search) + k_garner_flow / k_limbs (exact solution numerators)",
+                           "ms": c.recon_ms / args.steps,
                            "mac_per_s": c.recon_mac / (c.recon_ms / 1e3) if c.recon_ms > 0 else None},
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -452,6 +452,8 @@ struct slipcu_factor
     int overlap = 0, seq = 0;
     // approximate pivot search (k_fraccrt) of sessions that do not keep positional factors
     int frac = 0, fracW = 8, frac_col = -1;             // enabled, words for the next column, column searched that way
+    int frac_margin = 12;                               // words kept beyond the leading zero words of the last winner
+    int frac_verify = 0;                                // (tests) re-run every accepted choice through the exact scan
     struct { int cnt, nU, s, mode, diag_slot, W; } fq = { 0, 0, 0, 0, 0, 0 };
     struct FracKey *frackey = nullptr; size_t frac_rows = 0;
     uint64_t frac_cols = 0, frac_retries = 0, frac_fallbacks = 0;
@@ -1991,6 +1993,8 @@ static int session_common_init (slipcu_factor *F, int n, int channels)
     F->x_global = env_int ("SLIP_B200_X_GLOBAL", 0);
     F->garner_mode = env_int ("SLIP_B200_GARNER", 2);
     F->frac = env_int ("SLIP_B200_FRAC", 1);
+    F->frac_margin = std::max (0, env_int ("SLIP_B200_FRAC_MARGIN", 12));      // 0 in tests: forces the add-words retry
+    F->frac_verify = env_int ("SLIP_B200_FRAC_VERIFY", 0);
     CU (cudaFuncSetAttribute (k_garner_flow<1, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     CU (cudaFuncSetAttribute (k_garner_flow<2, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     CU (cudaFuncSetAttribute (k_garner_flow<3, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
@@ -2470,7 +2474,7 @@ extern "C" int slipcu_factor_column_wait (slipcu_factor *F, slipcu_pivot_info *i
         F->frac_cols++;
         while (!info->reserved[0] && info->best_slot >= 0 && info->reserved[1] > F->fq.W - 10 && F->fq.W < cap)
         {
-            const int W = std::min (cap, std::max (2 * F->fq.W, info->reserved[1] + 12));
+            const int W = std::min (cap, std::max (2 * F->fq.W, info->reserved[1] + 12));      // (always the full margin here)
             F->frac_retries++;
             int rc = run_frac (F, hc, F->fq.cnt, F->fq.nU, F->fq.s, F->fq.mode, F->fq.diag_slot, W);
             if (rc) return rc;
@@ -2491,8 +2495,25 @@ extern "C" int slipcu_factor_column_wait (slipcu_factor *F, slipcu_pivot_info *i
             g_d2h_bytes += sizeof (slipcu_pivot_info);
             *info = *F->h_info;
         }
-        else if (info->best_slot >= 0)
-            F->fracW = std::min (FRAC_WMAX, std::max (8, info->reserved[1] + 12));  // words for the next column
+        else
+        {
+            if (info->best_slot >= 0)
+                F->fracW = std::min (FRAC_WMAX, std::max (8, info->reserved[1] + F->frac_margin));  // words for the next column
+            if (F->frac_verify)
+            {   // self-check: the accepted choice must be what the exact scan finds
+                const slipcu_pivot_info got = *info;
+                int rc = run_garner (F, hc.base, F->fq.cnt, F->fq.nU, F->fq.cnt - F->fq.nU, F->fq.s, hc.sign);
+                if (rc == SLIPCU_OK) rc = run_exact_scan (F, hc, F->fq.cnt, F->fq.nU, F->fq.mode, F->fq.diag_slot);
+                if (rc) return rc;
+                CU (cudaMemcpyAsync (F->h_info, F->d_info, sizeof (slipcu_pivot_info), cudaMemcpyDeviceToHost, F->st));
+                CU (cudaStreamSynchronize (F->st));
+                const slipcu_pivot_info &ex = *F->h_info;
+                if (ex.best_slot != got.best_slot || ex.diag_eligible != got.diag_eligible
+                    || ex.diag_vs_best != got.diag_vs_best || (got.best_slot >= 0 && ex.best_sign != got.best_sign))
+                    return fail (SLIPCU_CUDA_ERROR, "approximate pivot search", "accepted choice differs from the exact scan");
+                F->frac_col = -1;
+            }
+        }
         info->reserved[0] = info->reserved[1] = info->reserved[2] = 0;
     }
     g_hw[5] += wall_s () - tw;

@@ -239,7 +239,7 @@ def test_channel_prime_dividing_a_pivot_is_retired(gpu, oracle):
                                  {"SLIP_B200_CH": "32", "SLIP_B200_X_GLOBAL": "1"}, {"SLIP_B200_GARNER": "1"},
                                  {"SLIP_B200_GARNER": "0"}, {"SLIP_B200_CPT": "2"}, {"SLIP_B200_CPT": "4"},
                                  {"SLIP_B200_GARNER_E": "1"}, {"SLIP_B200_GARNER_E": "3"}, {"SLIP_B200_GARNER_E": "5"},
-                                 {"SLIP_B200_GARNER_E": "6"}, {"SLIP_B200_OVERLAP": "0"}, {"SLIP_B200_FRAC": "0"},
+                                 {"SLIP_B200_GARNER_E": "6"}, {"SLIP_B200_OVERLAP": "0"}, {"SLIP_B200_FRAC": "0"}, {"SLIP_B200_FRAC_MARGIN": "0"},
                                  {"SLIP_B200_CPT": "2", "SLIP_B200_CH": "32", "SLIP_B200_X_GLOBAL": "1"}])
 def test_kernel_variants_agree(gpu, oracle, env):
     """The kernel configurations that large problems select automatically (wider channel blocks,
@@ -321,3 +321,36 @@ def test_long_steps_cross_chunk_boundaries(gpu, oracle, n):
     want = cases.run_oracle(oracle, n, cp, ri, vals, b, q)
     got = cases.run_library(gpu, n, cp, ri, vals, b, q)
     cases.assert_same_factorization(got, want, f"dense head n={n}")
+
+
+@pytest.mark.parametrize("env", [{"SLIP_B200_FRAC_VERIFY": "1"},
+                                 {"SLIP_B200_FRAC_VERIFY": "1", "SLIP_B200_FRAC_MARGIN": "0"}])
+@pytest.mark.parametrize("pivot", [capi.SLIP_SMALLEST, capi.SLIP_TOL_SMALLEST, capi.SLIP_LARGEST, capi.SLIP_TOL_LARGEST])
+@pytest.mark.parametrize("case", ["random30bit", "laplacian_small_ints"])
+def test_approximate_pivot_search_is_exact(gpu, pivot, env, case):
+    """SLIP_solve_mpq searches the pivots on approximate magnitudes (fractional CRT) and accepts a
+    choice only when it is proven.  With SLIP_B200_FRAC_VERIFY the library re-runs every accepted
+    choice through the exact reconstruction + scan and fails on any difference (slot, diagonal
+    flags, sign).  With no margin of words the columns first fail for lack of precision and are
+    repeated with more words; the small-integer Laplacian is full of ties, which go to the exact
+    scan.  The solution must satisfy A x = b exactly on every route."""
+    if case == "random30bit":
+        n, cp, ri, vals, b = synth.random_sparse(90, 6, 30, seed=41, nrhs=2)
+    else:
+        n, cp, ri, vals, b = synth.laplacian_2d(12, 8, seed=6, nrhs=2, rhs_bits=8)
+    q = cases.colamd_like_order(n, cp, ri)
+    tol = 0.3 if pivot in (capi.SLIP_TOL_SMALLEST, capi.SLIP_TOL_LARGEST) else None
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        o = gpu.default_options(pivot=pivot, order=capi.SLIP_NO_ORDERING, tol=tol)
+        A = gpu.sparse_from_csc(n, cp, ri, vals); B = gpu.dense_from_rows(b)
+        S = gpu.analyze(A, o, q=q)
+        x = gpu.solve_mpq(A, S, B, o)
+        assert gpu.dll.SLIP_check_solution(A, x, B) == 0
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v

@@ -1596,7 +1596,7 @@ __global__ void __launch_bounds__ (FRAC_WARPS * 32) k_fraccrt (FracArgs a)
             }
         }
         const int lim = min (32, s - i0);
-#pragma unroll 8
+#pragma unroll 4
         for (int j = 0; j < lim; ++j)
         {
             const u32 *ur = a.urec + (size_t) (i0 + j) * FRAC_WMAX;

@@ -294,6 +294,17 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
             /* while the GPU works: the part of the next pattern that does not depend on pivot k */
             int32_t ncnt = 0 ;
             if (k + 1 < n) ncnt = reach_unordered (A, S->q [k + 1], k, &P, pinv, mark, k + 2, stack, npat) ;
+            /* bookkeeping that does not depend on pivot k, also while the GPU works */
+            for (int32_t u = 0 ; u < nU ; u++)
+            {   /* work model: every L entry below the pivot of column upos[u] is updated once */
+                const int32_t j = upos [u] ;
+                const double len = (double) (P.ptr [j + 1] - P.ptr [j]) - P.nU [j] - 1 ;
+                const double w = ceil (cumbits_at [j] / 32.0) ;
+                work_updates += len ; work_limbmul += 3.0 * len * w * w ;
+            }
+            cumbits_at [k] = cum_bits ;
+            SLIP_TRY (patterns_reserve (&P, cnt)) ;
+            memcpy (P.rows + P.used, pat, (size_t) cnt * sizeof (int32_t)) ;
             t_sym += now_s () - tt ; tt = now_s () ;
             slipcu_pivot_info info ;
             rc = slipcu_factor_column_wait (dev, &info) ;
@@ -309,16 +320,6 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
                 pinv [prow] = k ; pinv [displaced] = oldpos ;
             }
             SLIP_TRY (slip_from_device_status (slipcu_factor_set_pivot (dev, k, slot))) ;
-            for (int32_t u = 0 ; u < nU ; u++)
-            {   /* work model: every L entry below the pivot of column upos[u] is updated once */
-                const int32_t j = upos [u] ;
-                const double len = (double) (P.ptr [j + 1] - P.ptr [j]) - P.nU [j] - 1 ;
-                const double w = ceil (cumbits_at [j] / 32.0) ;
-                work_updates += len ; work_limbmul += 3.0 * len * w * w ;
-            }
-            cumbits_at [k] = cum_bits ;
-            SLIP_TRY (patterns_reserve (&P, cnt)) ;
-            memcpy (P.rows + P.used, pat, (size_t) cnt * sizeof (int32_t)) ;
             P.used += cnt ;
             P.ptr [k + 1] = P.used ; P.nU [k] = nU ; P.piv [k] = slot ;
             if (k == n - 1)

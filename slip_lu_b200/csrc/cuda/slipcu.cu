@@ -1595,24 +1595,34 @@ __global__ void __launch_bounds__ (FRAC_WARPS * 32) k_fraccrt (FracArgs a)
                 c[e] = mont_redc (mont_mul (x, mi, pi, ni), pi, ni);        // standard form, < p_i
             }
         }
-        const int lim = min (32, s - i0);
-#pragma unroll 4
-        for (int j = 0; j < lim; ++j)
+        // the reciprocal words of eight channels are requested together (the loop is bound by the
+        // latency of these L2 loads); channels past s have c = 0 and read row s-1 again
+#pragma unroll 1
+        for (int j0 = 0; j0 < 32; j0 += 8)
         {
-            const u32 *ur = a.urec + (size_t) (i0 + j) * FRAC_WMAX;
-            u32 u[NW];
+            if (i0 + j0 >= s) break;
+            u32 u[8][NW];
 #pragma unroll
-            for (int q = 0; q < NW; ++q)
+            for (int j = 0; j < 8; ++j)
             {
-                const int l = lane + 32 * q;                  // word position, 0 = least significant
-                u[q] = (l < W) ? ur[W - 1 - l] : 0u;
+                const u32 *ur = a.urec + (size_t) min (i0 + j0 + j, s - 1) * FRAC_WMAX;
+#pragma unroll
+                for (int q = 0; q < NW; ++q)
+                {
+                    const int l = lane + 32 * q;              // word position, 0 = least significant
+                    u[j][q] = (l < W) ? ur[W - 1 - l] : 0u;
+                }
             }
 #pragma unroll
-            for (int e = 0; e < E; ++e)
+            for (int j = 0; j < 8; ++j)
             {
-                const u32 cj = __shfl_sync (full, c[e], j);
 #pragma unroll
-                for (int q = 0; q < NW; ++q) mac96 (a0[e][q], a1[e][q], a2[e][q], cj, u[q]);
+                for (int e = 0; e < E; ++e)
+                {
+                    const u32 cj = __shfl_sync (full, c[e], j0 + j);
+#pragma unroll
+                    for (int q = 0; q < NW; ++q) mac96 (a0[e][q], a1[e][q], a2[e][q], cj, u[j][q]);
+                }
             }
         }
     }

@@ -28,11 +28,17 @@ typedef struct
     int64_t *ptr ;       /* n+1 */
     int32_t *nU ;        /* n: size of the U part of each pattern */
     int32_t *piv ;       /* n: slot of the pivot */
+    /* depth-first search view of the L parts (same offsets as rows): a reorderable copy whose
+     * first pend[j] rows are the only ones the search has to follow (symmetric pruning) */
+    int32_t *prows ;
+    int32_t *pend ;      /* n */
+    int8_t *pruned ;     /* n */
 } pattern_store ;
 
 static void patterns_free (pattern_store *P)
 {
     SLIP_free (P->rows) ; SLIP_free (P->ptr) ; SLIP_free (P->nU) ; SLIP_free (P->piv) ;
+    SLIP_free (P->prows) ; SLIP_free (P->pend) ; SLIP_free (P->pruned) ;
     memset (P, 0, sizeof (*P)) ;
 }
 
@@ -44,7 +50,11 @@ static SLIP_info patterns_init (pattern_store *P, int32_t n, int64_t guess)
     P->ptr = (int64_t *) SLIP_calloc ((size_t) n + 1, sizeof (int64_t)) ;
     P->nU = (int32_t *) SLIP_calloc ((size_t) n, sizeof (int32_t)) ;
     P->piv = (int32_t *) SLIP_calloc ((size_t) n, sizeof (int32_t)) ;
-    if (!P->rows || !P->ptr || !P->nU || !P->piv) { patterns_free (P) ; return SLIP_OUT_OF_MEMORY ; }
+    P->prows = (int32_t *) SLIP_malloc ((size_t) P->cap * sizeof (int32_t)) ;
+    P->pend = (int32_t *) SLIP_calloc ((size_t) n, sizeof (int32_t)) ;
+    P->pruned = (int8_t *) SLIP_calloc ((size_t) n, sizeof (int8_t)) ;
+    if (!P->rows || !P->ptr || !P->nU || !P->piv || !P->prows || !P->pend || !P->pruned)
+    { patterns_free (P) ; return SLIP_OUT_OF_MEMORY ; }
     return SLIP_OK ;
 }
 
@@ -55,7 +65,10 @@ static SLIP_info patterns_reserve (pattern_store *P, int64_t extra)
     while (ncap < P->used + extra) ncap *= 2 ;
     int32_t *nr = (int32_t *) realloc (P->rows, (size_t) ncap * sizeof (int32_t)) ;
     if (!nr) return SLIP_OUT_OF_MEMORY ;
-    P->rows = nr ; P->cap = ncap ;
+    P->rows = nr ;
+    int32_t *np = (int32_t *) realloc (P->prows, (size_t) ncap * sizeof (int32_t)) ;
+    if (!np) return SLIP_OUT_OF_MEMORY ;
+    P->prows = np ; P->cap = ncap ;
     return SLIP_OK ;
 }
 
@@ -79,10 +92,10 @@ static int32_t reach_unordered (const SLIP_sparse *A, int32_t col, int32_t klim,
             const int32_t pos = pinv [r] ;
             out [cnt++] = r ;
             if (pos < klim)
-            {   /* row r is the pivot of column pos: follow the L part of that column */
-                const int32_t *rows = P->rows + P->ptr [pos] ;
-                const int32_t len = (int32_t) (P->ptr [pos + 1] - P->ptr [pos]) ;
-                for (int32_t m = P->nU [pos] ; m < len ; m++)
+            {   /* row r is the pivot of column pos: follow the (pruned) L part of that column */
+                const int32_t *rows = P->prows + P->ptr [pos] + P->nU [pos] ;
+                const int32_t len = P->pend [pos] ;
+                for (int32_t m = 0 ; m < len ; m++)
                 {
                     const int32_t rr = rows [m] ;
                     if (mark [rr] != stamp) { mark [rr] = stamp ; stack [sp++] = rr ; }
@@ -91,6 +104,36 @@ static int32_t reach_unordered (const SLIP_sparse *A, int32_t col, int32_t klim,
         }
     }
     return cnt ;
+}
+
+/* Symmetric pruning (Eisenstat & Liu; the pruning of left-looking LU codes such as KLU), after
+ * row prow became the pivot of column k: for every column j of the U part of column k whose L part
+ * contains prow, the rows of L(:,j) that are not pivotal yet are also rows of L(:,k) (column k
+ * reached j, so its pattern holds all of them), hence any later search that arrives at j finds
+ * them through prow -> column k.  Only the pivotal rows of L(:,j) stay visible: in the dense
+ * trailing part a search then costs O(columns) instead of O(entries).  The reach SET is unchanged,
+ * and the order of a pattern is fixed afterwards by order_by_position, so nothing else is affected. */
+static void prune_columns (pattern_store *P, int32_t k, int32_t prow, int32_t nU, const int32_t *upos,
+    const int32_t *pinv)
+{
+    for (int32_t u = 0 ; u < nU ; u++)
+    {
+        const int32_t j = upos [u] ;
+        if (P->pruned [j]) continue ;
+        int32_t *rj = P->prows + P->ptr [j] + P->nU [j] ;
+        const int32_t lj = P->pend [j] ;
+        int32_t m = 0 ;
+        while (m < lj && rj [m] != prow) m++ ;
+        if (m == lj) continue ;
+        int32_t head = 0, tail = lj ;
+        while (head < tail)
+        {
+            if (pinv [rj [head]] <= k) head++ ;
+            else { tail-- ; const int32_t t = rj [head] ; rj [head] = rj [tail] ; rj [tail] = t ; }
+        }
+        P->pend [j] = tail ;
+        P->pruned [j] = 1 ;
+    }
 }
 
 /* order a pattern by current row position (slip_sort_xi.c): positions are a permutation, so a
@@ -218,6 +261,8 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
     const int scheme = (int) option->pivot ;
     SLIP_info status = SLIP_OK ;
     const int timing = getenv ("SLIP_B200_TIMING") != NULL ;
+    const char *prune_env = getenv ("SLIP_B200_PRUNE") ;
+    const int use_pruning = !(prune_env && prune_env [0] == '0') ;      /* symmetric pruning of the reach (default on) */
     double t_sym = 0, t_dev = 0, t_piv = 0, t_begin = 0, t0 = now_s (), tt ;
     double work_updates = 0, work_limbmul = 0 ;
     double *cumbits_at = (double *) SLIP_calloc ((size_t) n, sizeof (double)) ;
@@ -305,6 +350,7 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
             cumbits_at [k] = cum_bits ;
             SLIP_TRY (patterns_reserve (&P, cnt)) ;
             memcpy (P.rows + P.used, pat, (size_t) cnt * sizeof (int32_t)) ;
+            memcpy (P.prows + P.used, pat, (size_t) cnt * sizeof (int32_t)) ;
             t_sym += now_s () - tt ; tt = now_s () ;
             slipcu_pivot_info info ;
             rc = slipcu_factor_column_wait (dev, &info) ;
@@ -322,6 +368,8 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
             SLIP_TRY (slip_from_device_status (slipcu_factor_set_pivot (dev, k, slot))) ;
             P.used += cnt ;
             P.ptr [k + 1] = P.used ; P.nU [k] = nU ; P.piv [k] = slot ;
+            P.pend [k] = cnt - nU ; P.pruned [k] = 0 ;
+            if (use_pruning) prune_columns (&P, k, prow, nU, upos, pinv) ;
             if (k == n - 1)
             {   /* det = rho[n-1], kept with the resident factors for the rational solve */
                 res = (slip_resident *) SLIP_calloc (1, sizeof (slip_resident)) ;

@@ -802,15 +802,29 @@ __global__ void __launch_bounds__ (TRI_THREADS * 4 / CPT, 2) k_trisolve (TriArgs
                                   + ((size_t) cb * d0.z) * 4 + (size_t) tid * 16;
         const u32 ldst = sb + (u32) tid * 16;
         const int lp = nrows * (CH / 4);               // 16-byte pieces of L rows, at most CPT per thread
-        if (tid < lp) cp_async16_off<0> (ldst, lsrc);
-        if (tid + NT < lp) cp_async16_off<NT * 16> (ldst, lsrc);
-        if (CPT == 4)
-        {
-            if (tid + 2 * NT < lp) cp_async16_off<2 * NT * 16> (ldst, lsrc);
-            if (tid + 3 * NT < lp) cp_async16_off<3 * NT * 16> (ldst, lsrc);
+        if (nrows == SM::R)
+        {   // full chunk (most of the bytes): no per-piece predicates
+            cp_async16_off<0> (ldst, lsrc);
+            cp_async16_off<NT * 16> (ldst, lsrc);
+            if (CPT == 4)
+            {
+                cp_async16_off<2 * NT * 16> (ldst, lsrc);
+                cp_async16_off<3 * NT * 16> (ldst, lsrc);
+            }
+            if (tid < RG) cp_async16 (sb + SM::L_BYTES + (u32) tid * 16, a.slots + (size_t) d0.w + (size_t) tid * 4);
         }
-        if (tid < min (nrows, RG))                     // one 16-byte group of targets per row group in use
-            cp_async16 (sb + SM::L_BYTES + (u32) tid * 16, a.slots + (size_t) d0.w + (size_t) tid * 4);
+        else
+        {
+            if (tid < lp) cp_async16_off<0> (ldst, lsrc);
+            if (tid + NT < lp) cp_async16_off<NT * 16> (ldst, lsrc);
+            if (CPT == 4)
+            {
+                if (tid + 2 * NT < lp) cp_async16_off<2 * NT * 16> (ldst, lsrc);
+                if (tid + 3 * NT < lp) cp_async16_off<3 * NT * 16> (ldst, lsrc);
+            }
+            if (tid < min (nrows, RG))                 // one 16-byte group of targets per row group in use
+                cp_async16 (sb + SM::L_BYTES + (u32) tid * 16, a.slots + (size_t) d0.w + (size_t) tid * 4);
+        }
         if ((d1.y & 0x10000u) && tid < CH / 4)
             cp_async16 (sb + SM::L_BYTES + SM::S_BYTES + (u32) tid * 16,
                         a.invrho + (size_t) d1.x * S + (size_t) cb * CH + 4 * tid);

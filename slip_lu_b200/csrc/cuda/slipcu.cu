@@ -881,15 +881,34 @@ __global__ void __launch_bounds__ (TRI_THREADS * 4 / CPT, 2) k_trisolve (TriArgs
             const u32 t[4] = { tq.x, tq.y, tq.z, tq.w };
             const u32 lrow = sb + (u32) rg * (CH * 4) + qc * 4;
             V l[4], w[4];
+            const u32 xsa = smem0 + qc * 4;            // (XS) shared-memory address of this thread's channels of row 0
 #pragma unroll
             for (int q = 0; q < 4; ++q)
             {
                 l[q] = ldsv<CPT> (lrow + q * RG * CH * 4);
-                if (XS || t[q] != spare) w[q] = ldv<CPT> (xb + t[q]);
+                if (XS && CPT == 4)
+                {   // predicated in place (no branch, the four rows stay interleaved): rows without
+                    // a target neither load nor store
+                    asm volatile ("{\n .reg .pred p;\n setp.ne.u32 p, %4, %5;\n"
+                                  " @p ld.shared.v4.u32 {%0,%1,%2,%3}, [%6];\n}"
+                                  : "=r"(w[q].v[0]), "=r"(w[q].v[1]), "=r"(w[q].v[2]), "=r"(w[q].v[3])
+                                  : "r"(t[q]), "r"(spare), "r"(xsa + t[q]));
+                }
+                else if (XS || t[q] != spare) w[q] = ldv<CPT> (xb + t[q]);
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-                if (XS || t[q] != spare) stv<CPT> (xb + t[q], sub_mulv<CPT> (w[q], l[q], negy, pv, niv));
+            {
+                if (XS && CPT == 4)
+                {
+                    const V r = sub_mulv<CPT> (w[q], l[q], negy, pv, niv);
+                    asm volatile ("{\n .reg .pred p;\n setp.ne.u32 p, %4, %5;\n"
+                                  " @p st.shared.v4.u32 [%6], {%0,%1,%2,%3};\n}"
+                                  :: "r"(r.v[0]), "r"(r.v[1]), "r"(r.v[2]), "r"(r.v[3]),
+                                     "r"(t[q]), "r"(spare), "r"(xsa + t[q]) : "memory");
+                }
+                else if (XS || t[q] != spare) stv<CPT> (xb + t[q], sub_mulv<CPT> (w[q], l[q], negy, pv, niv));
+            }
         }
         if (meta & 0x20000u) ++u;
         bc = (bc == TRI_BUFS - 1) ? 0 : bc + 1;

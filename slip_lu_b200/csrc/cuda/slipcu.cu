@@ -122,7 +122,7 @@ __device__ __forceinline__ u32 lazy_redc (u64 T, u32 p, u32 ninv)
 // ------------------------------------------------------------------------------------------------
 // channel primes and reconstruction tables (shared by all sessions, immutable once built)
 // ------------------------------------------------------------------------------------------------
-#define FRAC_WMAX 128          // words of the fixed-point reciprocals 1/p_i
+#define FRAC_WMAX 256          // words of the fixed-point reciprocals 1/p_i
 
 struct Tables
 {
@@ -2311,13 +2311,16 @@ static int run_frac (slipcu_factor *F, const HostCol &hc, int cnt, int nU, int s
     a.key = F->frackey;
     {
         ScopedTimer tm (F, &g_recon_ms);
-        const int NW = (W + 31) / 32;
+        int NW = (W + 31) / 32;
         int E = ne >= 4 * F->sms ? 4 : (ne >= F->sms ? 2 : 1);            // entries per CTA (they share the table loads)
         if (E == 4 && NW == 4) E = 2;                                     // keeps the partial sums within 48 KB
+        if (NW > 4) { E = 1; NW = NW <= 6 ? 6 : 8; }                      // long fractions: one entry per CTA
         const int grid = (ne + E - 1) / E;
         const size_t fsm = (size_t) FRAC_WARPS * E * NW * 32 * 3 * sizeof (u32) + (size_t) FRAC_WARPS * E * sizeof (int);
 #define FRAC_LAUNCH(EE, NN) k_fraccrt<EE, NN><<<grid, FRAC_WARPS * 32, fsm, F->st>>> (a)
-        if (E == 4) { if (NW == 1) FRAC_LAUNCH (4, 1); else if (NW == 2) FRAC_LAUNCH (4, 2); else if (NW == 3) FRAC_LAUNCH (4, 3); else FRAC_LAUNCH (4, 4); }
+        if (NW == 6) FRAC_LAUNCH (1, 6);
+        else if (NW == 8) FRAC_LAUNCH (1, 8);
+        else if (E == 4) { if (NW == 1) FRAC_LAUNCH (4, 1); else if (NW == 2) FRAC_LAUNCH (4, 2); else if (NW == 3) FRAC_LAUNCH (4, 3); else FRAC_LAUNCH (4, 4); }
         else if (E == 2) { if (NW == 1) FRAC_LAUNCH (2, 1); else if (NW == 2) FRAC_LAUNCH (2, 2); else if (NW == 3) FRAC_LAUNCH (2, 3); else FRAC_LAUNCH (2, 4); }
         else { if (NW == 1) FRAC_LAUNCH (1, 1); else if (NW == 2) FRAC_LAUNCH (1, 2); else if (NW == 3) FRAC_LAUNCH (1, 3); else FRAC_LAUNCH (1, 4); }
 #undef FRAC_LAUNCH

@@ -80,6 +80,14 @@ int slipcu_factor_column_launch (slipcu_factor *F, int k, int col, int cnt, int 
                                  int scheme, int diag_slot);
 int slipcu_factor_column_wait (slipcu_factor *F, slipcu_pivot_info *info);
 
+/* speculative first part of the column that will be column k: the steps of
+ * slip_REF_triangular_solve.c:150-232 with every pivot committed so far, on the pattern known
+ * before the pivot of column k-1 (rows sorted by position, nU of them pivotal, upos their pivot
+ * positions).  The following slipcu_factor_column_launch for column k starts from its result and
+ * applies the remaining steps (those from U slot nU on). */
+int slipcu_factor_spec_launch (slipcu_factor *F, int k, int col, int cnt, int nU,
+                               const int32_t *rows, const int32_t *upos);
+
 /* one reconstructed entry of the current column (used only for the rational tolerance test of
  * SLIP_TOL_SMALLEST / SLIP_TOL_LARGEST, slip_get_pivot.c:94-143).  limbs must hold stride words. */
 int slipcu_factor_fetch_entry (slipcu_factor *F, int k, int slot, uint32_t *limbs,

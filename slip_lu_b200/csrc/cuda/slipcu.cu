@@ -454,6 +454,10 @@ struct slipcu_factor
     int frac = 0, fracW = 8, frac_col = -1;             // enabled, words for the next column, column searched that way
     int frac_margin = 12;                               // words kept beyond the leading zero words of the last winner
     int frac_verify = 0;                                // (tests) re-run every accepted choice through the exact scan
+    // speculative first part of the next column (all steps but the one with the column in flight)
+    u32 *spec_buf = nullptr; size_t spec_words = 0;     // [S/CH][cnt][CH] normalised vector
+    int32_t *h_packet2 = nullptr;                       // pinned staging of its pattern
+    int32_t *spec_rows = nullptr; int spec_cnt = 0, spec_col = -1, spec_nU = 0;
     struct { int cnt, nU, s, mode, diag_slot, W; } fq = { 0, 0, 0, 0, 0, 0 };
     struct FracKey *frackey = nullptr; size_t frac_rows = 0;
     uint64_t frac_cols = 0, frac_retries = 0, frac_fallbacks = 0;
@@ -674,6 +678,9 @@ struct TriArgs
     const int32_t *pos;      // [n] row -> slot
     int x_in_smem;
     int nchunks;             // total pipeline chunks of this launch
+    const int32_t *upos;     // [nU] pivot position of each U slot (levels of the published U part)
+    int publish;             // 1: write true REF values; 0: leave the vector normalised (speculative first part)
+    int u0;                  // U slot of the first step in the chunk list
 };
 
 template <int CH>
@@ -842,12 +849,23 @@ __global__ void __launch_bounds__ (TRI_THREADS * 4 / CPT, 2) k_trisolve (TriArgs
         __syncthreads ();
         const u32 *src = a.src + (size_t) cb * a.src_total * CH;
         const int first = a.src_first + (int) (blockIdx.y * a.src_y_stride);
-        for (int i = tid; i < a.src_cnt * CH; i += NT)
-        {
-            const int e = i / CH, ch = i % CH;
-            const int row = a.src_rows ? a.src_rows[e] : e;
-            xs[a.pos[row] * CH + ch] = src[((size_t) first + (size_t) e * a.src_step) * CH + ch];
+        if (a.src_cnt >= 64)
+        {   // long source (dense right-hand side, speculative first part): CPT channels per access,
+            // one slot lookup per row
+            const int qs = (tid % TPR) * CPT;
+            for (int e = tid / TPR; e < a.src_cnt; e += NT / TPR)
+            {
+                const int row = a.src_rows ? a.src_rows[e] : e;
+                stv<CPT> (xs + (size_t) a.pos[row] * CH + qs, ldv<CPT> (src + ((size_t) first + (size_t) e * a.src_step) * CH + qs));
+            }
         }
+        else
+            for (int i = tid; i < a.src_cnt * CH; i += NT)
+            {
+                const int e = i / CH, ch = i % CH;
+                const int row = a.src_rows ? a.src_rows[e] : e;
+                xs[a.pos[row] * CH + ch] = src[((size_t) first + (size_t) e * a.src_step) * CH + ch];
+            }
     }
 
     const int qc = (tid % TPR) * CPT, rg = tid / TPR;  // first channel of this thread inside the block, row group
@@ -857,7 +875,7 @@ __global__ void __launch_bounds__ (TRI_THREADS * 4 / CPT, 2) k_trisolve (TriArgs
     V negy;
 #pragma unroll
     for (int i = 0; i < CPT; ++i) negy.v[i] = 0;
-    int u = 0;                                         // elimination step of the current chunk
+    int u = a.u0;                                      // elimination step (= U slot) of the current chunk
     int bc = 0, bi = TRI_BUFS - 1;                     // buffers of the chunk consumed / requested
     for (int c = 0; c < nchunks; ++c)
     {
@@ -919,7 +937,7 @@ __global__ void __launch_bounds__ (TRI_THREADS * 4 / CPT, 2) k_trisolve (TriArgs
     for (int t = rg; t < cnt; t += RG)
     {
         V v = ldv<CPT> (xs + t * CH + qc);
-        const int lvl = (t < nU) ? a.steps[t].j : a.k;           // level the entry is brought to
+        const int lvl = a.publish ? ((t < nU) ? a.upos[t] : a.k) : 0;      // level the entry is brought to
         if (lvl >= 1) v = mont_mulv<CPT> (v, ldv<CPT> (a.rho + (size_t) (lvl - 1) * S + c0), pv, niv);
         stv<CPT> (xg + t * CH + qc, v);
     }
@@ -1944,6 +1962,8 @@ extern "C" void slipcu_factor_free (slipcu_factor *F)
     pool_free (F->tmp_limbs); pool_free (F->tmp_nl);
     pool_free (F->slots); pool_free (F->steps); pool_free (F->chunks);
     if (F->h_packet) cudaFreeHost (F->h_packet);
+    if (F->h_packet2) cudaFreeHost (F->h_packet2);
+    pool_free (F->spec_buf);
     if (F->h_info) cudaFreeHost (F->h_info);
     if (F->ev) cudaEventDestroy (F->ev);
     if (F->ev0) cudaEventDestroy (F->ev0);
@@ -2068,6 +2088,7 @@ static int session_common_init (slipcu_factor *F, int n, int channels)
     CU (cudaMemset (F->bad, 0, sizeof (int32_t)));
     CU (cudaMemset (F->pos, 0, (size_t) n * sizeof (int32_t)));
     CU (cudaHostAlloc (&F->h_packet, ((size_t) 4 * n + 8) * sizeof (int32_t), cudaHostAllocDefault));
+    CU (cudaHostAlloc (&F->h_packet2, ((size_t) 4 * n + 8) * sizeof (int32_t), cudaHostAllocDefault));
     CU (cudaHostAlloc (&F->h_info, sizeof (slipcu_pivot_info), cudaHostAllocDefault));
     F->cols.resize (n);
     return SLIPCU_OK;
@@ -2371,12 +2392,99 @@ static int run_exact_scan (slipcu_factor *F, const HostCol &hc, int cnt, int nU,
     return SLIPCU_OK;
 }
 
+// uploads a pattern packet (rows, U positions, slot-list offsets, chunk offsets of the steps from
+// first_step on) and runs the symbolic pre-pass; returns the device copy and the chunk count
+static int upload_pattern (slipcu_factor *F, int32_t *staging, int cnt, int nU, const int32_t *rows, const int32_t *upos,
+                           int first_step, int32_t **dev_rows, int *nchunks_out)
+{
+    const int CH = F->CH;
+    memcpy (staging, rows, (size_t) cnt * sizeof (int32_t));
+    if (nU) memcpy (staging + cnt, upos, (size_t) nU * sizeof (int32_t));
+    int32_t *uoff = staging + cnt + nU;
+    int32_t *uchunk = uoff + nU + 1;
+    int64_t total = 0, nchunks = 0;
+    const int chunk_rows = tri_chunk_rows (CH);
+    for (int u = 0; u < nU; ++u)
+    {
+        uoff[u] = (int32_t) total; uchunk[u] = (int32_t) nchunks;
+        if (u < first_step) continue;                    // already applied by the speculative part
+        const HostCol &lj = F->cols[upos[u]];
+        const int len = lj.cnt - lj.nU;
+        total += tri_slot_extent (len, CH);
+        nchunks += (len + chunk_rows - 1) / chunk_rows;
+        if (total > INT32_MAX) return fail (SLIPCU_BAD_INPUT, "slipcu_factor_column", "column has too many updates");
+    }
+    uoff[nU] = (int32_t) total; uchunk[nU] = (int32_t) nchunks;
+    const size_t pk_ints = (size_t) cnt + 3 * (size_t) nU + 2;
+    int32_t *d = (int32_t *) F->ints.alloc (pk_ints * sizeof (int32_t));
+    if (!d) return fail (SLIPCU_OUT_OF_MEMORY, "slipcu_factor_column", "device memory exhausted");
+    CU (cudaMemcpyAsync (d, staging, pk_ints * sizeof (int32_t), cudaMemcpyHostToDevice, F->st));
+    g_h2d_bytes += (double) pk_ints * sizeof (int32_t);
+    int rc = prepare_steps (F, cnt, nU, d, d + cnt, d + cnt + nU, d + cnt + 2 * nU + 1, (int) total, (int) nchunks);
+    if (rc) return rc;
+    *dev_rows = d; *nchunks_out = (int) nchunks;
+    return SLIPCU_OK;
+}
+
+// Speculative first part of column `col` (to become column k of the factorization): eliminates
+// with every pivot that is already committed, on the pattern known before the pivot of column k-1,
+// and leaves the normalised vector in a scratch region.  Launched behind the pivot search of
+// column k-1, so that the GPU has work while the host takes its turn.
+extern "C" int slipcu_factor_spec_launch (slipcu_factor *F, int k, int col, int cnt, int nU,
+                                          const int32_t *rows, const int32_t *upos)
+{
+    if (!F || k < 1 || k >= F->n || cnt <= 0 || cnt > F->n || nU < 0 || nU > cnt || !rows)
+        return fail (SLIPCU_BAD_INPUT, "slipcu_factor_spec_launch", "bad argument");
+    const Tables &T = *F->tab;
+    const int S = F->S, CH = F->CH;
+    const size_t words = (size_t) cnt * S;
+    if (words > F->spec_words)
+    {
+        CU (cudaStreamSynchronize (F->st));
+        pool_free (F->spec_buf); F->spec_buf = nullptr;
+        const size_t want = std::max (words, std::min ((size_t) F->n * S, F->spec_words * 2));
+        CU (pool_alloc_t (&F->spec_buf, want * sizeof (u32)));
+        F->spec_words = want;
+    }
+    int32_t *d = nullptr; int nchunks = 0;
+    int rc = upload_pattern (F, F->h_packet2, cnt, nU, rows, upos, 0, &d, &nchunks);
+    if (rc) return rc;
+    TriArgs a;
+    a.k = k; a.S = S; a.cnt = cnt; a.nU = nU;
+    a.rows = d; a.steps = F->steps; a.chunks = F->chunks; a.slots = F->slots;
+    a.src = F->dA; a.src_total = F->nz; a.src_first = F->hAp[col]; a.src_step = 1;
+    a.src_cnt = F->hAp[col + 1] - F->hAp[col]; a.src_rows = F->dAi + F->hAp[col];
+    a.src_y_stride = 0;
+    a.out = F->spec_buf; a.out_y_stride = 0;
+    a.rho = F->rho; a.invrho = F->invrho;
+    a.p = T.p; a.ninv = T.ninv; a.pos = F->pos;
+    a.nchunks = nchunks; a.upos = d + cnt; a.publish = 0; a.u0 = 0;
+    size_t smem = 0;
+    rc = tri_geometry (F, a, &smem);
+    if (rc) return rc;
+    {
+        ScopedTimer tm (F, &g_tri_ms);
+        CU (launch_tri_any (CH, F->cpt, a, dim3 (S / CH, 1), smem, F->st));
+        if (debug_check ("k_trisolve(speculative)", F->st)) return fail (SLIPCU_CUDA_ERROR, "k_trisolve", "debug");
+    }
+    double upd = 0;
+    for (int u = 0; u < nU; ++u) { const HostCol &lj = F->cols[upos[u]]; upd += (double) (lj.cnt - lj.nU - 1); }
+    g_tri_bytes += upd * (double) S * 4.0;
+    g_tri_modmul += upd * (double) S * 4.0;
+    F->spec_rows = d; F->spec_cnt = cnt; F->spec_col = k; F->spec_nU = nU;
+    return SLIPCU_OK;
+}
+
 extern "C" int slipcu_factor_column_launch (slipcu_factor *F, int k, int col, int cnt, int nU,
                                             const int32_t *rows, const int32_t *upos, int recon_channels,
                                             int scheme, int diag_slot)
 {
     if (!F || k < 0 || k >= F->n || cnt <= 0 || cnt > F->n || nU < 0 || nU >= cnt || !rows)
         return fail (SLIPCU_BAD_INPUT, "slipcu_factor_column", "bad argument");
+    // a speculative first part exists for this column: start from its vector, apply the rest
+    const bool from_spec = (F->spec_col == k);
+    const int first_step = from_spec ? F->spec_nU : 0;
+    if (from_spec && first_step > nU) return fail (SLIPCU_BAD_INPUT, "slipcu_factor_column", "speculative part does not match");
     const Tables &T = *F->tab;
     const int S = F->S, CH = F->CH;
     double tw = wall_s ();
@@ -2389,41 +2497,30 @@ extern "C" int slipcu_factor_column_launch (slipcu_factor *F, int k, int col, in
     if (rc) return rc;
     g_hw[0] += wall_s () - tw; tw = wall_s ();
     // packet: pattern rows, pivot positions of the U part, slot-list offsets (padded to 4)
-    memcpy (F->h_packet, rows, (size_t) cnt * sizeof (int32_t));
-    if (nU) memcpy (F->h_packet + cnt, upos, (size_t) nU * sizeof (int32_t));
-    int32_t *uoff = F->h_packet + cnt + nU;
-    int32_t *uchunk = uoff + nU + 1;
-    int64_t total = 0, nchunks = 0;
-    const int chunk_rows = tri_chunk_rows (CH);
-    for (int u = 0; u < nU; ++u)
-    {
-        const HostCol &lj = F->cols[upos[u]];
-        const int len = lj.cnt - lj.nU;
-        uoff[u] = (int32_t) total; uchunk[u] = (int32_t) nchunks;
-        total += tri_slot_extent (len, CH);
-        nchunks += (len + chunk_rows - 1) / chunk_rows;
-        if (total > INT32_MAX) return fail (SLIPCU_BAD_INPUT, "slipcu_factor_column", "column has too many updates");
-    }
-    uoff[nU] = (int32_t) total; uchunk[nU] = (int32_t) nchunks;
-    const size_t pk_ints = (size_t) cnt + 3 * (size_t) nU + 2;
-    hc.rows = (int32_t *) F->ints.alloc (pk_ints * sizeof (int32_t));
-    if (!hc.rows) return fail (SLIPCU_OUT_OF_MEMORY, "slipcu_factor_column", "device memory exhausted");
-    CU (cudaMemcpyAsync (hc.rows, F->h_packet, pk_ints * sizeof (int32_t), cudaMemcpyHostToDevice, F->st));
-    g_h2d_bytes += (double) pk_ints * sizeof (int32_t);
-    rc = prepare_steps (F, cnt, nU, hc.rows, hc.rows + cnt, hc.rows + cnt + nU, hc.rows + cnt + 2 * nU + 1, (int) total, (int) nchunks);
+    int nchunks = 0;
+    rc = upload_pattern (F, F->h_packet, cnt, nU, rows, upos, first_step, &hc.rows, &nchunks);
     if (rc) return rc;
 
     g_hw[1] += wall_s () - tw; tw = wall_s ();
     TriArgs a;
     a.k = k; a.S = S; a.cnt = cnt; a.nU = nU;
     a.rows = hc.rows; a.steps = F->steps; a.chunks = F->chunks; a.slots = F->slots;
-    a.src = F->dA; a.src_total = F->nz; a.src_first = F->hAp[col]; a.src_step = 1;
-    a.src_cnt = F->hAp[col + 1] - F->hAp[col]; a.src_rows = F->dAi + F->hAp[col];
+    if (from_spec)
+    {   // the vector of the speculative part, row by row into the final slots
+        a.src = F->spec_buf; a.src_total = F->spec_cnt; a.src_first = 0; a.src_step = 1;
+        a.src_cnt = F->spec_cnt; a.src_rows = F->spec_rows;
+        F->spec_col = -1;
+    }
+    else
+    {
+        a.src = F->dA; a.src_total = F->nz; a.src_first = F->hAp[col]; a.src_step = 1;
+        a.src_cnt = F->hAp[col + 1] - F->hAp[col]; a.src_rows = F->dAi + F->hAp[col];
+    }
     a.src_y_stride = 0;
     a.out = hc.base; a.out_y_stride = 0;
     a.rho = F->rho; a.invrho = F->invrho;
     a.p = T.p; a.ninv = T.ninv; a.pos = F->pos;
-    a.nchunks = (int) nchunks;
+    a.nchunks = nchunks; a.upos = hc.rows + cnt; a.publish = 1; a.u0 = first_step;
     size_t smem = 0;
     rc = tri_geometry (F, a, &smem);
     if (rc) return rc;
@@ -2435,7 +2532,7 @@ extern "C" int slipcu_factor_column_launch (slipcu_factor *F, int k, int col, in
     g_hw[2] += wall_s () - tw; tw = wall_s ();
     {   // algorithmic work of this launch
         double upd = 0;
-        for (int u = 0; u < nU; ++u) { const HostCol &lj = F->cols[upos[u]]; upd += (double) (lj.cnt - lj.nU - 1); }
+        for (int u = first_step; u < nU; ++u) { const HostCol &lj = F->cols[upos[u]]; upd += (double) (lj.cnt - lj.nU - 1); }
         g_tri_bytes += (upd + (double) cnt) * (double) S * 4.0;
         g_tri_modmul += upd * (double) S * 4.0;
         if (const char *tf = getenv ("SLIP_B200_TRACE_FILE"))
@@ -2839,7 +2936,7 @@ extern "C" int slipcu_solve (slipcu_factor *F, int nrhs, const u32 *blimbs, cons
         a.out = dz; a.out_y_stride = (size_t) n * S;
         a.rho = F->rho; a.invrho = F->invrho;
         a.p = T.p; a.ninv = T.ninv; a.pos = F->pos;
-        a.nchunks = fwd_chunks;
+        a.nchunks = fwd_chunks; a.upos = dident; a.publish = 1; a.u0 = 0;
         size_t smem = 0;
         rc = tri_geometry (F, a, &smem);
         if (rc) goto done;

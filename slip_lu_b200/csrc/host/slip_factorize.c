@@ -263,6 +263,8 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
     const int timing = getenv ("SLIP_B200_TIMING") != NULL ;
     const char *prune_env = getenv ("SLIP_B200_PRUNE") ;
     const int use_pruning = !(prune_env && prune_env [0] == '0') ;      /* symmetric pruning of the reach (default on) */
+    const char *spec_env = getenv ("SLIP_B200_SPEC") ;
+    const int use_spec = (spec_env && spec_env [0] == '1') ;             /* speculative first part of the next column */
     double t_sym = 0, t_dev = 0, t_piv = 0, t_begin = 0, t0 = now_s (), tt ;
     double work_updates = 0, work_limbmul = 0 ;
     double *cumbits_at = (double *) SLIP_calloc ((size_t) n, sizeof (double)) ;
@@ -277,8 +279,10 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
     int32_t *pat = (int32_t *) SLIP_malloc ((size_t) n * sizeof (int32_t)) ;
     int32_t *upos = (int32_t *) SLIP_malloc ((size_t) n * sizeof (int32_t)) ;
     int32_t *npat = (int32_t *) SLIP_malloc ((size_t) n * sizeof (int32_t)) ;
+    int32_t *spat = (int32_t *) SLIP_malloc ((size_t) n * sizeof (int32_t)) ;      /* speculative pattern, ordered */
+    int32_t *supos = (int32_t *) SLIP_malloc ((size_t) n * sizeof (int32_t)) ;
     int32_t *posflag = (int32_t *) SLIP_calloc ((size_t) n, sizeof (int32_t)) ;
-    if (!colbits || !row_at || !mark || !stack || !pat || !upos || !cumbits_at || !npat || !posflag) { status = SLIP_OUT_OF_MEMORY ; goto cleanup ; }
+    if (!colbits || !row_at || !mark || !stack || !pat || !upos || !cumbits_at || !npat || !posflag || !spat || !supos) { status = SLIP_OUT_OF_MEMORY ; goto cleanup ; }
 
     for (int32_t a = 0 ; a < nz ; a++)
         if (A->i [a] < 0 || A->i [a] >= n) { status = SLIP_INCORRECT_INPUT ; goto cleanup ; }
@@ -339,6 +343,22 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
             /* while the GPU works: the part of the next pattern that does not depend on pivot k */
             int32_t ncnt = 0 ;
             if (k + 1 < n) ncnt = reach_unordered (A, S->q [k + 1], k, &P, pinv, mark, k + 2, stack, npat) ;
+            /* speculative first part of column k+1: every step except the one with column k, whose
+               pivot is not known yet, on the pattern found so far (the rest joins it below) */
+            if (use_spec && ncnt > 0)
+            {
+                memcpy (spat, npat, (size_t) ncnt * sizeof (int32_t)) ;
+                order_by_position (n, ncnt, spat, pinv, row_at, posflag, n + k + 2) ;
+                int32_t snU = 0 ;
+                for (int32_t t = 0 ; t < ncnt ; t++)
+                {
+                    const int32_t pos = pinv [spat [t]] ;
+                    if (pos < k) supos [snU++] = pos ;
+                }
+                rc = slipcu_factor_spec_launch (dev, k + 1, S->q [k + 1], ncnt, snU, spat, supos) ;
+                if (rc == SLIPCU_BAD_PRIME) { retry = 1 ; break ; }
+                SLIP_TRY (slip_from_device_status (rc)) ;
+            }
             /* bookkeeping that does not depend on pivot k, also while the GPU works */
             for (int32_t u = 0 ; u < nU ; u++)
             {   /* work model: every L entry below the pivot of column upos[u] is updated once */
@@ -477,6 +497,7 @@ cleanup:
     patterns_free (&P) ;
     SLIP_free (colbits) ; SLIP_free (row_at) ; SLIP_free (mark) ; SLIP_free (stack) ;
     SLIP_free (pat) ; SLIP_free (upos) ; SLIP_free (cumbits_at) ; SLIP_free (npat) ; SLIP_free (posflag) ;
+    SLIP_free (spat) ; SLIP_free (supos) ;
     return status ;
 }
 

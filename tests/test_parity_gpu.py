@@ -239,7 +239,7 @@ def test_channel_prime_dividing_a_pivot_is_retired(gpu, oracle):
                                  {"SLIP_B200_CH": "32", "SLIP_B200_X_GLOBAL": "1"}, {"SLIP_B200_GARNER": "1"},
                                  {"SLIP_B200_GARNER": "0"}, {"SLIP_B200_CPT": "2"}, {"SLIP_B200_CPT": "4"},
                                  {"SLIP_B200_GARNER_E": "1"}, {"SLIP_B200_GARNER_E": "3"}, {"SLIP_B200_GARNER_E": "5"},
-                                 {"SLIP_B200_GARNER_E": "6"}, {"SLIP_B200_OVERLAP": "0"}, {"SLIP_B200_FRAC": "0"}, {"SLIP_B200_FRAC_MARGIN": "0"}, {"SLIP_B200_PRUNE": "0"},
+                                 {"SLIP_B200_GARNER_E": "6"}, {"SLIP_B200_OVERLAP": "0"}, {"SLIP_B200_FRAC": "0"}, {"SLIP_B200_FRAC_MARGIN": "0"}, {"SLIP_B200_PRUNE": "0"}, {"SLIP_B200_SPEC": "1"},
                                  {"SLIP_B200_CPT": "2", "SLIP_B200_CH": "32", "SLIP_B200_X_GLOBAL": "1"}])
 def test_kernel_variants_agree(gpu, oracle, env):
     """The kernel configurations that large problems select automatically (wider channel blocks,

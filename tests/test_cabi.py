@@ -199,3 +199,45 @@ def test_bad_arguments(product):
     assert product.dll.SLIP_LU_factorize(None, None, None, None, None, None, o) == capi.SLIP_INCORRECT_INPUT
     assert product.dll.SLIP_LU_solve(None, None, None, None, None, None) == capi.SLIP_INCORRECT_INPUT
     assert product.dll.SLIP_LU_analyze(None, None, o) == capi.SLIP_INCORRECT_INPUT
+
+
+def test_header_is_layout_compatible_with_the_reference_header(tmp_path):
+    """Compiles one probe against include/SLIP_LU.h and one against the reference's own header
+    (where the reference tree is present) and compares sizeof / offsetof of every public struct and
+    the enum values: a program built against either header can be linked with either library."""
+    ref_inc = "/root/reference/SLIP_LU/Include"
+    if not os.path.exists(os.path.join(ref_inc, "SLIP_LU.h")):
+        pytest.skip("reference tree not present on this machine")
+    probe = r'''
+#include <stddef.h>
+#include <stdio.h>
+#include "SLIP_LU.h"
+#define F(s, m) printf (#s "." #m " %zu %zu\n", offsetof (s, m), sizeof (((s *) 0)->m))
+int main (void)
+{
+    printf ("sizeof %zu %zu %zu %zu\n", sizeof (SLIP_options), sizeof (SLIP_sparse), sizeof (SLIP_dense), sizeof (SLIP_LU_analysis)) ;
+    F (SLIP_options, pivot) ; F (SLIP_options, order) ; F (SLIP_options, tol) ; F (SLIP_options, print_level) ;
+    F (SLIP_options, prec) ; F (SLIP_options, SLIP_MPFR_ROUND) ;
+    F (SLIP_sparse, m) ; F (SLIP_sparse, n) ; F (SLIP_sparse, nzmax) ; F (SLIP_sparse, nz) ; F (SLIP_sparse, p) ;
+    F (SLIP_sparse, i) ; F (SLIP_sparse, x) ; F (SLIP_sparse, scale) ;
+    F (SLIP_dense, m) ; F (SLIP_dense, n) ; F (SLIP_dense, x) ; F (SLIP_dense, scale) ;
+    F (SLIP_LU_analysis, q) ; F (SLIP_LU_analysis, lnz) ; F (SLIP_LU_analysis, unz) ;
+    printf ("info %d %d %d %d %d\n", SLIP_OK, SLIP_OUT_OF_MEMORY, SLIP_SINGULAR, SLIP_INCORRECT_INPUT, SLIP_INCORRECT) ;
+    printf ("pivot %d %d %d %d %d %d\n", SLIP_SMALLEST, SLIP_DIAGONAL, SLIP_FIRST_NONZERO, SLIP_TOL_SMALLEST, SLIP_TOL_LARGEST, SLIP_LARGEST) ;
+    printf ("order %d %d %d\n", SLIP_NO_ORDERING, SLIP_COLAMD, SLIP_AMD) ;
+    return 0 ;
+}
+'''
+    src = tmp_path / "probe.c"
+    src.write_text(probe)
+    have_gmp_h = subprocess.run(["gcc", "-include", "gmp.h", "-include", "mpfr.h", "-E", "-x", "c", "/dev/null"],
+                                stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL).returncode == 0
+    abi = [] if have_gmp_h else ["-I" + os.path.join(ROOT, "include", "gmp_abi")]
+    outs = []
+    for name, inc in (("ours", [os.path.join(ROOT, "include")]),
+                      ("ref", [ref_inc, "/root/reference/SuiteSparse_config", "/root/reference/COLAMD/Include",
+                               "/root/reference/AMD/Include"])):
+        exe = tmp_path / f"probe_{name}"
+        subprocess.check_call(["gcc", "-w", "-o", str(exe), str(src)] + ["-I" + d for d in inc] + abi)
+        outs.append(subprocess.check_output([str(exe)], text=True))
+    assert outs[0] == outs[1]

@@ -8,8 +8,7 @@
  * SLIP_LU_factorize / SLIP_LU_solve / SLIP_solve_* runs on an NVIDIA B200 (sm_100a); the
  * library has no CPU path for it and returns an error if no device is present.
  *
- * Not provided: the SLIP_mpz_ / SLIP_mpq_ / SLIP_mpfr_ GMP wrappers (ref:1023-1156; call GMP/MPFR
- * directly) and this fork's experimental SLIP_LU_analyze_and_factorize{,1} (ref:866-886).  See
+ * Not provided: this fork's experimental SLIP_LU_analyze_and_factorize{,1} (ref:866-886).  See
  * DESIGN.md "scope".
  */
 #ifndef SLIP_Include
@@ -196,6 +195,63 @@ SLIP_info SLIP_get_double_soln (double **x_doub, mpq_t **x_mpq, int32_t n, int32
 SLIP_info SLIP_get_mpfr_soln (mpfr_t **x_mpfr, mpq_t **x_mpq, int32_t n, int32_t numRHS,
     SLIP_options *option) ;                                        /* ref:975-982 */
 SLIP_info SLIP_spok (SLIP_sparse *A, SLIP_options *option) ;
+
+/* ---- GMP / MPFR wrappers (ref:1023-1156, Source/SLIP_gmp.c) ----
+ * Kept for source compatibility (the reference's demos read and print through them).  Here they
+ * call GMP/MPFR and return SLIP_OK; the reference's setjmp guard against allocation failures inside
+ * GMP is not reproduced. */
+SLIP_info SLIP_gmp_fprintf (FILE *fp, const char *format, ...) ;
+SLIP_info SLIP_gmp_printf (const char *format, ...) ;
+SLIP_info SLIP_gmp_fscanf (FILE *fp, const char *format, ...) ;
+SLIP_info SLIP_mpfr_fprintf (FILE *fp, const char *format, ...) ;
+SLIP_info SLIP_mpz_init (mpz_t x) ;
+SLIP_info SLIP_mpz_init2 (mpz_t x, const uint64_t size) ;
+SLIP_info SLIP_mpz_init_set (mpz_t x, const mpz_t y) ;
+SLIP_info SLIP_mpz_set (mpz_t x, const mpz_t y) ;
+SLIP_info SLIP_mpz_set_ui (mpz_t x, const uint64_t y) ;
+SLIP_info SLIP_mpz_set_si (mpz_t x, const int32_t y) ;
+SLIP_info SLIP_mpz_set_q (mpz_t x, const mpq_t y) ;
+SLIP_info SLIP_mpz_mul (mpz_t a, const mpz_t b, const mpz_t c) ;
+SLIP_info SLIP_mpz_swap (mpz_t x, mpz_t y) ;
+SLIP_info SLIP_mpz_submul (mpz_t x, const mpz_t y, const mpz_t z) ;
+SLIP_info SLIP_mpz_divexact (mpz_t x, const mpz_t y, const mpz_t z) ;
+SLIP_info SLIP_mpz_gcd (mpz_t x, const mpz_t y, const mpz_t z) ;
+SLIP_info SLIP_mpz_lcm (mpz_t lcm, const mpz_t x, const mpz_t y) ;
+SLIP_info SLIP_mpz_abs (mpz_t x, const mpz_t y) ;
+SLIP_info SLIP_mpz_cmp (int32_t *r, const mpz_t x, const mpz_t y) ;
+SLIP_info SLIP_mpz_cmpabs (int32_t *r, const mpz_t x, const mpz_t y) ;
+SLIP_info SLIP_mpz_cmp_ui (int32_t *r, const mpz_t x, const uint64_t y) ;
+SLIP_info SLIP_mpz_sgn (int32_t *sgn, const mpz_t x) ;
+SLIP_info SLIP_mpz_sizeinbase (size_t *size, const mpz_t x, int32_t base) ;
+SLIP_info SLIP_mpq_init (mpq_t x) ;
+SLIP_info SLIP_mpq_set (mpq_t x, const mpq_t y) ;
+SLIP_info SLIP_mpq_set_z (mpq_t x, const mpz_t y) ;
+SLIP_info SLIP_mpq_set_d (mpq_t x, const double y) ;
+SLIP_info SLIP_mpq_set_ui (mpq_t x, const uint64_t y, const uint64_t z) ;
+SLIP_info SLIP_mpq_set_num (mpq_t x, const mpz_t y) ;
+SLIP_info SLIP_mpq_set_den (mpq_t x, const mpz_t y) ;
+SLIP_info SLIP_mpq_get_den (mpz_t x, const mpq_t y) ;
+SLIP_info SLIP_mpq_get_d (double *x, const mpq_t y) ;
+SLIP_info SLIP_mpq_abs (mpq_t x, const mpq_t y) ;
+SLIP_info SLIP_mpq_add (mpq_t x, const mpq_t y, const mpq_t z) ;
+SLIP_info SLIP_mpq_mul (mpq_t x, const mpq_t y, const mpq_t z) ;
+SLIP_info SLIP_mpq_div (mpq_t x, const mpq_t y, const mpq_t z) ;
+SLIP_info SLIP_mpq_cmp (int32_t *r, const mpq_t x, const mpq_t y) ;
+SLIP_info SLIP_mpq_cmp_ui (int32_t *r, const mpq_t x, const uint64_t num, const uint64_t den) ;
+SLIP_info SLIP_mpq_equal (int32_t *r, const mpq_t x, const mpq_t y) ;
+SLIP_info SLIP_mpfr_init2 (mpfr_t x, const uint64_t size) ;
+SLIP_info SLIP_mpfr_set_d (mpfr_t x, const double y, const mpfr_rnd_t rnd) ;
+SLIP_info SLIP_mpfr_set_q (mpfr_t x, const mpq_t y, const mpfr_rnd_t rnd) ;
+SLIP_info SLIP_mpfr_set_z (mpfr_t x, const mpz_t y, const mpfr_rnd_t rnd) ;
+SLIP_info SLIP_mpfr_abs (mpfr_t x, const mpfr_t y, const mpfr_rnd_t rnd) ;
+SLIP_info SLIP_mpfr_get_z (mpz_t x, const mpfr_t y, const mpfr_rnd_t rnd) ;
+SLIP_info SLIP_mpfr_get_d (double *x, const mpfr_t y, const mpfr_rnd_t rnd) ;
+SLIP_info SLIP_mpfr_mul (mpfr_t x, const mpfr_t y, const mpfr_t z, const mpfr_rnd_t rnd) ;
+SLIP_info SLIP_mpfr_mul_d (mpfr_t x, const mpfr_t y, const double z, const mpfr_rnd_t rnd) ;
+SLIP_info SLIP_mpfr_div_d (mpfr_t x, const mpfr_t y, const double z, const mpfr_rnd_t rnd) ;
+SLIP_info SLIP_mpfr_ui_pow_ui (mpfr_t x, const uint64_t y, const uint64_t z, const mpfr_rnd_t rnd) ;
+SLIP_info SLIP_mpfr_log2 (mpfr_t x, const mpfr_t y, const mpfr_rnd_t rnd) ;
+SLIP_info SLIP_mpfr_free_cache (void) ;
 
 /* ---- extensions of this implementation (not in the reference header) ----
  * The factors of the most recent SLIP_LU_factorize stay resident in GPU memory, keyed by the

@@ -241,3 +241,24 @@ int main (void)
         subprocess.check_call(["gcc", "-w", "-o", str(exe), str(src)] + ["-I" + d for d in inc] + abi)
         outs.append(subprocess.check_output([str(exe)], text=True))
     assert outs[0] == outs[1]
+
+
+def test_reference_demos_compile_and_link_unchanged(product, tmp_path):
+    """The reference's own demo programs (Demo/example*.c, SLIPLU.c with demos.c) are compiled with
+    -Wall -Werror against include/SLIP_LU.h and linked against libslip_lu_b200.so without a change:
+    every type, prototype and symbol they use is there (they are not run here: that needs a GPU;
+    the 10teams demo system is a golden fixture of the GPU tests)."""
+    demo = "/root/reference/SLIP_LU/Demo"
+    if not os.path.exists(os.path.join(demo, "demos.c")):
+        pytest.skip("reference tree not present on this machine")
+    have_gmp_h = subprocess.run(["gcc", "-include", "gmp.h", "-include", "mpfr.h", "-E", "-x", "c", "/dev/null"],
+                                stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL).returncode == 0
+    inc = ["-I" + os.path.join(ROOT, "include"), "-I" + demo]
+    libs = ["-lgmp", "-lmpfr"] if have_gmp_h else ["-l:libgmp.so.10", "-l:libmpfr.so.6"]
+    if not have_gmp_h:
+        inc.append("-I" + os.path.join(ROOT, "include", "gmp_abi"))
+    libdir = os.path.dirname(product.path)
+    for prog in ("example", "example2", "example3", "example4", "example5", "SLIPLU"):
+        subprocess.check_call(["gcc", "-Wall", "-Werror", "-Wno-unused", "-O1"] + inc +
+                              ["-o", str(tmp_path / prog), os.path.join(demo, prog + ".c"), os.path.join(demo, "demos.c"),
+                               "-L" + libdir, "-lslip_lu_b200", "-Wl,-rpath," + libdir] + libs + ["-lm"])

@@ -13,6 +13,7 @@ from slip_lu_b200.capi import MpqStruct, MpzStruct, gmp, int_to_mpz, mpq_to_pair
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(_HERE, "libref_oracle.so")
+DEMO_EXE = os.path.join(_HERE, "_ref", "demo_example2")
 REF_SO = os.path.join(_HERE, "_ref", "libslip_ref.so")
 
 
@@ -28,6 +29,11 @@ def build(force: bool = False) -> None:
         subprocess.check_call(["make", "-s", "-C", _HERE, "oracle"])
     if os.path.isdir("/root/reference/SLIP_LU/Source") and (force or not os.path.exists(REF_SO)):
         subprocess.check_call(["make", "-s", "-C", _HERE, "ref"])
+    # the reference's demo program linked against the product library (run by a GPU test)
+    product = os.path.join(os.path.dirname(_HERE), "slip_lu_b200", "libslip_lu_b200.so")
+    if os.path.isfile("/root/reference/SLIP_LU/Demo/example2.c") and os.path.exists(product) and \
+            (force or not os.path.exists(DEMO_EXE) or os.path.getmtime(DEMO_EXE) < os.path.getmtime(product)):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "demo"])
 
 
 _dll = None

@@ -10,14 +10,17 @@
 #include <stdarg.h>
 #include "slip_internal.h"
 
-/* ---- formatted input / output ---- */
+/* ---- formatted input / output ----
+ * As in the reference (SLIP_gmp.c:310-452) these return the COUNT on success -- characters written,
+ * fields stored -- and SLIP_INCORRECT_INPUT (negative) on failure, although the header types them
+ * SLIP_info: the demos test `ok < 3` after reading a triplet. */
 SLIP_info SLIP_gmp_fprintf (FILE *fp, const char *format, ...)
 {
     va_list args ;
     va_start (args, format) ;
     int n = gmp_vfprintf (fp, format, args) ;
     va_end (args) ;
-    return n < 0 ? SLIP_INCORRECT_INPUT : SLIP_OK ;
+    return n < 0 ? SLIP_INCORRECT_INPUT : (SLIP_info) n ;
 }
 
 SLIP_info SLIP_gmp_printf (const char *format, ...)
@@ -26,7 +29,7 @@ SLIP_info SLIP_gmp_printf (const char *format, ...)
     va_start (args, format) ;
     int n = gmp_vprintf (format, args) ;
     va_end (args) ;
-    return n < 0 ? SLIP_INCORRECT_INPUT : SLIP_OK ;
+    return n < 0 ? SLIP_INCORRECT_INPUT : (SLIP_info) n ;
 }
 
 SLIP_info SLIP_gmp_fscanf (FILE *fp, const char *format, ...)
@@ -35,7 +38,7 @@ SLIP_info SLIP_gmp_fscanf (FILE *fp, const char *format, ...)
     va_start (args, format) ;
     int n = gmp_vfscanf (fp, format, args) ;
     va_end (args) ;
-    return n < 0 ? SLIP_INCORRECT_INPUT : SLIP_OK ;
+    return n == EOF ? SLIP_INCORRECT_INPUT : (SLIP_info) n ;
 }
 
 SLIP_info SLIP_mpfr_fprintf (FILE *fp, const char *format, ...)
@@ -44,7 +47,8 @@ SLIP_info SLIP_mpfr_fprintf (FILE *fp, const char *format, ...)
     va_start (args, format) ;
     int n = mpfr_vfprintf (fp, format, args) ;
     va_end (args) ;
-    return n < 0 ? SLIP_INCORRECT_INPUT : SLIP_OK ;
+    mpfr_free_cache () ;
+    return n < 0 ? SLIP_INCORRECT_INPUT : (SLIP_info) n ;
 }
 
 /* ---- integers ---- */

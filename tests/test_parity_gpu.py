@@ -354,3 +354,30 @@ def test_approximate_pivot_search_is_exact(gpu, pivot, env, case):
                 os.environ.pop(k, None)
             else:
                 os.environ[k] = v
+
+
+def test_reference_demo_program_runs_unchanged(gpu, tmp_path):
+    """Demo/example2.c of the reference (BASELINE configs[0]: read a triplet matrix and a dense
+    right-hand side, SLIP_LU_analyze, SLIP_solve_mpq), compiled unmodified and linked against
+    libslip_lu_b200.so by `make -C oracle demo`, run on the 10teams system written out from the
+    golden fixture in the demo's own file formats."""
+    import subprocess
+    from oracle import binding as ob
+    if not os.path.exists(ob.DEMO_EXE):
+        pytest.skip("oracle/_ref/demo_example2 was not built (needs the reference tree at build time)")
+    g = cases.load_golden("10teams_default")
+    n, cp, ri, vals, b = cases.golden_system(g)
+    mat, rhs = tmp_path / "mat.txt", tmp_path / "rhs.txt"
+    with open(mat, "w") as f:
+        f.write(f"{n} {n} {cp[n]}\n")
+        for j in range(n):
+            for a in range(cp[j], cp[j + 1]):
+                f.write(f"{ri[a] + 1} {j + 1} {vals[a]}\n")          # 1-based triplets
+    with open(rhs, "w") as f:
+        f.write(f"{n} {len(b[0])}\n")
+        for row in b:
+            f.write(" ".join(str(v) for v in row) + "\n")
+    out = subprocess.run([ob.DEMO_EXE, str(mat), str(rhs)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert "all tests passed" in out.stdout, out.stdout + out.stderr
+    assert "SLIP LU Factor & Solve time" in out.stdout

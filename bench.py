@@ -184,6 +184,16 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
+    # stdout carries exactly one JSON line: anything libraries print to fd 1 on the way (NCCL prints
+    # its version there) is sent to stderr, the result goes to the saved descriptor
+    sys.stdout.flush()
+    result_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(result_fd, (json.dumps(obj) + "\n").encode())
+
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -207,7 +217,7 @@ def main():
         import __graft_entry__ as entry
         entry.build()
         r = run_reference(args, rank)
-        print(json.dumps({
+        emit({
             "impl": "reference", "metric": "limb_mul_ops_per_s", "value": r["value"], "unit": "limb-mul/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * r["seconds"], "higher_is_better": True, "scaling": "weak",
@@ -216,7 +226,7 @@ def main():
                              "sample": r["sample"]},
             "factor_solve_seconds": r["seconds"], "ref_updates": r["updates"],
             "e2e": {"value": r["value"], "unit": "limb-mul/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}))
+            "gpu_launches": 0})
         return
 
     # ------------------------------------------------------------------ B200 arm
@@ -344,7 +354,7 @@ def main():
         r = run_reference(sub, 0)
         out["cpu_baseline"] = {"value": r["value"], "unit": "limb-mul/s", "cores": r["cores"],
                                "kind": r["kind"], "sample": r["sample"], "seconds": r["seconds"]}
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 

@@ -265,6 +265,11 @@ int SLIP_B200_set_device (int device) ;
  * entry updates, schoolbook-equivalent 32-bit limb multiplies, seconds (symbolic, device, set-up,
  * total).  Returns the number of values written. */
 int SLIP_B200_last_stats (double *out, int cap) ;
+/* [10] channels the a-priori (Hadamard) bound asks for, [11] restarts of the bound mode with more
+ * channels, [12] right-hand sides whose numerators were verified exactly (A N = det b).
+ * SLIP_B200_last_pinv: the row permutation chosen by the calling thread's last SLIP_solve_* call
+ * (that path keeps L and U on the GPU; pinv is what it shares with SLIP_LU_factorize's output). */
+int SLIP_B200_last_pinv (int32_t *out, int cap) ;
 
 #ifdef __cplusplus
 }

@@ -37,6 +37,8 @@ typedef struct
     int32_t diag_vs_best;   /* cmp(|diag|, |best|): -1, 0, +1 (valid if diag_eligible) */
     int32_t bad_channel;    /* 0, or 1 + index of a channel whose prime divides an earlier pivot */
     int32_t reserved[3];
+    int32_t bound_units;    /* bound mode: proven upper bound of 64*log2 |entry| over the column */
+    int32_t pad[3];
 } slipcu_pivot_info;
 
 /* receives column k of the factorization as positional integers.  `limbs` holds `cnt` rows of
@@ -57,7 +59,15 @@ int  slipcu_set_device (int device);
  *   Avalue_off has nz+1 entries: limbs of entry a are Alimbs[Avalue_off[a] .. Avalue_off[a+1]). */
 int slipcu_factor_begin (slipcu_factor **F, int n, int nz, const int32_t *Ap, const int32_t *Ai,
                          const uint32_t *Alimbs, const int64_t *Avalue_off, const int8_t *Asign,
-                         int channels, int keep_positional);
+                         int channels, int keep_positional, int bound_mode);
+/* bound_mode = 0: `channels` covers a proven a-priori bound (Hadamard) of every entry of L and U.
+ *   1: `channels` is smaller than that.  The session then proves the size of every column as it
+ *   goes (a bound propagated through the elimination from the MEASURED sizes of the finished
+ *   columns) and reports it in slipcu_pivot_info.bound_units; the caller compares it with
+ *   slipcu_factor_capacity_units and restarts with more channels when a column does not fit.
+ *   GMP pays for the actual size of its operands (slip_REF_triangular_solve.c:150-232 on mpz_t);
+ *   this is how the residue representation does the same without giving up exactness. */
+int slipcu_factor_capacity_units (const slipcu_factor *F);
 /* keep_positional = 1: every entry of L and U is reconstructed as a positional integer and kept
  *   for slipcu_factor_download (SLIP_LU_factorize).  0: only what the pivot scan needs is
  *   reconstructed (SLIP_solve_*: the factors never leave the GPU). */
@@ -77,16 +87,18 @@ int slipcu_factor_column (slipcu_factor *F, int k, int col, int cnt, int nU,
  * the GPU works: _launch enqueues everything and returns, _wait blocks for the scan result. */
 int slipcu_factor_column_launch (slipcu_factor *F, int k, int col, int cnt, int nU,
                                  const int32_t *rows, const int32_t *upos, int recon_channels,
-                                 int scheme, int diag_slot);
+                                 int scheme, int diag_slot, int spec_slot);
 int slipcu_factor_column_wait (slipcu_factor *F, slipcu_pivot_info *info);
 
-/* speculative first part of the column that will be column k: the steps of
- * slip_REF_triangular_solve.c:150-232 with every pivot committed so far, on the pattern known
- * before the pivot of column k-1 (rows sorted by position, nU of them pivotal, upos their pivot
- * positions).  The following slipcu_factor_column_launch for column k starts from its result and
- * applies the remaining steps (those from U slot nU on). */
-int slipcu_factor_spec_launch (slipcu_factor *F, int k, int col, int cnt, int nU,
+/* lookahead: the bulk part of the column that will be column k, i.e. the steps of
+ * slip_REF_triangular_solve.c:150-232 with every pivot committed so far, on the pattern reachable
+ * through those columns (rows sorted by position, nU of them pivotal, upos their pivot positions),
+ * in lookahead slot `slot` (0 .. SLIPCU_SPEC_SLOTS-1), on the slot's own stream beside the column
+ * in flight.  The later slipcu_factor_column_launch (.., spec_slot = slot) for column k starts from
+ * its result and applies the remaining steps (those from U slot nU on). */
+int slipcu_factor_spec_launch (slipcu_factor *F, int slot, int k, int col, int cnt, int nU,
                                const int32_t *rows, const int32_t *upos);
+#define SLIPCU_SPEC_SLOTS 16
 
 /* one reconstructed entry of the current column (used only for the rational tolerance test of
  * SLIP_TOL_SMALLEST / SLIP_TOL_LARGEST, slip_get_pivot.c:94-143).  limbs must hold stride words. */
@@ -131,10 +143,10 @@ int  slipcu_factor_channels (const slipcu_factor *F);
 double slipcu_channel_bits (int count);
 void slipcu_factor_free (slipcu_factor *F);
 
-/* after SLIPCU_BAD_PRIME: which channel (index into the prime list) failed; then retire it so
- * that the next session does not use it */
-int  slipcu_factor_bad_channel (slipcu_factor *F, int *channel);
-int  slipcu_retire_channel (int channel);
+/* after SLIPCU_BAD_PRIME: which channel prime failed (0: none); then retire it, by value, so that
+ * the next session does not use it */
+int  slipcu_factor_bad_prime (slipcu_factor *F, uint32_t *prime);
+int  slipcu_retire_prime (uint32_t prime);
 
 /* counters for bench.py: kernels launched by this library since process start, and the
  * accumulated device time (ms, CUDA events) and algorithmic bytes of the triangular-solve kernel */

@@ -53,6 +53,7 @@ def dll() -> C.CDLL:
         _dll.ro_solve.argtypes = [C.c_int, C.c_int, P(RoCsc), P(RoCsc), P(MpzStruct), P(C.c_int),
                                   P(MpzStruct), P(MpqStruct)]
         _dll.ro_free_csc.argtypes = [P(RoCsc)]
+        _dll.ro_set_column_limit.argtypes = [C.c_int]
         _dll.ro_digest_mpz.restype = C.c_uint64
         _dll.ro_digest_mpz.argtypes = [P(MpzStruct), C.c_int]
         _dll.ro_digest_csc.restype = C.c_uint64
@@ -121,8 +122,11 @@ class OracleFactors:
             pass
 
 
-def factorize(n: int, colptr, rowidx, values, q, pivot: int = 3, tol: float = 1.0) -> OracleFactors:
+def factorize(n: int, colptr, rowidx, values, q, pivot: int = 3, tol: float = 1.0,
+              max_cols: int = 0) -> OracleFactors:
+    """max_cols > 0: only the first max_cols columns (bench.py's bounded sample of a large job)."""
     d = dll()
+    d.ro_set_column_limit(max_cols)
     Ax = MpzArray(values)
     Ap = (C.c_int * (n + 1))(*colptr)
     Ai = (C.c_int * len(rowidx))(*rowidx)

@@ -19,7 +19,7 @@
  * PARITY PIN: the reference ships no golden output vectors for this path (its demos only
  * print timings and run SLIP_check_solution), so this oracle is pinned against outputs of
  * the reference itself: oracle/_ref/libslip_ref.so (the unmodified reference compiled by
- * oracle/Makefile) in tests/test_oracle_vs_reference.py, and against the committed fixtures
+ * oracle/Makefile) in tests/test_oracle.py, and against the committed fixtures
  * tests/golden/*.json generated from that library by tests/golden/make_golden.py.
  *
  * The REF update is written once in its closed form
@@ -206,6 +206,12 @@ static int choose_pivot (int scheme, double tol, int col, const int *pattern, in
  *   L, U     : outputs (allocated here); row indices are final positions (pinv applied)
  *   rhos     : n initialised mpz_t, receives the pivots; pinv: n ints
  * ------------------------------------------------------------------------------------- */
+/* bench.py's bounded sample of a workload the CPU cannot finish: only the first ro_column_limit
+ * columns are factorized (a left-looking factorization never looks at later columns, so they are
+ * exactly the first columns of the complete job); 0 = all.  L and U then hold those columns. */
+static int ro_column_limit = 0;
+void ro_set_column_limit (int m) { ro_column_limit = m > 0 ? m : 0; }
+
 int ro_factorize (int n, const int *Ap, const int *Ai, mpz_t *Ax, const int *q,
                   int scheme, double tol, ro_csc *L, ro_csc *U, mpz_t *rhos, int *pinv)
 {
@@ -225,7 +231,8 @@ int ro_factorize (int n, const int *Ap, const int *Ai, mpz_t *Ax, const int *q,
     if (!row_at || !pivotal || !hist || !mark || !stack || !pattern || !x) return RO_OUT_OF_MEMORY;
     for (int r = 0; r < n; r++) { mpz_init (x[r]); pinv[r] = r; row_at[r] = r; }
 
-    for (int k = 0; k < n && status == RO_OK; k++)
+    const int kend = (ro_column_limit > 0 && ro_column_limit < n) ? ro_column_limit : n;
+    for (int k = 0; k < kend && status == RO_OK; k++)
     {
         int col = q[k];
         L->p[k] = L->nz; U->p[k] = U->nz;
@@ -284,7 +291,7 @@ int ro_factorize (int n, const int *Ap, const int *Ai, mpz_t *Ax, const int *q,
     }
     if (status == RO_OK)
     {
-        L->p[n] = L->nz; U->p[n] = U->nz;
+        for (int k = kend; k <= n; k++) { L->p[k] = L->nz; U->p[k] = U->nz; }
         for (int m = 0; m < L->nz; m++) L->i[m] = pinv[L->i[m]];
         for (int m = 0; m < U->nz; m++) U->i[m] = pinv[U->i[m]];
     }

@@ -137,10 +137,11 @@ struct Tables
     // approximate magnitudes (k_fraccrt): Minv[(s-1)*S + i] = (p_0..p_{s-1} / p_i)^-1 mod p_i in
     // Montgomery form for i < s; Urec[i] = floor(2^(32*FRAC_WMAX) / p_i), most significant word first
     u32 *Minv = nullptr, *Urec = nullptr;
+    int32_t *cum_ub = nullptr; // [S+1] upper bound of 64 log2 (p_0..p_{c-1}) (bound mode)
     ~Tables ()
     {
         cudaFree (p); cudaFree (ninv); cudaFree (r2); cudaFree (one);
-        cudaFree (C); cudaFree (invB); cudaFree (Bpos); cudaFree (Minv); cudaFree (Urec);
+        cudaFree (C); cudaFree (invB); cudaFree (Bpos); cudaFree (Minv); cudaFree (Urec); cudaFree (cum_ub);
     }
 };
 
@@ -263,6 +264,12 @@ static int build_tables (int S, std::shared_ptr<Tables> &out)
     CU (cudaMemcpy (T->r2, r2.data (), S * sizeof (u32), cudaMemcpyHostToDevice));
     CU (cudaMemcpy (T->one, one.data (), S * sizeof (u32), cudaMemcpyHostToDevice));
     CU (cudaMemcpy (T->Bpos, B.data (), B.size () * sizeof (u32), cudaMemcpyHostToDevice));
+    {
+        std::vector<int32_t> cu (S + 1);
+        for (int c = 0; c <= S; ++c) cu[c] = (int32_t) ceil (64.0 * T->cumbits[c]) + 1;
+        CU (cudaMalloc (&T->cum_ub, (S + 1) * sizeof (int32_t)));
+        CU (cudaMemcpy (T->cum_ub, cu.data (), (S + 1) * sizeof (int32_t), cudaMemcpyHostToDevice));
+    }
     CU (cudaMemset (T->C, 0, (size_t) S * S * sizeof (u32)));
     k_build_tables<<<(S + 127) / 128, 128>>> (S, T->p, T->ninv, T->r2, T->one, T->C, T->invB);
     g_launches++;
@@ -316,11 +323,14 @@ extern "C" double slipcu_channel_bits (int count)
     return b;
 }
 
-extern "C" int slipcu_retire_channel (int channel)
+// retires a channel prime BY VALUE (an index would be into the failing session's snapshot of the
+// prime list, which another thread may have changed since)
+extern "C" int slipcu_retire_prime (uint32_t prime)
 {
     std::lock_guard<std::mutex> lk (g_tab_mutex);
-    if (channel < 0 || (size_t) channel >= g_primes.size ()) return SLIPCU_BAD_INPUT;
-    g_primes.erase (g_primes.begin () + channel);
+    auto it = std::find (g_primes.begin (), g_primes.end (), prime);
+    if (it == g_primes.end ()) return SLIPCU_OK;        // someone else retired it already
+    g_primes.erase (it);
     g_tables.reset ();          // live sessions keep their own reference
     return SLIPCU_OK;
 }
@@ -414,16 +424,42 @@ struct ColDesc            // one finished column, as the kernels see it
     int32_t nU;           // size of the U part (the pivot itself is an L-part slot)
     int32_t pivslot;      // slot of the pivot
     int32_t pad;
+    const int32_t *mag;   // (bound mode) upper bounds of log2 |entry| in 1/64 bit, [cnt]; candidates hold measured values
 };
 
 struct StepInfo;
 struct ChunkInfo;
 struct TimedRange;
 
+// per-launch symbolic workspace: the row -> slot map, slot lists, step and chunk tables of one
+// column, with the stream they are built and consumed on.  The column in flight has one; every
+// lookahead slot (bulk part of a later column, running beside it) has its own.
+struct WorkCtx
+{
+    cudaStream_t st = nullptr;
+    int32_t *pos = nullptr;                  // [n]
+    int32_t *slots = nullptr; size_t slots_cap = 0;
+    StepInfo *steps = nullptr; size_t steps_cap = 0;
+    ChunkInfo *chunks = nullptr; size_t chunks_cap = 0;
+    int32_t *h_packet = nullptr;             // pinned staging of the pattern packet
+};
+#define SPEC_SLOTS 16
+struct SpecSlot                              // bulk part of a column that is not the current one yet
+{
+    WorkCtx w;
+    u32 *buf = nullptr; size_t words = 0;    // [S/CH][cnt][CH] normalised vector
+    int32_t *mag = nullptr; size_t mag_cap = 0;
+    int32_t *rows = nullptr;                 // device copy of its pattern
+    int cnt = 0, col = -1, nU = 0;           // col: factorization column it belongs to (-1: free)
+    cudaEvent_t done = nullptr, consumed = nullptr;
+    bool consumed_pending = false;
+};
+
 struct HostCol
 {
     u32 *base = nullptr; int32_t *rows = nullptr; int cnt = 0, nU = 0, s = 0, stride = 0;
     u32 *limbs = nullptr; int32_t *nl = nullptr; int8_t *sign = nullptr;
+    int32_t *mag = nullptr;
 };
 
 struct slipcu_factor
@@ -437,7 +473,6 @@ struct slipcu_factor
     u32 *dA = nullptr;                       // residues of A, [S/CH][nz][CH]
     u32 *rho = nullptr, *invrho = nullptr;    // [n][S]
     ColDesc *desc = nullptr;                 // [n]
-    int32_t *pos = nullptr;                  // [n]
     int32_t *bad = nullptr;                  // device flag
     u32 *dig = nullptr; size_t dig_rows = 0; // [dig_rows][S] digit scratch in use (= digbuf[i])
     int32_t *topd = nullptr;                 // [dig_rows]
@@ -454,28 +489,30 @@ struct slipcu_factor
     int frac = 0, fracW = 8, frac_col = -1;             // enabled, words for the next column, column searched that way
     int frac_margin = 12;                               // words kept beyond the leading zero words of the last winner
     int frac_verify = 0;                                // (tests) re-run every accepted choice through the exact scan
-    // speculative first part of the next column (all steps but the one with the column in flight)
-    u32 *spec_buf = nullptr; size_t spec_words = 0;     // [S/CH][cnt][CH] normalised vector
-    int32_t *h_packet2 = nullptr;                       // pinned staging of its pattern
-    int32_t *spec_rows = nullptr; int spec_cnt = 0, spec_col = -1, spec_nU = 0;
+    // lookahead: bulk parts (every step with a pivot that is already committed) of the next columns,
+    // each on its own stream beside the column in flight
+    SpecSlot spec[SPEC_SLOTS];
+    cudaEvent_t ev_commit = nullptr;                    // recorded after every pivot commit
     struct { int cnt, nU, s, mode, diag_slot, W; } fq = { 0, 0, 0, 0, 0, 0 };
     struct FracKey *frackey = nullptr; size_t frac_rows = 0;
     uint64_t frac_cols = 0, frac_retries = 0, frac_fallbacks = 0;
     Arena resid, ints, limbs;
     std::vector<HostCol> cols;
     std::vector<int32_t> hAp;
-    int32_t *h_packet = nullptr;             // pinned staging for the per-column pattern
+    WorkCtx mc;                              // workspace of the column in flight (stream = st)
     slipcu_pivot_info *h_info = nullptr;     // pinned
     slipcu_pivot_info *d_info = nullptr;
     size_t smem_limit = 0;
     int keep_positional = 1, rows_are_positions = 0, x_global = 0, cur = -1;
     std::vector<struct TimedRange> ranges;      // profiling: event pairs not yet read
     u32 *tmp_limbs = nullptr; int32_t *tmp_nl = nullptr; int tmp_stride = 0;
-    int32_t *slots = nullptr; size_t slots_cap = 0;      // slot lists of the current column
-    StepInfo *steps = nullptr; size_t steps_cap = 0;
-    ChunkInfo *chunks = nullptr; size_t chunks_cap = 0;
     int sms = 148;
     int garner_mode = 2;
+    // bound mode (see tri_mag_cta): fewer channels than the Hadamard bound, every column's size proven
+    int mag_on = 0;
+    int32_t *Amag = nullptr;                 // [nz] 64 log2 |a| of the input entries, rounded up
+    int32_t *rho_mag = nullptr;              // [n]  measured 64 log2 |rho_k|
+    int32_t *bound = nullptr;                // device: largest bound of the column in flight
     slipcu_factor () : resid ((size_t) 512 << 20), ints ((size_t) 16 << 20), limbs ((size_t) 256 << 20) {}
 };
 
@@ -497,16 +534,16 @@ static cudaEvent_t take_event ()
 }
 struct ScopedTimer
 {
-    slipcu_factor *F; double *acc; cudaEvent_t a = nullptr;
-    ScopedTimer (slipcu_factor *F_, double *acc_) : F (F_), acc (acc_)
+    slipcu_factor *F; double *acc; cudaEvent_t a = nullptr; cudaStream_t st;
+    ScopedTimer (slipcu_factor *F_, double *acc_, cudaStream_t st_ = nullptr) : F (F_), acc (acc_), st (st_ ? st_ : F_->wst)
     {
-        if (g_profiling) { a = take_event (); cudaEventRecord (a, F->wst); }
+        if (g_profiling) { a = take_event (); cudaEventRecord (a, st); }
     }
     ~ScopedTimer ()
     {
         if (!a) return;
         cudaEvent_t b = take_event ();
-        cudaEventRecord (b, F->wst);
+        cudaEventRecord (b, st);
         F->ranges.push_back ({a, b, acc});
     }
 };
@@ -594,7 +631,7 @@ struct __align__ (16) ChunkInfo   // one pipeline chunk (rows of one step); 32 b
     int32_t slot_off;     // offset of the chunk's slot list
     int32_t j;            // pivot position of the step
     int32_t meta;         // rows | first chunk of its step << 16 | last chunk << 17
-    int32_t pad0, pad1;
+    const int32_t *msrc;  // (bound mode) magnitudes of the chunk's L rows
 };
 
 __global__ void k_setpos (int cnt, const int32_t *rows, int32_t *pos)
@@ -639,7 +676,7 @@ __global__ void k_slots (int nU, int total, int CH, int cnt, const int32_t *upos
         c.lsrc = d.base + (size_t) (d.nU + r0) * CH; c.cbstride = d.cnt * CH;
         c.slot_off = uoff[u] + r0; c.j = upos[u];
         c.meta = min (R, len - r0) | ((r0 == 0) << 16) | ((r0 + R >= len) << 17);
-        c.pad0 = 0; c.pad1 = 0;
+        c.msrc = d.mag ? d.mag + d.nU + r0 : nullptr;
         chunks[uchunk[u] + ci] = c;
     }
 }
@@ -681,6 +718,14 @@ struct TriArgs
     const int32_t *upos;     // [nU] pivot position of each U slot (levels of the published U part)
     int publish;             // 1: write true REF values; 0: leave the vector normalised (speculative first part)
     int u0;                  // U slot of the first step in the chunk list
+    // bound mode (sessions that carry fewer channels than the Hadamard bound asks for): one extra
+    // CTA (blockIdx.x == S/CH) propagates upper bounds of log2 |w_t| through the same work list
+    int mag_on;
+    const int32_t *mag_src;  // magnitudes of the source entries (entry e of the scatter above)
+    int32_t *mag_out;        // [cnt] bounds of the published entries (or of the normalised vector)
+    const int32_t *rho_mag;  // [n] measured log2 |rho_k| (upper bound; the lower bound is MAG_GAP less)
+    int32_t *bound_out;      // largest published bound of this launch
+    int smem_bytes;          // dynamic shared memory of the launch
 };
 
 template <int CH>
@@ -766,6 +811,152 @@ template <int CPT> __device__ __forceinline__ ChanVec<CPT> negv (const ChanVec<C
     return r;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Bound mode: a rigorous size bound for every entry of a column, computed alongside the residues.
+//
+// A session may carry fewer channels than the Hadamard bound of the input asks for (real LP bases
+// have determinants of a few hundred bits against Hadamard bounds of tens of thousands).  What
+// makes that exact rather than a guess is this pass: with mb_t >= log2 |w_t| for the normalised
+// vector, the update  w_t <- w_t - l_tj * w_j / rho_j  gives
+//     mb_t <- log2 (2^mb_t + 2^(lmag_tj + mb_j - lb(rho_j)))          (rounded up)
+// where lmag and the pivot sizes are MEASURED on the finished columns (from their mixed-radix
+// digits).  By induction over the columns: if the bound of column k is below the capacity of the
+// channels, its reconstruction is exact, so its measured magnitudes are the true ones, so the bound
+// of column k+1 holds.  A column whose bound does not fit aborts the factorization, which restarts
+// with more channels.  Magnitudes are int32 in units of 1/64 bit, MAG_NEG = the entry is zero.
+// ------------------------------------------------------------------------------------------------
+#define MAG_UNIT 64
+#define MAG_NEG (-(1 << 30))
+#define MAG_GAP 96            // a measured magnitude m means  m - MAG_GAP <= 64 log2 |v| <= m
+
+__device__ __forceinline__ int32_t mag_lse (int32_t a, int32_t b)
+{   // upper bound of 64 log2 (2^(a/64) + 2^(b/64))
+    if (a == MAG_NEG) return b;
+    if (b == MAG_NEG) return a;
+    const int32_t hi = max (a, b), d = hi - min (a, b);
+    if (d >= 40 * MAG_UNIT) return hi + 1;
+    return hi + __float2int_ru (64.0f * log2f (1.0f + exp2f (-(float) d * (1.0f / 64.0f)))) + 1;
+}
+__device__ __forceinline__ int32_t mag_log2_ub (u32 v)
+{   // upper bound of 64 log2 v for v >= 1
+    return __float2int_ru (64.0f * log2f (__uint2float_ru (v))) + 1;
+}
+__device__ __forceinline__ void cp_async4 (u32 dst_smem, const void *src)
+{
+    asm volatile ("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst_smem), "l"(src) : "memory");
+}
+
+// The bound CTA of a k_trisolve launch.  Same chunk descriptors, same slot lists (stored in the
+// order the consumer threads of the residue CTAs read them: entry 4g+q is chunk row g + q*RG) and
+// the same three-stage cp.async ring, but a row is one int32 instead of CH residues.
+template <int CH, int NT>
+__device__ __noinline__ void tri_mag_cta (const TriArgs &a, unsigned char *smem_raw)
+{
+    constexpr int RG = TRI_THREADS / (CH / 4), R = 4 * RG;
+    constexpr int MSTAGE = R * 4 + R * 4 + 16;               // targets, magnitudes, rho_mag[j]
+    constexpr int RING_BYTES = TRI_RING * (int) sizeof (ChunkInfo);
+    const int tid = threadIdx.x, cnt = a.cnt, nU = a.nU, nchunks = a.nchunks;
+    const bool in_smem = (size_t) (cnt + 1) * 4 + 16 + RING_BYTES + TRI_BUFS * MSTAGE <= (size_t) a.smem_bytes;
+    const u32 smem0 = smem_u32 (smem_raw);
+    const u32 vec_bytes = in_smem ? (u32) ((((size_t) (cnt + 1) * 4) + 15) & ~(size_t) 15) : 0u;
+    int32_t *mb = in_smem ? (int32_t *) smem_raw : a.mag_out;      // working vector (global when the pattern is too long)
+    const u32 ring = smem0 + vec_bytes;
+    const u32 stage0 = ring + RING_BYTES;
+    const int spare = cnt * CH * 4;
+
+    auto fetch_desc = [&] (int X, int half)
+    {
+        cp_async16 (ring + (u32) (X % TRI_RING) * (u32) sizeof (ChunkInfo) + half * 16,
+                    (const unsigned char *) (a.chunks + X) + half * 16);
+    };
+    auto issue = [&] (int rs, u32 sb)
+    {
+        const u32 da = ring + (u32) rs * (u32) sizeof (ChunkInfo);
+        const uint4 d0 = lds128 (da);                  // lsrc (lo, hi), cbstride, slot_off
+        const uint4 d1 = lds128 (da + 16);             // j, meta, msrc (lo, hi)
+        const int nrows = (int) (d1.y & 0xffffu);
+        const int32_t *msrc = (const int32_t *) (((unsigned long long) d1.w << 32) | d1.z);
+        if (tid < min (nrows, RG)) cp_async16 (sb + (u32) tid * 16, a.slots + (size_t) d0.w + (size_t) tid * 4);
+        for (int r = tid; r < nrows; r += NT) cp_async4 (sb + R * 4 + (u32) r * 4, msrc + r);
+        if ((d1.y & 0x10000u) && tid == 0) cp_async4 (sb + 2 * R * 4, a.rho_mag + (int) d1.x);
+    };
+
+    if (tid < 8 && (tid >> 1) < nchunks) fetch_desc (tid >> 1, tid & 1);
+    cp_async_commit ();
+    cp_async_wait<0> ();
+    __syncthreads ();
+    for (int c = 0; c < TRI_BUFS - 1; ++c) { if (c < nchunks) issue (c, stage0 + (u32) c * MSTAGE); cp_async_commit (); }
+    for (int i = tid; i <= (in_smem ? cnt : cnt - 1); i += NT) mb[i] = MAG_NEG;
+    __syncthreads ();
+    for (int e = tid; e < a.src_cnt; e += NT)
+    {
+        const int row = a.src_rows ? a.src_rows[e] : e;
+        mb[a.pos[row]] = a.mag_src[e];
+    }
+
+    int u = a.u0, bc = 0, bi = TRI_BUFS - 1;
+    int32_t y = MAG_NEG;
+    for (int c = 0; c < nchunks; ++c)
+    {
+        cp_async_wait<TRI_BUFS - 2> ();
+        __syncthreads ();
+        if (c + TRI_BUFS - 1 < nchunks) issue ((c + TRI_BUFS - 1) % TRI_RING, stage0 + (u32) bi * MSTAGE);
+        if (tid < 2 && c + 4 < nchunks) fetch_desc (c + 4, tid);
+        cp_async_commit ();
+        const unsigned char *sbp = smem_raw + vec_bytes + RING_BYTES + (size_t) bc * MSTAGE;
+        const u32 meta = lds64 (ring + (u32) (c % TRI_RING) * (u32) sizeof (ChunkInfo) + 16).y;
+        const int nrows = (int) (meta & 0xffffu);
+        if (meta & 0x10000u)
+        {   // yhat_j = w_j / rho_j with |rho_j| >= 2^((rho_mag - MAG_GAP)/64)
+            const int32_t wj = mb[u];
+            const int32_t rm = *reinterpret_cast<const int32_t *> (sbp + 2 * R * 4);
+            y = (wj == MAG_NEG) ? MAG_NEG : wj - (rm - MAG_GAP);
+        }
+        if (y != MAG_NEG)
+        {
+            const int ext = (nrows == R) ? R : 4 * min (nrows, RG);
+            for (int e = tid; e < ext; e += NT)
+            {
+                const int t = reinterpret_cast<const int32_t *> (sbp)[e];
+                const int r = (e >> 2) + (e & 3) * RG;
+                if (t != spare && r < nrows)
+                {
+                    const int32_t lm = reinterpret_cast<const int32_t *> (sbp + R * 4)[r];
+                    if (lm != MAG_NEG)
+                    {
+                        const int slot = t / (CH * 4);
+                        mb[slot] = mag_lse (mb[slot], lm + y);
+                    }
+                }
+            }
+        }
+        if (meta & 0x20000u) ++u;
+        bc = (bc == TRI_BUFS - 1) ? 0 : bc + 1;
+        bi = (bi == TRI_BUFS - 1) ? 0 : bi + 1;
+    }
+    __syncthreads ();
+    // publish: U(j,k) = w_j rho_{j-1}, candidates = w_t rho_{k-1}; the largest bound goes to the host
+    int32_t mx = MAG_NEG;
+    for (int t = tid; t < cnt; t += NT)
+    {
+        int32_t v = mb[t];
+        const int lvl = a.publish ? ((t < nU) ? a.upos[t] : a.k) : 0;
+        if (v != MAG_NEG && lvl >= 1) v += a.rho_mag[lvl - 1];
+        a.mag_out[t] = v;
+        mx = max (mx, v);
+    }
+    if (a.publish && a.bound_out)
+    {
+        __shared__ int32_t s_mx;
+        if (tid == 0) s_mx = MAG_NEG;
+        __syncthreads ();
+        atomicMax (&s_mx, mx);
+        __syncthreads ();
+        if (tid == 0) *a.bound_out = s_mx;
+    }
+}
+
 // All threads of the CTA are consumers; every thread also copies its share of the chunk that is
 // two positions ahead in the work list with 16-byte cp.async (LDGSTS): TRI_BUFS-1 chunks are in
 // flight per CTA while one is consumed.  The chunk descriptors travel through a small ring in
@@ -784,6 +975,11 @@ __global__ void __launch_bounds__ (TRI_THREADS * 4 / CPT, 2) k_trisolve (TriArgs
     constexpr int NT = TRI_THREADS * 4 / CPT, TPR = CH / CPT, RG = SM::RG;
     extern __shared__ __align__ (128) unsigned char smem_raw[];
     const int tid = threadIdx.x;
+    if (a.mag_on && blockIdx.x == (unsigned) (a.S / CH))
+    {   // the bound CTA of the launch (first right-hand side / the column itself only)
+        if (blockIdx.y == 0) tri_mag_cta<CH, NT> (a, smem_raw);
+        return;
+    }
     const int cb = blockIdx.x, S = a.S, cnt = a.cnt, nU = a.nU, nchunks = a.nchunks;
     u32 *xg = a.out + (size_t) blockIdx.y * a.out_y_stride + (size_t) cb * cnt * CH;
     u32 *xs = XS ? (u32 *) smem_raw : xg;
@@ -1876,10 +2072,20 @@ __device__ __forceinline__ int better (const u32 *dig, size_t ds, const int32_t 
 __global__ void __launch_bounds__ (256) k_pivot_scan (int cnt, int nU, int mode, int diag_slot,
                                                        const u32 *dig, size_t ds, const int32_t *topd,
                                                        const int8_t *sign, const int32_t *bad,
-                                                       slipcu_pivot_info *info)
+                                                       slipcu_pivot_info *info,
+                                                       int32_t *mag, const int32_t *cum_ub, const int32_t *bound)
 {
     __shared__ int sbest[256];
     int best = -1;
+    if (mag)
+    {   // bound mode: the candidates' bounds are replaced by their measured sizes,
+        // B_top * d <= |v| < B_top * (d + 1) with d the top mixed-radix digit
+        for (int e = nU + threadIdx.x; e < cnt; e += blockDim.x)
+        {
+            const int t = topd[e];
+            mag[e] = t < 0 ? MAG_NEG : cum_ub[t] + mag_log2_ub (dig[(size_t) e * ds + t] + 1u);
+        }
+    }
     for (int e = nU + threadIdx.x; e < cnt; e += blockDim.x)
         if (topd[e] >= 0) best = better (dig, ds, topd, mode, best, e);
     sbest[threadIdx.x] = best;
@@ -1899,6 +2105,7 @@ __global__ void __launch_bounds__ (256) k_pivot_scan (int cnt, int nU, int mode,
         info->diag_eligible = de;
         info->diag_vs_best = (de && best >= 0) ? cmp_mag (dig, ds, topd, diag_slot, best) : 0;
         info->bad_channel = *bad;
+        info->bound_units = bound ? *bound : 0;
     }
 }
 
@@ -1907,10 +2114,10 @@ __global__ void __launch_bounds__ (256) k_pivot_scan (int cnt, int nU, int mode,
 // ------------------------------------------------------------------------------------------------
 __global__ void k_pivot_commit (int k, int S, int CH, int slot, ColDesc d, ColDesc *desc,
                                 u32 *rho, u32 *invrho,
-                                const u32 *p, const u32 *ninv, const u32 *one, int32_t *bad)
+                                const u32 *p, const u32 *ninv, const u32 *one, int32_t *bad, int32_t *rho_mag)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c == 0) { d.pivslot = slot; desc[k] = d; }
+    if (c == 0) { d.pivslot = slot; desc[k] = d; if (rho_mag) rho_mag[k] = d.mag[slot]; }
     if (c >= S) return;
     const u32 pc = p[c], ni = ninv[c];
     const u32 v = d.base[((size_t) (c / CH) * d.cnt + slot) * CH + (c % CH)];
@@ -1940,6 +2147,21 @@ static int env_int (const char *name, int dflt)
     return (v && *v) ? atoi (v) : dflt;
 }
 
+static void free_workctx (WorkCtx &w)
+{
+    pool_free (w.pos); pool_free (w.slots); pool_free (w.steps); pool_free (w.chunks);
+    if (w.h_packet) cudaFreeHost (w.h_packet);
+    w = WorkCtx ();
+}
+static int init_workctx (WorkCtx &w, int n, cudaStream_t st)
+{
+    w.st = st;
+    CU (pool_alloc_t (&w.pos, (size_t) n * sizeof (int32_t)));
+    CU (cudaMemsetAsync (w.pos, 0, (size_t) n * sizeof (int32_t), st));
+    CU (cudaHostAlloc (&w.h_packet, ((size_t) 4 * n + 8) * sizeof (int32_t), cudaHostAllocDefault));
+    return SLIPCU_OK;
+}
+
 extern "C" void slipcu_factor_free (slipcu_factor *F)
 {
     if (!F) return;
@@ -1953,17 +2175,25 @@ extern "C" void slipcu_factor_free (slipcu_factor *F)
     flush_timers (F);
     pool_free (F->dAp); pool_free (F->dAi); pool_free (F->dA);
     pool_free (F->rho); pool_free (F->invrho);
-    pool_free (F->desc); pool_free (F->pos); pool_free (F->bad);
+    pool_free (F->desc); pool_free (F->bad);
     pool_free (F->digbuf[0]); pool_free (F->topdbuf[0]); pool_free (F->digbuf[1]); pool_free (F->topdbuf[1]);
     pool_free (F->d_info); pool_free (F->frackey);
+    pool_free (F->Amag); pool_free (F->rho_mag); pool_free (F->bound);
     if (getenv ("SLIP_B200_TIMING") && F->frac)
         fprintf (stderr, "slipcu pivot search: %llu columns by approximate magnitudes, %llu word-count retries, %llu exact fallbacks\n",
                  (unsigned long long) F->frac_cols, (unsigned long long) F->frac_retries, (unsigned long long) F->frac_fallbacks);
     pool_free (F->tmp_limbs); pool_free (F->tmp_nl);
-    pool_free (F->slots); pool_free (F->steps); pool_free (F->chunks);
-    if (F->h_packet) cudaFreeHost (F->h_packet);
-    if (F->h_packet2) cudaFreeHost (F->h_packet2);
-    pool_free (F->spec_buf);
+    free_workctx (F->mc);
+    for (SpecSlot &sl : F->spec)
+    {
+        if (sl.w.st) cudaStreamSynchronize (sl.w.st);
+        free_workctx (sl.w);
+        pool_free (sl.buf); pool_free (sl.mag);
+        if (sl.done) cudaEventDestroy (sl.done);
+        if (sl.consumed) cudaEventDestroy (sl.consumed);
+        if (sl.w.st) cudaStreamDestroy (sl.w.st);
+    }
+    if (F->ev_commit) cudaEventDestroy (F->ev_commit);
     if (F->h_info) cudaFreeHost (F->h_info);
     if (F->ev) cudaEventDestroy (F->ev);
     if (F->ev0) cudaEventDestroy (F->ev0);
@@ -1980,6 +2210,13 @@ extern "C" void slipcu_factor_free (slipcu_factor *F)
 }
 
 extern "C" int slipcu_factor_channels (const slipcu_factor *F) { return F ? F->S : 0; }
+// largest bound (units of 1/64 bit) a column may report and still be reconstructed exactly from
+// the session's channels: |v| < M/2 with two bits to spare
+extern "C" int slipcu_factor_capacity_units (const slipcu_factor *F)
+{
+    if (!F) return 0;
+    return (int) floor (64.0 * F->tab->cumbits[F->S]) - 3 * 64;
+}
 
 static int ensure_digits (slipcu_factor *F, size_t rows)
 {
@@ -2071,7 +2308,7 @@ static int session_common_init (slipcu_factor *F, int n, int channels)
     F->cpt = env_int ("SLIP_B200_CPT", 4);             // channels per thread of k_trisolve: 4 or 2
     if (F->cpt != 2 && F->cpt != 4) F->cpt = 4;
     F->threads = TRI_THREADS * 4 / F->cpt;
-    rc = tri_configure (smem_optin);
+    rc = tri_configure (smem_optin - 1024);      // static shared memory of the kernels (a few words) comes out of the same budget
     if (rc) return rc;
 
     CU (cudaStreamCreateWithFlags (&F->st, cudaStreamNonBlocking));
@@ -2082,13 +2319,12 @@ static int session_common_init (slipcu_factor *F, int n, int channels)
     CU (pool_alloc_t (&F->rho, (size_t) n * S * sizeof (u32)));
     CU (pool_alloc_t (&F->invrho, (size_t) n * S * sizeof (u32)));
     CU (pool_alloc_t (&F->desc, (size_t) n * sizeof (ColDesc)));
-    CU (pool_alloc_t (&F->pos, (size_t) n * sizeof (int32_t)));
     CU (pool_alloc_t (&F->bad, sizeof (int32_t)));
     CU (pool_alloc_t (&F->d_info, sizeof (slipcu_pivot_info)));
     CU (cudaMemset (F->bad, 0, sizeof (int32_t)));
-    CU (cudaMemset (F->pos, 0, (size_t) n * sizeof (int32_t)));
-    CU (cudaHostAlloc (&F->h_packet, ((size_t) 4 * n + 8) * sizeof (int32_t), cudaHostAllocDefault));
-    CU (cudaHostAlloc (&F->h_packet2, ((size_t) 4 * n + 8) * sizeof (int32_t), cudaHostAllocDefault));
+    rc = init_workctx (F->mc, n, F->st);
+    if (rc) return rc;
+    CU (cudaEventCreateWithFlags (&F->ev_commit, cudaEventDisableTiming));
     CU (cudaHostAlloc (&F->h_info, sizeof (slipcu_pivot_info), cudaHostAllocDefault));
     F->cols.resize (n);
     return SLIPCU_OK;
@@ -2096,7 +2332,7 @@ static int session_common_init (slipcu_factor *F, int n, int channels)
 
 extern "C" int slipcu_factor_begin (slipcu_factor **out, int n, int nz, const int32_t *Ap,
                                     const int32_t *Ai, const u32 *Alimbs, const int64_t *Aoff,
-                                    const int8_t *Asign, int channels, int keep_positional)
+                                    const int8_t *Asign, int channels, int keep_positional, int bound_mode)
 {
     if (!out || n <= 0 || nz <= 0 || !Ap || !Ai || !Alimbs || !Aoff || !Asign || channels <= 0)
         return fail (SLIPCU_BAD_INPUT, "slipcu_factor_begin", "bad argument");
@@ -2106,6 +2342,28 @@ extern "C" int slipcu_factor_begin (slipcu_factor **out, int n, int nz, const in
     if (rc) return rc;
     F->nz = nz;
     F->keep_positional = keep_positional ? 1 : 0;
+    if (bound_mode)
+    {   // input magnitudes from the limb strings: 64 log2 |a| rounded up
+        F->mag_on = 1;
+        F->frac = 0;                     // measured sizes come from the exact digits
+        std::vector<int32_t> am (nz);
+        for (int e = 0; e < nz; ++e)
+        {
+            const int64_t l0 = Aoff[e], l1 = Aoff[e + 1];
+            if (Asign[e] == 0 || l1 == l0) { am[e] = MAG_NEG; continue; }
+            int64_t top = l1 - 1;
+            while (top > l0 && Alimbs[top] == 0) --top;
+            double v = (double) Alimbs[top];
+            if (top > l0) v += ((double) Alimbs[top - 1] + 1.0) / 4294967296.0; else v += 0.0;
+            if (v <= 0) { am[e] = MAG_NEG; continue; }
+            am[e] = (int32_t) ceil (64.0 * (log2 (v) + 32.0 * (double) (top - l0)) + 1e-6) + 1;
+        }
+        CU (pool_alloc_t (&F->Amag, (size_t) nz * sizeof (int32_t)));
+        CU (pool_alloc_t (&F->rho_mag, (size_t) n * sizeof (int32_t)));
+        CU (pool_alloc_t (&F->bound, sizeof (int32_t)));
+        CU (cudaMemcpy (F->Amag, am.data (), (size_t) nz * sizeof (int32_t), cudaMemcpyHostToDevice));
+        CU (cudaMemset (F->bound, 0, sizeof (int32_t)));
+    }
     if (F->keep_positional && env_int ("SLIP_B200_OVERLAP", 1))
     {   // second stream for the positional reconstruction (see the session struct)
         F->overlap = 1;
@@ -2174,44 +2432,44 @@ static cudaError_t launch_tri_any (int CH, int cpt, const TriArgs &a, dim3 grid,
 
 // symbolic pre-pass on the device: pos[], the slot lists and the step table of a column whose
 // pattern (rows), step positions (upos) and slot-list offsets (uoff, nU+1 entries) are on the device
-static int prepare_steps (slipcu_factor *F, int cnt, int nU, const int32_t *rows, const int32_t *upos,
+static int prepare_steps (slipcu_factor *F, WorkCtx &w, int cnt, int nU, const int32_t *rows, const int32_t *upos,
                           const int32_t *uoff, const int32_t *uchunk, int total, int nchunks)
 {
-    if ((size_t) nchunks > F->chunks_cap)
+    if ((size_t) nchunks > w.chunks_cap)
     {
-        CU (cudaStreamSynchronize (F->st));
-        pool_free (F->chunks); F->chunks = nullptr;
-        size_t want = std::max ((size_t) nchunks, std::max<size_t> (F->chunks_cap * 2, 1024));
-        CU (pool_alloc_t (&F->chunks, want * sizeof (ChunkInfo)));
-        F->chunks_cap = want;
+        CU (cudaStreamSynchronize (w.st));
+        pool_free (w.chunks); w.chunks = nullptr;
+        size_t want = std::max ((size_t) nchunks, std::max<size_t> (w.chunks_cap * 2, 1024));
+        CU (pool_alloc_t (&w.chunks, want * sizeof (ChunkInfo)));
+        w.chunks_cap = want;
     }
-    if ((size_t) total > F->slots_cap)
+    if ((size_t) total > w.slots_cap)
     {
-        CU (cudaStreamSynchronize (F->st));
-        pool_free (F->slots); F->slots = nullptr;
-        size_t want = std::max ((size_t) total, F->slots_cap * 2);
-        CU (pool_alloc_t (&F->slots, want * sizeof (int32_t)));
-        F->slots_cap = want;
+        CU (cudaStreamSynchronize (w.st));
+        pool_free (w.slots); w.slots = nullptr;
+        size_t want = std::max ((size_t) total, w.slots_cap * 2);
+        CU (pool_alloc_t (&w.slots, want * sizeof (int32_t)));
+        w.slots_cap = want;
     }
-    if ((size_t) nU > F->steps_cap)
+    if ((size_t) nU > w.steps_cap)
     {
-        CU (cudaStreamSynchronize (F->st));
-        pool_free (F->steps); F->steps = nullptr;
-        size_t want = std::max ((size_t) nU, std::max<size_t> (F->steps_cap * 2, 256));
-        CU (pool_alloc_t (&F->steps, want * sizeof (StepInfo)));
-        F->steps_cap = want;
+        CU (cudaStreamSynchronize (w.st));
+        pool_free (w.steps); w.steps = nullptr;
+        size_t want = std::max ((size_t) nU, std::max<size_t> (w.steps_cap * 2, 256));
+        CU (pool_alloc_t (&w.steps, want * sizeof (StepInfo)));
+        w.steps_cap = want;
     }
-    ScopedTimer tm_other (F, &g_other_ms);
-    k_setpos<<<(cnt + 255) / 256, 256, 0, F->st>>> (cnt, rows, F->pos);
+    ScopedTimer tm_other (F, &g_other_ms, w.st);
+    k_setpos<<<(cnt + 255) / 256, 256, 0, w.st>>> (cnt, rows, w.pos);
     g_launches++;
     CU (cudaGetLastError ());
-    if (debug_check ("k_setpos", F->st)) return fail (SLIPCU_CUDA_ERROR, "k_setpos", "debug");
+    if (debug_check ("k_setpos", w.st)) return fail (SLIPCU_CUDA_ERROR, "k_setpos", "debug");
     if (nU > 0 && total > 0)
     {
-        k_slots<<<(total + 255) / 256, 256, 0, F->st>>> (nU, total, F->CH, cnt, upos, uoff, uchunk, F->desc, F->pos, F->slots, F->steps, F->chunks);
+        k_slots<<<(total + 255) / 256, 256, 0, w.st>>> (nU, total, F->CH, cnt, upos, uoff, uchunk, F->desc, w.pos, w.slots, w.steps, w.chunks);
         g_launches++;
         CU (cudaGetLastError ());
-        if (debug_check ("k_slots", F->st)) return fail (SLIPCU_CUDA_ERROR, "k_slots", "debug");
+        if (debug_check ("k_slots", w.st)) return fail (SLIPCU_CUDA_ERROR, "k_slots", "debug");
     }
     return SLIPCU_OK;
 }
@@ -2371,6 +2629,11 @@ static int alloc_column (slipcu_factor *F, HostCol &hc, int cnt, int s)
     hc.stride = (s + 1) & ~1;
     hc.base = (u32 *) F->resid.alloc ((size_t) cnt * F->S * sizeof (u32));
     hc.sign = (int8_t *) F->ints.alloc ((size_t) cnt);
+    if (F->mag_on)
+    {
+        hc.mag = (int32_t *) F->ints.alloc ((size_t) cnt * sizeof (int32_t));
+        if (!hc.mag) return fail (SLIPCU_OUT_OF_MEMORY, "alloc_column", "device memory exhausted");
+    }
     if (F->keep_positional)
     {
         hc.limbs = (u32 *) F->limbs.alloc ((size_t) cnt * hc.stride * sizeof (u32));
@@ -2385,7 +2648,8 @@ static int run_exact_scan (slipcu_factor *F, const HostCol &hc, int cnt, int nU,
 {
     ScopedTimer tm_scan (F, &g_other_ms);
     k_pivot_scan<<<1, 256, 0, F->st>>> (cnt, nU, mode, diag_slot, F->dig, (size_t) F->S + 4, F->topd,
-                                        hc.sign, F->bad, F->d_info);
+                                        hc.sign, F->bad, F->d_info,
+                                        F->mag_on ? hc.mag : nullptr, F->tab->cum_ub, F->mag_on ? F->bound : nullptr);
     g_launches++;
     CU (cudaGetLastError ());
     if (debug_check ("k_pivot_scan", F->st)) return fail (SLIPCU_CUDA_ERROR, "k_pivot_scan", "debug");
@@ -2394,10 +2658,11 @@ static int run_exact_scan (slipcu_factor *F, const HostCol &hc, int cnt, int nU,
 
 // uploads a pattern packet (rows, U positions, slot-list offsets, chunk offsets of the steps from
 // first_step on) and runs the symbolic pre-pass; returns the device copy and the chunk count
-static int upload_pattern (slipcu_factor *F, int32_t *staging, int cnt, int nU, const int32_t *rows, const int32_t *upos,
+static int upload_pattern (slipcu_factor *F, WorkCtx &w, int cnt, int nU, const int32_t *rows, const int32_t *upos,
                            int first_step, int32_t **dev_rows, int *nchunks_out)
 {
     const int CH = F->CH;
+    int32_t *staging = w.h_packet;
     memcpy (staging, rows, (size_t) cnt * sizeof (int32_t));
     if (nU) memcpy (staging + cnt, upos, (size_t) nU * sizeof (int32_t));
     int32_t *uoff = staging + cnt + nU;
@@ -2407,7 +2672,7 @@ static int upload_pattern (slipcu_factor *F, int32_t *staging, int cnt, int nU, 
     for (int u = 0; u < nU; ++u)
     {
         uoff[u] = (int32_t) total; uchunk[u] = (int32_t) nchunks;
-        if (u < first_step) continue;                    // already applied by the speculative part
+        if (u < first_step) continue;                    // already applied by the bulk part
         const HostCol &lj = F->cols[upos[u]];
         const int len = lj.cnt - lj.nU;
         total += tri_slot_extent (len, CH);
@@ -2418,75 +2683,105 @@ static int upload_pattern (slipcu_factor *F, int32_t *staging, int cnt, int nU, 
     const size_t pk_ints = (size_t) cnt + 3 * (size_t) nU + 2;
     int32_t *d = (int32_t *) F->ints.alloc (pk_ints * sizeof (int32_t));
     if (!d) return fail (SLIPCU_OUT_OF_MEMORY, "slipcu_factor_column", "device memory exhausted");
-    CU (cudaMemcpyAsync (d, staging, pk_ints * sizeof (int32_t), cudaMemcpyHostToDevice, F->st));
+    CU (cudaMemcpyAsync (d, staging, pk_ints * sizeof (int32_t), cudaMemcpyHostToDevice, w.st));
     g_h2d_bytes += (double) pk_ints * sizeof (int32_t);
-    int rc = prepare_steps (F, cnt, nU, d, d + cnt, d + cnt + nU, d + cnt + 2 * nU + 1, (int) total, (int) nchunks);
+    int rc = prepare_steps (F, w, cnt, nU, d, d + cnt, d + cnt + nU, d + cnt + 2 * nU + 1, (int) total, (int) nchunks);
     if (rc) return rc;
     *dev_rows = d; *nchunks_out = (int) nchunks;
     return SLIPCU_OK;
 }
 
-// Speculative first part of column `col` (to become column k of the factorization): eliminates
-// with every pivot that is already committed, on the pattern known before the pivot of column k-1,
-// and leaves the normalised vector in a scratch region.  Launched behind the pivot search of
-// column k-1, so that the GPU has work while the host takes its turn.
-extern "C" int slipcu_factor_spec_launch (slipcu_factor *F, int k, int col, int cnt, int nU,
+// Bulk part of column `col` (to become column k of the factorization) in lookahead slot `slot`:
+// eliminates with every pivot that is already committed, on the pattern reachable through those
+// columns, and leaves the normalised vector in the slot's buffer.  Runs on the slot's own stream
+// beside the column in flight (it only reads finished columns), so that several columns advance at
+// once when the channel count is too small to fill the GPU with one.
+extern "C" int slipcu_factor_spec_launch (slipcu_factor *F, int slot, int k, int col, int cnt, int nU,
                                           const int32_t *rows, const int32_t *upos)
 {
-    if (!F || k < 1 || k >= F->n || cnt <= 0 || cnt > F->n || nU < 0 || nU > cnt || !rows)
+    if (!F || slot < 0 || slot >= SPEC_SLOTS || k < 1 || k >= F->n || cnt <= 0 || cnt > F->n || nU < 0 || nU > cnt || !rows)
         return fail (SLIPCU_BAD_INPUT, "slipcu_factor_spec_launch", "bad argument");
     const Tables &T = *F->tab;
     const int S = F->S, CH = F->CH;
-    const size_t words = (size_t) cnt * S;
-    if (words > F->spec_words)
+    SpecSlot &sl = F->spec[slot];
+    if (!sl.w.st)
     {
-        CU (cudaStreamSynchronize (F->st));
-        pool_free (F->spec_buf); F->spec_buf = nullptr;
-        const size_t want = std::max (words, std::min ((size_t) F->n * S, F->spec_words * 2));
-        CU (pool_alloc_t (&F->spec_buf, want * sizeof (u32)));
-        F->spec_words = want;
+        cudaStream_t st = nullptr;
+        CU (cudaStreamCreateWithFlags (&st, cudaStreamNonBlocking));
+        int rc0 = init_workctx (sl.w, F->n, st);
+        if (rc0) return rc0;
+        CU (cudaEventCreateWithFlags (&sl.done, cudaEventDisableTiming));
+        CU (cudaEventCreateWithFlags (&sl.consumed, cudaEventDisableTiming));
+    }
+    WorkCtx &w = sl.w;
+    // the slot's previous vector may still be read by the column launch that consumed it
+    if (sl.consumed_pending) { CU (cudaStreamWaitEvent (w.st, sl.consumed, 0)); sl.consumed_pending = false; }
+    // every pivot committed so far is visible to this stream
+    CU (cudaStreamWaitEvent (w.st, F->ev_commit, 0));
+    const size_t words = (size_t) cnt * S;
+    if (words > sl.words)
+    {
+        CU (cudaStreamSynchronize (w.st));
+        pool_free (sl.buf); sl.buf = nullptr;
+        const size_t want = std::max (words, std::min ((size_t) F->n * S, sl.words * 2));
+        CU (pool_alloc_t (&sl.buf, want * sizeof (u32)));
+        sl.words = want;
+    }
+    if (F->mag_on && (size_t) cnt > sl.mag_cap)
+    {
+        CU (cudaStreamSynchronize (w.st));
+        pool_free (sl.mag); sl.mag = nullptr;
+        const size_t want = std::max ((size_t) cnt, std::min ((size_t) F->n, sl.mag_cap * 2));
+        CU (pool_alloc_t (&sl.mag, want * sizeof (int32_t)));
+        sl.mag_cap = want;
     }
     int32_t *d = nullptr; int nchunks = 0;
-    int rc = upload_pattern (F, F->h_packet2, cnt, nU, rows, upos, 0, &d, &nchunks);
+    int rc = upload_pattern (F, w, cnt, nU, rows, upos, 0, &d, &nchunks);
     if (rc) return rc;
-    TriArgs a;
+    TriArgs a; memset (&a, 0, sizeof (a));
     a.k = k; a.S = S; a.cnt = cnt; a.nU = nU;
-    a.rows = d; a.steps = F->steps; a.chunks = F->chunks; a.slots = F->slots;
+    a.rows = d; a.steps = w.steps; a.chunks = w.chunks; a.slots = w.slots;
     a.src = F->dA; a.src_total = F->nz; a.src_first = F->hAp[col]; a.src_step = 1;
     a.src_cnt = F->hAp[col + 1] - F->hAp[col]; a.src_rows = F->dAi + F->hAp[col];
     a.src_y_stride = 0;
-    a.out = F->spec_buf; a.out_y_stride = 0;
+    a.out = sl.buf; a.out_y_stride = 0;
     a.rho = F->rho; a.invrho = F->invrho;
-    a.p = T.p; a.ninv = T.ninv; a.pos = F->pos;
+    a.p = T.p; a.ninv = T.ninv; a.pos = w.pos;
     a.nchunks = nchunks; a.upos = d + cnt; a.publish = 0; a.u0 = 0;
+    a.mag_on = F->mag_on; a.mag_src = F->mag_on ? F->Amag + F->hAp[col] : nullptr; a.mag_out = sl.mag;
+    a.rho_mag = F->rho_mag; a.bound_out = nullptr;
     size_t smem = 0;
     rc = tri_geometry (F, a, &smem);
     if (rc) return rc;
+    a.smem_bytes = (int) smem;
     {
-        ScopedTimer tm (F, &g_tri_ms);
-        CU (launch_tri_any (CH, F->cpt, a, dim3 (S / CH, 1), smem, F->st));
-        if (debug_check ("k_trisolve(speculative)", F->st)) return fail (SLIPCU_CUDA_ERROR, "k_trisolve", "debug");
+        ScopedTimer tm (F, &g_tri_ms, w.st);
+        CU (launch_tri_any (CH, F->cpt, a, dim3 (S / CH + (F->mag_on ? 1 : 0), 1), smem, w.st));
+        if (debug_check ("k_trisolve(bulk part)", w.st)) return fail (SLIPCU_CUDA_ERROR, "k_trisolve", "debug");
     }
+    CU (cudaEventRecord (sl.done, w.st));
     double upd = 0;
     for (int u = 0; u < nU; ++u) { const HostCol &lj = F->cols[upos[u]]; upd += (double) (lj.cnt - lj.nU - 1); }
     g_tri_bytes += upd * (double) S * 4.0;
     g_tri_modmul += upd * (double) S * 4.0;
-    F->spec_rows = d; F->spec_cnt = cnt; F->spec_col = k; F->spec_nU = nU;
+    sl.rows = d; sl.cnt = cnt; sl.col = k; sl.nU = nU;
     return SLIPCU_OK;
 }
 
 extern "C" int slipcu_factor_column_launch (slipcu_factor *F, int k, int col, int cnt, int nU,
                                             const int32_t *rows, const int32_t *upos, int recon_channels,
-                                            int scheme, int diag_slot)
+                                            int scheme, int diag_slot, int spec_slot)
 {
-    if (!F || k < 0 || k >= F->n || cnt <= 0 || cnt > F->n || nU < 0 || nU >= cnt || !rows)
+    if (!F || k < 0 || k >= F->n || cnt <= 0 || cnt > F->n || nU < 0 || nU >= cnt || !rows || spec_slot >= SPEC_SLOTS)
         return fail (SLIPCU_BAD_INPUT, "slipcu_factor_column", "bad argument");
-    // a speculative first part exists for this column: start from its vector, apply the rest
-    const bool from_spec = (F->spec_col == k);
-    const int first_step = from_spec ? F->spec_nU : 0;
-    if (from_spec && first_step > nU) return fail (SLIPCU_BAD_INPUT, "slipcu_factor_column", "speculative part does not match");
+    // a bulk part exists for this column: start from its vector, apply the remaining steps
+    SpecSlot *sl = (spec_slot >= 0 && F->spec[spec_slot].col == k) ? &F->spec[spec_slot] : nullptr;
+    const bool from_spec = sl != nullptr;
+    const int first_step = from_spec ? sl->nU : 0;
+    if (from_spec && first_step > nU) return fail (SLIPCU_BAD_INPUT, "slipcu_factor_column", "bulk part does not match");
     const Tables &T = *F->tab;
     const int S = F->S, CH = F->CH;
+    WorkCtx &w = F->mc;
     double tw = wall_s ();
     int s = std::min (std::max (recon_channels, 1), S);
     HostCol &hc = F->cols[k];
@@ -2498,36 +2793,45 @@ extern "C" int slipcu_factor_column_launch (slipcu_factor *F, int k, int col, in
     g_hw[0] += wall_s () - tw; tw = wall_s ();
     // packet: pattern rows, pivot positions of the U part, slot-list offsets (padded to 4)
     int nchunks = 0;
-    rc = upload_pattern (F, F->h_packet, cnt, nU, rows, upos, first_step, &hc.rows, &nchunks);
+    rc = upload_pattern (F, w, cnt, nU, rows, upos, first_step, &hc.rows, &nchunks);
     if (rc) return rc;
 
     g_hw[1] += wall_s () - tw; tw = wall_s ();
-    TriArgs a;
+    TriArgs a; memset (&a, 0, sizeof (a));
     a.k = k; a.S = S; a.cnt = cnt; a.nU = nU;
-    a.rows = hc.rows; a.steps = F->steps; a.chunks = F->chunks; a.slots = F->slots;
+    a.rows = hc.rows; a.steps = w.steps; a.chunks = w.chunks; a.slots = w.slots;
     if (from_spec)
-    {   // the vector of the speculative part, row by row into the final slots
-        a.src = F->spec_buf; a.src_total = F->spec_cnt; a.src_first = 0; a.src_step = 1;
-        a.src_cnt = F->spec_cnt; a.src_rows = F->spec_rows;
-        F->spec_col = -1;
+    {   // the vector of the bulk part, row by row into the final slots
+        CU (cudaStreamWaitEvent (F->st, sl->done, 0));
+        a.src = sl->buf; a.src_total = sl->cnt; a.src_first = 0; a.src_step = 1;
+        a.src_cnt = sl->cnt; a.src_rows = sl->rows;
+        a.mag_src = sl->mag;
     }
     else
     {
         a.src = F->dA; a.src_total = F->nz; a.src_first = F->hAp[col]; a.src_step = 1;
         a.src_cnt = F->hAp[col + 1] - F->hAp[col]; a.src_rows = F->dAi + F->hAp[col];
+        a.mag_src = F->mag_on ? F->Amag + F->hAp[col] : nullptr;
     }
     a.src_y_stride = 0;
     a.out = hc.base; a.out_y_stride = 0;
     a.rho = F->rho; a.invrho = F->invrho;
-    a.p = T.p; a.ninv = T.ninv; a.pos = F->pos;
+    a.p = T.p; a.ninv = T.ninv; a.pos = w.pos;
     a.nchunks = nchunks; a.upos = hc.rows + cnt; a.publish = 1; a.u0 = first_step;
+    a.mag_on = F->mag_on; a.mag_out = hc.mag; a.rho_mag = F->rho_mag; a.bound_out = F->bound;
     size_t smem = 0;
     rc = tri_geometry (F, a, &smem);
     if (rc) return rc;
+    a.smem_bytes = (int) smem;
     {
         ScopedTimer tm (F, &g_tri_ms);
-        CU (launch_tri_any (CH, F->cpt, a, dim3 (S / CH, 1), smem, F->st));
+        CU (launch_tri_any (CH, F->cpt, a, dim3 (S / CH + (F->mag_on ? 1 : 0), 1), smem, F->st));
         if (debug_check ("k_trisolve(column)", F->st)) return fail (SLIPCU_CUDA_ERROR, "k_trisolve", "debug");
+    }
+    if (from_spec)
+    {
+        CU (cudaEventRecord (sl->consumed, F->st));
+        sl->consumed_pending = true; sl->col = -1;
     }
     g_hw[2] += wall_s () - tw; tw = wall_s ();
     {   // algorithmic work of this launch
@@ -2668,7 +2972,7 @@ extern "C" int slipcu_factor_column (slipcu_factor *F, int k, int col, int cnt, 
                                      const int32_t *rows, const int32_t *upos, int recon_channels,
                                      int scheme, int diag_slot, slipcu_pivot_info *info)
 {
-    int rc = slipcu_factor_column_launch (F, k, col, cnt, nU, rows, upos, recon_channels, scheme, diag_slot);
+    int rc = slipcu_factor_column_launch (F, k, col, cnt, nU, rows, upos, recon_channels, scheme, diag_slot, -1);
     if (rc) return rc;
     return slipcu_factor_column_wait (F, info);
 }
@@ -2727,11 +3031,14 @@ extern "C" int slipcu_factor_set_pivot (slipcu_factor *F, int k, int slot)
     const Tables &T = *F->tab;
     ColDesc d;
     d.base = hc.base; d.rows = hc.rows; d.cnt = hc.cnt; d.nU = hc.nU; d.pivslot = slot; d.pad = 0;
+    d.mag = F->mag_on ? hc.mag : nullptr;
     k_pivot_commit<<<(F->S + 255) / 256, 256, 0, F->st>>> (k, F->S, F->CH, slot, d, F->desc, F->rho,
-                                                           F->invrho, T.p, T.ninv, T.one, F->bad);
+                                                           F->invrho, T.p, T.ninv, T.one, F->bad,
+                                                           F->mag_on ? F->rho_mag : nullptr);
     g_launches++;
     CU (cudaGetLastError ());
     if (debug_check ("k_pivot_commit", F->st)) return fail (SLIPCU_CUDA_ERROR, "k_pivot_commit", "debug");
+    if (!F->rows_are_positions) CU (cudaEventRecord (F->ev_commit, F->st));
     return SLIPCU_OK;
 }
 
@@ -2816,12 +3123,12 @@ static int check_channels (slipcu_factor *F)
     return SLIPCU_OK;
 }
 
-extern "C" int slipcu_factor_bad_channel (slipcu_factor *F, int *channel)
+extern "C" int slipcu_factor_bad_prime (slipcu_factor *F, uint32_t *prime)
 {
     int32_t bad = 0;
     CU (cudaMemcpyAsync (&bad, F->bad, sizeof (bad), cudaMemcpyDeviceToHost, F->st));
     CU (cudaStreamSynchronize (F->st));
-    if (channel) *channel = bad - 1;
+    if (prime) *prime = (bad >= 1 && bad <= F->tab->S) ? F->tab->hp[bad - 1] : 0u;
     return SLIPCU_OK;
 }
 
@@ -2918,24 +3225,24 @@ extern "C" int slipcu_solve (slipcu_factor *F, int nrhs, const u32 *blimbs, cons
         CUG (pool_alloc_t (&duoff, (2 * (size_t) n + 2) * sizeof (int32_t)));
         CUG (cudaMemcpyAsync (duoff, uoff.data (), (2 * (size_t) n + 2) * sizeof (int32_t), cudaMemcpyHostToDevice, F->st));
         CUG (cudaStreamSynchronize (F->st));
-        rc = prepare_steps (F, n, n, F->rows_are_positions ? dident : drow_at, dident, duoff, duoff + n + 1, (int) tot, (int) nch);
+        rc = prepare_steps (F, F->mc, n, n, F->rows_are_positions ? dident : drow_at, dident, duoff, duoff + n + 1, (int) tot, (int) nch);
         if (rc) goto done;
     }
     for (int r0 = 0; r0 < nrhs; r0 += batch)
     {
         const int nb = std::min (batch, nrhs - r0);
-        TriArgs a;
+        TriArgs a; memset (&a, 0, sizeof (a));
         a.k = n; a.S = S; a.cnt = n; a.nU = n;
         // slots are positions.  Resident sessions store original rows (slot of row r = pinv[r]);
         // uploaded sessions store positions (identity map), b rows are then routed through pinv.
         a.rows = F->rows_are_positions ? dident : drow_at;
-        a.steps = F->steps; a.chunks = F->chunks; a.slots = F->slots;
+        a.steps = F->mc.steps; a.chunks = F->mc.chunks; a.slots = F->mc.slots;
         a.src = dB; a.src_total = total; a.src_first = r0; a.src_step = nrhs; a.src_cnt = n;
         a.src_rows = F->rows_are_positions ? dpinv : nullptr;
         a.src_y_stride = 1;
         a.out = dz; a.out_y_stride = (size_t) n * S;
         a.rho = F->rho; a.invrho = F->invrho;
-        a.p = T.p; a.ninv = T.ninv; a.pos = F->pos;
+        a.p = T.p; a.ninv = T.ninv; a.pos = F->mc.pos;
         a.nchunks = fwd_chunks; a.upos = dident; a.publish = 1; a.u0 = 0;
         size_t smem = 0;
         rc = tri_geometry (F, a, &smem);
@@ -2944,7 +3251,7 @@ extern "C" int slipcu_solve (slipcu_factor *F, int nrhs, const u32 *blimbs, cons
         if (debug_check ("k_trisolve(forward)", F->st)) { rc = fail (SLIPCU_CUDA_ERROR, "k_trisolve(forward)", "debug"); goto done; }
         BackArgs b;
         b.n = n; b.S = S; b.z = dz; b.z_y_stride = (size_t) n * S;
-        b.desc = F->desc; b.rho = F->rho; b.invrho = F->invrho; b.p = T.p; b.ninv = T.ninv; b.pos = F->pos;
+        b.desc = F->desc; b.rho = F->rho; b.invrho = F->invrho; b.p = T.p; b.ninv = T.ninv; b.pos = F->mc.pos;
         g_launches++;
         if (CH == 8) k_backsub<8><<<dim3 (S / CH, nb), 256, 0, F->st>>> (b);
         else if (CH == 16) k_backsub<16><<<dim3 (S / CH, nb), 256, 0, F->st>>> (b);

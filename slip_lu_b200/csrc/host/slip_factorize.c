@@ -249,9 +249,17 @@ static int assemble_column (void *user, int k, int cnt, int stride, const uint32
     return 0 ;
 }
 
+/* one column whose pattern is being prepared ahead of the column in flight */
+typedef struct
+{
+    int32_t *pat ;       /* rows reached through the columns < klim (unordered), later the full ordered pattern */
+    int32_t *mark ;      /* n: mark [r] == stamp <=> r is in pat */
+    int32_t cnt, klim, stamp, spec_slot ;
+} ahead_col ;
+
 SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A, SLIP_LU_analysis *S,
     mpz_t *rhos, int32_t *pinv, SLIP_options *option, int want_host_factors, slip_resident **resident,
-    double rhs_bits)
+    double rhs_bits, int min_channels)
 {
     if (!A || !S || !pinv || !option || !A->p || !A->x || !A->i || !S->q || A->n <= 0 || A->n != A->m)
         return SLIP_INCORRECT_INPUT ;
@@ -263,8 +271,6 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
     const int timing = getenv ("SLIP_B200_TIMING") != NULL ;
     const char *prune_env = getenv ("SLIP_B200_PRUNE") ;
     const int use_pruning = !(prune_env && prune_env [0] == '0') ;      /* symmetric pruning of the reach (default on) */
-    const char *spec_env = getenv ("SLIP_B200_SPEC") ;
-    const int use_spec = (spec_env && spec_env [0] == '1') ;             /* speculative first part of the next column */
     double t_sym = 0, t_dev = 0, t_piv = 0, t_begin = 0, t0 = now_s (), tt ;
     double work_updates = 0, work_limbmul = 0 ;
     double *cumbits_at = (double *) SLIP_calloc ((size_t) n, sizeof (double)) ;
@@ -272,17 +278,17 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
     pattern_store P = {0} ;
     slipcu_factor *dev = NULL ;
     slip_resident *res = NULL ;
+    ahead_col ring [SLIPCU_SPEC_SLOTS] ;
+    memset (ring, 0, sizeof (ring)) ;
+    int ring_size = 0, restarts = 0, bound_restarts = 0 ;
     double *colbits = (double *) SLIP_malloc ((size_t) n * sizeof (double)) ;
     int32_t *row_at = (int32_t *) SLIP_malloc ((size_t) n * sizeof (int32_t)) ;
-    int32_t *mark = (int32_t *) SLIP_calloc ((size_t) n, sizeof (int32_t)) ;
     int32_t *stack = (int32_t *) SLIP_malloc ((size_t) n * sizeof (int32_t)) ;
-    int32_t *pat = (int32_t *) SLIP_malloc ((size_t) n * sizeof (int32_t)) ;
     int32_t *upos = (int32_t *) SLIP_malloc ((size_t) n * sizeof (int32_t)) ;
-    int32_t *npat = (int32_t *) SLIP_malloc ((size_t) n * sizeof (int32_t)) ;
-    int32_t *spat = (int32_t *) SLIP_malloc ((size_t) n * sizeof (int32_t)) ;      /* speculative pattern, ordered */
+    int32_t *spat = (int32_t *) SLIP_malloc ((size_t) n * sizeof (int32_t)) ;      /* bulk-part pattern, ordered */
     int32_t *supos = (int32_t *) SLIP_malloc ((size_t) n * sizeof (int32_t)) ;
     int32_t *posflag = (int32_t *) SLIP_calloc ((size_t) n, sizeof (int32_t)) ;
-    if (!colbits || !row_at || !mark || !stack || !pat || !upos || !cumbits_at || !npat || !posflag || !spat || !supos) { status = SLIP_OUT_OF_MEMORY ; goto cleanup ; }
+    if (!colbits || !row_at || !stack || !upos || !cumbits_at || !posflag || !spat || !supos) { status = SLIP_OUT_OF_MEMORY ; goto cleanup ; }
 
     for (int32_t a = 0 ; a < nz ; a++)
         if (A->i [a] < 0 || A->i [a] >= n) { status = SLIP_INCORRECT_INPUT ; goto cleanup ; }
@@ -295,7 +301,25 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
     for (int32_t j = 0 ; j < n ; j++) { total_bits += colbits [j] ; if (colbits [j] < min_bits) min_bits = colbits [j] ; }
     /* a right-hand side known up front (SLIP_solve_*) may need more room than the factors */
     const double extra = rhs_bits > min_bits ? rhs_bits - min_bits : 0.0 ;
-    const int channels = slip_channels_for_bits (total_bits + extra) + SLIP_B200_SPARE_CHANNELS ;
+    const int channels_full = slip_channels_for_bits (total_bits + extra) + SLIP_B200_SPARE_CHANNELS ;
+    /* The Hadamard bound is what a residue system must carry to be safe a priori, and on real LP
+       bases it is one to two orders of magnitude above the sizes that occur (NSR8K: 29 361 bits
+       against a 704-bit determinant).  GMP pays for actual operand sizes; to do the same the
+       factorization starts with a fraction of the channels in BOUND MODE -- every column's size is
+       then proven on the device from the measured sizes of the finished columns, see
+       slip_b200_device.h -- and restarts with four times as many when a column does not fit. */
+    int channels = channels_full ;
+    {
+        const char *ad = getenv ("SLIP_B200_ADAPTIVE"), *sc = getenv ("SLIP_B200_START_CHANNELS") ;
+        if (!(ad && ad [0] == '0'))
+        {
+            int start = sc && *sc ? atoi (sc) : channels_full / 16 ;
+            if (start < 32) start = 32 ;
+            if (start < min_channels) start = min_channels ;
+            start = (start + 31) & ~31 ;
+            if (2 * start <= channels_full) channels = start ;
+        }
+    }
 
     {   /* A as limb strings */
         int64_t words = 0 ;
@@ -306,26 +330,65 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
 
     for (int attempt = 0 ; ; attempt++)
     {
-        int retry = 0 ;
+        int retry = 0, grow = 0 ;
+        const int bound_mode = channels < channels_full ;
         SLIP_TRY (patterns_init (&P, n, (int64_t) S->lnz + S->unz)) ;
         tt = now_s () ;
         SLIP_TRY (slip_from_device_status (slipcu_factor_begin (&dev, n, nz, A->p, A->i, Al.limbs, Al.off,
-            Al.sign, channels, want_host_factors))) ;
+            Al.sign, channels, want_host_factors, bound_mode))) ;
         t_begin += now_s () - tt ;
         const int S_dev = slipcu_factor_channels (dev) ;
-        for (int32_t r = 0 ; r < n ; r++) { pinv [r] = r ; row_at [r] = r ; mark [r] = 0 ; posflag [r] = 0 ; }
+        const int cap_units = slipcu_factor_capacity_units (dev) ;
+        /* lookahead depth: with few channels one column cannot fill the GPU, so the bulk parts of
+           the next columns run beside it; with thousands of channels a column is HBM-bound on
+           its own and the second launch per column costs more than it hides */
+        int look = S_dev <= 512 ? 6 : 0 ;
+        { const char *lk = getenv ("SLIP_B200_LOOKAHEAD") ; if (lk && *lk) look = atoi (lk) ; }
+        if (look < 0) look = 0 ;
+        if (look > SLIPCU_SPEC_SLOTS - 1) look = SLIPCU_SPEC_SLOTS - 1 ;
+        const int D = look > 1 ? look : 1 ;
+        ring_size = D + 1 ;
+        for (int i = 0 ; i < ring_size ; i++)
+        {
+            if (!ring [i].pat) ring [i].pat = (int32_t *) SLIP_malloc ((size_t) n * sizeof (int32_t)) ;
+            if (!ring [i].mark) ring [i].mark = (int32_t *) SLIP_malloc ((size_t) n * sizeof (int32_t)) ;
+            if (!ring [i].pat || !ring [i].mark) { status = SLIP_OUT_OF_MEMORY ; goto cleanup ; }
+            memset (ring [i].mark, 0, (size_t) n * sizeof (int32_t)) ;
+            ring [i].cnt = 0 ; ring [i].spec_slot = -1 ;
+        }
+        for (int32_t r = 0 ; r < n ; r++) { pinv [r] = r ; row_at [r] = r ; posflag [r] = 0 ; }
         double cum_bits = 0 ;
         work_updates = 0 ; work_limbmul = 0 ;
-        /* pattern of column 0; afterwards the pattern of column k+1 is prepared (up to the effect
-           of pivot k) while the GPU works on column k */
-        int32_t cnt = reach_unordered (A, S->q [0], 0, &P, pinv, mark, 1, stack, pat) ;
+        /* the patterns of the first D columns start from the entries of A alone */
+        for (int32_t c = 0 ; c < D && c < n ; c++)
+        {
+            ahead_col *e = &ring [c % ring_size] ;
+            e->klim = 0 ; e->stamp = c + 1 ; e->spec_slot = -1 ;
+            e->cnt = reach_unordered (A, S->q [c], 0, &P, pinv, e->mark, e->stamp, stack, e->pat) ;
+        }
         for (int32_t k = 0 ; k < n ; k++)
         {
             const int32_t col = S->q [k] ;
+            ahead_col *e = &ring [k % ring_size] ;
+            int32_t *pat = e->pat ;
             tt = now_s () ;
             cum_bits += colbits [col] ;
-            int s_k = slip_channels_for_bits (cum_bits) ;
-            if (s_k > S_dev) s_k = S_dev ;
+            const int s_had = slip_channels_for_bits (cum_bits) ;
+            const int s_k = s_had > S_dev ? S_dev : s_had ;
+            /* the columns committed since the pattern was started: when the pivot row of column j
+               is in the pattern, its column of L (rows that were not pivotal at time j) joins it */
+            int32_t cnt = e->cnt ;
+            for (int32_t j = e->klim ; j < k ; j++)
+            {
+                if (e->mark [row_at [j]] != e->stamp) continue ;
+                const int32_t *rj = P.rows + P.ptr [j] ;
+                const int32_t cj = (int32_t) (P.ptr [j + 1] - P.ptr [j]) ;
+                for (int32_t t = P.nU [j] ; t < cj ; t++)
+                {
+                    const int32_t rr = rj [t] ;
+                    if (e->mark [rr] != e->stamp) { e->mark [rr] = e->stamp ; pat [cnt++] = rr ; }
+                }
+            }
             order_by_position (n, cnt, pat, pinv, row_at, posflag, k + 1) ;
             int32_t nU = 0, diag_slot = -1 ;
             for (int32_t t = 0 ; t < cnt ; t++)
@@ -336,28 +399,37 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
             }
             if (cnt == nU) { status = SLIP_SINGULAR ; goto cleanup ; }    /* no candidate row at all */
             t_sym += now_s () - tt ; tt = now_s () ;
-            int rc = slipcu_factor_column_launch (dev, k, col, cnt, nU, pat, upos, s_k, scheme, diag_slot) ;
+            int rc = slipcu_factor_column_launch (dev, k, col, cnt, nU, pat, upos, s_k, scheme, diag_slot, e->spec_slot) ;
+            e->spec_slot = -1 ;
             if (rc == SLIPCU_BAD_PRIME) { retry = 1 ; break ; }
             SLIP_TRY (slip_from_device_status (rc)) ;
             t_dev += now_s () - tt ; tt = now_s () ;
-            /* while the GPU works: the part of the next pattern that does not depend on pivot k */
-            int32_t ncnt = 0 ;
-            if (k + 1 < n) ncnt = reach_unordered (A, S->q [k + 1], k, &P, pinv, mark, k + 2, stack, npat) ;
-            /* speculative first part of column k+1: every step except the one with column k, whose
-               pivot is not known yet, on the pattern found so far (the rest joins it below) */
-            if (use_spec && ncnt > 0)
+            /* while the GPU works: the pattern of column k+D as far as the committed columns
+               (those before k) determine it, and its bulk part on the device */
+            if (k + D < n)
             {
-                memcpy (spat, npat, (size_t) ncnt * sizeof (int32_t)) ;
-                order_by_position (n, ncnt, spat, pinv, row_at, posflag, n + k + 2) ;
-                int32_t snU = 0 ;
-                for (int32_t t = 0 ; t < ncnt ; t++)
+                const int32_t c = k + D ;
+                ahead_col *f = &ring [c % ring_size] ;
+                f->klim = k ; f->stamp = c + 1 ; f->spec_slot = -1 ;
+                f->cnt = reach_unordered (A, S->q [c], k, &P, pinv, f->mark, f->stamp, stack, f->pat) ;
+                if (look > 0 && k > 0)
                 {
-                    const int32_t pos = pinv [spat [t]] ;
-                    if (pos < k) supos [snU++] = pos ;
+                    memcpy (spat, f->pat, (size_t) f->cnt * sizeof (int32_t)) ;
+                    order_by_position (n, f->cnt, spat, pinv, row_at, posflag, n + c + 2) ;
+                    int32_t snU = 0 ;
+                    for (int32_t t = 0 ; t < f->cnt ; t++)
+                    {
+                        const int32_t pos = pinv [spat [t]] ;
+                        if (pos < k) supos [snU++] = pos ;
+                    }
+                    if (snU > 0)
+                    {
+                        rc = slipcu_factor_spec_launch (dev, c % ring_size, c, S->q [c], f->cnt, snU, spat, supos) ;
+                        if (rc == SLIPCU_BAD_PRIME) { retry = 1 ; break ; }
+                        SLIP_TRY (slip_from_device_status (rc)) ;
+                        f->spec_slot = c % ring_size ;
+                    }
                 }
-                rc = slipcu_factor_spec_launch (dev, k + 1, S->q [k + 1], ncnt, snU, spat, supos) ;
-                if (rc == SLIPCU_BAD_PRIME) { retry = 1 ; break ; }
-                SLIP_TRY (slip_from_device_status (rc)) ;
             }
             /* bookkeeping that does not depend on pivot k, also while the GPU works */
             for (int32_t u = 0 ; u < nU ; u++)
@@ -377,6 +449,11 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
             if (rc == SLIPCU_BAD_PRIME) { retry = 1 ; break ; }
             SLIP_TRY (slip_from_device_status (rc)) ;
             t_dev += now_s () - tt ; tt = now_s () ;
+            if (bound_mode && s_had > S_dev && info.bound_units > cap_units)
+            {   /* the column is not proven to fit the channels carried: start over with more */
+                grow = (int) ceil (((double) info.bound_units / 64.0 + 4.0) / SLIP_B200_CHANNEL_BITS) ;
+                retry = 1 ; break ;
+            }
             int32_t slot = -1 ;
             SLIP_TRY (decide_pivot (dev, k, scheme, option->tol, diag_slot, &info, &slot)) ;
             const int32_t prow = pat [slot] ;
@@ -404,34 +481,35 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
                 SLIP_free (w) ;
                 SLIP_TRY (slip_from_device_status (rc)) ;
             }
-            else if (mark [prow] == k + 2)
-            {   /* the new pivot row is in the next pattern: its column of L (the candidate rows of
-                   column k, none of them pivotal yet) joins it */
-                for (int32_t t = nU ; t < cnt ; t++)
-                {
-                    const int32_t rr = pat [t] ;
-                    if (mark [rr] != k + 2) { mark [rr] = k + 2 ; npat [ncnt++] = rr ; }
-                }
-            }
-            { int32_t *sw = pat ; pat = npat ; npat = sw ; }
-            cnt = ncnt ;
             t_piv += now_s () - tt ;
         }
         if (!retry)
         {   /* the last pivot is only checked against the channel primes here */
-            int bad = -1 ;
-            SLIP_TRY (slip_from_device_status (slipcu_factor_bad_channel (dev, &bad))) ;
-            if (bad >= 0) retry = 1 ;
+            uint32_t badp = 0 ;
+            SLIP_TRY (slip_from_device_status (slipcu_factor_bad_prime (dev, &badp))) ;
+            if (badp) retry = 1 ;
         }
         if (!retry) break ;
-        {   /* a channel prime divides a pivot (probability ~ n*S/2^31): retire it and start over */
-            int bad = -1 ;
-            slipcu_factor_bad_channel (dev, &bad) ;
+        {
+            uint32_t badp = 0 ;
+            if (!grow) slipcu_factor_bad_prime (dev, &badp) ;
             slipcu_factor_free (dev) ; dev = NULL ;
             if (res) { slip_resident_free (res) ; res = NULL ; }
             patterns_free (&P) ;
-            if (bad < 0 || attempt >= 4) { slip_set_error ("could not find usable channel primes") ; status = SLIP_INCORRECT ; goto cleanup ; }
-            slipcu_retire_channel (bad) ;
+            if (grow)
+            {   /* bound mode ran out of room: four times the channels, at least what the failed
+                   column asked for, at most the Hadamard count (which needs no proof) */
+                int next = 4 * channels ;
+                if (next < grow + grow / 4) next = grow + grow / 4 ;
+                next = (next + 31) & ~31 ;
+                channels = (2 * next <= channels_full) ? next : channels_full ;
+                bound_restarts++ ;
+            }
+            else
+            {   /* a channel prime divides a pivot (probability ~ n*S/2^31): retire it and start over */
+                if (!badp || ++restarts > 4) { slip_set_error ("could not find usable channel primes") ; status = SLIP_INCORRECT ; goto cleanup ; }
+                slipcu_retire_prime (badp) ;
+            }
         }
     }
 
@@ -440,6 +518,8 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
         for (int32_t k = 0 ; k < n ; k++) { lnz += (double) (P.ptr [k + 1] - P.ptr [k]) - P.nU [k] ; unz += P.nU [k] + 1 ; }
         slip_last_stats.n = n ; slip_last_stats.nnz_L = lnz ; slip_last_stats.nnz_U = unz ;
         slip_last_stats.channels = slipcu_factor_channels (dev) ;
+        slip_last_stats.channels_hadamard = channels_full ;
+        slip_last_stats.bound_restarts = bound_restarts ;
         slip_last_stats.updates = work_updates ; slip_last_stats.limb_mul_equiv = work_limbmul ;
         slip_last_stats.t_symbolic = t_sym ; slip_last_stats.t_device = t_dev ; slip_last_stats.t_begin = t_begin ;
         slip_last_stats.t_factor_total = now_s () - t0 ;
@@ -484,9 +564,18 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
 
     res->dev = dev ; dev = NULL ;
     res->n = n ;
+    res->proven_channels = channels >= channels_full ;
     res->total_bits = total_bits ;
     res->min_col_bits = min_bits ;
     res->Lx = want_host_factors ? (const void *) L->x : NULL ;
+    res->Ux = want_host_factors ? (const void *) U->x : NULL ;
+    if (want_host_factors && !res->proven_channels)
+    {   /* SLIP_LU_solve has no A: bound-mode factors keep a copy to verify their solutions with */
+        res->A_copy = slip_sparse_copy (A) ;
+        res->q_copy = (int32_t *) SLIP_malloc ((size_t) n * sizeof (int32_t)) ;
+        if (!res->A_copy || !res->q_copy) { status = SLIP_OUT_OF_MEMORY ; goto cleanup ; }
+        memcpy (res->q_copy, S->q, (size_t) n * sizeof (int32_t)) ;
+    }
     if (resident) { *resident = res ; res = NULL ; }
     else if (want_host_factors) { slip_resident_add (res) ; res = NULL ; }
 
@@ -495,9 +584,10 @@ cleanup:
     if (res) slip_resident_free (res) ;
     slip_limbs_free (&Al) ;
     patterns_free (&P) ;
-    SLIP_free (colbits) ; SLIP_free (row_at) ; SLIP_free (mark) ; SLIP_free (stack) ;
-    SLIP_free (pat) ; SLIP_free (upos) ; SLIP_free (cumbits_at) ; SLIP_free (npat) ; SLIP_free (posflag) ;
+    SLIP_free (colbits) ; SLIP_free (row_at) ; SLIP_free (stack) ;
+    SLIP_free (upos) ; SLIP_free (cumbits_at) ; SLIP_free (posflag) ;
     SLIP_free (spat) ; SLIP_free (supos) ;
+    for (int i = 0 ; i < SLIPCU_SPEC_SLOTS ; i++) { SLIP_free (ring [i].pat) ; SLIP_free (ring [i].mark) ; }
     return status ;
 }
 
@@ -506,5 +596,5 @@ SLIP_info SLIP_LU_factorize (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A, SLI
 {
     if (!A || !L || !U || !S || !rhos || !pinv || !option || !A->p || !A->x || !A->i)
         return SLIP_INCORRECT_INPUT ;
-    return slip_factorize_driver (L, U, A, S, rhos, pinv, option, 1, NULL, 0.0) ;
+    return slip_factorize_driver (L, U, A, S, rhos, pinv, option, 1, NULL, 0.0, 0) ;
 }

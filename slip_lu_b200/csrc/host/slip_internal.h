@@ -41,6 +41,9 @@ typedef struct
     double updates ;           /* REF entry updates (one per L entry per elimination step) */
     double limb_mul_equiv ;    /* schoolbook-equivalent 32-bit limb multiplies of those updates */
     double t_symbolic, t_device, t_begin, t_factor_total ;
+    double channels_hadamard ; /* channels the a-priori (Hadamard) bound asks for */
+    double bound_restarts ;    /* bound-mode restarts with more channels */
+    double verified_solves ;   /* solves whose numerators were verified exactly (A N = det b) */
 } slip_b200_stats ;
 extern __thread slip_b200_stats slip_last_stats ;
 void slip_set_error (const char *msg) ;
@@ -53,16 +56,22 @@ int slip_channels_for_bits (double bits) ;
 /* resident factorizations (GPU-side L, U, rho), keyed by the host L object */
 typedef struct slip_resident
 {
-    const void *Lx ;              /* L->x of the owning factorization (NULL: anonymous) */
+    const void *Lx, *Ux ;         /* L->x, U->x of the owning factorization (NULL: anonymous) */
+    int holders, unlinked ;       /* registry reference count (see slip_limbs.c) */
     slipcu_factor *dev ;
     int32_t n ;
     double total_bits ;           /* sum of the column bounds of A */
     double min_col_bits ;
+    int proven_channels ;         /* 1: the session's channels cover the Hadamard bound */
+    SLIP_sparse *A_copy ;         /* bound-mode factors kept for SLIP_LU_solve: the input, to verify solutions */
+    int32_t *q_copy ;
     mpz_t det ;                   /* rho[n-1] */
     struct slip_resident *next ;
 } slip_resident ;
 
-slip_resident *slip_resident_find (const void *Lx) ;
+slip_resident *slip_resident_acquire (const void *Lx, const void *Ux, int32_t n, mpz_srcptr det) ;
+void slip_resident_release (slip_resident *r) ;
+void slip_resident_drop_all (void) ;
 void slip_resident_add (slip_resident *r) ;
 void slip_resident_drop (const void *Lx) ;          /* frees device memory */
 void slip_resident_free (slip_resident *r) ;
@@ -70,8 +79,13 @@ void slip_resident_free (slip_resident *r) ;
 /* the shared driver behind SLIP_LU_factorize and SLIP_solve_* */
 SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A, SLIP_LU_analysis *S,
     mpz_t *rhos, int32_t *pinv, SLIP_options *option, int want_host_factors, slip_resident **resident,
-    double rhs_bits) ;
-SLIP_info slip_solve_resident (mpq_t **x, SLIP_dense *b, slip_resident *r, const int32_t *pinv) ;
+    double rhs_bits, int min_channels) ;
+/* solve with resident factors; A, q (may be NULL) allow a bound-mode session to verify its result.
+ * Returns SLIP_B200_NEED_CHANNELS when the session's channels could not be shown to suffice. */
+#define SLIP_B200_NEED_CHANNELS ((SLIP_info) (-100))
+SLIP_info slip_solve_resident (mpq_t **x, SLIP_dense *b, slip_resident *r, const int32_t *pinv,
+    const SLIP_sparse *A, const int32_t *q) ;
+SLIP_sparse *slip_sparse_copy (const SLIP_sparse *A) ;
 
 SLIP_info slip_expand_double_array (mpz_t *x_out, double *x, mpq_t scale, int32_t n, SLIP_options *option) ;
 SLIP_info slip_expand_double_mat (mpz_t **x_out, double **x, mpq_t scale, int32_t m, int32_t n, SLIP_options *option) ;

@@ -100,26 +100,48 @@ int slip_channels_for_bits (double bits)
     return (int) c ;
 }
 
-/* ---- resident factorizations ---- */
+/* ---- resident factorizations ----
+ * SLIP_LU_factorize leaves L, U and the pivots on the GPU; SLIP_LU_solve finds them again through
+ * this registry.  An entry is keyed by the addresses of L->x AND U->x together with n, and a hit
+ * is only used if rhos[n-1] equals the determinant the entry was built with, so that an array
+ * released by other means and reallocated at the same address is not mistaken for the factors.
+ * Entries are reference counted: a solve holds its entry, and a concurrent SLIP_delete_sparse only
+ * unlinks it; the last holder frees the device memory.  SLIP_finalize drops everything. */
 static pthread_mutex_t reg_lock = PTHREAD_MUTEX_INITIALIZER ;
 static slip_resident *reg_head = NULL ;
 
-slip_resident *slip_resident_find (const void *Lx)
+slip_resident *slip_resident_acquire (const void *Lx, const void *Ux, int32_t n, mpz_srcptr det)
 {
     slip_resident *hit = NULL ;
     if (!Lx) return NULL ;
     pthread_mutex_lock (&reg_lock) ;
-    for (slip_resident *r = reg_head ; r ; r = r->next) if (r->Lx == Lx) { hit = r ; break ; }
+    for (slip_resident *r = reg_head ; r ; r = r->next)
+        if (r->Lx == Lx && r->Ux == Ux && r->n == n && det && mpz_cmp (r->det, det) == 0) { hit = r ; r->holders++ ; break ; }
     pthread_mutex_unlock (&reg_lock) ;
     return hit ;
 }
 
+void slip_resident_release (slip_resident *r)
+{
+    if (!r) return ;
+    int last ;
+    pthread_mutex_lock (&reg_lock) ;
+    last = (--r->holders == 0 && r->unlinked) ;
+    pthread_mutex_unlock (&reg_lock) ;
+    if (last) slip_resident_free (r) ;
+}
+
 void slip_resident_add (slip_resident *r)
 {
+    slip_resident *old = NULL ;
     pthread_mutex_lock (&reg_lock) ;
+    /* a second factorization into the same L object replaces the first */
+    for (slip_resident **pp = &reg_head ; *pp ; pp = &(*pp)->next)
+        if ((*pp)->Lx == r->Lx) { old = *pp ; *pp = old->next ; old->unlinked = 1 ; if (old->holders) old = NULL ; break ; }
     r->next = reg_head ;
     reg_head = r ;
     pthread_mutex_unlock (&reg_lock) ;
+    slip_resident_free (old) ;
 }
 
 void slip_resident_free (slip_resident *r)
@@ -127,6 +149,8 @@ void slip_resident_free (slip_resident *r)
     if (!r) return ;
     if (r->dev) slipcu_factor_free (r->dev) ;
     if (r->det->_mp_d) mpz_clear (r->det) ;
+    if (r->A_copy) SLIP_delete_sparse (&r->A_copy) ;
+    SLIP_free (r->q_copy) ;
     SLIP_free (r) ;
 }
 
@@ -136,7 +160,25 @@ void slip_resident_drop (const void *Lx)
     slip_resident *victim = NULL ;
     pthread_mutex_lock (&reg_lock) ;
     for (slip_resident **pp = &reg_head ; *pp ; pp = &(*pp)->next)
-        if ((*pp)->Lx == Lx) { victim = *pp ; *pp = victim->next ; break ; }
+        if ((*pp)->Lx == Lx)
+        {
+            victim = *pp ; *pp = victim->next ; victim->unlinked = 1 ;
+            if (victim->holders) victim = NULL ;          /* the solve that holds it frees it */
+            break ;
+        }
     pthread_mutex_unlock (&reg_lock) ;
     slip_resident_free (victim) ;
+}
+
+void slip_resident_drop_all (void)
+{
+    for (;;)
+    {
+        slip_resident *victim = NULL ;
+        pthread_mutex_lock (&reg_lock) ;
+        if (reg_head) { victim = reg_head ; reg_head = victim->next ; victim->unlinked = 1 ; if (victim->holders) victim = (slip_resident *) 1 ; }
+        pthread_mutex_unlock (&reg_lock) ;
+        if (!victim) break ;
+        if (victim != (slip_resident *) 1) slip_resident_free (victim) ;
+    }
 }

@@ -35,6 +35,7 @@ void SLIP_initialize_expert (void *(*MyMalloc) (size_t), void *(*MyRealloc) (voi
 
 void SLIP_finalize (void)
 {
+    slip_resident_drop_all () ;       /* GPU-resident factors of objects the caller never deleted */
     mpfr_free_cache () ;
 }
 
@@ -72,11 +73,13 @@ __thread slip_b200_stats slip_last_stats ;
  * t_factor_total of the last factorization run by the calling thread; returns the count written */
 int SLIP_B200_last_stats (double *out, int cap)
 {
-    const double v [10] = { slip_last_stats.n, slip_last_stats.nnz_L, slip_last_stats.nnz_U,
+    const double v [13] = { slip_last_stats.n, slip_last_stats.nnz_L, slip_last_stats.nnz_U,
         slip_last_stats.channels, slip_last_stats.updates, slip_last_stats.limb_mul_equiv,
         slip_last_stats.t_symbolic, slip_last_stats.t_device, slip_last_stats.t_begin,
-        slip_last_stats.t_factor_total } ;
+        slip_last_stats.t_factor_total,
+        /* [10] channels the Hadamard bound asks for, [11] bound-mode restarts, [12] verified solves */
+        slip_last_stats.channels_hadamard, slip_last_stats.bound_restarts, slip_last_stats.verified_solves } ;
     int k = 0 ;
-    for ( ; k < 10 && k < cap ; k++) out [k] = v [k] ;
+    for ( ; k < 13 && k < cap ; k++) out [k] = v [k] ;
     return k ;
 }

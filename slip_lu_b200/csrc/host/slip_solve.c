@@ -20,7 +20,38 @@ typedef struct
 {
     mpq_t **x ;
     mpz_srcptr det ;
+    /* verification of a bound-mode result (NULL: the channel count is proven a priori) */
+    const SLIP_sparse *A ; const int32_t *q ; const SLIP_dense *b ;
+    int failed ;
 } rational_ctx ;
+
+/* Exact check of one right-hand side: sum_i A(:,q[i]) * N_i == det * b(:,c) over the integers.
+ * x = N/det is then THE solution of A x = b (A is nonsingular: every pivot was nonzero), whatever
+ * the channel count it was reconstructed from -- a wrong reconstruction cannot pass. */
+static int numerators_verify (const rational_ctx *ctx, int c, int n)
+{
+    const SLIP_sparse *A = ctx->A ;
+    int ok = 1 ;
+    mpz_t *acc = SLIP_create_mpz_array (n) ;
+    mpz_t t ;
+    if (!acc) return 0 ;
+    mpz_init (t) ;
+    for (int32_t i = 0 ; i < n ; i++)
+    {
+        mpz_srcptr Ni = mpq_numref (ctx->x [i][c]) ;
+        if (mpz_sgn (Ni) == 0) continue ;
+        const int32_t col = ctx->q [i] ;
+        for (int32_t a = A->p [col] ; a < A->p [col + 1] ; a++) mpz_addmul (acc [A->i [a]], A->x [a], Ni) ;
+    }
+    for (int32_t r = 0 ; r < n && ok ; r++)
+    {
+        mpz_mul (t, ctx->det, ctx->b->x [r][c]) ;
+        if (mpz_cmp (t, acc [r]) != 0) ok = 0 ;
+    }
+    mpz_clear (t) ;
+    SLIP_delete_mpz_array (&acc, n) ;
+    return ok ;
+}
 
 static int rational_column (void *user, int c, int cnt, int stride, const uint32_t *limbs,
     const int32_t *nl, const int8_t *sign)
@@ -28,18 +59,26 @@ static int rational_column (void *user, int c, int cnt, int stride, const uint32
     rational_ctx *ctx = (rational_ctx *) user ;
     #pragma omp parallel for schedule(dynamic, 8) if (cnt > 16)
     for (int t = 0 ; t < cnt ; t++)
+        slip_mpz_from_words (mpq_numref (ctx->x [t][c]), limbs + (size_t) t * stride, nl [t], sign [t]) ;
+    if (ctx->A && !ctx->failed && !numerators_verify (ctx, c, cnt)) ctx->failed = 1 ;
+    if (ctx->failed) return 0 ;
+    #pragma omp parallel for schedule(dynamic, 8) if (cnt > 16)
+    for (int t = 0 ; t < cnt ; t++)
     {
         mpq_ptr q = ctx->x [t][c] ;
-        slip_mpz_from_words (mpq_numref (q), limbs + (size_t) t * stride, nl [t], sign [t]) ;
         mpz_set (mpq_denref (q), ctx->det) ;
         mpq_canonicalize (q) ;
     }
     return 0 ;
 }
 
-/* verified = 0: the channel count behind r is only an estimate of the result size; the solve then
- * reconstructs over every channel and reports SLIP_INCORRECT if the two top channels were needed */
-static SLIP_info solve_on_device (mpq_t **x, SLIP_dense *b, slip_resident *r, const int32_t *pinv, int verified)
+/* mode 1: the channels behind r are proven to hold the result (Cramer/Hadamard bound of det*x).
+ * mode 0: they are an estimate (factors uploaded without A): reconstruct over every channel and
+ *         report SLIP_INCORRECT if the two top channels were needed.
+ * Bound-mode sessions (fewer channels than the a-priori bound) whose channels do not cover the
+ * Cramer bound reconstruct over every channel and VERIFY the numerators exactly against A. */
+static SLIP_info solve_on_device (mpq_t **x, SLIP_dense *b, slip_resident *r, const int32_t *pinv, int verified,
+    const SLIP_sparse *A, const int32_t *q)
 {
     SLIP_info status = SLIP_OK ;
     const int32_t n = r->n, nrhs = b->n ;
@@ -56,26 +95,48 @@ static SLIP_info solve_on_device (mpq_t **x, SLIP_dense *b, slip_resident *r, co
     }
     {
         const int have = slipcu_factor_channels (r->dev) ;
-        int s = have ;
+        int s = have, check = 0 ;
         if (verified)
         {   /* Cramer: det*x_i is the determinant of A with one column replaced by b */
             s = slip_channels_for_bits (r->total_bits - r->min_col_bits + slip_dense_max_column_bits (b)) ;
-            if (s > have) { status = SLIP_INCORRECT_INPUT ; goto cleanup ; }
+            if (s > have)
+            {
+                if (r->proven_channels || !A || !q) { status = SLIP_B200_NEED_CHANNELS ; goto cleanup ; }
+                s = have ; check = 1 ;
+            }
         }
         int32_t top = -1 ;
-        rational_ctx ctx = { x, r->det } ;
+        rational_ctx ctx = { x, r->det, check ? A : NULL, q, b, 0 } ;
         SLIP_TRY (slip_from_device_status (slipcu_solve (r->dev, nrhs, bl.limbs, bl.off, bl.sign, pinv, s,
             rational_column, &ctx, &top))) ;
         if (!verified && top >= have - 2) status = SLIP_INCORRECT ;
+        if (check) { slip_last_stats.verified_solves += nrhs ; if (ctx.failed) status = SLIP_B200_NEED_CHANNELS ; }
     }
 cleanup:
     slip_limbs_free (&bl) ;
     return status ;
 }
 
-SLIP_info slip_solve_resident (mpq_t **x, SLIP_dense *b, slip_resident *r, const int32_t *pinv)
+SLIP_info slip_solve_resident (mpq_t **x, SLIP_dense *b, slip_resident *r, const int32_t *pinv,
+    const SLIP_sparse *A, const int32_t *q)
 {
-    return solve_on_device (x, b, r, pinv, 1) ;
+    return solve_on_device (x, b, r, pinv, 1, A, q) ;
+}
+
+SLIP_sparse *slip_sparse_copy (const SLIP_sparse *A)
+{
+    SLIP_sparse *C = SLIP_create_sparse () ;
+    if (!C) return NULL ;
+    const int32_t n = A->n, nz = A->p [n] ;
+    C->m = A->m ; C->n = n ; C->nz = nz ; C->nzmax = nz ;
+    C->p = (int32_t *) SLIP_malloc ((size_t) (n + 1) * sizeof (int32_t)) ;
+    C->i = (int32_t *) SLIP_malloc ((size_t) (nz > 0 ? nz : 1) * sizeof (int32_t)) ;
+    C->x = SLIP_create_mpz_array (nz) ;
+    if (!C->p || !C->i || !C->x) { SLIP_delete_sparse (&C) ; return NULL ; }
+    memcpy (C->p, A->p, (size_t) (n + 1) * sizeof (int32_t)) ;
+    memcpy (C->i, A->i, (size_t) nz * sizeof (int32_t)) ;
+    for (int32_t a = 0 ; a < nz ; a++) mpz_set (C->x [a], A->x [a]) ;
+    return C ;
 }
 
 /* resident session from host-side factors (L, U, rhos given as mpz_t) */
@@ -146,31 +207,39 @@ SLIP_info SLIP_LU_solve (mpq_t **x, SLIP_dense *b, const mpz_t *rhos, const SLIP
     if (!x || !b || !rhos || !pinv || !L || !U || !b->x || !L->p || !L->i || !L->x || !U->p || !U->i || !U->x)
         return SLIP_INCORRECT_INPUT ;
     SLIP_info status = SLIP_OK ;
-    slip_resident *r = slip_resident_find (L->x), *tmp = NULL ;
+    const int32_t n = L->n ;
+    for (int32_t r0 = 0 ; r0 < n ; r0++) if (pinv [r0] < 0 || pinv [r0] >= n) return SLIP_INCORRECT_INPUT ;
+    slip_resident *r = slip_resident_acquire (L->x, U->x, n, rhos [n - 1]), *tmp = NULL ;
     const double bbits = slip_dense_max_column_bits (b) ;
     int need = -1 ;
+    double tot_bits = 0, min_bits = 0 ;
     if (r)
-    {   /* do the resident factors carry enough channels for this right-hand side? */
+    {   /* do the resident factors carry enough channels for this right-hand side?  (bound-mode
+           factors: the result is verified against the copy of A kept with them) */
         need = slip_channels_for_bits (r->total_bits - r->min_col_bits + bbits) ;
-        if (need <= slipcu_factor_channels (r->dev)) return solve_on_device (x, b, r, pinv, 1) ;
+        tot_bits = r->total_bits ; min_bits = r->min_col_bits ;
+        status = solve_on_device (x, b, r, pinv, 1, r->A_copy, r->q_copy) ;
+        slip_resident_release (r) ; r = NULL ;
+        if (status != SLIP_B200_NEED_CHANNELS) return status ;
+        status = SLIP_OK ;
     }
     /* Factors that are not resident (or too narrow) are re-encoded from the host copies.  With
      * the bound of the resident factorization at hand the channel count is exact.  Without it
      * (L, U from elsewhere) there is no A to bound det*x with, so the count is estimated from
      * the factors, the result is reconstructed over all channels, and the two top channels must
      * stay empty; otherwise the channels are doubled and the solve repeated. */
-    const int32_t n = L->n ;
     int channels = need > 0 ? need + SLIP_B200_SPARE_CHANNELS
         : slip_channels_for_bits (max_bits_sparse (L) + max_bits_sparse (U) + bbits + 2.0 * log2 ((double) n + 1.0) + 64.0) + 2 ;
     for (int attempt = 0 ; attempt < 8 ; attempt++)
     {
         SLIP_TRY (upload_factors (&tmp, L, U, rhos, channels)) ;
-        if (need > 0) { tmp->total_bits = r->total_bits ; tmp->min_col_bits = r->min_col_bits ; }
-        status = solve_on_device (x, b, tmp, pinv, need > 0) ;
+        if (need > 0) { tmp->total_bits = tot_bits ; tmp->min_col_bits = min_bits ; tmp->proven_channels = 1 ; }
+        status = solve_on_device (x, b, tmp, pinv, need > 0, NULL, NULL) ;
         slip_resident_free (tmp) ; tmp = NULL ;
         if (status != SLIP_INCORRECT || need > 0) break ;
         channels *= 2 ;
     }
+    if (status == SLIP_B200_NEED_CHANNELS) status = SLIP_INCORRECT ;
 cleanup:
     if (tmp) slip_resident_free (tmp) ;
     return status ;
@@ -203,6 +272,18 @@ SLIP_info SLIP_scale_x (mpq_t **x, SLIP_sparse *A, SLIP_dense *b)
     return SLIP_OK ;
 }
 
+static __thread int32_t *last_pinv = NULL ;
+static __thread int32_t last_pinv_n = 0 ;
+
+/* row permutation of the last SLIP_solve_* call of this thread (the factors of that path never
+ * reach the host, so this is how tests compare its pivoting with the reference's pinv) */
+int SLIP_B200_last_pinv (int32_t *out, int cap)
+{
+    int k = 0 ;
+    for ( ; k < last_pinv_n && k < cap ; k++) out [k] = last_pinv [k] ;
+    return k ;
+}
+
 /* factor on the GPU, solve on the GPU; L and U never come to the host */
 static SLIP_info solve_exact (mpq_t **x, SLIP_sparse *A, SLIP_LU_analysis *S, SLIP_dense *b, SLIP_options *option)
 {
@@ -211,11 +292,26 @@ static SLIP_info solve_exact (mpq_t **x, SLIP_sparse *A, SLIP_LU_analysis *S, SL
     const int32_t n = A->n ;
     int32_t *pinv = (int32_t *) SLIP_malloc ((size_t) n * sizeof (int32_t)) ;
     if (!pinv) return SLIP_OUT_OF_MEMORY ;
-    double t0 = now_s () ;
-    SLIP_TRY (slip_factorize_driver (NULL, NULL, A, S, NULL, pinv, option, 0, &r, slip_dense_max_column_bits (b))) ;
-    double t1 = now_s () ;
-    SLIP_TRY (slip_solve_resident (x, b, r, pinv)) ;
-    if (getenv ("SLIP_B200_TIMING")) fprintf (stderr, "slip_lu_b200 timing: factor %.3fs solve %.3fs\n", t1 - t0, now_s () - t1) ;
+    int min_channels = 0 ;
+    for (int attempt = 0 ; ; attempt++)
+    {
+        double t0 = now_s () ;
+        SLIP_TRY (slip_factorize_driver (NULL, NULL, A, S, NULL, pinv, option, 0, &r, slip_dense_max_column_bits (b), min_channels)) ;
+        double t1 = now_s () ;
+        status = slip_solve_resident (x, b, r, pinv, A, S->q) ;
+        if (getenv ("SLIP_B200_TIMING")) fprintf (stderr, "slip_lu_b200 timing: factor %.3fs solve %.3fs\n", t1 - t0, now_s () - t1) ;
+        if (status != SLIP_B200_NEED_CHANNELS) break ;
+        /* the factors fitted the channels but det*x does not (a large right-hand side): again
+           with four times the channels */
+        min_channels = 4 * slipcu_factor_channels (r->dev) ;
+        slip_resident_free (r) ; r = NULL ;
+        if (attempt >= 6) { status = SLIP_INCORRECT ; goto cleanup ; }
+    }
+    if (status != SLIP_OK) goto cleanup ;
+    {
+        int32_t *keep = (int32_t *) realloc (last_pinv, (size_t) n * sizeof (int32_t)) ;
+        if (keep) { last_pinv = keep ; last_pinv_n = n ; memcpy (last_pinv, pinv, (size_t) n * sizeof (int32_t)) ; }
+    }
     SLIP_TRY (SLIP_permute_x (x, n, b->n, S)) ;
     SLIP_TRY (SLIP_scale_x (x, A, b)) ;
 cleanup:

@@ -50,8 +50,13 @@ typedef int (*slipcu_column_sink) (void *user, int k, int cnt, int stride,
 
 const char *slipcu_last_error (void);
 int  slipcu_device_count (void);
-/* set the CUDA device used by this thread's subsequent calls (multi-GPU sharding, one rank per GPU) */
+/* choose the CUDA device of this PROCESS (multi-GPU sharding: one rank per GPU).  Sessions created
+ * afterwards, on any thread, live on that device; every entry point makes its session's device
+ * current, and the allocation pool and the channel tables are kept per device. */
 int  slipcu_set_device (int device);
+/* diagnostics: measured 32-bit integer-multiply peaks of the device (register-resident chains of
+ * IMAD.WIDE, IMAD and IMAD.HI), the denominators of bench.py's roofline.int_mul */
+int  slipcu_measure_imad_peak (double *wide_per_s, double *lo_per_s, double *hi_per_s);
 
 /* -- factorization session -------------------------------------------------------------------
  * slipcu_factor_begin: uploads A (CSC; values as limb strings) and reduces it into `channels`

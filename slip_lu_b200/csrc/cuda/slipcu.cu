@@ -22,6 +22,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <atomic>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -148,7 +149,7 @@ struct Tables
 static std::mutex g_tab_mutex;
 static std::vector<u32> g_primes;          // descending from 2^31 - 1, retired ones removed
 static u32 g_next_candidate = 0x7fffffffu;
-static std::shared_ptr<Tables> g_tables;
+static std::map<int, std::shared_ptr<Tables>> g_tables_by_device;   // tables live in device memory: one set per device
 
 static u32 powmod_u32 (u32 b, u32 e, u32 m)
 {
@@ -303,6 +304,9 @@ static int build_tables (int S, std::shared_ptr<Tables> &out)
 static int get_tables (int S, std::shared_ptr<Tables> &out)
 {
     std::lock_guard<std::mutex> lk (g_tab_mutex);
+    int dev = 0;
+    CU (cudaGetDevice (&dev));
+    std::shared_ptr<Tables> &g_tables = g_tables_by_device[dev];
     if (g_tables && g_tables->S >= S) { out = g_tables; return SLIPCU_OK; }
     int want = S;
     if (g_tables) want = std::max (S, g_tables->S + g_tables->S / 4);
@@ -331,7 +335,7 @@ extern "C" int slipcu_retire_prime (uint32_t prime)
     auto it = std::find (g_primes.begin (), g_primes.end (), prime);
     if (it == g_primes.end ()) return SLIPCU_OK;        // someone else retired it already
     g_primes.erase (it);
-    g_tables.reset ();          // live sessions keep their own reference
+    g_tables_by_device.clear ();          // live sessions keep their own reference
     return SLIPCU_OK;
 }
 
@@ -341,10 +345,10 @@ extern "C" int slipcu_retire_prime (uint32_t prime)
 // (one per SLIP_solve_* call), so freed blocks are kept and handed to the next session instead of
 // going back to the driver.  Blocks are rounded to power-of-two sizes >= 1 MB.
 // ------------------------------------------------------------------------------------------------
-#include <map>
 static std::mutex g_pool_mutex;
-static std::multimap<size_t, void *> g_pool_free;          // size -> block
-static std::map<void *, size_t> g_pool_size;               // every live or cached block
+typedef std::pair<int, size_t> PoolKey;                    // (device, size): a block only serves its own device
+static std::multimap<PoolKey, void *> g_pool_free;         // -> block
+static std::map<void *, PoolKey> g_pool_size;              // every live or cached block
 static size_t g_pool_cached = 0;
 
 static size_t pool_round (size_t bytes)
@@ -354,15 +358,17 @@ static size_t pool_round (size_t bytes)
     return r;
 }
 static void pool_trim_locked ()
-{
+{   // cudaFree takes the block's device from the pointer: no device switch needed
     for (auto &kv : g_pool_free) { cudaFree (kv.second); g_pool_size.erase (kv.second); }
     g_pool_free.clear (); g_pool_cached = 0;
 }
 static cudaError_t pool_alloc (void **out, size_t bytes)
 {
     const size_t want = pool_round (std::max<size_t> (bytes, 1));
+    int dev = 0;
+    { cudaError_t e0 = cudaGetDevice (&dev); if (e0 != cudaSuccess) return e0; }
     std::lock_guard<std::mutex> lk (g_pool_mutex);
-    auto it = g_pool_free.find (want);
+    auto it = g_pool_free.find (PoolKey (dev, want));
     if (it != g_pool_free.end ())
     {
         *out = it->second; g_pool_cached -= want; g_pool_free.erase (it);
@@ -375,7 +381,7 @@ static cudaError_t pool_alloc (void **out, size_t bytes)
         pool_trim_locked ();
         e = cudaMalloc (out, want);
     }
-    if (e == cudaSuccess) g_pool_size[*out] = want;
+    if (e == cudaSuccess) g_pool_size[*out] = PoolKey (dev, want);
     return e;
 }
 static void pool_free (void *ptr)
@@ -385,7 +391,7 @@ static void pool_free (void *ptr)
     auto it = g_pool_size.find (ptr);
     if (it == g_pool_size.end ()) { cudaFree (ptr); return; }
     g_pool_free.insert ({it->second, ptr});
-    g_pool_cached += it->second;
+    g_pool_cached += it->second.second;
 }
 template <typename T> static cudaError_t pool_alloc_t (T **out, size_t bytes) { return pool_alloc ((void **) out, bytes); }
 
@@ -2135,9 +2141,81 @@ extern "C" int slipcu_device_count (void)
     if (cudaGetDeviceCount (&n) != cudaSuccess) { cudaGetLastError (); return 0; }
     return n;
 }
+// The device is a property of the PROCESS (one process per GPU), not of the calling thread: CUDA's
+// current device is per thread, so a session created on a worker thread would otherwise land on
+// device 0.  Sessions take g_device when it is set, and every entry point makes the session's own
+// device current before it touches the runtime.
+static std::atomic<int> g_device{-1};
 extern "C" int slipcu_set_device (int device)
 {
     CU (cudaSetDevice (device));
+    g_device = device;
+    return SLIPCU_OK;
+}
+#define USE_DEVICE(F) CU (cudaSetDevice ((F)->device))
+
+// ------------------------------------------------------------------------------------------------
+// 32-bit integer-multiply peak of the device, measured: register-resident chains of one multiply
+// form (kind 0: mad.wide.u32 = IMAD.WIDE, 1: mad.lo.u32 = IMAD, 2: mul.hi.u32 = IMAD.HI), eight
+// independent chains per thread, enough warps to fill every scheduler.  bench.py reports the
+// kernels' multiply rates against these numbers (roofline.int_mul).
+// ------------------------------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__ (256) k_imad_peak (int iters, u32 *out)
+{
+    u32 a[8], b = blockIdx.x * 40503u + 12345u;
+    u64 w[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a[i] = (threadIdx.x + 1u) * 2654435761u + i; w[i] = a[i]; }
+    for (int it = 0; it < iters; ++it)
+    {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+        {
+            // every multiplicand depends on the previous result, so nothing is loop-invariant
+            if (KIND == 0) w[i] = (u64) (u32) w[i] * b + w[i];
+            else if (KIND == 1) a[i] = a[i] * b + a[(i + 1) & 7];
+            else a[i] = __umulhi (a[i], b) + 0x9e3779b9u;
+        }
+    }
+    u64 t = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += w[i] + a[i];
+    if ((u32) t == 0xdeadbeefu) out[0] = (u32) (t >> 32);    // practically never true: keeps the chains alive
+}
+
+extern "C" int slipcu_measure_imad_peak (double *wide_per_s, double *lo_per_s, double *hi_per_s)
+{
+    int dev = 0, sms = 148;
+    if (g_device.load () >= 0) CU (cudaSetDevice (g_device.load ()));
+    CU (cudaGetDevice (&dev));
+    cudaDeviceGetAttribute (&sms, cudaDevAttrMultiProcessorCount, dev);
+    u32 *out = nullptr;
+    CU (cudaMalloc (&out, 4));
+    cudaEvent_t e0, e1;
+    CU (cudaEventCreate (&e0)); CU (cudaEventCreate (&e1));
+    const int grid = sms * 8, iters = 1 << 14;
+    const double ops = (double) grid * 256.0 * (double) iters * 8.0;
+    double *res[3] = { wide_per_s, lo_per_s, hi_per_s };
+    for (int kind = 0; kind < 3; ++kind)
+    {
+        double best = 0;
+        for (int rep = 0; rep < 4; ++rep)
+        {
+            CU (cudaEventRecord (e0, 0));
+            if (kind == 0) k_imad_peak<0><<<grid, 256>>> (iters, out);
+            else if (kind == 1) k_imad_peak<1><<<grid, 256>>> (iters, out);
+            else k_imad_peak<2><<<grid, 256>>> (iters, out);
+            CU (cudaEventRecord (e1, 0));
+            CU (cudaEventSynchronize (e1));
+            float ms = 0;
+            CU (cudaEventElapsedTime (&ms, e0, e1));
+            if (rep > 0 && ms > 0) best = std::max (best, ops / (ms * 1e-3));
+            g_launches++;
+        }
+        if (res[kind]) *res[kind] = best;
+    }
+    cudaEventDestroy (e0); cudaEventDestroy (e1); cudaFree (out);
     return SLIPCU_OK;
 }
 
@@ -2272,7 +2350,8 @@ static int session_common_init (slipcu_factor *F, int n, int channels)
         cudaGetLastError ();
         return fail (SLIPCU_CUDA_ERROR, "slip_lu_b200", "no CUDA device: this library has no CPU path");
     }
-    CU (cudaGetDevice (&F->device));
+    if (g_device.load () >= 0) { F->device = g_device.load (); CU (cudaSetDevice (F->device)); }
+    else CU (cudaGetDevice (&F->device));
     F->n = n;
     const int S = (channels + 31) & ~31;
     int rc = get_tables (S, F->tab);
@@ -2701,6 +2780,7 @@ extern "C" int slipcu_factor_spec_launch (slipcu_factor *F, int slot, int k, int
 {
     if (!F || slot < 0 || slot >= SPEC_SLOTS || k < 1 || k >= F->n || cnt <= 0 || cnt > F->n || nU < 0 || nU > cnt || !rows)
         return fail (SLIPCU_BAD_INPUT, "slipcu_factor_spec_launch", "bad argument");
+    USE_DEVICE (F);
     const Tables &T = *F->tab;
     const int S = F->S, CH = F->CH;
     SpecSlot &sl = F->spec[slot];
@@ -2774,6 +2854,7 @@ extern "C" int slipcu_factor_column_launch (slipcu_factor *F, int k, int col, in
 {
     if (!F || k < 0 || k >= F->n || cnt <= 0 || cnt > F->n || nU < 0 || nU >= cnt || !rows || spec_slot >= SPEC_SLOTS)
         return fail (SLIPCU_BAD_INPUT, "slipcu_factor_column", "bad argument");
+    USE_DEVICE (F);
     // a bulk part exists for this column: start from its vector, apply the remaining steps
     SpecSlot *sl = (spec_slot >= 0 && F->spec[spec_slot].col == k) ? &F->spec[spec_slot] : nullptr;
     const bool from_spec = sl != nullptr;
@@ -2909,6 +2990,7 @@ extern "C" int slipcu_factor_column_launch (slipcu_factor *F, int k, int col, in
 extern "C" int slipcu_factor_column_wait (slipcu_factor *F, slipcu_pivot_info *info)
 {
     if (!F || !info || F->cur < 0) return fail (SLIPCU_BAD_INPUT, "slipcu_factor_column_wait", "bad argument");
+    USE_DEVICE (F);
     double tw = wall_s ();
     CU (cudaEventSynchronize (F->ev));
     g_d2h_bytes += sizeof (slipcu_pivot_info);
@@ -2988,6 +3070,7 @@ extern "C" int slipcu_factor_fetch_entry (slipcu_factor *F, int k, int slot, u32
     if (!F || k < 0 || k >= F->n) return fail (SLIPCU_BAD_INPUT, "slipcu_factor_fetch_entry", "bad column");
     HostCol &hc = F->cols[k];
     if (slot < 0 || slot >= hc.cnt) return fail (SLIPCU_BAD_INPUT, "slipcu_factor_fetch_entry", "bad slot");
+    USE_DEVICE (F);
     if (F->keep_positional)
     {
         if (F->st2) CU (cudaStreamSynchronize (F->st2));       // the column's limbs come from the side stream
@@ -3028,6 +3111,7 @@ extern "C" int slipcu_factor_set_pivot (slipcu_factor *F, int k, int slot)
     if (!F || k < 0 || k >= F->n) return fail (SLIPCU_BAD_INPUT, "slipcu_factor_set_pivot", "bad column");
     HostCol &hc = F->cols[k];
     if (slot < hc.nU || slot >= hc.cnt) return fail (SLIPCU_BAD_INPUT, "slipcu_factor_set_pivot", "bad slot");
+    USE_DEVICE (F);
     const Tables &T = *F->tab;
     ColDesc d;
     d.base = hc.base; d.rows = hc.rows; d.cnt = hc.cnt; d.nU = hc.nU; d.pivslot = slot; d.pad = 0;
@@ -3126,6 +3210,8 @@ static int check_channels (slipcu_factor *F)
 extern "C" int slipcu_factor_bad_prime (slipcu_factor *F, uint32_t *prime)
 {
     int32_t bad = 0;
+    if (!F) return fail (SLIPCU_BAD_INPUT, "slipcu_factor_bad_prime", "bad argument");
+    USE_DEVICE (F);
     CU (cudaMemcpyAsync (&bad, F->bad, sizeof (bad), cudaMemcpyDeviceToHost, F->st));
     CU (cudaStreamSynchronize (F->st));
     if (prime) *prime = (bad >= 1 && bad <= F->tab->S) ? F->tab->hp[bad - 1] : 0u;
@@ -3135,6 +3221,7 @@ extern "C" int slipcu_factor_bad_prime (slipcu_factor *F, uint32_t *prime)
 extern "C" int slipcu_factor_download (slipcu_factor *F, slipcu_column_sink sink, void *user)
 {
     if (!F || !sink) return fail (SLIPCU_BAD_INPUT, "slipcu_factor_download", "bad argument");
+    USE_DEVICE (F);
     { int rcb = check_channels (F); if (rcb) return rcb; }
     size_t maxw = 0; int maxc = 0;
     for (auto &hc : F->cols) { maxw = std::max (maxw, (size_t) hc.cnt * hc.stride); maxc = std::max (maxc, hc.cnt); }

@@ -330,7 +330,7 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
 
     for (int attempt = 0 ; ; attempt++)
     {
-        int retry = 0, grow = 0 ;
+        int retry = 0, grow = 0, tight = 0 ;
         const int bound_mode = channels < channels_full ;
         SLIP_TRY (patterns_init (&P, n, (int64_t) S->lnz + S->unz)) ;
         tt = now_s () ;
@@ -452,6 +452,10 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
             if (bound_mode && s_had > S_dev && info.bound_units > cap_units)
             {   /* the column is not proven to fit the channels carried: start over with more */
                 grow = (int) ceil (((double) info.bound_units / 64.0 + 4.0) / SLIP_B200_CHANNEL_BITS) ;
+                /* proven size of this column against its Hadamard prefix bound: when the sizes run
+                   close to the bound (random wide entries: ratio ~0.97) no smaller channel count
+                   will do, and the next attempt goes straight to the a-priori count */
+                tight = cum_bits > 64.0 && (double) info.bound_units / 64.0 >= 0.75 * cum_bits ;
                 retry = 1 ; break ;
             }
             int32_t slot = -1 ;
@@ -502,7 +506,7 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
                 int next = 4 * channels ;
                 if (next < grow + grow / 4) next = grow + grow / 4 ;
                 next = (next + 31) & ~31 ;
-                channels = (2 * next <= channels_full) ? next : channels_full ;
+                channels = (!tight && 2 * next <= channels_full) ? next : channels_full ;
                 bound_restarts++ ;
             }
             else

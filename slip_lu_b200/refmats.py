@@ -9,7 +9,11 @@ from __future__ import annotations
 
 import math
 import os
+import sys
 from typing import Dict, List, Tuple
+
+if hasattr(sys, "set_int_max_str_digits"):
+    sys.set_int_max_str_digits(0)      # the digests below hash decimal strings of integers of tens of kbit
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PACKED = os.path.join(ROOT, "tests", "golden", "mats", "refmats.npz")
@@ -64,10 +68,44 @@ def load(name: str) -> Tuple[int, List[int], List[int], List[int], List[List[int
 
 
 def records() -> Dict[str, dict]:
-    """What the unmodified reference computed for each packed system (digests, sizes, its seconds)."""
+    """What the unmodified reference computed for each packed system and each synthetic system below
+    (digests, sizes, its seconds in the build container)."""
     import json
-    with open(RECORDS) as fh:
-        return {r["name"]: r for r in json.load(fh)["records"]}
+    out = {}
+    for path in (RECORDS, SYNTH_RECORDS):
+        if os.path.exists(path):
+            with open(path) as fh:
+                out.update({r["name"]: r for r in json.load(fh)["records"]})
+    return out
+
+
+# Synthetic systems of the BASELINE config families that are pinned by reference digests
+# (tests/golden/make_synth_records.py); regenerated from their seeds, nothing stored.
+SYNTH_RECORDS = os.path.join(ROOT, "tests", "golden", "synth_records.json")
+BENCH_SEED = 20261018
+SYNTH = {
+    "synth/rand240": dict(family="configs[1] generator (random sparse, 10 nnz/col, 32-bit)", gen="random", n=240, seed=BENCH_SEED),
+    "synth/rand600": dict(family="configs[1] generator (random sparse, 10 nnz/col, 32-bit)", gen="random", n=600, seed=BENCH_SEED),
+    "synth/lap24": dict(family="configs[2] generator (2D Laplacian pattern, 64-bit)", gen="laplacian", m=24, seed=7),
+    "synth/lap32": dict(family="configs[2] generator (2D Laplacian pattern, 64-bit)", gen="laplacian", m=32, seed=7),
+}
+
+
+def synth_system(name: str):
+    """(n, I, J, X, b) of a synthetic system, as triplets in CSC order."""
+    from . import synth
+    d = SYNTH[name]
+    if d["gen"] == "random":
+        n, cp, ri, vals, b = synth.random_sparse(d["n"], 10, 32, seed=d["seed"], nrhs=1)
+    else:
+        n, cp, ri, vals, b = synth.laplacian_2d(d["m"], 64, seed=d["seed"], nrhs=1)
+    J = [j for j in range(n) for _ in range(cp[j], cp[j + 1])]
+    return n, list(ri), J, list(vals), b
+
+
+def system(name: str):
+    """A packed reference system or a synthetic one, by name."""
+    return synth_system(name) if name in SYNTH else load(name)
 
 
 def hadamard_bits(n: int, J, X) -> float:

@@ -20,6 +20,8 @@ def test_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
+    # the arm runs a bounded sample and must say which: the n it ran, and that it is not the headline configuration
+    assert "n=60" in d["config"]["workload"] and d["config"]["same_config"] is False and d["same_config"] is False
 
 
 def test_reference_arm_is_silent_on_other_ranks():

@@ -299,13 +299,28 @@ def cpu_solve_system(ref, system):
     return dt
 
 
+def cpu_leg_subprocess(argv, timeout=900):
+    """Every reference (CPU) leg runs in its OWN process: the reference's SLIP_initialize installs its
+    allocation-tracking hooks into the process-wide libgmp (mp_set_memory_functions), and those hooks
+    are not thread-safe, while the product's host layer calls GMP from OpenMP threads -- the two
+    libraries must not share a process once the product is computing."""
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        env.pop(k, None)
+    r = subprocess.run([sys.executable, os.path.abspath(__file__)] + argv, capture_output=True, text=True,
+                       timeout=timeout, cwd=ROOT, env=env)
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    if r.returncode != 0 or not lines:
+        return {"error": (r.stderr or "no output")[-300:]}
+    return json.loads(lines[-1])
+
+
 H2H = ["synth/rand240", "NSR8K", "prob159", "synth/lap24"]
 
 
 def head_to_head(lib, with_cpu):
     from slip_lu_b200 import refmats
     recs = refmats.records()
-    ref = reference_lib() if with_cpu else None
     out = []
     for name in H2H:
         try:
@@ -322,10 +337,14 @@ def head_to_head(lib, with_cpu):
                         "channels_needed": math.ceil((rec["det_bits"] + 2) / 30.99),
                         "cpu_s_build_container": rec["ref_seconds"]["solve_mpq"]})
         row.update(g)
-        if ref is not None:
-            row["cpu_s"] = cpu_solve_system(ref, system)
-            row["cpu_kind"] = "unmodified reference, 1 thread, this box"
-            row["ratio"] = row["cpu_s"] / row["gpu_e2e_s"]
+        if with_cpu:
+            leg = cpu_leg_subprocess(["--cpu-leg", name])
+            if "cpu_s" in leg:
+                row["cpu_s"] = leg["cpu_s"]
+                row["cpu_kind"] = leg["kind"]
+                row["ratio"] = row["cpu_s"] / row["gpu_e2e_s"]
+            else:
+                row["cpu_error"] = leg.get("error")
         out.append(row)
     return out
 
@@ -506,6 +525,7 @@ def main():
     ap.add_argument("--ref-n", type=int, default=240)
     ap.add_argument("--seed", type=int, default=SEED)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-leg", default=None, help="(internal) time the unmodified reference on one named head-to-head system and print {cpu_s}")
     ap.add_argument("--extras", default="all", help="all | none | comma list of h2h,laplacian,lu,sharded,intmul")
     ap.add_argument("--lap-grid", type=int, default=40, help="grid side of the configs[2]-family block")
     ap.add_argument("--batch-systems", type=int, default=512)
@@ -548,6 +568,18 @@ def main():
             pass
         os.environ["OMP_NUM_THREADS"] = str(len(mine))
         os.environ.setdefault("OMP_PROC_BIND", "false")
+
+    if args.cpu_leg:
+        from slip_lu_b200 import refmats
+        import __graft_entry__ as entry
+        entry.build()
+        ref = reference_lib()
+        if ref is None:
+            emit({"error": "oracle/_ref/libslip_ref.so is not built"})
+            return
+        emit({"cpu_s": cpu_solve_system(ref, refmats.system(args.cpu_leg)), "workload": args.cpu_leg,
+              "kind": "unmodified reference (oracle/_ref), 1 thread, this box, own process"})
+        return
 
     if args.impl == "reference":
         if rank != 0:
@@ -701,13 +733,14 @@ def main():
         return r
 
     if world == 1 and not args.no_cpu_baseline:
-        sub = argparse.Namespace(**vars(args))
-        sub.steps, sub.warmup = 1, 0
-        r = run_reference(sub, 0)
-        out["cpu_baseline"] = {"value": r["value"], "unit": "limb-mul/s", "cores": r["cores"],
-                               "kind": r["kind"], "sample": r["sample"], "seconds": r["seconds"],
-                               "same_config": False,
-                               "note": "bounded sample (n=%d), not the headline configuration: see head_to_head for measured same-configuration ratios" % args.ref_n}
+        r = timed_block("cpu_baseline", lambda: cpu_leg_subprocess(
+            ["--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-n", str(args.ref_n), "--n", str(args.n),
+             "--seed", str(args.seed)]))
+        if "cpu_baseline" in r:
+            out["cpu_baseline"] = dict(r["cpu_baseline"], seconds=r["factor_solve_seconds"], same_config=False,
+                                       note="bounded sample (n=%d), not the headline configuration: see head_to_head for measured same-configuration ratios" % args.ref_n)
+        else:
+            out["cpu_baseline"] = {"error": r.get("error")}
     if world == 1 and "h2h" in extras:
         out["head_to_head"] = timed_block("head_to_head", lambda: head_to_head(lib, with_cpu=not args.no_cpu_baseline))
     if world == 1 and "laplacian" in extras:

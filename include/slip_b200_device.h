@@ -37,7 +37,7 @@ typedef struct
     int32_t diag_vs_best;   /* cmp(|diag|, |best|): -1, 0, +1 (valid if diag_eligible) */
     int32_t bad_channel;    /* 0, or 1 + index of a channel whose prime divides an earlier pivot */
     int32_t reserved[3];
-    int32_t bound_units;    /* bound mode: proven upper bound of 64*log2 |entry| over the column */
+    int32_t bound_units;    /* bound mode: proven upper bound of 64*log2 |entry| over the column; measured mode: largest measured candidate */
     int32_t pad[3];
 } slipcu_pivot_info;
 
@@ -71,7 +71,17 @@ int slipcu_factor_begin (slipcu_factor **F, int n, int nz, const int32_t *Ap, co
  *   columns) and reports it in slipcu_pivot_info.bound_units; the caller compares it with
  *   slipcu_factor_capacity_units and restarts with more channels when a column does not fit.
  *   GMP pays for the actual size of its operands (slip_REF_triangular_solve.c:150-232 on mpz_t);
- *   this is how the residue representation does the same without giving up exactness. */
+ *   this is how the residue representation does the same without giving up exactness.
+ *   2: MEASURED mode, for callers that verify their final result exactly (SLIP_solve_*: the
+ *   numerators N of x are checked against A N = det b over the integers, and x is unique).
+ *   Residue arithmetic is exact for the TRUE integers whatever the channel count, and a candidate
+ *   with a nonzero residue is truly nonzero, so every pivot sequence the session produces is a valid
+ *   factorization; too few channels can only mislead the magnitude comparison of the pivot search.
+ *   The session therefore measures the candidates of every column (bound_units = the largest one;
+ *   a value that does not fit the channels reconstructs as a uniform residue of the modulus, i.e.
+ *   full size, except with probability 2^-35) and the caller restarts with more channels when the
+ *   measured size reaches the capacity.  No bound is propagated, so determinants far below their
+ *   Hadamard bound (LP bases) run on the channels their values need. */
 int slipcu_factor_capacity_units (const slipcu_factor *F);
 /* keep_positional = 1: every entry of L and U is reconstructed as a positional integer and kept
  *   for slipcu_factor_download (SLIP_LU_factorize).  0: only what the pivot scan needs is

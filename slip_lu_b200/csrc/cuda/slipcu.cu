@@ -447,7 +447,8 @@ struct WorkCtx
     int32_t *slots = nullptr; size_t slots_cap = 0;
     StepInfo *steps = nullptr; size_t steps_cap = 0;
     ChunkInfo *chunks = nullptr; size_t chunks_cap = 0;
-    int32_t *h_packet = nullptr;             // pinned staging of the pattern packet
+    int32_t *h_packet = nullptr;             // pattern packet in mapped host memory (read by k_prep)
+    int32_t *h_packet_dev = nullptr;         // its device address
 };
 #define SPEC_SLOTS 16
 struct SpecSlot                              // bulk part of a column that is not the current one yet
@@ -515,7 +516,11 @@ struct slipcu_factor
     int sms = 148;
     int garner_mode = 2;
     // bound mode (see tri_mag_cta): fewer channels than the Hadamard bound, every column's size proven
+    unsigned *done_ctr = nullptr;            // device counter of the fused reconstruction + scan launches
+    struct { int k, slot; } pending_commit = { -1, -1 };     // pivot chosen, commit folded into the next column's first kernel
+    int frac_min_s = 256;                    // approximate pivot search only from this many channels on
     int mag_on = 0;
+    int measured = 0;                        // measured mode: sizes of the candidates are measured, the result is verified exactly by the caller
     int32_t *Amag = nullptr;                 // [nz] 64 log2 |a| of the input entries, rounded up
     int32_t *rho_mag = nullptr;              // [n]  measured 64 log2 |rho_k|
     int32_t *bound = nullptr;                // device: largest bound of the column in flight
@@ -1189,6 +1194,120 @@ __global__ void __launch_bounds__ (512) k_backsub (BackArgs a)
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_pivot_scan: exact nonzero / magnitude scan over the candidate slots (nU..cnt-1)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int cmp_mag (const u32 *dig, size_t ds, const int32_t *topd, int e1, int e2)
+{
+    const int t1 = topd[e1], t2 = topd[e2];
+    if (t1 != t2) return t1 < t2 ? -1 : 1;
+    for (int t = t1; t >= 0; --t)
+    {
+        const u32 d1 = dig[(size_t) e1 * ds + t], d2 = dig[(size_t) e2 * ds + t];
+        if (d1 != d2) return d1 < d2 ? -1 : 1;
+    }
+    return 0;
+}
+// mode: 0 smallest, 1 largest, 2 first nonzero.  Ties go to the earlier slot.
+__device__ __forceinline__ int better (const u32 *dig, size_t ds, const int32_t *topd, int mode, int x, int y)
+{
+    if (x < 0) return y;
+    if (y < 0) return x;
+    if (mode == 2) return x < y ? x : y;
+    int c = cmp_mag (dig, ds, topd, x, y);
+    if (mode == 1) c = -c;
+    if (c < 0) return x;
+    if (c > 0) return y;
+    return x < y ? x : y;
+}
+
+struct ScanArgs
+{
+    int cnt, nU, mode, diag_slot;
+    const u32 *dig; size_t ds; const int32_t *topd; const int8_t *sign; const int32_t *bad;
+    slipcu_pivot_info *info;          // mapped host memory
+    int32_t *mag; const int32_t *cum_ub; const int32_t *bound; int measured;
+};
+
+// the scan itself, by all threads of one CTA of any size (<= 512 threads)
+__device__ __noinline__ void pivot_scan_body (const ScanArgs &a)
+{
+    __shared__ int sbest[512];
+    __shared__ int32_t s_meas;
+    const int cnt = a.cnt, nU = a.nU, mode = a.mode;
+    const u32 *dig = a.dig; const size_t ds = a.ds; const int32_t *topd = a.topd;
+    int best = -1;
+    if (a.measured)
+    {   // measured mode: the largest candidate, B_top * d <= |v| < B_top * (d + 1) with d the top
+        // mixed-radix digit.  A value that does not fit the channels reconstructs as a random
+        // residue of the modulus and shows up here as (almost) full size.
+        if (threadIdx.x == 0) s_meas = MAG_NEG;
+        __syncthreads ();
+        int32_t mx = MAG_NEG;
+        for (int e = nU + threadIdx.x; e < cnt; e += blockDim.x)
+        {
+            const int t = topd[e];
+            if (t >= 0) mx = max (mx, a.cum_ub[t] + mag_log2_ub (dig[(size_t) e * ds + t] + 1u));
+        }
+        atomicMax (&s_meas, mx);
+    }
+    if (a.mag)
+    {   // bound mode: the candidates' bounds are replaced by their measured sizes
+        for (int e = nU + threadIdx.x; e < cnt; e += blockDim.x)
+        {
+            const int t = topd[e];
+            a.mag[e] = t < 0 ? MAG_NEG : a.cum_ub[t] + mag_log2_ub (dig[(size_t) e * ds + t] + 1u);
+        }
+    }
+    for (int e = nU + threadIdx.x; e < cnt; e += blockDim.x)
+        if (topd[e] >= 0) best = better (dig, ds, topd, mode, best, e);
+    sbest[threadIdx.x] = best;
+    __syncthreads ();
+    if (threadIdx.x < 32)
+    {
+        int b = -1;
+        for (int i = threadIdx.x; i < (int) blockDim.x; i += 32) b = better (dig, ds, topd, mode, b, sbest[i]);
+        for (int off = 16; off > 0; off >>= 1)
+        {
+            const int o = __shfl_down_sync (0xffffffffu, b, off);
+            b = better (dig, ds, topd, mode, b, o);
+        }
+        if (threadIdx.x == 0)
+        {
+            best = b;
+            slipcu_pivot_info *info = a.info;
+            info->best_slot = best;
+            info->best_sign = best >= 0 ? a.sign[best] : 0;
+            const int de = (a.diag_slot >= nU && a.diag_slot < cnt && topd[a.diag_slot] >= 0) ? 1 : 0;
+            info->diag_eligible = de;
+            info->diag_vs_best = (de && best >= 0) ? cmp_mag (dig, ds, topd, a.diag_slot, best) : 0;
+            info->bad_channel = *a.bad;
+            info->bound_units = a.measured ? s_meas : (a.bound ? *a.bound : 0);
+        }
+    }
+}
+
+__global__ void __launch_bounds__ (256) k_pivot_scan (ScanArgs a) { pivot_scan_body (a); }
+
+// Tail of the reconstruction kernels: the last CTA of the grid to finish runs the pivot scan, so a
+// column costs one launch less on the path to its pivot.
+__device__ __forceinline__ void scan_by_last_block (const ScanArgs &sc, unsigned *done_ctr)
+{
+    __shared__ int s_last;
+    __threadfence ();
+    __syncthreads ();
+    if (threadIdx.x == 0)
+    {
+        const unsigned prev = atomicAdd (done_ctr, 1u);
+        s_last = (prev == gridDim.x - 1);
+        if (s_last) *done_ctr = 0;                     // ready for the next launch
+    }
+    __syncthreads ();
+    if (!s_last) return;
+    __threadfence ();
+    pivot_scan_body (sc);
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_garner: residues -> mixed-radix digits of |x| (+ sign), one warp per entry.
 //   x mod M = d_0 + d_1 p_0 + d_2 p_0 p_1 + ...,   d_t = (x_t - sum_{u<t} d_u C[u][t]) / B_t mod p_t
 // ------------------------------------------------------------------------------------------------
@@ -1202,13 +1321,15 @@ struct GarnerArgs
     int32_t *topd;              // highest nonzero digit index of |x| (-1 for zero)
     int8_t *sign;
     const u32 *p, *ninv, *C, *invB;
+    int scan_on; unsigned *done_ctr;      // fused pivot scan (see scan_by_last_block)
+    ScanArgs sc;
 };
-
 __global__ void __launch_bounds__ (128) k_garner (GarnerArgs a)
 {
     const int lane = threadIdx.x & 31;
     const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (w >= a.ne) return;
+    if (w < a.ne)
+    {
     const int e = a.e0 + w;
     const int s = a.s, S = a.S, CH = a.CH;
     u32 *dg = a.dig + (size_t) e * a.dstride;
@@ -1289,6 +1410,8 @@ __global__ void __launch_bounds__ (128) k_garner (GarnerArgs a)
     // zero-pad the digit row up to the next multiple of 4 (vector loads in later passes)
     for (int t = s + lane; t < ((s + 3) & ~3); t += 32) dg[t] = 0;
     if (lane == 0) { a.topd[e] = top; a.sign[e] = top < 0 ? 0 : (neg ? -1 : 1); }
+    }
+    if (a.scan_on) scan_by_last_block (a.sc, a.done_ctr);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1432,7 +1555,8 @@ __global__ void __launch_bounds__ (512) k_garner_tiled (GarnerArgs a)
     }
     __syncthreads ();
     // sign, magnitude digits and top digit: one warp per entry
-    if (w >= E || g0 + w >= a.ne) return;
+    if (w < E && g0 + w < a.ne)
+    {
     const int e = a.e0 + g0 + w;
     u32 *dg = a.dig + (size_t) e * a.dstride;
     bool neg = false;
@@ -1473,6 +1597,8 @@ __global__ void __launch_bounds__ (512) k_garner_tiled (GarnerArgs a)
     }
     for (int t = s + lane; t < ((s + 3) & ~3); t += 32) dg[t] = 0;
     if (lane == 0) { a.topd[e] = top; a.sign[e] = top < 0 ? 0 : (neg ? -1 : 1); }
+    }
+    if (a.scan_on) scan_by_last_block (a.sc, a.done_ctr);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1630,7 +1756,8 @@ __global__ void __launch_bounds__ (384, 1) k_garner_flow (GarnerArgs a)
     }
     __syncthreads ();
     // sign, magnitude digits and top digit: one warp per entry
-    if (w >= E || g0 + w >= a.ne) return;
+    if (w < E && g0 + w < a.ne)
+    {
     const int e = a.e0 + g0 + w;
     u32 *dg = a.dig + (size_t) e * a.dstride;
     bool neg = false;
@@ -1671,6 +1798,8 @@ __global__ void __launch_bounds__ (384, 1) k_garner_flow (GarnerArgs a)
     }
     for (int t = s + lane; t < ((s + 3) & ~3); t += 32) dg[t] = 0;
     if (lane == 0) { a.topd[e] = top; a.sign[e] = top < 0 ? 0 : (neg ? -1 : 1); }
+    }
+    if (a.scan_on) scan_by_last_block (a.sc, a.done_ctr);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2049,87 +2178,47 @@ __global__ void __launch_bounds__ (256) k_fracselect (FracSel a)
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_pivot_scan: exact nonzero / magnitude scan over the candidate slots (nU..cnt-1)
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int cmp_mag (const u32 *dig, size_t ds, const int32_t *topd, int e1, int e2)
-{
-    const int t1 = topd[e1], t2 = topd[e2];
-    if (t1 != t2) return t1 < t2 ? -1 : 1;
-    for (int t = t1; t >= 0; --t)
-    {
-        const u32 d1 = dig[(size_t) e1 * ds + t], d2 = dig[(size_t) e2 * ds + t];
-        if (d1 != d2) return d1 < d2 ? -1 : 1;
-    }
-    return 0;
-}
-// mode: 0 smallest, 1 largest, 2 first nonzero.  Ties go to the earlier slot.
-__device__ __forceinline__ int better (const u32 *dig, size_t ds, const int32_t *topd, int mode, int x, int y)
-{
-    if (x < 0) return y;
-    if (y < 0) return x;
-    if (mode == 2) return x < y ? x : y;
-    int c = cmp_mag (dig, ds, topd, x, y);
-    if (mode == 1) c = -c;
-    if (c < 0) return x;
-    if (c > 0) return y;
-    return x < y ? x : y;
-}
-
-__global__ void __launch_bounds__ (256) k_pivot_scan (int cnt, int nU, int mode, int diag_slot,
-                                                       const u32 *dig, size_t ds, const int32_t *topd,
-                                                       const int8_t *sign, const int32_t *bad,
-                                                       slipcu_pivot_info *info,
-                                                       int32_t *mag, const int32_t *cum_ub, const int32_t *bound)
-{
-    __shared__ int sbest[256];
-    int best = -1;
-    if (mag)
-    {   // bound mode: the candidates' bounds are replaced by their measured sizes,
-        // B_top * d <= |v| < B_top * (d + 1) with d the top mixed-radix digit
-        for (int e = nU + threadIdx.x; e < cnt; e += blockDim.x)
-        {
-            const int t = topd[e];
-            mag[e] = t < 0 ? MAG_NEG : cum_ub[t] + mag_log2_ub (dig[(size_t) e * ds + t] + 1u);
-        }
-    }
-    for (int e = nU + threadIdx.x; e < cnt; e += blockDim.x)
-        if (topd[e] >= 0) best = better (dig, ds, topd, mode, best, e);
-    sbest[threadIdx.x] = best;
-    __syncthreads ();
-    for (int w = blockDim.x >> 1; w > 0; w >>= 1)
-    {
-        if ((int) threadIdx.x < w)
-            sbest[threadIdx.x] = better (dig, ds, topd, mode, sbest[threadIdx.x], sbest[threadIdx.x + w]);
-        __syncthreads ();
-    }
-    if (threadIdx.x == 0)
-    {
-        best = sbest[0];
-        info->best_slot = best;
-        info->best_sign = best >= 0 ? sign[best] : 0;
-        const int de = (diag_slot >= nU && diag_slot < cnt && topd[diag_slot] >= 0) ? 1 : 0;
-        info->diag_eligible = de;
-        info->diag_vs_best = (de && best >= 0) ? cmp_mag (dig, ds, topd, diag_slot, best) : 0;
-        info->bad_channel = *bad;
-        info->bound_units = bound ? *bound : 0;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 // k_pivot_commit: rho_k, rho_k^-1, rho_k / rho_{k-1} in every channel; column descriptor
 // ------------------------------------------------------------------------------------------------
-__global__ void k_pivot_commit (int k, int S, int CH, int slot, ColDesc d, ColDesc *desc,
-                                u32 *rho, u32 *invrho,
-                                const u32 *p, const u32 *ninv, const u32 *one, int32_t *bad, int32_t *rho_mag)
+struct CommitArgs
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c == 0) { d.pivslot = slot; desc[k] = d; if (rho_mag) rho_mag[k] = d.mag[slot]; }
-    if (c >= S) return;
-    const u32 pc = p[c], ni = ninv[c];
-    const u32 v = d.base[((size_t) (c / CH) * d.cnt + slot) * CH + (c % CH)];
-    if (v == 0) atomicCAS (bad, 0, c + 1);
-    rho[(size_t) k * S + c] = v;
-    invrho[(size_t) k * S + c] = mont_pow (v, pc - 2, one[c], pc, ni);
+    int k, S, CH, slot; ColDesc d; ColDesc *desc; u32 *rho, *invrho;
+    const u32 *p, *ninv, *one; int32_t *bad; int32_t *rho_mag;
+};
+__device__ __forceinline__ void pivot_commit_body (const CommitArgs &a, int c)
+{
+    if (c == 0) { ColDesc d = a.d; d.pivslot = a.slot; a.desc[a.k] = d; if (a.rho_mag) a.rho_mag[a.k] = d.mag[a.slot]; }
+    if (c >= a.S) return;
+    const u32 pc = a.p[c], ni = a.ninv[c];
+    const u32 v = a.d.base[((size_t) (c / a.CH) * a.d.cnt + a.slot) * a.CH + (c % a.CH)];
+    if (v == 0) atomicCAS (a.bad, 0, c + 1);
+    a.rho[(size_t) a.k * a.S + c] = v;
+    a.invrho[(size_t) a.k * a.S + c] = mont_pow (v, pc - 2, a.one[c], pc, ni);
+}
+__global__ void k_pivot_commit (CommitArgs a) { pivot_commit_body (a, blockIdx.x * blockDim.x + threadIdx.x); }
+
+// First kernel of a column: brings the pattern packet over from mapped host memory (no copy-engine
+// operation), fills the row -> slot map, and commits the PREVIOUS column's pivot in its spare
+// blocks (the host decided it a moment ago; nothing of this kernel depends on it).
+struct PrepArgs
+{
+    int cnt, pk_ints, copy_blocks, has_commit;
+    const int32_t *h_packet; int32_t *d_packet; int32_t *pos;
+    CommitArgs c;
+};
+__global__ void __launch_bounds__ (256) k_prep (PrepArgs a)
+{
+    if ((int) blockIdx.x < a.copy_blocks)
+    {
+        const int i = blockIdx.x * 256 + threadIdx.x;
+        if (i < a.pk_ints)
+        {
+            const int32_t v = a.h_packet[i];
+            a.d_packet[i] = v;
+            if (i < a.cnt) a.pos[v] = i;
+        }
+    }
+    else if (a.has_commit) pivot_commit_body (a.c, ((int) blockIdx.x - a.copy_blocks) * 256 + threadIdx.x);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2236,7 +2325,8 @@ static int init_workctx (WorkCtx &w, int n, cudaStream_t st)
     w.st = st;
     CU (pool_alloc_t (&w.pos, (size_t) n * sizeof (int32_t)));
     CU (cudaMemsetAsync (w.pos, 0, (size_t) n * sizeof (int32_t), st));
-    CU (cudaHostAlloc (&w.h_packet, ((size_t) 4 * n + 8) * sizeof (int32_t), cudaHostAllocDefault));
+    CU (cudaHostAlloc (&w.h_packet, ((size_t) 4 * n + 8) * sizeof (int32_t), cudaHostAllocMapped));
+    CU (cudaHostGetDevicePointer ((void **) &w.h_packet_dev, w.h_packet, 0));
     return SLIPCU_OK;
 }
 
@@ -2255,8 +2345,8 @@ extern "C" void slipcu_factor_free (slipcu_factor *F)
     pool_free (F->rho); pool_free (F->invrho);
     pool_free (F->desc); pool_free (F->bad);
     pool_free (F->digbuf[0]); pool_free (F->topdbuf[0]); pool_free (F->digbuf[1]); pool_free (F->topdbuf[1]);
-    pool_free (F->d_info); pool_free (F->frackey);
-    pool_free (F->Amag); pool_free (F->rho_mag); pool_free (F->bound);
+    pool_free (F->frackey);
+    pool_free (F->Amag); pool_free (F->rho_mag); pool_free (F->bound); pool_free (F->done_ctr);
     if (getenv ("SLIP_B200_TIMING") && F->frac)
         fprintf (stderr, "slipcu pivot search: %llu columns by approximate magnitudes, %llu word-count retries, %llu exact fallbacks\n",
                  (unsigned long long) F->frac_cols, (unsigned long long) F->frac_retries, (unsigned long long) F->frac_fallbacks);
@@ -2293,7 +2383,9 @@ extern "C" int slipcu_factor_channels (const slipcu_factor *F) { return F ? F->S
 extern "C" int slipcu_factor_capacity_units (const slipcu_factor *F)
 {
     if (!F) return 0;
-    return (int) floor (64.0 * F->tab->cumbits[F->S]) - 3 * 64;
+    // measured mode: 36 bits of headroom, so that a value that wrapped around the modulus (uniform
+    // below it) passes as fitting with probability 2^-35 -- and then the caller's exact check decides
+    return (int) floor (64.0 * F->tab->cumbits[F->S]) - (F->measured ? 36 : 3) * 64;
 }
 
 static int ensure_digits (slipcu_factor *F, size_t rows)
@@ -2399,12 +2491,17 @@ static int session_common_init (slipcu_factor *F, int n, int channels)
     CU (pool_alloc_t (&F->invrho, (size_t) n * S * sizeof (u32)));
     CU (pool_alloc_t (&F->desc, (size_t) n * sizeof (ColDesc)));
     CU (pool_alloc_t (&F->bad, sizeof (int32_t)));
-    CU (pool_alloc_t (&F->d_info, sizeof (slipcu_pivot_info)));
     CU (cudaMemset (F->bad, 0, sizeof (int32_t)));
+    CU (pool_alloc_t (&F->done_ctr, sizeof (unsigned)));
+    CU (cudaMemset (F->done_ctr, 0, sizeof (unsigned)));
+    F->frac_min_s = std::max (16, env_int ("SLIP_B200_FRAC_MIN_S", 256));
     rc = init_workctx (F->mc, n, F->st);
     if (rc) return rc;
     CU (cudaEventCreateWithFlags (&F->ev_commit, cudaEventDisableTiming));
-    CU (cudaHostAlloc (&F->h_info, sizeof (slipcu_pivot_info), cudaHostAllocDefault));
+    // the scan result goes straight into mapped host memory (a 48-byte store over PCIe instead of a
+    // copy-engine operation per column); the event behind the kernel publishes it to the host
+    CU (cudaHostAlloc (&F->h_info, sizeof (slipcu_pivot_info), cudaHostAllocMapped));
+    CU (cudaHostGetDevicePointer ((void **) &F->d_info, F->h_info, 0));
     F->cols.resize (n);
     return SLIPCU_OK;
 }
@@ -2421,7 +2518,12 @@ extern "C" int slipcu_factor_begin (slipcu_factor **out, int n, int nz, const in
     if (rc) return rc;
     F->nz = nz;
     F->keep_positional = keep_positional ? 1 : 0;
-    if (bound_mode)
+    if (bound_mode == 2)
+    {   // measured mode (see slip_b200_device.h)
+        F->measured = 1;
+        F->frac = 0;                     // measured sizes come from the exact digits
+    }
+    else if (bound_mode)
     {   // input magnitudes from the limb strings: 64 log2 |a| rounded up
         F->mag_on = 1;
         F->frac = 0;                     // measured sizes come from the exact digits
@@ -2509,10 +2611,37 @@ static cudaError_t launch_tri_any (int CH, int cpt, const TriArgs &a, dim3 grid,
     return launch_tri<32, 4> (a, grid, smem, st);
 }
 
+static CommitArgs make_commit_args (slipcu_factor *F, int k, int slot)
+{
+    const HostCol &hc = F->cols[k];
+    const Tables &T = *F->tab;
+    CommitArgs c;
+    c.k = k; c.S = F->S; c.CH = F->CH; c.slot = slot;
+    c.d.base = hc.base; c.d.rows = hc.rows; c.d.cnt = hc.cnt; c.d.nU = hc.nU; c.d.pivslot = slot; c.d.pad = 0;
+    c.d.mag = F->mag_on ? hc.mag : nullptr;
+    c.desc = F->desc; c.rho = F->rho; c.invrho = F->invrho; c.p = T.p; c.ninv = T.ninv; c.one = T.one;
+    c.bad = F->bad; c.rho_mag = F->mag_on ? F->rho_mag : nullptr;
+    return c;
+}
+// a pivot whose commit has not been enqueued yet (it normally rides in the next column's k_prep)
+static int flush_commit (slipcu_factor *F)
+{
+    if (F->pending_commit.k < 0) return SLIPCU_OK;
+    const CommitArgs c = make_commit_args (F, F->pending_commit.k, F->pending_commit.slot);
+    F->pending_commit.k = -1;
+    k_pivot_commit<<<(F->S + 255) / 256, 256, 0, F->st>>> (c);
+    g_launches++;
+    CU (cudaGetLastError ());
+    if (debug_check ("k_pivot_commit", F->st)) return fail (SLIPCU_CUDA_ERROR, "k_pivot_commit", "debug");
+    if (!F->rows_are_positions) CU (cudaEventRecord (F->ev_commit, F->st));
+    return SLIPCU_OK;
+}
+
 // symbolic pre-pass on the device: pos[], the slot lists and the step table of a column whose
 // pattern (rows), step positions (upos) and slot-list offsets (uoff, nU+1 entries) are on the device
 static int prepare_steps (slipcu_factor *F, WorkCtx &w, int cnt, int nU, const int32_t *rows, const int32_t *upos,
-                          const int32_t *uoff, const int32_t *uchunk, int total, int nchunks)
+                          const int32_t *uoff, const int32_t *uchunk, int total, int nchunks,
+                          int packet_ints = 0, bool with_commit = false)
 {
     if ((size_t) nchunks > w.chunks_cap)
     {
@@ -2539,10 +2668,33 @@ static int prepare_steps (slipcu_factor *F, WorkCtx &w, int cnt, int nU, const i
         w.steps_cap = want;
     }
     ScopedTimer tm_other (F, &g_other_ms, w.st);
-    k_setpos<<<(cnt + 255) / 256, 256, 0, w.st>>> (cnt, rows, w.pos);
-    g_launches++;
-    CU (cudaGetLastError ());
-    if (debug_check ("k_setpos", w.st)) return fail (SLIPCU_CUDA_ERROR, "k_setpos", "debug");
+    if (packet_ints > 0)
+    {   // the packet sits in mapped host memory: one kernel copies it to `rows`, fills pos[] and
+        // (main stream only) commits the pivot that is still pending
+        PrepArgs pa; memset (&pa, 0, sizeof (pa));
+        pa.cnt = cnt; pa.pk_ints = packet_ints; pa.copy_blocks = (packet_ints + 255) / 256;
+        pa.h_packet = w.h_packet_dev; pa.d_packet = const_cast<int32_t *> (rows); pa.pos = w.pos;
+        int blocks = pa.copy_blocks;
+        if (with_commit && F->pending_commit.k >= 0)
+        {
+            pa.has_commit = 1;
+            pa.c = make_commit_args (F, F->pending_commit.k, F->pending_commit.slot);
+            F->pending_commit.k = -1;
+            blocks += (F->S + 255) / 256;
+        }
+        k_prep<<<blocks, 256, 0, w.st>>> (pa);
+        g_launches++;
+        CU (cudaGetLastError ());
+        if (debug_check ("k_prep", w.st)) return fail (SLIPCU_CUDA_ERROR, "k_prep", "debug");
+        if (pa.has_commit && !F->rows_are_positions) CU (cudaEventRecord (F->ev_commit, w.st));
+    }
+    else
+    {
+        k_setpos<<<(cnt + 255) / 256, 256, 0, w.st>>> (cnt, rows, w.pos);
+        g_launches++;
+        CU (cudaGetLastError ());
+        if (debug_check ("k_setpos", w.st)) return fail (SLIPCU_CUDA_ERROR, "k_setpos", "debug");
+    }
     if (nU > 0 && total > 0)
     {
         k_slots<<<(total + 255) / 256, 256, 0, w.st>>> (nU, total, F->CH, cnt, upos, uoff, uchunk, F->desc, w.pos, w.slots, w.steps, w.chunks);
@@ -2572,11 +2724,14 @@ static int check_channels (slipcu_factor *F);
 
 
 // mixed-radix digits + sign of entries e0..e0+ne-1 of a residue region (digit row = entry index)
-static int run_garner (slipcu_factor *F, const u32 *base, int region_cnt, int e0, int ne, int s, int8_t *sign)
+static int run_garner (slipcu_factor *F, const u32 *base, int region_cnt, int e0, int ne, int s, int8_t *sign,
+                       const ScanArgs *scan = nullptr)
 {
     if (ne <= 0) return SLIPCU_OK;
     const Tables &T = *F->tab;
     GarnerArgs g;
+    g.scan_on = scan ? 1 : 0; g.done_ctr = F->done_ctr;
+    if (scan) g.sc = *scan; else memset (&g.sc, 0, sizeof (g.sc));
     g.cnt = region_cnt; g.e0 = e0; g.ne = ne; g.s = s; g.CH = F->CH; g.S = T.S;
     g.base = base; g.dig = F->dig; g.dstride = (size_t) F->S + 4; g.topd = F->topd; g.sign = sign;
     g.p = T.p; g.ninv = T.ninv; g.C = T.C; g.invB = T.invB;
@@ -2723,12 +2878,20 @@ static int alloc_column (slipcu_factor *F, HostCol &hc, int cnt, int s)
     return SLIPCU_OK;
 }
 
+static ScanArgs make_scan_args (slipcu_factor *F, const HostCol &hc, int cnt, int nU, int mode, int diag_slot)
+{
+    ScanArgs a;
+    a.cnt = cnt; a.nU = nU; a.mode = mode; a.diag_slot = diag_slot;
+    a.dig = F->dig; a.ds = (size_t) F->S + 4; a.topd = F->topd; a.sign = hc.sign; a.bad = F->bad; a.info = F->d_info;
+    a.mag = F->mag_on ? hc.mag : nullptr; a.cum_ub = F->tab->cum_ub; a.bound = F->mag_on ? F->bound : nullptr;
+    a.measured = F->measured;
+    return a;
+}
+
 static int run_exact_scan (slipcu_factor *F, const HostCol &hc, int cnt, int nU, int mode, int diag_slot)
 {
     ScopedTimer tm_scan (F, &g_other_ms);
-    k_pivot_scan<<<1, 256, 0, F->st>>> (cnt, nU, mode, diag_slot, F->dig, (size_t) F->S + 4, F->topd,
-                                        hc.sign, F->bad, F->d_info,
-                                        F->mag_on ? hc.mag : nullptr, F->tab->cum_ub, F->mag_on ? F->bound : nullptr);
+    k_pivot_scan<<<1, 256, 0, F->st>>> (make_scan_args (F, hc, cnt, nU, mode, diag_slot));
     g_launches++;
     CU (cudaGetLastError ());
     if (debug_check ("k_pivot_scan", F->st)) return fail (SLIPCU_CUDA_ERROR, "k_pivot_scan", "debug");
@@ -2762,9 +2925,9 @@ static int upload_pattern (slipcu_factor *F, WorkCtx &w, int cnt, int nU, const 
     const size_t pk_ints = (size_t) cnt + 3 * (size_t) nU + 2;
     int32_t *d = (int32_t *) F->ints.alloc (pk_ints * sizeof (int32_t));
     if (!d) return fail (SLIPCU_OUT_OF_MEMORY, "slipcu_factor_column", "device memory exhausted");
-    CU (cudaMemcpyAsync (d, staging, pk_ints * sizeof (int32_t), cudaMemcpyHostToDevice, w.st));
     g_h2d_bytes += (double) pk_ints * sizeof (int32_t);
-    int rc = prepare_steps (F, w, cnt, nU, d, d + cnt, d + cnt + nU, d + cnt + 2 * nU + 1, (int) total, (int) nchunks);
+    int rc = prepare_steps (F, w, cnt, nU, d, d + cnt, d + cnt + nU, d + cnt + 2 * nU + 1, (int) total, (int) nchunks,
+                            (int) pk_ints, &w == &F->mc);
     if (rc) return rc;
     *dev_rows = d; *nchunks_out = (int) nchunks;
     return SLIPCU_OK;
@@ -2942,7 +3105,7 @@ extern "C" int slipcu_factor_column_launch (slipcu_factor *F, int k, int col, in
     }
     const int mode = (scheme == 2) ? 2 : ((scheme == 4 || scheme == 5) ? 1 : 0);
     F->frac_col = -1;
-    if (F->frac && !F->keep_positional && mode != 2 && s >= 16)
+    if (F->frac && !F->keep_positional && mode != 2 && s >= F->frac_min_s)
     {   // magnitudes only: no digits unless the choice turns out to be too close to call
         const int W = std::min (std::max (F->fracW, 8), frac_word_cap (s));
         rc = run_frac (F, hc, cnt, nU, s, mode, diag_slot, W);
@@ -2952,15 +3115,14 @@ extern "C" int slipcu_factor_column_launch (slipcu_factor *F, int k, int col, in
     }
     else
     {
+        // reconstruction of the candidates with the pivot scan in its last CTA
         const int e0 = (F->keep_positional && !ov) ? 0 : nU;
-        rc = run_garner (F, hc.base, cnt, e0, cnt - e0, s, hc.sign);
+        const ScanArgs sc = make_scan_args (F, hc, cnt, nU, mode, diag_slot);
+        rc = run_garner (F, hc.base, cnt, e0, cnt - e0, s, hc.sign, &sc);
         if (rc) return rc;
         if (ov) CU (cudaEventRecord (F->ev_gl, F->st));
         g_hw[3] += wall_s () - tw; tw = wall_s ();
-        rc = run_exact_scan (F, hc, cnt, nU, mode, diag_slot);
-        if (rc) return rc;
     }
-    CU (cudaMemcpyAsync (F->h_info, F->d_info, sizeof (slipcu_pivot_info), cudaMemcpyDeviceToHost, F->st));
     CU (cudaEventRecord (F->ev, F->st));
     if (ov)
     {   // side stream: digits of the U part, then positional limbs of the whole column
@@ -3007,7 +3169,6 @@ extern "C" int slipcu_factor_column_wait (slipcu_factor *F, slipcu_pivot_info *i
             F->frac_retries++;
             int rc = run_frac (F, hc, F->fq.cnt, F->fq.nU, F->fq.s, F->fq.mode, F->fq.diag_slot, W);
             if (rc) return rc;
-            CU (cudaMemcpyAsync (F->h_info, F->d_info, sizeof (slipcu_pivot_info), cudaMemcpyDeviceToHost, F->st));
             CU (cudaStreamSynchronize (F->st));
             g_d2h_bytes += sizeof (slipcu_pivot_info);
             *info = *F->h_info;
@@ -3016,10 +3177,12 @@ extern "C" int slipcu_factor_column_wait (slipcu_factor *F, slipcu_pivot_info *i
         {
             F->frac_fallbacks++;
             F->frac_col = -1;
+            // matrices full of ties (small integer entries) send most columns here: the exact path
+            // alone is cheaper than a failed approximate search in front of it
+            if (F->frac_cols >= 32 && 4 * F->frac_fallbacks > F->frac_cols) F->frac = 0;
             int rc = run_garner (F, hc.base, F->fq.cnt, F->fq.nU, F->fq.cnt - F->fq.nU, F->fq.s, hc.sign);
             if (rc == SLIPCU_OK) rc = run_exact_scan (F, hc, F->fq.cnt, F->fq.nU, F->fq.mode, F->fq.diag_slot);
             if (rc) return rc;
-            CU (cudaMemcpyAsync (F->h_info, F->d_info, sizeof (slipcu_pivot_info), cudaMemcpyDeviceToHost, F->st));
             CU (cudaStreamSynchronize (F->st));
             g_d2h_bytes += sizeof (slipcu_pivot_info);
             *info = *F->h_info;
@@ -3034,7 +3197,6 @@ extern "C" int slipcu_factor_column_wait (slipcu_factor *F, slipcu_pivot_info *i
                 int rc = run_garner (F, hc.base, F->fq.cnt, F->fq.nU, F->fq.cnt - F->fq.nU, F->fq.s, hc.sign);
                 if (rc == SLIPCU_OK) rc = run_exact_scan (F, hc, F->fq.cnt, F->fq.nU, F->fq.mode, F->fq.diag_slot);
                 if (rc) return rc;
-                CU (cudaMemcpyAsync (F->h_info, F->d_info, sizeof (slipcu_pivot_info), cudaMemcpyDeviceToHost, F->st));
                 CU (cudaStreamSynchronize (F->st));
                 const slipcu_pivot_info &ex = *F->h_info;
                 if (ex.best_slot != got.best_slot || ex.diag_eligible != got.diag_eligible
@@ -3112,17 +3274,11 @@ extern "C" int slipcu_factor_set_pivot (slipcu_factor *F, int k, int slot)
     HostCol &hc = F->cols[k];
     if (slot < hc.nU || slot >= hc.cnt) return fail (SLIPCU_BAD_INPUT, "slipcu_factor_set_pivot", "bad slot");
     USE_DEVICE (F);
-    const Tables &T = *F->tab;
-    ColDesc d;
-    d.base = hc.base; d.rows = hc.rows; d.cnt = hc.cnt; d.nU = hc.nU; d.pivslot = slot; d.pad = 0;
-    d.mag = F->mag_on ? hc.mag : nullptr;
-    k_pivot_commit<<<(F->S + 255) / 256, 256, 0, F->st>>> (k, F->S, F->CH, slot, d, F->desc, F->rho,
-                                                           F->invrho, T.p, T.ninv, T.one, F->bad,
-                                                           F->mag_on ? F->rho_mag : nullptr);
-    g_launches++;
-    CU (cudaGetLastError ());
-    if (debug_check ("k_pivot_commit", F->st)) return fail (SLIPCU_CUDA_ERROR, "k_pivot_commit", "debug");
-    if (!F->rows_are_positions) CU (cudaEventRecord (F->ev_commit, F->st));
+    int rc = flush_commit (F);               // at most one pivot is ever pending
+    if (rc) return rc;
+    F->pending_commit.k = k; F->pending_commit.slot = slot;
+    // sessions built from host factors have no next column launch to carry the commit
+    if (F->rows_are_positions) return flush_commit (F);
     return SLIPCU_OK;
 }
 
@@ -3212,6 +3368,7 @@ extern "C" int slipcu_factor_bad_prime (slipcu_factor *F, uint32_t *prime)
     int32_t bad = 0;
     if (!F) return fail (SLIPCU_BAD_INPUT, "slipcu_factor_bad_prime", "bad argument");
     USE_DEVICE (F);
+    { int rcf = flush_commit (F); if (rcf) return rcf; }
     CU (cudaMemcpyAsync (&bad, F->bad, sizeof (bad), cudaMemcpyDeviceToHost, F->st));
     CU (cudaStreamSynchronize (F->st));
     if (prime) *prime = (bad >= 1 && bad <= F->tab->S) ? F->tab->hp[bad - 1] : 0u;
@@ -3222,6 +3379,7 @@ extern "C" int slipcu_factor_download (slipcu_factor *F, slipcu_column_sink sink
 {
     if (!F || !sink) return fail (SLIPCU_BAD_INPUT, "slipcu_factor_download", "bad argument");
     USE_DEVICE (F);
+    { int rcf = flush_commit (F); if (rcf) return rcf; }
     { int rcb = check_channels (F); if (rcb) return rcb; }
     size_t maxw = 0; int maxc = 0;
     for (auto &hc : F->cols) { maxw = std::max (maxw, (size_t) hc.cnt * hc.stride); maxc = std::max (maxc, hc.cnt); }
@@ -3246,6 +3404,7 @@ extern "C" int slipcu_solve (slipcu_factor *F, int nrhs, const u32 *blimbs, cons
     if (!F || nrhs <= 0 || !blimbs || !boff || !bsign || !pinv || !sink)
         return fail (SLIPCU_BAD_INPUT, "slipcu_solve", "bad argument");
     CU (cudaSetDevice (F->device));
+    { int rcf = flush_commit (F); if (rcf) return rcf; }
     { int rcb = check_channels (F); if (rcb) return rcb; }
     const Tables &T = *F->tab;
     const int n = F->n, S = F->S, CH = F->CH;
@@ -3261,6 +3420,8 @@ extern "C" int slipcu_solve (slipcu_factor *F, int nrhs, const u32 *blimbs, cons
     u32 *h_limbs = nullptr; int32_t *h_nl = nullptr; int8_t *h_sign = nullptr;
     const int stride = (s + 1) & ~1;
     int rc = SLIPCU_OK;
+    double tw_sub = 0, tw_recon = 0, tw_sink = 0;
+    const bool timing = getenv ("SLIP_B200_TIMING") != nullptr;
     if (top_digit_max) *top_digit_max = -1;
     std::vector<int32_t> row_at (n), ident (n);
     for (int r = 0; r < n; ++r) { row_at[pinv[r]] = r; ident[r] = r; }
@@ -3318,6 +3479,7 @@ extern "C" int slipcu_solve (slipcu_factor *F, int nrhs, const u32 *blimbs, cons
     for (int r0 = 0; r0 < nrhs; r0 += batch)
     {
         const int nb = std::min (batch, nrhs - r0);
+        double tw0 = wall_s ();
         TriArgs a; memset (&a, 0, sizeof (a));
         a.k = n; a.S = S; a.cnt = n; a.nU = n;
         // slots are positions.  Resident sessions store original rows (slot of row r = pinv[r]);
@@ -3345,8 +3507,10 @@ extern "C" int slipcu_solve (slipcu_factor *F, int nrhs, const u32 *blimbs, cons
         else k_backsub<32><<<dim3 (S / CH, nb), 256, 0, F->st>>> (b);
         CUG (cudaGetLastError ());
         if (debug_check ("k_backsub", F->st)) { rc = fail (SLIPCU_CUDA_ERROR, "k_backsub", "debug"); goto done; }
+        if (timing) { cudaStreamSynchronize (F->st); tw_sub += wall_s () - tw0; }
         for (int r = 0; r < nb; ++r)
         {
+            double tw1 = wall_s ();
             HostCol hc;
             hc.cnt = n; hc.s = s; hc.stride = stride; hc.limbs = dlimbs; hc.nl = dnl; hc.sign = dsign;
             rc = run_garner (F, dz + (size_t) r * n * S, n, 0, n, s, dsign);
@@ -3360,10 +3524,14 @@ extern "C" int slipcu_solve (slipcu_factor *F, int nrhs, const u32 *blimbs, cons
                 CUG (cudaStreamSynchronize (F->st));
                 for (int t = 0; t < n; ++t) *top_digit_max = std::max (*top_digit_max, h_nl[t]);
             }
+            if (timing) { cudaStreamSynchronize (F->st); tw_recon += wall_s () - tw1; tw1 = wall_s (); }
             rc = stream_column (F, r0 + r, hc, sink, user, h_limbs, h_nl, h_sign);
             if (rc) goto done;
+            if (timing) tw_sink += wall_s () - tw1;
         }
     }
+    if (timing) fprintf (stderr, "slipcu_solve wall: substitutions %.3f reconstruction %.3f d2h+sink %.3f (nrhs %d, n %d, channels %d, recon channels %d)\n",
+                         tw_sub, tw_recon, tw_sink, nrhs, n, S, s);
 done:
     cudaStreamSynchronize (F->st);
     flush_timers (F);

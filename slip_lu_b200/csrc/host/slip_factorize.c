@@ -331,7 +331,16 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
     for (int attempt = 0 ; ; attempt++)
     {
         int retry = 0, grow = 0, tight = 0 ;
-        const int bound_mode = channels < channels_full ;
+        /* fewer channels than the a-priori bound: sessions whose factors go to the host prove every
+           column's size (mode 1); SLIP_solve_* sessions verify their result exactly at the end, so
+           measured sizes are enough there (mode 2, see slip_b200_device.h).  SLIP_B200_BOUND=proven
+           keeps mode 1 for both (tests). */
+        int bound_mode = 0 ;
+        if (channels < channels_full)
+        {
+            const char *bm = getenv ("SLIP_B200_BOUND") ;
+            bound_mode = (want_host_factors || (bm && bm [0] == 'p')) ? 1 : 2 ;
+        }
         SLIP_TRY (patterns_init (&P, n, (int64_t) S->lnz + S->unz)) ;
         tt = now_s () ;
         SLIP_TRY (slip_from_device_status (slipcu_factor_begin (&dev, n, nz, A->p, A->i, Al.limbs, Al.off,
@@ -344,6 +353,8 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
            its own and the second launch per column costs more than it hides */
         int look = S_dev <= 512 ? 6 : 0 ;
         { const char *lk = getenv ("SLIP_B200_LOOKAHEAD") ; if (lk && *lk) look = atoi (lk) ; }
+        double look_min = 1e6 ;          /* element updates (rows x channels) below which a bulk part is not launched */
+        { const char *lm = getenv ("SLIP_B200_LOOK_MIN") ; if (lm && *lm) look_min = atof (lm) ; }
         if (look < 0) look = 0 ;
         if (look > SLIPCU_SPEC_SLOTS - 1) look = SLIPCU_SPEC_SLOTS - 1 ;
         const int D = look > 1 ? look : 1 ;
@@ -422,7 +433,12 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
                         const int32_t pos = pinv [spat [t]] ;
                         if (pos < k) supos [snU++] = pos ;
                     }
-                    if (snU > 0)
+                    /* worth a launch of its own only if there is real work in it: three more
+                       launches per column cost the host more than a few short steps save the GPU */
+                    double bulk = 0 ;
+                    for (int32_t u = 0 ; u < snU ; u++)
+                        bulk += (double) (P.ptr [supos [u] + 1] - P.ptr [supos [u]] - P.nU [supos [u]]) ;
+                    if (snU > 0 && bulk * (double) S_dev >= look_min)
                     {
                         rc = slipcu_factor_spec_launch (dev, c % ring_size, c, S->q [c], f->cnt, snU, spat, supos) ;
                         if (rc == SLIPCU_BAD_PRIME) { retry = 1 ; break ; }

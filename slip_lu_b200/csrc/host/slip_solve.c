@@ -53,14 +53,19 @@ static int numerators_verify (const rational_ctx *ctx, int c, int n)
     return ok ;
 }
 
+static __thread double t_sink_import = 0, t_sink_verify = 0, t_sink_canon = 0 ;
+
 static int rational_column (void *user, int c, int cnt, int stride, const uint32_t *limbs,
     const int32_t *nl, const int8_t *sign)
 {
     rational_ctx *ctx = (rational_ctx *) user ;
+    double tt = now_s () ;
     #pragma omp parallel for schedule(dynamic, 8) if (cnt > 16)
     for (int t = 0 ; t < cnt ; t++)
         slip_mpz_from_words (mpq_numref (ctx->x [t][c]), limbs + (size_t) t * stride, nl [t], sign [t]) ;
+    t_sink_import += now_s () - tt ; tt = now_s () ;
     if (ctx->A && !ctx->failed && !numerators_verify (ctx, c, cnt)) ctx->failed = 1 ;
+    t_sink_verify += now_s () - tt ; tt = now_s () ;
     if (ctx->failed) return 0 ;
     #pragma omp parallel for schedule(dynamic, 8) if (cnt > 16)
     for (int t = 0 ; t < cnt ; t++)
@@ -69,6 +74,7 @@ static int rational_column (void *user, int c, int cnt, int stride, const uint32
         mpz_set (mpq_denref (q), ctx->det) ;
         mpq_canonicalize (q) ;
     }
+    t_sink_canon += now_s () - tt ;
     return 0 ;
 }
 
@@ -299,7 +305,12 @@ static SLIP_info solve_exact (mpq_t **x, SLIP_sparse *A, SLIP_LU_analysis *S, SL
         SLIP_TRY (slip_factorize_driver (NULL, NULL, A, S, NULL, pinv, option, 0, &r, slip_dense_max_column_bits (b), min_channels)) ;
         double t1 = now_s () ;
         status = slip_solve_resident (x, b, r, pinv, A, S->q) ;
-        if (getenv ("SLIP_B200_TIMING")) fprintf (stderr, "slip_lu_b200 timing: factor %.3fs solve %.3fs\n", t1 - t0, now_s () - t1) ;
+        if (getenv ("SLIP_B200_TIMING"))
+        {
+            fprintf (stderr, "slip_lu_b200 timing: factor %.3fs solve %.3fs (host sink: limbs->mpz %.3fs, exact verification %.3fs, canonical rationals %.3fs)\n",
+                t1 - t0, now_s () - t1, t_sink_import, t_sink_verify, t_sink_canon) ;
+            t_sink_import = t_sink_verify = t_sink_canon = 0 ;
+        }
         if (status != SLIP_B200_NEED_CHANNELS) break ;
         /* the factors fitted the channels but det*x does not (a large right-hand side): again
            with four times the channels */

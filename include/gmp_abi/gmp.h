@@ -129,6 +129,10 @@ int __gmp_sscanf (const char *, const char *, ...);
 #define mpz_divexact    __gmpz_divexact
 #define mpz_divexact_ui __gmpz_divexact_ui
 #define mpz_tdiv_q      __gmpz_tdiv_q
+#define mpz_tdiv_r      __gmpz_tdiv_r
+#define mpz_divisible_ui_p __gmpz_divisible_ui_p
+#define mpz_gcd_ui      __gmpz_gcd_ui
+#define mpz_fits_ulong_p __gmpz_fits_ulong_p
 #define mpz_tdiv_q_2exp __gmpz_tdiv_q_2exp
 #define mpz_tdiv_r_2exp __gmpz_tdiv_r_2exp
 #define mpz_fdiv_ui     __gmpz_fdiv_ui
@@ -190,6 +194,10 @@ void __gmpz_abs (mpz_ptr, mpz_srcptr);
 void __gmpz_divexact (mpz_ptr, mpz_srcptr, mpz_srcptr);
 void __gmpz_divexact_ui (mpz_ptr, mpz_srcptr, unsigned long);
 void __gmpz_tdiv_q (mpz_ptr, mpz_srcptr, mpz_srcptr);
+void __gmpz_tdiv_r (mpz_ptr, mpz_srcptr, mpz_srcptr);
+int  __gmpz_divisible_ui_p (mpz_srcptr, unsigned long int);
+unsigned long int __gmpz_gcd_ui (mpz_ptr, mpz_srcptr, unsigned long int);
+int  __gmpz_fits_ulong_p (mpz_srcptr);
 void __gmpz_tdiv_q_2exp (mpz_ptr, mpz_srcptr, mp_bitcnt_t);
 void __gmpz_tdiv_r_2exp (mpz_ptr, mpz_srcptr, mp_bitcnt_t);
 unsigned long int __gmpz_fdiv_ui (mpz_srcptr, unsigned long int);

@@ -141,10 +141,13 @@ int slipcu_factor_upload (slipcu_factor **F, int n, int channels, const int32_t 
 /* -- solve ------------------------------------------------------------------------------------
  * slipcu_solve: exact forward substitution, scaling by det and back substitution
  *   (SLIP_LU_solve.c:74-91, slip_forward_sub.c, slip_array_mul.c, slip_back_sub.c) for nrhs
- *   right-hand sides against the resident factors.  b is row-major n x nrhs in ORIGINAL row
- *   order; pinv is the final inverse row permutation.  The sink receives one "column" per
+ *   right-hand sides against the resident factors.  b holds the right-hand sides one after the
+ *   other (entry i of right-hand side c at index c*n + i), rows in ORIGINAL order; pinv is the final
+ *   inverse row permutation (checked to be a permutation).  The sink receives one "column" per
  *   right-hand side: cnt = n entries in factor (position) order holding det * x_i, the numerators
- *   of slip_array_div.c. */
+ *   of slip_array_div.c.  Right-hand sides are processed in batches (one launch of each kernel per
+ *   batch, SLIP_B200_SOLVE_BATCH_MB of device memory); the sink of a batch runs on the calling
+ *   thread while the GPU works on the next batch. */
 int slipcu_solve (slipcu_factor *F, int nrhs, const uint32_t *blimbs, const int64_t *bvalue_off,
                   const int8_t *bsign, const int32_t *pinv, int recon_channels,
                   slipcu_column_sink sink, void *user, int32_t *top_digit_max);

@@ -718,10 +718,10 @@ struct TriArgs
     const int32_t *slots;    // slot lists
     // source vector to scatter: src_cnt entries, entry e at residue index src_first + e*src_step,
     // going to the slot of row src_rows[e] (or row e when src_rows == nullptr)
-    const u32 *src; int src_total; int src_first, src_step, src_cnt; const int32_t *src_rows;
+    const u32 *src; size_t src_total; int64_t src_first; int src_step, src_cnt; const int32_t *src_rows;
     size_t src_y_stride;     // added to src_first per blockIdx.y (multiple right-hand sides)
-    u32 *out;                // [S/CH][cnt][CH] result region (+ blockIdx.y * out_y_stride words)
-    size_t out_y_stride;
+    u32 *out;                // result: channel block cb of right-hand side y at out + cb * out_cb_stride + y * out_y_stride
+    size_t out_y_stride, out_cb_stride;      // (one column: out_cb_stride = cnt * CH)
     const u32 *rho, *invrho, *p, *ninv;      // [n][S] pivots and their inverses (Montgomery form)
     const int32_t *pos;      // [n] row -> slot
     int x_in_smem;
@@ -737,6 +737,7 @@ struct TriArgs
     const int32_t *rho_mag;  // [n] measured log2 |rho_k| (upper bound; the lower bound is MAG_GAP less)
     int32_t *bound_out;      // largest published bound of this launch
     int smem_bytes;          // dynamic shared memory of the launch
+    int rhs_fastest;         // 1: blockIdx.x = right-hand side, blockIdx.y = channel block (see slipcu_solve)
 };
 
 template <int CH>
@@ -991,8 +992,12 @@ __global__ void __launch_bounds__ (TRI_THREADS * 4 / CPT, 2) k_trisolve (TriArgs
         if (blockIdx.y == 0) tri_mag_cta<CH, NT> (a, smem_raw);
         return;
     }
-    const int cb = blockIdx.x, S = a.S, cnt = a.cnt, nU = a.nU, nchunks = a.nchunks;
-    u32 *xg = a.out + (size_t) blockIdx.y * a.out_y_stride + (size_t) cb * cnt * CH;
+    // Several right-hand sides: CTAs of the same channel block are neighbours in the grid, run at
+    // the same time and stream the same chunks of L, which then come from HBM once and from L2 for
+    // the others (DRAM reads of a batch ~ 4 S nnz(L), not that times the batch size).
+    const int cb = a.rhs_fastest ? blockIdx.y : blockIdx.x, by = a.rhs_fastest ? blockIdx.x : blockIdx.y;
+    const int S = a.S, cnt = a.cnt, nU = a.nU, nchunks = a.nchunks;
+    u32 *xg = a.out + (size_t) by * a.out_y_stride + (size_t) cb * a.out_cb_stride;
     u32 *xs = XS ? (u32 *) smem_raw : xg;
     const u32 smem0 = smem_u32 (smem_raw);
     const u32 ring = smem0 + (XS ? (u32) SM::x_bytes (cnt) : 0u);
@@ -1055,7 +1060,7 @@ __global__ void __launch_bounds__ (TRI_THREADS * 4 / CPT, 2) k_trisolve (TriArgs
         for (int i = tid; i < words; i += NT) xs[i] = 0;
         __syncthreads ();
         const u32 *src = a.src + (size_t) cb * a.src_total * CH;
-        const int first = a.src_first + (int) (blockIdx.y * a.src_y_stride);
+        const size_t first = (size_t) a.src_first + (size_t) by * a.src_y_stride;
         if (a.src_cnt >= 64)
         {   // long source (dense right-hand side, speculative first part): CPT channels per access,
             // one slot lookup per row
@@ -1063,7 +1068,7 @@ __global__ void __launch_bounds__ (TRI_THREADS * 4 / CPT, 2) k_trisolve (TriArgs
             for (int e = tid / TPR; e < a.src_cnt; e += NT / TPR)
             {
                 const int row = a.src_rows ? a.src_rows[e] : e;
-                stv<CPT> (xs + (size_t) a.pos[row] * CH + qs, ldv<CPT> (src + ((size_t) first + (size_t) e * a.src_step) * CH + qs));
+                stv<CPT> (xs + (size_t) a.pos[row] * CH + qs, ldv<CPT> (src + (first + (size_t) e * a.src_step) * CH + qs));
             }
         }
         else
@@ -1071,7 +1076,7 @@ __global__ void __launch_bounds__ (TRI_THREADS * 4 / CPT, 2) k_trisolve (TriArgs
             {
                 const int e = i / CH, ch = i % CH;
                 const int row = a.src_rows ? a.src_rows[e] : e;
-                xs[a.pos[row] * CH + ch] = src[((size_t) first + (size_t) e * a.src_step) * CH + ch];
+                xs[a.pos[row] * CH + ch] = src[(first + (size_t) e * a.src_step) * CH + ch];
             }
     }
 
@@ -1156,7 +1161,8 @@ __global__ void __launch_bounds__ (TRI_THREADS * 4 / CPT, 2) k_trisolve (TriArgs
 struct BackArgs
 {
     int n, S;
-    u32 *z; size_t z_y_stride;      // [S/CH][n][CH] per right-hand side
+    u32 *z; size_t z_y_stride, z_cb_stride;     // channel block cb of right-hand side y at z + cb * z_cb_stride + y * z_y_stride
+    int rhs_fastest;                // grid order as in k_trisolve
     const ColDesc *desc; const u32 *rho, *invrho, *p, *ninv;
     const int32_t *pos;             // row -> position (final pinv)
 };
@@ -1165,9 +1171,10 @@ template <int CH>
 __global__ void __launch_bounds__ (512) k_backsub (BackArgs a)
 {
     const int tid = threadIdx.x, ch = tid % CH, rg = tid / CH, RG = blockDim.x / CH;
-    const int cb = blockIdx.x, c = cb * CH + ch, S = a.S, n = a.n;
+    const int cb = a.rhs_fastest ? blockIdx.y : blockIdx.x, by = a.rhs_fastest ? blockIdx.x : blockIdx.y;
+    const int c = cb * CH + ch, S = a.S, n = a.n;
     const u32 p = a.p[c], ni = a.ninv[c];
-    u32 *z = a.z + (size_t) blockIdx.y * a.z_y_stride + (size_t) cb * n * CH;
+    u32 *z = a.z + (size_t) by * a.z_y_stride + (size_t) cb * a.z_cb_stride;
     const u32 det = a.rho[(size_t) (n - 1) * S + c];
     for (int t = rg; t < n; t += RG) z[t * CH + ch] = mont_mul (z[t * CH + ch], det, p, ni);
     __syncthreads ();
@@ -2419,6 +2426,8 @@ template <int CH, bool XS, int CPT> static cudaError_t tri_configure_one (int sm
 template <int CPT> static cudaError_t tri_configure_cpt (int smem_optin)
 {
     cudaError_t e;
+    if ((e = tri_configure_one<4, true, CPT> (smem_optin)) != cudaSuccess) return e;
+    if ((e = tri_configure_one<4, false, CPT> (smem_optin)) != cudaSuccess) return e;
     if ((e = tri_configure_one<8, true, CPT> (smem_optin)) != cudaSuccess) return e;
     if ((e = tri_configure_one<16, true, CPT> (smem_optin)) != cudaSuccess) return e;
     if ((e = tri_configure_one<32, true, CPT> (smem_optin)) != cudaSuccess) return e;
@@ -2455,10 +2464,13 @@ static int session_common_init (slipcu_factor *F, int n, int channels)
     int sms = 148;
     cudaDeviceGetAttribute (&sms, cudaDevAttrMultiProcessorCount, F->device);
     int CH = 8;
+    // few channels (LP bases, measured mode): 4-channel blocks double the CTAs of a column, whose
+    // single chain of steps is otherwise streamed by S/8 < 64 CTAs on 148 SMs
+    if (S <= 512) CH = 4;
     if (S / 16 >= 16 * sms) CH = 16;
     if (S / 32 >= 16 * sms) CH = 32;
     CH = env_int ("SLIP_B200_CH", CH);
-    if (CH != 8 && CH != 16 && CH != 32) CH = 16;
+    if (CH != 4 && CH != 8 && CH != 16 && CH != 32) CH = 16;
     F->CH = CH;
     F->sms = sms;
     F->x_global = env_int ("SLIP_B200_X_GLOBAL", 0);
@@ -2593,6 +2605,7 @@ static cudaError_t launch_tri (const TriArgs &a, dim3 grid, size_t smem, cudaStr
 }
 static size_t tri_smem_bytes (int CH, int cnt, bool x_in_smem)
 {
+    if (CH == 4) return TriSmem<4>::total (cnt, x_in_smem);
     if (CH == 8) return TriSmem<8>::total (cnt, x_in_smem);
     if (CH == 16) return TriSmem<16>::total (cnt, x_in_smem);
     return TriSmem<32>::total (cnt, x_in_smem);
@@ -2602,10 +2615,12 @@ static cudaError_t launch_tri_any (int CH, int cpt, const TriArgs &a, dim3 grid,
     g_launches++; g_tri_launches++;
     if (cpt == 2)
     {
+        if (CH == 4) return launch_tri<4, 2> (a, grid, smem, st);
         if (CH == 8) return launch_tri<8, 2> (a, grid, smem, st);
         if (CH == 16) return launch_tri<16, 2> (a, grid, smem, st);
         return launch_tri<32, 2> (a, grid, smem, st);
     }
+    if (CH == 4) return launch_tri<4, 4> (a, grid, smem, st);
     if (CH == 8) return launch_tri<8, 4> (a, grid, smem, st);
     if (CH == 16) return launch_tri<16, 4> (a, grid, smem, st);
     return launch_tri<32, 4> (a, grid, smem, st);
@@ -2987,7 +3002,7 @@ extern "C" int slipcu_factor_spec_launch (slipcu_factor *F, int slot, int k, int
     a.src = F->dA; a.src_total = F->nz; a.src_first = F->hAp[col]; a.src_step = 1;
     a.src_cnt = F->hAp[col + 1] - F->hAp[col]; a.src_rows = F->dAi + F->hAp[col];
     a.src_y_stride = 0;
-    a.out = sl.buf; a.out_y_stride = 0;
+    a.out = sl.buf; a.out_y_stride = 0; a.out_cb_stride = (size_t) cnt * CH;
     a.rho = F->rho; a.invrho = F->invrho;
     a.p = T.p; a.ninv = T.ninv; a.pos = w.pos;
     a.nchunks = nchunks; a.upos = d + cnt; a.publish = 0; a.u0 = 0;
@@ -3058,7 +3073,7 @@ extern "C" int slipcu_factor_column_launch (slipcu_factor *F, int k, int col, in
         a.mag_src = F->mag_on ? F->Amag + F->hAp[col] : nullptr;
     }
     a.src_y_stride = 0;
-    a.out = hc.base; a.out_y_stride = 0;
+    a.out = hc.base; a.out_y_stride = 0; a.out_cb_stride = (size_t) cnt * CH;
     a.rho = F->rho; a.invrho = F->invrho;
     a.p = T.p; a.ninv = T.ninv; a.pos = w.pos;
     a.nchunks = nchunks; a.upos = hc.rows + cnt; a.publish = 1; a.u0 = first_step;
@@ -3397,6 +3412,40 @@ extern "C" int slipcu_factor_download (slipcu_factor *F, slipcu_column_sink sink
 // ------------------------------------------------------------------------------------------------
 // solve
 // ------------------------------------------------------------------------------------------------
+// pinned host buffers are expensive to create (cudaHostAlloc runs at ~0.3 s per GB): kept per process
+static std::mutex g_hpool_mutex;
+static std::multimap<size_t, void *> g_hpool_free;
+static std::map<void *, size_t> g_hpool_size;
+static cudaError_t host_pool_alloc (void **out, size_t bytes)
+{
+    const size_t want = pool_round (std::max<size_t> (bytes, 1));
+    {
+        std::lock_guard<std::mutex> lk (g_hpool_mutex);
+        auto it = g_hpool_free.find (want);
+        if (it != g_hpool_free.end ()) { *out = it->second; g_hpool_free.erase (it); return cudaSuccess; }
+    }
+    cudaError_t e = cudaHostAlloc (out, want, cudaHostAllocPortable);
+    if (e == cudaSuccess) { std::lock_guard<std::mutex> lk (g_hpool_mutex); g_hpool_size[*out] = want; }
+    return e;
+}
+static void host_pool_free (void *ptr)
+{
+    if (!ptr) return;
+    std::lock_guard<std::mutex> lk (g_hpool_mutex);
+    auto it = g_hpool_size.find (ptr);
+    if (it == g_hpool_size.end ()) { cudaFreeHost (ptr); return; }
+    g_hpool_free.insert ({it->second, ptr});
+}
+
+// b: nrhs right-hand sides of n entries, entry (row i, right-hand side c) at index c * n + i.
+//
+// The right-hand sides go through in batches.  A batch is one launch of every kernel: the residues
+// of its b, the forward substitution (k_trisolve with a dense source, one CTA per channel block and
+// right-hand side, CTAs of one channel block adjacent in the grid so that they share their reads of
+// L through L2), the back substitution, ONE reconstruction launch and ONE limb launch for all its
+// numerators, one copy to the host.  Two sets of buffers alternate: while the host turns batch i
+// into rationals (the sink: limb import, exact verification, canonical form -- the part that costs
+// the reference the same GMP time per entry), the GPU works on batch i + 1.
 extern "C" int slipcu_solve (slipcu_factor *F, int nrhs, const u32 *blimbs, const int64_t *boff,
                              const int8_t *bsign, const int32_t *pinv, int recon_channels,
                              slipcu_column_sink sink, void *user, int32_t *top_digit_max)
@@ -3410,54 +3459,64 @@ extern "C" int slipcu_solve (slipcu_factor *F, int nrhs, const u32 *blimbs, cons
     const int n = F->n, S = F->S, CH = F->CH;
     const int s = std::min (std::max (recon_channels, 1), S);
     if (recon_channels > S) return fail (SLIPCU_BAD_INPUT, "slipcu_solve", "right-hand side needs more channels than the session holds");
-    const int total = n * nrhs;
-    // right-hand sides handled per batch so that the work vectors stay within a memory budget
-    size_t budget = (size_t) env_int ("SLIP_B200_SOLVE_BATCH_MB", 4096) << 20;
-    int batch = (int) std::max<size_t> (1, std::min<size_t> ((size_t) nrhs, budget / ((size_t) n * S * sizeof (u32))));
-
-    u32 *dl = nullptr, *dB = nullptr, *dz = nullptr, *dlimbs = nullptr; int64_t *doff = nullptr; int8_t *dsg = nullptr;
-    int32_t *drow_at = nullptr, *dident = nullptr, *dnl = nullptr; int8_t *dsign = nullptr;
-    u32 *h_limbs = nullptr; int32_t *h_nl = nullptr; int8_t *h_sign = nullptr;
     const int stride = (s + 1) & ~1;
-    int rc = SLIPCU_OK;
-    double tw_sub = 0, tw_recon = 0, tw_sink = 0;
+    std::vector<int32_t> row_at (n, -1), ident (n);
+    for (int r = 0; r < n; ++r)
+    {   // pinv must be a permutation of 0..n-1
+        if (pinv[r] < 0 || pinv[r] >= n || row_at[pinv[r]] >= 0) return fail (SLIPCU_BAD_INPUT, "slipcu_solve", "pinv is not a permutation");
+        row_at[pinv[r]] = r; ident[r] = r;
+    }
+    // batch size: work vectors, digit scratch and limb buffers of a batch within the memory budget,
+    // and at least four batches when there are many right-hand sides (so that host and GPU overlap)
+    const size_t budget = (size_t) std::max (1, env_int ("SLIP_B200_SOLVE_BATCH_MB", 1024)) << 20;
+    const size_t per_rhs = (size_t) n * ((size_t) S * 4 + ((size_t) S + 4) * 4 + 2 * (size_t) stride * 4);
+    int batch = (int) std::max<size_t> (1, std::min<size_t> ((size_t) nrhs, budget / std::max<size_t> (per_rhs, 1)));
+    if (nrhs >= 8) batch = std::min (batch, (nrhs + 3) / 4);
+    if ((int64_t) batch * n > (int64_t) INT32_MAX / 2) batch = std::max (1, (int) ((int64_t) (INT32_MAX / 2) / n));
+    const int nbatches = (nrhs + batch - 1) / batch;
+    const size_t bn = (size_t) batch * n;
+
+    u32 *dl = nullptr, *dB = nullptr, *dz = nullptr; int64_t *doff = nullptr; int8_t *dsg = nullptr;
+    int32_t *drow_at = nullptr, *dident = nullptr, *dpinv = nullptr, *duoff = nullptr;
+    struct Buf { u32 *dlimbs = nullptr; int32_t *dnl = nullptr; int8_t *dsign = nullptr;
+                 u32 *h_limbs = nullptr; int32_t *h_nl = nullptr; int8_t *h_sign = nullptr; int32_t *h_topd = nullptr;
+                 cudaEvent_t done = nullptr; int r0 = 0, nb = 0; bool busy = false; } buf[2];
+    int rc = SLIPCU_OK, fwd_chunks = 0;
+    double tw_gpu_launch = 0, tw_wait = 0, tw_sink = 0;
     const bool timing = getenv ("SLIP_B200_TIMING") != nullptr;
     if (top_digit_max) *top_digit_max = -1;
-    std::vector<int32_t> row_at (n), ident (n);
-    for (int r = 0; r < n; ++r) { row_at[pinv[r]] = r; ident[r] = r; }
-    int32_t *dpinv = nullptr, *duoff = nullptr; int fwd_chunks = 0;
+    const size_t total = (size_t) n * nrhs;
     const size_t nl = (size_t) boff[total];
+    const int nbuf = nbatches > 1 ? 2 : 1;
 #define CUG(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail (e_ == cudaErrorMemoryAllocation ? SLIPCU_OUT_OF_MEMORY : SLIPCU_CUDA_ERROR, #call, cudaGetErrorString (e_)); goto done; } } while (0)
     CUG (pool_alloc_t (&dl, std::max<size_t> (nl, 1) * sizeof (u32)));
-    CUG (pool_alloc_t (&doff, (size_t) (total + 1) * sizeof (int64_t)));
-    CUG (pool_alloc_t (&dsg, (size_t) total));
-    CUG (pool_alloc_t (&dB, (size_t) total * S * sizeof (u32)));
-    CUG (pool_alloc_t (&dz, (size_t) batch * n * S * sizeof (u32)));
-    CUG (pool_alloc_t (&dlimbs, (size_t) n * stride * sizeof (u32)));
+    CUG (pool_alloc_t (&doff, (total + 1) * sizeof (int64_t)));
+    CUG (pool_alloc_t (&dsg, total));
+    CUG (pool_alloc_t (&dB, bn * S * sizeof (u32)));
+    CUG (pool_alloc_t (&dz, bn * S * sizeof (u32)));
     CUG (pool_alloc_t (&drow_at, (size_t) n * sizeof (int32_t)));
     CUG (pool_alloc_t (&dident, (size_t) n * sizeof (int32_t)));
     CUG (pool_alloc_t (&dpinv, (size_t) n * sizeof (int32_t)));
-    CUG (pool_alloc_t (&dnl, (size_t) n * sizeof (int32_t)));
-    CUG (pool_alloc_t (&dsign, (size_t) n));
-    CUG (cudaHostAlloc (&h_limbs, (size_t) n * stride * sizeof (u32), cudaHostAllocDefault));
-    CUG (cudaHostAlloc (&h_nl, (size_t) n * sizeof (int32_t), cudaHostAllocDefault));
-    CUG (cudaHostAlloc (&h_sign, (size_t) n, cudaHostAllocDefault));
+    for (int i = 0; i < nbuf; ++i)
+    {
+        CUG (pool_alloc_t (&buf[i].dlimbs, bn * stride * sizeof (u32)));
+        CUG (pool_alloc_t (&buf[i].dnl, bn * sizeof (int32_t)));
+        CUG (pool_alloc_t (&buf[i].dsign, bn));
+        CUG (host_pool_alloc ((void **) &buf[i].h_limbs, bn * stride * sizeof (u32)));
+        CUG (host_pool_alloc ((void **) &buf[i].h_nl, bn * sizeof (int32_t)));
+        CUG (host_pool_alloc ((void **) &buf[i].h_sign, bn));
+        CUG (host_pool_alloc ((void **) &buf[i].h_topd, bn * sizeof (int32_t)));
+        CUG (cudaEventCreateWithFlags (&buf[i].done, cudaEventDisableTiming));
+    }
     CUG (cudaMemcpyAsync (dl, blimbs, nl * sizeof (u32), cudaMemcpyHostToDevice, F->st));
-    CUG (cudaMemcpyAsync (doff, boff, (size_t) (total + 1) * sizeof (int64_t), cudaMemcpyHostToDevice, F->st));
-    CUG (cudaMemcpyAsync (dsg, bsign, (size_t) total, cudaMemcpyHostToDevice, F->st));
+    CUG (cudaMemcpyAsync (doff, boff, (total + 1) * sizeof (int64_t), cudaMemcpyHostToDevice, F->st));
+    CUG (cudaMemcpyAsync (dsg, bsign, total, cudaMemcpyHostToDevice, F->st));
     CUG (cudaMemcpyAsync (drow_at, row_at.data (), (size_t) n * sizeof (int32_t), cudaMemcpyHostToDevice, F->st));
     CUG (cudaMemcpyAsync (dident, ident.data (), (size_t) n * sizeof (int32_t), cudaMemcpyHostToDevice, F->st));
     CUG (cudaMemcpyAsync (dpinv, pinv, (size_t) n * sizeof (int32_t), cudaMemcpyHostToDevice, F->st));
     g_h2d_bytes += (double) nl * 4 + (double) (total + 1) * 8 + (double) total + 3.0 * n * 4;
-    rc = ensure_digits (F, (size_t) n);
+    rc = ensure_digits (F, bn);
     if (rc) goto done;
-    {
-        const int per = 256 / CH;
-        dim3 grid ((total + per - 1) / per, S / CH);
-        k_residues<<<grid, 256, 0, F->st>>> (total, CH, dl, doff, dsg, T.p, T.ninv, T.r2, dB);
-        g_launches++;
-        CUG (cudaGetLastError ());
-    }
     {   // symbolic pre-pass of the forward substitution: every column of L is one step
         std::vector<int32_t> uoff (2 * (size_t) n + 2);
         int64_t tot = 0, nch = 0;
@@ -3476,62 +3535,84 @@ extern "C" int slipcu_solve (slipcu_factor *F, int nrhs, const u32 *blimbs, cons
         rc = prepare_steps (F, F->mc, n, n, F->rows_are_positions ? dident : drow_at, dident, duoff, duoff + n + 1, (int) tot, (int) nch);
         if (rc) goto done;
     }
-    for (int r0 = 0; r0 < nrhs; r0 += batch)
+    for (int bi = 0; bi <= nbatches; ++bi)
     {
-        const int nb = std::min (batch, nrhs - r0);
         double tw0 = wall_s ();
-        TriArgs a; memset (&a, 0, sizeof (a));
-        a.k = n; a.S = S; a.cnt = n; a.nU = n;
-        // slots are positions.  Resident sessions store original rows (slot of row r = pinv[r]);
-        // uploaded sessions store positions (identity map), b rows are then routed through pinv.
-        a.rows = F->rows_are_positions ? dident : drow_at;
-        a.steps = F->mc.steps; a.chunks = F->mc.chunks; a.slots = F->mc.slots;
-        a.src = dB; a.src_total = total; a.src_first = r0; a.src_step = nrhs; a.src_cnt = n;
-        a.src_rows = F->rows_are_positions ? dpinv : nullptr;
-        a.src_y_stride = 1;
-        a.out = dz; a.out_y_stride = (size_t) n * S;
-        a.rho = F->rho; a.invrho = F->invrho;
-        a.p = T.p; a.ninv = T.ninv; a.pos = F->mc.pos;
-        a.nchunks = fwd_chunks; a.upos = dident; a.publish = 1; a.u0 = 0;
-        size_t smem = 0;
-        rc = tri_geometry (F, a, &smem);
-        if (rc) goto done;
-        CUG (launch_tri_any (CH, F->cpt, a, dim3 (S / CH, nb), smem, F->st));
-        if (debug_check ("k_trisolve(forward)", F->st)) { rc = fail (SLIPCU_CUDA_ERROR, "k_trisolve(forward)", "debug"); goto done; }
-        BackArgs b;
-        b.n = n; b.S = S; b.z = dz; b.z_y_stride = (size_t) n * S;
-        b.desc = F->desc; b.rho = F->rho; b.invrho = F->invrho; b.p = T.p; b.ninv = T.ninv; b.pos = F->mc.pos;
-        g_launches++;
-        if (CH == 8) k_backsub<8><<<dim3 (S / CH, nb), 256, 0, F->st>>> (b);
-        else if (CH == 16) k_backsub<16><<<dim3 (S / CH, nb), 256, 0, F->st>>> (b);
-        else k_backsub<32><<<dim3 (S / CH, nb), 256, 0, F->st>>> (b);
-        CUG (cudaGetLastError ());
-        if (debug_check ("k_backsub", F->st)) { rc = fail (SLIPCU_CUDA_ERROR, "k_backsub", "debug"); goto done; }
-        if (timing) { cudaStreamSynchronize (F->st); tw_sub += wall_s () - tw0; }
-        for (int r = 0; r < nb; ++r)
-        {
-            double tw1 = wall_s ();
-            HostCol hc;
-            hc.cnt = n; hc.s = s; hc.stride = stride; hc.limbs = dlimbs; hc.nl = dnl; hc.sign = dsign;
-            rc = run_garner (F, dz + (size_t) r * n * S, n, 0, n, s, dsign);
+        if (bi < nbatches)
+        {   // enqueue batch bi
+            Buf &B = buf[bi % nbuf];
+            const int r0 = bi * batch, nb = std::min (batch, nrhs - r0);
+            const size_t cntb = (size_t) nb * n;            // entries of the batch; region [S/CH][cntb][CH]
+            B.r0 = r0; B.nb = nb;
+            {
+                const int per = 256 / CH;
+                dim3 grid ((unsigned) ((cntb + per - 1) / per), S / CH);
+                k_residues<<<grid, 256, 0, F->st>>> ((int) cntb, CH, dl, doff + (size_t) r0 * n, dsg + (size_t) r0 * n, T.p, T.ninv, T.r2, dB);
+                g_launches++;
+                CUG (cudaGetLastError ());
+            }
+            TriArgs a; memset (&a, 0, sizeof (a));
+            a.k = n; a.S = S; a.cnt = n; a.nU = n;
+            // slots are positions.  Resident sessions store original rows (slot of row r = pinv[r]);
+            // uploaded sessions store positions (identity map), b rows are then routed through pinv.
+            a.rows = F->rows_are_positions ? dident : drow_at;
+            a.steps = F->mc.steps; a.chunks = F->mc.chunks; a.slots = F->mc.slots;
+            a.src = dB; a.src_total = cntb; a.src_first = 0; a.src_step = 1; a.src_cnt = n;
+            a.src_rows = F->rows_are_positions ? dpinv : nullptr;
+            a.src_y_stride = (size_t) n;
+            a.out = dz; a.out_y_stride = (size_t) n * CH; a.out_cb_stride = cntb * CH;
+            a.rho = F->rho; a.invrho = F->invrho;
+            a.p = T.p; a.ninv = T.ninv; a.pos = F->mc.pos;
+            a.nchunks = fwd_chunks; a.upos = dident; a.publish = 1; a.u0 = 0;
+            a.rhs_fastest = 1;
+            size_t smem = 0;
+            rc = tri_geometry (F, a, &smem);
             if (rc) goto done;
-            rc = run_limbs (F, 0, n, 0, stride, s, dlimbs, dnl);
+            CUG (launch_tri_any (CH, F->cpt, a, dim3 (nb, S / CH), smem, F->st));
+            if (debug_check ("k_trisolve(forward)", F->st)) { rc = fail (SLIPCU_CUDA_ERROR, "k_trisolve(forward)", "debug"); goto done; }
+            BackArgs b;
+            b.n = n; b.S = S; b.z = dz; b.z_y_stride = (size_t) n * CH; b.z_cb_stride = cntb * CH; b.rhs_fastest = 1;
+            b.desc = F->desc; b.rho = F->rho; b.invrho = F->invrho; b.p = T.p; b.ninv = T.ninv; b.pos = F->mc.pos;
+            g_launches++;
+            if (CH == 4) k_backsub<4><<<dim3 (nb, S / CH), 256, 0, F->st>>> (b);
+            else if (CH == 8) k_backsub<8><<<dim3 (nb, S / CH), 256, 0, F->st>>> (b);
+            else if (CH == 16) k_backsub<16><<<dim3 (nb, S / CH), 256, 0, F->st>>> (b);
+            else k_backsub<32><<<dim3 (nb, S / CH), 256, 0, F->st>>> (b);
+            CUG (cudaGetLastError ());
+            if (debug_check ("k_backsub", F->st)) { rc = fail (SLIPCU_CUDA_ERROR, "k_backsub", "debug"); goto done; }
+            // numerators of the whole batch: one reconstruction launch, one limb launch
+            rc = run_garner (F, dz, (int) cntb, 0, (int) cntb, s, B.dsign);
+            if (rc) goto done;
+            rc = run_limbs (F, 0, (int) cntb, 0, stride, s, B.dlimbs, B.dnl);
             if (rc) goto done;
             CUG (cudaEventRecord (F->ev_end, F->st));
-            if (top_digit_max)
-            {   // highest mixed-radix digit in use: lets the caller verify an estimated bound
-                CUG (cudaMemcpyAsync (h_nl, F->topd, (size_t) n * sizeof (int32_t), cudaMemcpyDeviceToHost, F->st));
-                CUG (cudaStreamSynchronize (F->st));
-                for (int t = 0; t < n; ++t) *top_digit_max = std::max (*top_digit_max, h_nl[t]);
+            CUG (cudaMemcpyAsync (B.h_limbs, B.dlimbs, cntb * stride * sizeof (u32), cudaMemcpyDeviceToHost, F->st));
+            CUG (cudaMemcpyAsync (B.h_nl, B.dnl, cntb * sizeof (int32_t), cudaMemcpyDeviceToHost, F->st));
+            CUG (cudaMemcpyAsync (B.h_sign, B.dsign, cntb, cudaMemcpyDeviceToHost, F->st));
+            if (top_digit_max) CUG (cudaMemcpyAsync (B.h_topd, F->topd, cntb * sizeof (int32_t), cudaMemcpyDeviceToHost, F->st));
+            CUG (cudaEventRecord (B.done, F->st));
+            B.busy = true;
+            g_d2h_bytes += (double) cntb * stride * 4 + (double) cntb * 5;
+        }
+        tw_gpu_launch += wall_s () - tw0; tw0 = wall_s ();
+        if (bi > 0)
+        {   // hand batch bi - 1 to the sink while the GPU works on batch bi
+            Buf &B = buf[(bi - 1) % nbuf];
+            CUG (cudaEventSynchronize (B.done));
+            tw_wait += wall_s () - tw0; tw0 = wall_s ();
+            B.busy = false;
+            for (int r = 0; r < B.nb; ++r)
+            {
+                const size_t e0 = (size_t) r * n;
+                if (top_digit_max) for (int t = 0; t < n; ++t) *top_digit_max = std::max (*top_digit_max, B.h_topd[e0 + t]);
+                const int rs = sink (user, B.r0 + r, n, stride, B.h_limbs + e0 * stride, B.h_nl + e0, B.h_sign + e0);
+                if (rs) { rc = fail (rs, "column sink", "host sink failed"); goto done; }
             }
-            if (timing) { cudaStreamSynchronize (F->st); tw_recon += wall_s () - tw1; tw1 = wall_s (); }
-            rc = stream_column (F, r0 + r, hc, sink, user, h_limbs, h_nl, h_sign);
-            if (rc) goto done;
-            if (timing) tw_sink += wall_s () - tw1;
+            tw_sink += wall_s () - tw0;
         }
     }
-    if (timing) fprintf (stderr, "slipcu_solve wall: substitutions %.3f reconstruction %.3f d2h+sink %.3f (nrhs %d, n %d, channels %d, recon channels %d)\n",
-                         tw_sub, tw_recon, tw_sink, nrhs, n, S, s);
+    if (timing) fprintf (stderr, "slipcu_solve wall: enqueue %.3f wait-for-gpu %.3f host sink %.3f (nrhs %d in %d batches of %d, n %d, channels %d, recon channels %d)\n",
+                         tw_gpu_launch, tw_wait, tw_sink, nrhs, nbatches, batch, n, S, s);
 done:
     cudaStreamSynchronize (F->st);
     flush_timers (F);
@@ -3540,11 +3621,14 @@ done:
         float ms = 0;
         if (cudaEventElapsedTime (&ms, F->ev_start, F->ev_end) == cudaSuccess) g_device_ms += ms; else cudaGetLastError ();
     }
-    pool_free (dl); pool_free (doff); pool_free (dsg); pool_free (dB); pool_free (dz); pool_free (dlimbs);
-    pool_free (drow_at); pool_free (dident); pool_free (dpinv); pool_free (duoff); pool_free (dnl); pool_free (dsign);
-    if (h_limbs) cudaFreeHost (h_limbs);
-    if (h_nl) cudaFreeHost (h_nl);
-    if (h_sign) cudaFreeHost (h_sign);
+    pool_free (dl); pool_free (doff); pool_free (dsg); pool_free (dB); pool_free (dz);
+    pool_free (drow_at); pool_free (dident); pool_free (dpinv); pool_free (duoff);
+    for (int i = 0; i < 2; ++i)
+    {
+        pool_free (buf[i].dlimbs); pool_free (buf[i].dnl); pool_free (buf[i].dsign);
+        host_pool_free (buf[i].h_limbs); host_pool_free (buf[i].h_nl); host_pool_free (buf[i].h_sign); host_pool_free (buf[i].h_topd);
+        if (buf[i].done) cudaEventDestroy (buf[i].done);
+    }
 #undef CUG
     return rc;
 }

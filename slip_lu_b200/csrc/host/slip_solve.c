@@ -23,7 +23,138 @@ typedef struct
     /* verification of a bound-mode result (NULL: the channel count is proven a priori) */
     const SLIP_sparse *A ; const int32_t *q ; const SLIP_dense *b ;
     int failed ;
+    /* |det| = Ds * Dr: Ds collects the prime factors below SMALL_PRIME_BOUND, Dr is the rest */
+    int split_done ;
+    mpz_t D, Ds, Dr ;
 } rational_ctx ;
+
+/* ---- canonical form of N_t / det for a whole column with ONE big gcd ----
+ * mpq_canonicalize costs a gcd of two numbers of the size of det per entry (the mpq_div of
+ * slip_array_div.c does the same in the reference).  All entries share the denominator, which allows
+ * this instead: split |det| = Ds * Dr (Ds: every prime factor < 2^16, found by trial division once
+ * per solve).  Any prime common to some N_t and Dr divides P = prod_t N_t mod Dr, so if
+ * gcd (P, Dr) = 1 -- one gcd per column, a modular product per entry -- no N_t shares a factor with
+ * Dr and gcd (N_t, det) = gcd (N_t mod Ds, Ds), a small-operand gcd.  Otherwise (rare) the entries
+ * that share a factor with gcd (P, Dr) get a full gcd.  The result is the canonical form GMP
+ * produces (positive denominator, no common factor): bit-identical to the reference's x. */
+#define SMALL_PRIME_BOUND 65536
+
+static void det_split (rational_ctx *ctx)
+{
+    mpz_init (ctx->D) ; mpz_init_set_ui (ctx->Ds, 1) ; mpz_init (ctx->Dr) ;
+    mpz_abs (ctx->D, ctx->det) ;
+    mpz_set (ctx->Dr, ctx->D) ;
+    static uint8_t *sieve = NULL ;
+    #pragma omp critical (slip_b200_sieve)
+    if (!sieve)
+    {
+        uint8_t *sv = (uint8_t *) calloc (SMALL_PRIME_BOUND, 1) ;
+        if (sv)
+        {
+            for (uint32_t i = 2 ; i * i < SMALL_PRIME_BOUND ; i++)
+                if (!sv [i]) for (uint32_t j = i * i ; j < SMALL_PRIME_BOUND ; j += i) sv [j] = 1 ;
+            sieve = sv ;
+        }
+    }
+    if (sieve && mpz_cmp_ui (ctx->Dr, 1) > 0)
+        for (uint32_t p = 2 ; p < SMALL_PRIME_BOUND ; p++)
+        {
+            if (sieve [p]) continue ;
+            while (mpz_divisible_ui_p (ctx->Dr, p))
+            {
+                mpz_divexact_ui (ctx->Dr, ctx->Dr, p) ;
+                mpz_mul_ui (ctx->Ds, ctx->Ds, p) ;
+            }
+        }
+    ctx->split_done = 1 ;
+}
+
+static void canonical_column (rational_ctx *ctx, int c, int cnt) ;
+static void rational_ctx_clear (rational_ctx *ctx) ;
+
+/* test hook (not part of the public interface; tests/test_canonical.py): x[t][0] holds numerators
+ * N_t with any denominator; on return x[t][0] = N_t / det in canonical form */
+int slip_b200_canonical_column_selftest (mpq_t **x, int32_t n, const mpz_t det)
+{
+    if (!x || n <= 0 || mpz_sgn (det) == 0) return -1 ;
+    rational_ctx ctx ;
+    memset (&ctx, 0, sizeof (ctx)) ;
+    ctx.x = x ; ctx.det = det ;
+    canonical_column (&ctx, 0, n) ;
+    rational_ctx_clear (&ctx) ;
+    return 0 ;
+}
+
+static void rational_ctx_clear (rational_ctx *ctx)
+{
+    if (ctx->split_done) { mpz_clear (ctx->D) ; mpz_clear (ctx->Ds) ; mpz_clear (ctx->Dr) ; ctx->split_done = 0 ; }
+}
+
+/* x[t][c] <- N_t / det in canonical form, N_t already in the numerators */
+static void canonical_column (rational_ctx *ctx, int c, int cnt)
+{
+    if (!ctx->split_done) det_split (ctx) ;
+    const int det_neg = mpz_sgn (ctx->det) < 0 ;
+    const int rough = mpz_cmp_ui (ctx->Dr, 1) > 0 ;
+    mpz_t G ;                    /* gcd (prod N_t mod Dr, Dr) */
+    mpz_init_set_ui (G, 1) ;
+    if (rough)
+    {
+        mpz_t P ;
+        mpz_init_set_ui (P, 1) ;
+        #pragma omp parallel if (cnt > 16)
+        {
+            mpz_t part, tmp ;
+            mpz_init_set_ui (part, 1) ; mpz_init (tmp) ;
+            #pragma omp for schedule(static) nowait
+            for (int t = 0 ; t < cnt ; t++)
+            {
+                mpz_srcptr N = mpq_numref (ctx->x [t][c]) ;
+                if (mpz_sgn (N) == 0) continue ;
+                mpz_mul (tmp, part, N) ;
+                mpz_tdiv_r (part, tmp, ctx->Dr) ;
+            }
+            #pragma omp critical (slip_b200_prod)
+            { mpz_mul (tmp, P, part) ; mpz_tdiv_r (P, tmp, ctx->Dr) ; }
+            mpz_clear (part) ; mpz_clear (tmp) ;
+        }
+        mpz_gcd (G, P, ctx->Dr) ;
+        mpz_clear (P) ;
+    }
+    const int g_trivial = mpz_cmp_ui (G, 1) == 0 ;
+    const int ds_small = mpz_fits_ulong_p (ctx->Ds) ;
+    const unsigned long ds_ul = ds_small ? mpz_get_ui (ctx->Ds) : 0 ;
+    #pragma omp parallel if (cnt > 16)
+    {
+        mpz_t g, t2 ;
+        mpz_init (g) ; mpz_init (t2) ;
+        #pragma omp for schedule(dynamic, 16)
+        for (int t = 0 ; t < cnt ; t++)
+        {
+            mpq_ptr q = ctx->x [t][c] ;
+            mpz_ptr N = mpq_numref (q), Dn = mpq_denref (q) ;
+            if (mpz_sgn (N) == 0) { mpz_set_ui (Dn, 1) ; continue ; }
+            /* smooth part */
+            if (ds_small)
+            {
+                if (ds_ul > 1) mpz_set_ui (g, mpz_gcd_ui (NULL, N, ds_ul)) ; else mpz_set_ui (g, 1) ;
+            }
+            else mpz_gcd (g, N, ctx->Ds) ;
+            /* rough part: only entries that share a factor with G can share one with Dr */
+            if (!g_trivial)
+            {
+                mpz_gcd (t2, N, G) ;
+                if (mpz_cmp_ui (t2, 1) != 0) { mpz_gcd (t2, N, ctx->Dr) ; mpz_mul (g, g, t2) ; }
+            }
+            if (mpz_cmp_ui (g, 1) == 0) mpz_set (Dn, ctx->D) ;
+            else { mpz_divexact (N, N, g) ; mpz_divexact (Dn, ctx->D, g) ; }
+            if (det_neg) mpz_neg (N, N) ;
+        }
+        mpz_clear (g) ; mpz_clear (t2) ;
+    }
+    mpz_clear (G) ;
+}
+
 
 /* Exact check of one right-hand side: sum_i A(:,q[i]) * N_i == det * b(:,c) over the integers.
  * x = N/det is then THE solution of A x = b (A is nonsingular: every pivot was nonzero), whatever
@@ -67,13 +198,17 @@ static int rational_column (void *user, int c, int cnt, int stride, const uint32
     if (ctx->A && !ctx->failed && !numerators_verify (ctx, c, cnt)) ctx->failed = 1 ;
     t_sink_verify += now_s () - tt ; tt = now_s () ;
     if (ctx->failed) return 0 ;
-    #pragma omp parallel for schedule(dynamic, 8) if (cnt > 16)
-    for (int t = 0 ; t < cnt ; t++)
-    {
-        mpq_ptr q = ctx->x [t][c] ;
-        mpz_set (mpq_denref (q), ctx->det) ;
-        mpq_canonicalize (q) ;
+    if (getenv ("SLIP_B200_CANON_GMP"))
+    {   /* the per-entry route (tests compare the two) */
+        #pragma omp parallel for schedule(dynamic, 8) if (cnt > 16)
+        for (int t = 0 ; t < cnt ; t++)
+        {
+            mpq_ptr q = ctx->x [t][c] ;
+            mpz_set (mpq_denref (q), ctx->det) ;
+            mpq_canonicalize (q) ;
+        }
     }
+    else canonical_column (ctx, c, cnt) ;
     t_sink_canon += now_s () - tt ;
     return 0 ;
 }
@@ -96,8 +231,9 @@ static SLIP_info solve_on_device (mpq_t **x, SLIP_dense *b, slip_resident *r, co
         for (int32_t i = 0 ; i < n ; i++)
             for (int32_t c = 0 ; c < nrhs ; c++) words += slip_mpz_words (b->x [i][c]) ;
         SLIP_TRY (slip_limbs_begin (&bl, (int64_t) n * nrhs, words)) ;
-        for (int32_t i = 0 ; i < n ; i++)
-            for (int32_t c = 0 ; c < nrhs ; c++) slip_limbs_put (&bl, (int64_t) i * nrhs + c, b->x [i][c]) ;
+        /* right-hand side c occupies entries c*n .. c*n+n-1 (a batch of them is one contiguous range) */
+        for (int32_t c = 0 ; c < nrhs ; c++)
+            for (int32_t i = 0 ; i < n ; i++) slip_limbs_put (&bl, (int64_t) c * n + i, b->x [i][c]) ;
     }
     {
         const int have = slipcu_factor_channels (r->dev) ;
@@ -112,9 +248,12 @@ static SLIP_info solve_on_device (mpq_t **x, SLIP_dense *b, slip_resident *r, co
             }
         }
         int32_t top = -1 ;
-        rational_ctx ctx = { x, r->det, check ? A : NULL, q, b, 0 } ;
-        SLIP_TRY (slip_from_device_status (slipcu_solve (r->dev, nrhs, bl.limbs, bl.off, bl.sign, pinv, s,
-            rational_column, &ctx, &top))) ;
+        rational_ctx ctx ;
+        memset (&ctx, 0, sizeof (ctx)) ;
+        ctx.x = x ; ctx.det = r->det ; ctx.A = check ? A : NULL ; ctx.q = q ; ctx.b = b ;
+        const int rc_dev = slipcu_solve (r->dev, nrhs, bl.limbs, bl.off, bl.sign, pinv, s, rational_column, &ctx, &top) ;
+        rational_ctx_clear (&ctx) ;
+        SLIP_TRY (slip_from_device_status (rc_dev)) ;
         if (!verified && top >= have - 2) status = SLIP_INCORRECT ;
         if (check) { slip_last_stats.verified_solves += nrhs ; if (ctx.failed) status = SLIP_B200_NEED_CHANNELS ; }
     }

@@ -610,8 +610,14 @@ __device__ __forceinline__ u32 smem_u32 (const void *p) { return (u32) __cvta_ge
 // target slots (one per entry of the L column used), shared by all channel blocks.
 // ------------------------------------------------------------------------------------------------
 #define TRI_THREADS 256       // threads of a k_trisolve CTA when a thread owns 4 channels
-#define TRI_BUFS 3            // shared-memory chunk buffers: two chunks in flight while one is consumed
-#define TRI_RING 8            // chunk descriptors kept in shared memory
+// Shared-memory chunk buffers and chunk descriptors kept in shared memory.  With thousands of
+// channels there are two CTAs per SM and hundreds per launch: three buffers (two chunks in flight
+// while one is consumed) keep HBM busy.  Sessions of few channels (4-channel blocks: LP bases whose
+// values need a few hundred bits) have a few dozen CTAs on 148 SMs, each alone on its SM and
+// paced by memory latency, and their steps are short (a chunk is often 2-4 KB): eight buffers put
+// seven chunks in flight per CTA.
+static __host__ __device__ constexpr int tri_bufs (int CH) { return CH == 4 ? 8 : 3; }
+static __host__ __device__ constexpr int tri_ring (int CH) { return CH == 4 ? 16 : 8; }
 
 // Every thread of k_trisolve owns 4 channels, so CH/4 threads share a row and a CTA covers
 // TRI_THREADS/(CH/4) rows at a time; a pipeline chunk is four such row groups (16 KB of L).
@@ -748,11 +754,12 @@ struct TriSmem
     static constexpr int L_BYTES = R * CH * 4;                   // 16 KB
     static constexpr int S_BYTES = R * 4;
     static constexpr int STAGE = (L_BYTES + S_BYTES + CH * 4 + 127) & ~127;   // L rows, targets, 1/rho_j
-    static constexpr int RING_BYTES = TRI_RING * (int) sizeof (ChunkInfo);
+    static constexpr int BUFS = tri_bufs (CH), RING = tri_ring (CH);
+    static constexpr int RING_BYTES = RING * (int) sizeof (ChunkInfo);
     static __host__ __device__ size_t x_bytes (int cnt) { return ((size_t) (cnt + 1) * CH * 4 + 127) & ~(size_t) 127; }
     static __host__ __device__ size_t total (int cnt, bool x_in_smem)
     {
-        return (x_in_smem ? x_bytes (cnt) : (size_t) 0) + RING_BYTES + (size_t) TRI_BUFS * STAGE;
+        return (x_in_smem ? x_bytes (cnt) : (size_t) 0) + RING_BYTES + (size_t) BUFS * STAGE;
     }
 };
 
@@ -867,6 +874,7 @@ __device__ __noinline__ void tri_mag_cta (const TriArgs &a, unsigned char *smem_
 {
     constexpr int RG = TRI_THREADS / (CH / 4), R = 4 * RG;
     constexpr int MSTAGE = R * 4 + R * 4 + 16;               // targets, magnitudes, rho_mag[j]
+    constexpr int TRI_BUFS = tri_bufs (CH), TRI_RING = tri_ring (CH);
     constexpr int RING_BYTES = TRI_RING * (int) sizeof (ChunkInfo);
     const int tid = threadIdx.x, cnt = a.cnt, nU = a.nU, nchunks = a.nchunks;
     const bool in_smem = (size_t) (cnt + 1) * 4 + 16 + RING_BYTES + TRI_BUFS * MSTAGE <= (size_t) a.smem_bytes;
@@ -894,7 +902,9 @@ __device__ __noinline__ void tri_mag_cta (const TriArgs &a, unsigned char *smem_
         if ((d1.y & 0x10000u) && tid == 0) cp_async4 (sb + 2 * R * 4, a.rho_mag + (int) d1.x);
     };
 
-    if (tid < 8 && (tid >> 1) < nchunks) fetch_desc (tid >> 1, tid & 1);
+    // descriptors 0 .. 2 BUFS - 3: chunk c + BUFS - 1 is issued at iteration c, when only the copy
+    // groups up to iteration c - BUFS + 1 are known to have landed
+    if (tid < 2 * (2 * TRI_BUFS - 2) && (tid >> 1) < nchunks) fetch_desc (tid >> 1, tid & 1);
     cp_async_commit ();
     cp_async_wait<0> ();
     __syncthreads ();
@@ -914,7 +924,7 @@ __device__ __noinline__ void tri_mag_cta (const TriArgs &a, unsigned char *smem_
         cp_async_wait<TRI_BUFS - 2> ();
         __syncthreads ();
         if (c + TRI_BUFS - 1 < nchunks) issue ((c + TRI_BUFS - 1) % TRI_RING, stage0 + (u32) bi * MSTAGE);
-        if (tid < 2 && c + 4 < nchunks) fetch_desc (c + 4, tid);
+        if (tid < 2 && c + 2 * TRI_BUFS - 2 < nchunks) fetch_desc (c + 2 * TRI_BUFS - 2, tid);
         cp_async_commit ();
         const unsigned char *sbp = smem_raw + vec_bytes + RING_BYTES + (size_t) bc * MSTAGE;
         const u32 meta = lds64 (ring + (u32) (c % TRI_RING) * (u32) sizeof (ChunkInfo) + 16).y;
@@ -972,7 +982,7 @@ __device__ __noinline__ void tri_mag_cta (const TriArgs &a, unsigned char *smem_
 // All threads of the CTA are consumers; every thread also copies its share of the chunk that is
 // two positions ahead in the work list with 16-byte cp.async (LDGSTS): TRI_BUFS-1 chunks are in
 // flight per CTA while one is consumed.  The chunk descriptors travel through a small ring in
-// shared memory, requested four chunks ahead in the same copy groups, so that the loop has no
+// shared memory, requested 2 BUFS - 2 chunks ahead in the same copy groups, so that the loop has no
 // global load of its own.  (A TMA bulk-copy producer was measured first: with three small bulk
 // copies per elimination step the copy engine, not HBM, set the pace -- about 1.1 us per step
 // regardless of pipeline depth; see profiles/.)  One __syncthreads per chunk both publishes the
@@ -980,10 +990,11 @@ __device__ __noinline__ void tri_mag_cta (const TriArgs &a, unsigned char *smem_
 // A thread owns CPT channels of a row: CPT = 4 gives 256-thread CTAs, CPT = 2 gives 512-thread CTAs
 // (twice the warps per SM for the same shared memory, at more instructions per element).
 template <int CH, bool XS, int CPT>
-__global__ void __launch_bounds__ (TRI_THREADS * 4 / CPT, 2) k_trisolve (TriArgs a)
+__global__ void __launch_bounds__ (TRI_THREADS * 4 / CPT, CH == 4 ? 1 : 2) k_trisolve (TriArgs a)
 {
     typedef TriSmem<CH> SM;
     typedef ChanVec<CPT> V;
+    constexpr int TRI_BUFS = SM::BUFS, TRI_RING = SM::RING;
     constexpr int NT = TRI_THREADS * 4 / CPT, TPR = CH / CPT, RG = SM::RG;
     extern __shared__ __align__ (128) unsigned char smem_raw[];
     const int tid = threadIdx.x;
@@ -1050,7 +1061,9 @@ __global__ void __launch_bounds__ (TRI_THREADS * 4 / CPT, 2) k_trisolve (TriArgs
     };
 
     // prologue: the first descriptors, then the first chunks, are requested while the vector is initialised
-    if (tid < 8 && (tid >> 1) < nchunks) fetch_desc (tid >> 1, tid & 1);
+    // descriptors 0 .. 2 BUFS - 3: chunk c + BUFS - 1 is issued at iteration c, when only the copy
+    // groups up to iteration c - BUFS + 1 are known to have landed
+    if (tid < 2 * (2 * TRI_BUFS - 2) && (tid >> 1) < nchunks) fetch_desc (tid >> 1, tid & 1);
     cp_async_commit ();
     cp_async_wait<0> ();
     __syncthreads ();
@@ -1094,7 +1107,7 @@ __global__ void __launch_bounds__ (TRI_THREADS * 4 / CPT, 2) k_trisolve (TriArgs
         cp_async_wait<TRI_BUFS - 2> ();                // this thread's copies of chunk c have landed
         __syncthreads ();                              // ... and everyone's; chunk c-1 is fully applied
         if (c + TRI_BUFS - 1 < nchunks) issue ((c + TRI_BUFS - 1) % TRI_RING, stage0 + (u32) bi * SM::STAGE);
-        if (tid < 2 && c + 4 < nchunks) fetch_desc (c + 4, tid);
+        if (tid < 2 && c + 2 * TRI_BUFS - 2 < nchunks) fetch_desc (c + 2 * TRI_BUFS - 2, tid);
         cp_async_commit ();
         const u32 sb = stage0 + (u32) bc * SM::STAGE;
         const u32 meta = lds64 (ring + (u32) (c % TRI_RING) * (u32) sizeof (ChunkInfo) + 16).y;

@@ -246,6 +246,28 @@ def roofline_of(c, peak, peak_src, t_dev=None):
             "kernel_share_of_step": (c.trisolve_ms / 1e3) / t_dev if t_dev else None}
 
 
+def exact_check_integers(lib, system, x):
+    """A x = b, exactly, over the integers: with D = lcm of the denominators of x and N = D x,
+    sum_j A_ij N_j == D b_i for every row.  Same statement as SLIP_check_solution, which does it in
+    rational arithmetic (a gcd per operation: minutes at the sizes of the Laplacian block)."""
+    from slip_lu_b200 import capi
+    n, I, J, X, b = system
+    nrhs = len(b[0])
+    for c in range(nrhs):
+        pairs = [capi.mpq_to_pair(x[r][c]) for r in range(n)]
+        D = max((d for _, d in pairs), default=1)
+        for _, d in pairs:
+            if D % d:
+                D = D * d // math.gcd(D, d)
+        N = [a * (D // d) for a, d in pairs]
+        acc = [0] * n
+        for i, j, v in zip(I, J, X):
+            acc[i] += v * N[j]
+        if any(acc[i] != D * b[i][c] for i in range(n)):
+            return False
+    return True
+
+
 def gpu_solve_system(lib, name, system, rec, repeat=2, profile=False):
     """analyze + solve_mpq of a named system (triplets); best wall time of `repeat` runs after one
     warm-up, parity of x and of the row permutation against the reference's recorded digests."""
@@ -279,7 +301,8 @@ def gpu_solve_system(lib, name, system, rec, repeat=2, profile=False):
                 out["parity"] = {"x": str(refmats.digest_mpq_mat(lib, x, n, nrhs)) == rec["digests"]["x_solve_mpq"],
                                  "pinv": refmats.digest_ints(list(pv)) == rec["digests"]["pinv"]}
             else:
-                out["parity"] = {"A x = b exact": lib.dll.SLIP_check_solution(A, x, B) == 0}
+                out["parity"] = {"A x = b exact (integer arithmetic: sum_j A_ij N_j == D b_i, D = lcm of the denominators)":
+                                 exact_check_integers(lib, system, x)}
         lib.free_mpq_mat(x, n, nrhs); lib.free_analysis(S)
     lib.free_dense(B); lib.free_sparse(A); lib.free_options(o)
     return out
@@ -527,7 +550,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-leg", default=None, help="(internal) time the unmodified reference on one named head-to-head system and print {cpu_s}")
     ap.add_argument("--extras", default="all", help="all | none | comma list of h2h,laplacian,lu,sharded,intmul")
-    ap.add_argument("--lap-grid", type=int, default=40, help="grid side of the configs[2]-family block")
+    ap.add_argument("--lap-grid", type=int, default=64, help="grid side of the configs[2]-family block")
     ap.add_argument("--batch-systems", type=int, default=512)
     ap.add_argument("--batch-n", type=int, default=500)
     ap.add_argument("--mrhs-n", type=int, default=10000)

@@ -37,8 +37,12 @@ typedef struct
     int32_t diag_vs_best;   /* cmp(|diag|, |best|): -1, 0, +1 (valid if diag_eligible) */
     int32_t bad_channel;    /* 0, or 1 + index of a channel whose prime divides an earlier pivot */
     int32_t reserved[3];
-    int32_t bound_units;    /* bound mode: proven upper bound of 64*log2 |entry| over the column; measured mode: largest measured candidate */
-    int32_t pad[3];
+    int32_t bound_units;    /* bound mode: proven upper bound of 64*log2 |entry| so far; measured mode: largest measured candidate so far (running maxima over the session) */
+    int32_t singular_col;   /* 0, or 1 + the first column whose candidates were all zero (running: the
+                               caller may skip slipcu_factor_column_wait for columns with a single
+                               candidate, whose pivot needs no search, and learns of a zero there
+                               from the next column it does wait for) */
+    int32_t pad[2];
 } slipcu_pivot_info;
 
 /* receives column k of the factorization as positional integers.  `limbs` holds `cnt` rows of
@@ -104,6 +108,10 @@ int slipcu_factor_column_launch (slipcu_factor *F, int k, int col, int cnt, int 
                                  const int32_t *rows, const int32_t *upos, int recon_channels,
                                  int scheme, int diag_slot, int spec_slot);
 int slipcu_factor_column_wait (slipcu_factor *F, slipcu_pivot_info *info);
+/* A column with exactly one candidate (cnt - nU == 1) has its pivot without a search: the caller may
+ * go straight to slipcu_factor_set_pivot (k, nU) and on to the next column without _wait; the
+ * column's reconstruction and scan still run (sizes, zero test) and report through the running
+ * fields of the next slipcu_pivot_info. */
 
 /* lookahead: the bulk part of the column that will be column k, i.e. the steps of
  * slip_REF_triangular_solve.c:150-232 with every pivot committed so far, on the pattern reachable

@@ -447,9 +447,17 @@ struct WorkCtx
     int32_t *slots = nullptr; size_t slots_cap = 0;
     StepInfo *steps = nullptr; size_t steps_cap = 0;
     ChunkInfo *chunks = nullptr; size_t chunks_cap = 0;
-    int32_t *h_packet = nullptr;             // pattern packet in mapped host memory (read by k_prep)
-    int32_t *h_packet_dev = nullptr;         // its device address
+    // pattern packets in mapped host memory (read by k_prep).  The host does not wait for every
+    // column (a column with a single candidate has its pivot before the GPU has looked at it), so
+    // the packet of the next column must not overwrite one that k_prep has not read yet: a ring
+    // of PK_RING buffers, each guarded by an event recorded behind its k_prep.
+    int32_t *h_packet = nullptr;             // PK_RING buffers of pk_stride ints
+    int32_t *h_packet_dev = nullptr;         // device address of the ring
+    size_t pk_stride = 0; int pk_next = 0, pk_cur = 0;
+    cudaEvent_t pk_ev[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+    bool pk_busy[8] = { false, false, false, false, false, false, false, false };
 };
+#define PK_RING 8
 #define SPEC_SLOTS 16
 struct SpecSlot                              // bulk part of a column that is not the current one yet
 {
@@ -510,13 +518,14 @@ struct slipcu_factor
     slipcu_pivot_info *h_info = nullptr;     // pinned
     slipcu_pivot_info *d_info = nullptr;
     size_t smem_limit = 0;
-    int keep_positional = 1, rows_are_positions = 0, x_global = 0, cur = -1;
+    int keep_positional = 1, rows_are_positions = 0, x_global = 0, cur = -1, cur_launch = 0;
     std::vector<struct TimedRange> ranges;      // profiling: event pairs not yet read
     u32 *tmp_limbs = nullptr; int32_t *tmp_nl = nullptr; int tmp_stride = 0;
     int sms = 148;
     int garner_mode = 2;
     // bound mode (see tri_mag_cta): fewer channels than the Hadamard bound, every column's size proven
     unsigned *done_ctr = nullptr;            // device counter of the fused reconstruction + scan launches
+    int32_t *run_flags = nullptr;            // device: [0] first column (k+1) without a nonzero candidate, [1] largest measured size so far
     struct { int k, slot; } pending_commit = { -1, -1 };     // pivot chosen, commit folded into the next column's first kernel
     int frac_min_s = 256;                    // approximate pivot search only from this many channels on
     int mag_on = 0;
@@ -975,7 +984,7 @@ __device__ __noinline__ void tri_mag_cta (const TriArgs &a, unsigned char *smem_
         __syncthreads ();
         atomicMax (&s_mx, mx);
         __syncthreads ();
-        if (tid == 0) *a.bound_out = s_mx;
+        if (tid == 0) atomicMax (a.bound_out, s_mx);       // running maximum over the session
     }
 }
 
@@ -1246,6 +1255,7 @@ struct ScanArgs
     const u32 *dig; size_t ds; const int32_t *topd; const int8_t *sign; const int32_t *bad;
     slipcu_pivot_info *info;          // mapped host memory
     int32_t *mag; const int32_t *cum_ub; const int32_t *bound; int measured;
+    int k; int32_t *run_flags;        // see slipcu_factor::run_flags
 };
 
 // the scan itself, by all threads of one CTA of any size (<= 512 threads)
@@ -1301,7 +1311,12 @@ __device__ __noinline__ void pivot_scan_body (const ScanArgs &a)
             info->diag_eligible = de;
             info->diag_vs_best = (de && best >= 0) ? cmp_mag (dig, ds, topd, a.diag_slot, best) : 0;
             info->bad_channel = *a.bad;
-            info->bound_units = a.measured ? s_meas : (a.bound ? *a.bound : 0);
+            // running values: the host does not look at every column (single-candidate columns go
+            // on without waiting), so what it must not miss accumulates on the device
+            if (best < 0) atomicCAS (&a.run_flags[0], 0, a.k + 1);
+            info->singular_col = a.run_flags[0];
+            if (a.measured) { atomicMax (&a.run_flags[1], s_meas); info->bound_units = a.run_flags[1]; }
+            else info->bound_units = a.bound ? *a.bound : 0;
         }
     }
 }
@@ -2120,6 +2135,7 @@ struct FracSel
     int ne, nU, mode, diag_slot, W;     // candidates (slots nU .. nU+ne-1), 0 smallest / 1 largest
     const FracKey *key; const int32_t *bad;
     slipcu_pivot_info *info;
+    int k; int32_t *run_flags;
 };
 // order of the approximate magnitudes: more leading zero words is smaller, then the key words
 __device__ __forceinline__ int frac_cmp (const FracKey &x, const FracKey &y)
@@ -2191,6 +2207,9 @@ __global__ void __launch_bounds__ (256) k_fracselect (FracSel a)
         info->diag_eligible = de;
         info->diag_vs_best = (de && best >= 0 && dr != best) ? (a.mode == 0 ? 1 : -1) : 0;
         info->bad_channel = *a.bad;
+        if (best < 0) atomicCAS (&a.run_flags[0], 0, a.k + 1);
+        info->singular_col = a.run_flags[0];
+        info->bound_units = 0;
         info->reserved[0] = s_uncertain ? 0 : 1;      // 1: the choice is proven
         info->reserved[1] = best >= 0 ? a.key[best].lead : 0;
         info->reserved[2] = a.W;
@@ -2338,6 +2357,7 @@ static void free_workctx (WorkCtx &w)
 {
     pool_free (w.pos); pool_free (w.slots); pool_free (w.steps); pool_free (w.chunks);
     if (w.h_packet) cudaFreeHost (w.h_packet);
+    for (cudaEvent_t e : w.pk_ev) if (e) cudaEventDestroy (e);
     w = WorkCtx ();
 }
 static int init_workctx (WorkCtx &w, int n, cudaStream_t st)
@@ -2345,8 +2365,10 @@ static int init_workctx (WorkCtx &w, int n, cudaStream_t st)
     w.st = st;
     CU (pool_alloc_t (&w.pos, (size_t) n * sizeof (int32_t)));
     CU (cudaMemsetAsync (w.pos, 0, (size_t) n * sizeof (int32_t), st));
-    CU (cudaHostAlloc (&w.h_packet, ((size_t) 4 * n + 8) * sizeof (int32_t), cudaHostAllocMapped));
+    w.pk_stride = ((size_t) 4 * n + 8 + 31) & ~(size_t) 31;
+    CU (cudaHostAlloc (&w.h_packet, w.pk_stride * PK_RING * sizeof (int32_t), cudaHostAllocMapped));
     CU (cudaHostGetDevicePointer ((void **) &w.h_packet_dev, w.h_packet, 0));
+    for (int i = 0; i < PK_RING; ++i) CU (cudaEventCreateWithFlags (&w.pk_ev[i], cudaEventDisableTiming));
     return SLIPCU_OK;
 }
 
@@ -2366,7 +2388,7 @@ extern "C" void slipcu_factor_free (slipcu_factor *F)
     pool_free (F->desc); pool_free (F->bad);
     pool_free (F->digbuf[0]); pool_free (F->topdbuf[0]); pool_free (F->digbuf[1]); pool_free (F->topdbuf[1]);
     pool_free (F->frackey);
-    pool_free (F->Amag); pool_free (F->rho_mag); pool_free (F->bound); pool_free (F->done_ctr);
+    pool_free (F->Amag); pool_free (F->rho_mag); pool_free (F->bound); pool_free (F->done_ctr); pool_free (F->run_flags);
     if (getenv ("SLIP_B200_TIMING") && F->frac)
         fprintf (stderr, "slipcu pivot search: %llu columns by approximate magnitudes, %llu word-count retries, %llu exact fallbacks\n",
                  (unsigned long long) F->frac_cols, (unsigned long long) F->frac_retries, (unsigned long long) F->frac_fallbacks);
@@ -2519,6 +2541,11 @@ static int session_common_init (slipcu_factor *F, int n, int channels)
     CU (cudaMemset (F->bad, 0, sizeof (int32_t)));
     CU (pool_alloc_t (&F->done_ctr, sizeof (unsigned)));
     CU (cudaMemset (F->done_ctr, 0, sizeof (unsigned)));
+    {
+        const int32_t init[2] = { 0, MAG_NEG };
+        CU (pool_alloc_t (&F->run_flags, 2 * sizeof (int32_t)));
+        CU (cudaMemcpy (F->run_flags, init, sizeof (init), cudaMemcpyHostToDevice));
+    }
     F->frac_min_s = std::max (16, env_int ("SLIP_B200_FRAC_MIN_S", 256));
     rc = init_workctx (F->mc, n, F->st);
     if (rc) return rc;
@@ -2701,7 +2728,7 @@ static int prepare_steps (slipcu_factor *F, WorkCtx &w, int cnt, int nU, const i
         // (main stream only) commits the pivot that is still pending
         PrepArgs pa; memset (&pa, 0, sizeof (pa));
         pa.cnt = cnt; pa.pk_ints = packet_ints; pa.copy_blocks = (packet_ints + 255) / 256;
-        pa.h_packet = w.h_packet_dev; pa.d_packet = const_cast<int32_t *> (rows); pa.pos = w.pos;
+        pa.h_packet = w.h_packet_dev + (size_t) w.pk_cur * w.pk_stride; pa.d_packet = const_cast<int32_t *> (rows); pa.pos = w.pos;
         int blocks = pa.copy_blocks;
         if (with_commit && F->pending_commit.k >= 0)
         {
@@ -2715,6 +2742,8 @@ static int prepare_steps (slipcu_factor *F, WorkCtx &w, int cnt, int nU, const i
         CU (cudaGetLastError ());
         if (debug_check ("k_prep", w.st)) return fail (SLIPCU_CUDA_ERROR, "k_prep", "debug");
         if (pa.has_commit && !F->rows_are_positions) CU (cudaEventRecord (F->ev_commit, w.st));
+        CU (cudaEventRecord (w.pk_ev[w.pk_cur], w.st));
+        w.pk_busy[w.pk_cur] = true;
     }
     else
     {
@@ -2872,7 +2901,7 @@ static int run_frac (slipcu_factor *F, const HostCol &hc, int cnt, int nU, int s
     }
     FracSel q;
     q.ne = ne; q.nU = nU; q.mode = mode; q.diag_slot = diag_slot; q.W = W;
-    q.key = F->frackey; q.bad = F->bad; q.info = F->d_info;
+    q.key = F->frackey; q.bad = F->bad; q.info = F->d_info; q.k = F->cur_launch; q.run_flags = F->run_flags;
     {
         ScopedTimer tm (F, &g_other_ms);
         k_fracselect<<<1, 256, 0, F->st>>> (q);
@@ -2913,6 +2942,7 @@ static ScanArgs make_scan_args (slipcu_factor *F, const HostCol &hc, int cnt, in
     a.dig = F->dig; a.ds = (size_t) F->S + 4; a.topd = F->topd; a.sign = hc.sign; a.bad = F->bad; a.info = F->d_info;
     a.mag = F->mag_on ? hc.mag : nullptr; a.cum_ub = F->tab->cum_ub; a.bound = F->mag_on ? F->bound : nullptr;
     a.measured = F->measured;
+    a.k = F->cur_launch; a.run_flags = F->run_flags;
     return a;
 }
 
@@ -2932,7 +2962,10 @@ static int upload_pattern (slipcu_factor *F, WorkCtx &w, int cnt, int nU, const 
                            int first_step, int32_t **dev_rows, int *nchunks_out)
 {
     const int CH = F->CH;
-    int32_t *staging = w.h_packet;
+    const int pk = w.pk_next;
+    w.pk_next = (w.pk_next + 1) % PK_RING; w.pk_cur = pk;
+    if (w.pk_busy[pk]) { CU (cudaEventSynchronize (w.pk_ev[pk])); w.pk_busy[pk] = false; }
+    int32_t *staging = w.h_packet + (size_t) pk * w.pk_stride;
     memcpy (staging, rows, (size_t) cnt * sizeof (int32_t));
     if (nU) memcpy (staging + cnt, upos, (size_t) nU * sizeof (int32_t));
     int32_t *uoff = staging + cnt + nU;
@@ -3133,7 +3166,9 @@ extern "C" int slipcu_factor_column_launch (slipcu_factor *F, int k, int col, in
     }
     const int mode = (scheme == 2) ? 2 : ((scheme == 4 || scheme == 5) ? 1 : 0);
     F->frac_col = -1;
-    if (F->frac && !F->keep_positional && mode != 2 && s >= F->frac_min_s)
+    F->cur_launch = k;
+    const bool single = (cnt - nU == 1);             // no search needed: exact zero test and size only
+    if (F->frac && !F->keep_positional && mode != 2 && s >= F->frac_min_s && !single)
     {   // magnitudes only: no digits unless the choice turns out to be too close to call
         const int W = std::min (std::max (F->fracW, 8), frac_word_cap (s));
         rc = run_frac (F, hc, cnt, nU, s, mode, diag_slot, W);
@@ -3236,7 +3271,8 @@ extern "C" int slipcu_factor_column_wait (slipcu_factor *F, slipcu_pivot_info *i
         info->reserved[0] = info->reserved[1] = info->reserved[2] = 0;
     }
     g_hw[5] += wall_s () - tw;
-    if (info->bad_channel) return fail (SLIPCU_BAD_PRIME, "slipcu_factor_column", "channel prime divides a pivot");
+    // a zero pivot of a column the host did not wait for also raises the bad-channel flag: singular first
+    if (info->bad_channel && !info->singular_col) return fail (SLIPCU_BAD_PRIME, "slipcu_factor_column", "channel prime divides a pivot");
     return SLIPCU_OK;
 }
 

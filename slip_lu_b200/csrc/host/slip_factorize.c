@@ -271,6 +271,8 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
     const int timing = getenv ("SLIP_B200_TIMING") != NULL ;
     const char *prune_env = getenv ("SLIP_B200_PRUNE") ;
     const int use_pruning = !(prune_env && prune_env [0] == '0') ;      /* symmetric pruning of the reach (default on) */
+    const char *single_env = getenv ("SLIP_B200_SINGLE") ;
+    const int use_single = !(single_env && single_env [0] == '0') ;      /* no round trip for single-candidate columns */
     double t_sym = 0, t_dev = 0, t_piv = 0, t_begin = 0, t0 = now_s (), tt ;
     double work_updates = 0, work_limbmul = 0 ;
     double *cumbits_at = (double *) SLIP_calloc ((size_t) n, sizeof (double)) ;
@@ -355,6 +357,8 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
         { const char *lk = getenv ("SLIP_B200_LOOKAHEAD") ; if (lk && *lk) look = atoi (lk) ; }
         double look_min = 1e6 ;          /* element updates (rows x channels) below which a bulk part is not launched */
         { const char *lm = getenv ("SLIP_B200_LOOK_MIN") ; if (lm && *lm) look_min = atof (lm) ; }
+        int look_steps = 32 ;            /* elimination steps from which a bulk part is launched whatever its volume */
+        { const char *ls = getenv ("SLIP_B200_LOOK_STEPS") ; if (ls && *ls) look_steps = atoi (ls) ; }
         if (look < 0) look = 0 ;
         if (look > SLIPCU_SPEC_SLOTS - 1) look = SLIPCU_SPEC_SLOTS - 1 ;
         const int D = look > 1 ? look : 1 ;
@@ -438,7 +442,10 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
                     double bulk = 0 ;
                     for (int32_t u = 0 ; u < snU ; u++)
                         bulk += (double) (P.ptr [supos [u] + 1] - P.ptr [supos [u]] - P.nU [supos [u]]) ;
-                    if (snU > 0 && bulk * (double) S_dev >= look_min)
+                    /* ... or a long chain: every step costs the column ~0.3 us of latency whatever
+                       its size (barrier, yhat_j, barrier), and a chain run beside the column in
+                       flight is off the path to the pivot */
+                    if (snU > 0 && (bulk * (double) S_dev >= look_min || snU >= look_steps))
                     {
                         rc = slipcu_factor_spec_launch (dev, c % ring_size, c, S->q [c], f->cnt, snU, spat, supos) ;
                         if (rc == SLIPCU_BAD_PRIME) { retry = 1 ; break ; }
@@ -460,11 +467,29 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
             memcpy (P.rows + P.used, pat, (size_t) cnt * sizeof (int32_t)) ;
             memcpy (P.prows + P.used, pat, (size_t) cnt * sizeof (int32_t)) ;
             t_sym += now_s () - tt ; tt = now_s () ;
+            /* a single candidate is the pivot whatever its value (zero: singular, reported by
+               the device with the next column that is waited for): no round trip for this column */
+            const int single = use_single && (cnt - nU == 1) && k < n - 1 ;
+            if (single)
+            {
+                const int32_t prow1 = pat [nU] ;
+                const int32_t oldpos = pinv [prow1], displaced = row_at [k] ;
+                row_at [k] = prow1 ; row_at [oldpos] = displaced ;
+                pinv [prow1] = k ; pinv [displaced] = oldpos ;
+                SLIP_TRY (slip_from_device_status (slipcu_factor_set_pivot (dev, k, nU))) ;
+                P.used += cnt ;
+                P.ptr [k + 1] = P.used ; P.nU [k] = nU ; P.piv [k] = nU ;
+                P.pend [k] = cnt - nU ; P.pruned [k] = 0 ;
+                if (use_pruning) prune_columns (&P, k, prow1, nU, upos, pinv) ;
+                t_piv += now_s () - tt ;
+                continue ;
+            }
             slipcu_pivot_info info ;
             rc = slipcu_factor_column_wait (dev, &info) ;
             if (rc == SLIPCU_BAD_PRIME) { retry = 1 ; break ; }
             SLIP_TRY (slip_from_device_status (rc)) ;
             t_dev += now_s () - tt ; tt = now_s () ;
+            if (info.singular_col) { status = SLIP_SINGULAR ; goto cleanup ; }
             if (bound_mode && s_had > S_dev && info.bound_units > cap_units)
             {   /* the column is not proven to fit the channels carried: start over with more */
                 grow = (int) ceil (((double) info.bound_units / 64.0 + 4.0) / SLIP_B200_CHANNEL_BITS) ;

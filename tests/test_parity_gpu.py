@@ -71,6 +71,21 @@ def test_singular_and_edge_inputs(gpu):
     with pytest.raises(capi.SlipError) as e:
         gpu.factorize(A, S, o)
     assert e.value.code == capi.SLIP_SINGULAR
+    # the zero sits in a column with a single candidate, which the host does not wait for: the
+    # device reports it with the next column; same answer through SLIP_solve_mpq and with the
+    # no-wait path switched off
+    B = gpu.dense_from_rows([[1], [2], [3]])
+    for single in ("1", "0"):
+        os.environ["SLIP_B200_SINGLE"] = single
+        try:
+            with pytest.raises(capi.SlipError) as e:
+                gpu.solve_mpq(A, S, B, o)
+            assert e.value.code == capi.SLIP_SINGULAR
+            with pytest.raises(capi.SlipError) as e:
+                gpu.factorize(A, S, o)
+            assert e.value.code == capi.SLIP_SINGULAR
+        finally:
+            del os.environ["SLIP_B200_SINGLE"]
     # structurally singular: empty row
     A = gpu.sparse_from_csc(3, [0, 1, 2, 3], [0, 0, 2], [1, 2, 3])
     S = gpu.analyze(A, o)
@@ -238,6 +253,7 @@ def test_channel_prime_dividing_a_pivot_is_retired(gpu, oracle):
 @pytest.mark.parametrize("env", [{"SLIP_B200_CH": "4"}, {"SLIP_B200_CH": "8"}, {"SLIP_B200_CH": "4", "SLIP_B200_X_GLOBAL": "1"},
                                  {"SLIP_B200_CH": "4", "SLIP_B200_CPT": "2"}, {"SLIP_B200_CANON_GMP": "1"},
                                  {"SLIP_B200_LOOKAHEAD": "0"}, {"SLIP_B200_LOOKAHEAD": "3", "SLIP_B200_LOOK_MIN": "0"},
+                                 {"SLIP_B200_SINGLE": "0"}, {"SLIP_B200_LOOKAHEAD": "6", "SLIP_B200_LOOK_STEPS": "1"},
                                  {"SLIP_B200_CH": "16"}, {"SLIP_B200_CH": "32"}, {"SLIP_B200_X_GLOBAL": "1"},
                                  {"SLIP_B200_CH": "32", "SLIP_B200_X_GLOBAL": "1"}, {"SLIP_B200_GARNER": "1"},
                                  {"SLIP_B200_GARNER": "0"}, {"SLIP_B200_CPT": "2"}, {"SLIP_B200_CPT": "4"},

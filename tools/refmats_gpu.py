@@ -37,7 +37,7 @@ def main():
     if names == ["all"]:
         names = list(recs)
     for name in names:
-        n, I, J, X, b = refmats.load(name)
+        n, I, J, X, b = refmats.system(name)
         rec = recs[name]
         A = lib.sparse_from_triplets(n, I, J, X)
         B = lib.dense_from_rows(b)

@@ -1450,6 +1450,115 @@ __global__ void __launch_bounds__ (128) k_garner (GarnerArgs a)
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_garner_small: the same digits for sessions of few channels (s <= 128).  With a few dozen
+// channels the reconstruction is nothing but the latency of its serial chain, and k_garner pays a
+// global load of C inside every step of it (~30 us per column at s = 64, the largest item on the
+// path to the pivot of an LP basis).  Here the CTA first copies the s x s corner of C into shared
+// memory (coalesced, one round trip), then one warp per entry runs the chain out of registers and
+// shared memory: lane l owns the digits l, l+32, l+64, l+96; step i = the owner finishes d_i, a
+// shuffle hands it round, every lane adds d_i C[i][t] to its later digits.
+// ------------------------------------------------------------------------------------------------
+#define GS_MAX 128
+__global__ void __launch_bounds__ (128) k_garner_small (GarnerArgs a)
+{
+    extern __shared__ u32 gs_c[];                       // [s][s]  C[u][t], u < t
+    const int lane = threadIdx.x & 31;
+    const int s = a.s, S = a.S, CH = a.CH;
+    const unsigned full = 0xffffffffu;
+    for (int i = threadIdx.x; i < s * s; i += blockDim.x)
+    {
+        const int u = i / s, t = i - u * s;
+        gs_c[i] = (u < t) ? a.C[(size_t) u * S + t] : 0u;
+    }
+    __syncthreads ();
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w < a.ne)
+    {
+    const int e = a.e0 + w;
+    u32 *dg = a.dig + (size_t) e * a.dstride;
+    u32 pt[4], nit[4], ib[4], v[4], dgt[4];
+    u64 T[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+    {
+        const int t = lane + 32 * j, tt = t < s ? t : s - 1;
+        pt[j] = a.p[tt]; nit[j] = a.ninv[tt]; ib[j] = a.invB[tt];
+        v[j] = mont_redc (a.base[((size_t) (tt / CH) * a.cnt + e) * CH + (tt % CH)], pt[j], nit[j]);
+        T[j] = 0; dgt[j] = 0;
+    }
+#pragma unroll
+    for (int jo = 0; jo < 4; ++jo)
+    {
+        if (32 * jo >= s) break;
+        const int iend = min (32, s - 32 * jo);
+        for (int il = 0; il < iend; ++il)
+        {
+            const int i = 32 * jo + il;
+            u32 di = 0;
+            if (lane == il)
+            {
+                const u32 acc = lazy_redc (T[jo], pt[jo], nit[jo]);
+                const u32 diff = v[jo] >= acc ? v[jo] - acc : v[jo] + pt[jo] - acc;
+                di = mont_mul (diff, ib[jo], pt[jo], nit[jo]);
+                dgt[jo] = di;
+            }
+            di = __shfl_sync (full, di, il);
+            const u32 *crow = gs_c + i * s;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+            {
+                const int t = lane + 32 * j;
+                if (j >= jo && t > i && t < s) lazy_mac (T[j], di, crow[t], pt[j]);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const int t = lane + 32 * j; if (t < s) dg[t] = dgt[j]; }
+    __syncwarp ();
+    // sign: x is negative iff x mod M > (M-1)/2, whose digits are (p_t - 1)/2
+    bool neg = false;
+    for (int t0 = ((s - 1) / 32) * 32; t0 >= 0; t0 -= 32)
+    {
+        const int t = t0 + lane;
+        u32 d = 0, h = 0;
+        if (t < s) { d = dg[t]; h = (a.p[t] - 1) >> 1; }
+        const unsigned ne = __ballot_sync (full, d != h);
+        if (ne)
+        {
+            const int top = 31 - __clz (ne);
+            neg = __shfl_sync (full, (int) (d > h), top) != 0;
+            break;
+        }
+    }
+    if (neg)
+    {   // |x| = M - (x mod M): complement every digit, then add one
+        for (int t = lane; t < s; t += 32) dg[t] = a.p[t] - 1 - dg[t];
+        __syncwarp ();
+        if (lane == 0)
+        {
+            for (int t = 0; t < s; ++t)
+            {
+                u32 d = dg[t] + 1;
+                if (d == a.p[t]) dg[t] = 0; else { dg[t] = d; break; }
+            }
+        }
+        __syncwarp ();
+    }
+    int top = -1;
+    for (int t0 = ((s - 1) / 32) * 32; t0 >= 0; t0 -= 32)
+    {
+        const int t = t0 + lane;
+        const u32 d = (t < s) ? dg[t] : 0u;
+        const unsigned nzm = __ballot_sync (full, d != 0);
+        if (nzm) { top = t0 + 31 - __clz (nzm); break; }
+    }
+    for (int t = s + lane; t < ((s + 3) & ~3); t += 32) dg[t] = 0;
+    if (lane == 0) { a.topd[e] = top; a.sign[e] = top < 0 ? 0 : (neg ? -1 : 1); }
+    }
+    if (a.scan_on) scan_by_last_block (a.sc, a.done_ctr);
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_garner_tiled: same result as k_garner, organised like a blocked triangular solve so that the
 // table C is read once per E entries and the long dependency chain is one CTA-wide step per 32
 // digits.  A CTA of W warps reconstructs E entries.  Digit block b (positions 32b..32b+31) is owned
@@ -2513,6 +2622,7 @@ static int session_common_init (slipcu_factor *F, int n, int channels)
     F->frac = env_int ("SLIP_B200_FRAC", 1);
     F->frac_margin = std::max (0, env_int ("SLIP_B200_FRAC_MARGIN", 12));      // 0 in tests: forces the add-words retry
     F->frac_verify = env_int ("SLIP_B200_FRAC_VERIFY", 0);
+    CU (cudaFuncSetAttribute (k_garner_small, cudaFuncAttributeMaxDynamicSharedMemorySize, GS_MAX * GS_MAX * (int) sizeof (u32)));
     CU (cudaFuncSetAttribute (k_garner_flow<1, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     CU (cudaFuncSetAttribute (k_garner_flow<2, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     CU (cudaFuncSetAttribute (k_garner_flow<3, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
@@ -2793,7 +2903,9 @@ static int run_garner (slipcu_factor *F, const u32 *base, int region_cnt, int e0
     g.base = base; g.dig = F->dig; g.dstride = (size_t) F->S + 4; g.topd = F->topd; g.sign = sign;
     g.p = T.p; g.ninv = T.ninv; g.C = T.C; g.invB = T.invB;
     ScopedTimer tm (F, &g_recon_ms);
-    if (F->garner_mode == 0 || s < 64)
+    if (s <= GS_MAX && F->garner_mode >= 2)
+        k_garner_small<<<(ne + 3) / 4, 128, (size_t) s * s * sizeof (u32), F->wst>>> (g);
+    else if (F->garner_mode == 0 || s < 64)
         k_garner<<<(ne + 3) / 4, 128, 0, F->wst>>> (g);
     else
     {

@@ -189,6 +189,8 @@ typedef struct
     double   device_ms;           /* CUDA-event time from "A resident in HBM" to "solution numerators
                                      reconstructed in HBM", accumulated over slipcu_solve calls */
     double   other_ms;            /* symbolic pre-pass + pivot scan kernels (profiling mode) */
+    double   trisolve_union_ms;   /* time during which at least one k_trisolve launch was running (launches
+                                     on the lookahead streams overlap: trisolve_ms counts shared time twice) */
 } slipcu_counters;
 void slipcu_get_counters (slipcu_counters *out);
 void slipcu_reset_counters (void);

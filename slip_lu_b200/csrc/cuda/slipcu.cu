@@ -395,6 +395,34 @@ static void pool_free (void *ptr)
 }
 template <typename T> static cudaError_t pool_alloc_t (T **out, size_t bytes) { return pool_alloc ((void **) out, bytes); }
 
+// pinned host buffers are expensive to create (cudaHostAlloc runs at ~0.3 s per GB, and both it and
+// cudaFreeHost serialise against every other thread's work on the device): kept per process.
+// Blocks of at least 4 KB, power-of-two sizes.
+static std::mutex g_hpool_mutex;
+static std::multimap<size_t, void *> g_hpool_free;
+static std::map<void *, size_t> g_hpool_size;
+static cudaError_t host_pool_alloc (void **out, size_t bytes)
+{
+    size_t want = 4096;
+    while (want < bytes) want <<= 1;
+    {
+        std::lock_guard<std::mutex> lk (g_hpool_mutex);
+        auto it = g_hpool_free.find (want);
+        if (it != g_hpool_free.end ()) { *out = it->second; g_hpool_free.erase (it); return cudaSuccess; }
+    }
+    cudaError_t e = cudaHostAlloc (out, want, cudaHostAllocPortable | cudaHostAllocMapped);
+    if (e == cudaSuccess) { std::lock_guard<std::mutex> lk (g_hpool_mutex); g_hpool_size[*out] = want; }
+    return e;
+}
+static void host_pool_free (void *ptr)
+{
+    if (!ptr) return;
+    std::lock_guard<std::mutex> lk (g_hpool_mutex);
+    auto it = g_hpool_size.find (ptr);
+    if (it == g_hpool_size.end ()) { cudaFreeHost (ptr); return; }
+    g_hpool_free.insert ({it->second, ptr});
+}
+
 // ------------------------------------------------------------------------------------------------
 // device memory arena (bump allocation in large chunks; columns never straddle a chunk)
 // ------------------------------------------------------------------------------------------------
@@ -542,6 +570,11 @@ struct slipcu_factor
 struct TimedRange { cudaEvent_t a, b; double *acc; };
 static std::vector<cudaEvent_t> g_event_pool;
 static std::mutex g_event_mutex;
+// Launches of k_trisolve may overlap (lookahead streams): the sum of their durations counts shared
+// time twice, so the intervals themselves are kept, relative to a base event, and the bench reads
+// the length of their union (time during which at least one k_trisolve was running).
+static cudaEvent_t g_base_ev = nullptr;
+static std::vector<std::pair<float, float>> g_tri_intervals;
 static cudaEvent_t take_event ()
 {
     {
@@ -578,7 +611,16 @@ static void flush_timers (slipcu_factor *F)
         if (cudaEventQuery (r.b) == cudaErrorNotReady) { later.push_back (r); continue; }   // side stream still busy
         float ms = 0;
         if (cudaEventElapsedTime (&ms, r.a, r.b) == cudaSuccess) *r.acc += ms; else cudaGetLastError ();
-        g_event_pool.push_back (r.a); g_event_pool.push_back (r.b);
+        if (r.acc == &g_tri_ms)
+        {
+            if (!g_base_ev) { g_base_ev = r.a; r.a = nullptr; }          // first launch after a reset: kept as the base
+            float t0 = 0, t1 = 0;
+            if (cudaEventElapsedTime (&t0, g_base_ev, r.a ? r.a : g_base_ev) == cudaSuccess
+                && cudaEventElapsedTime (&t1, g_base_ev, r.b) == cudaSuccess) g_tri_intervals.push_back ({t0, t1});
+            else cudaGetLastError ();
+        }
+        if (r.a) g_event_pool.push_back (r.a);
+        g_event_pool.push_back (r.b);
     }
     F->ranges.swap (later);
 }
@@ -2465,7 +2507,7 @@ static int env_int (const char *name, int dflt)
 static void free_workctx (WorkCtx &w)
 {
     pool_free (w.pos); pool_free (w.slots); pool_free (w.steps); pool_free (w.chunks);
-    if (w.h_packet) cudaFreeHost (w.h_packet);
+    host_pool_free (w.h_packet);
     for (cudaEvent_t e : w.pk_ev) if (e) cudaEventDestroy (e);
     w = WorkCtx ();
 }
@@ -2475,7 +2517,7 @@ static int init_workctx (WorkCtx &w, int n, cudaStream_t st)
     CU (pool_alloc_t (&w.pos, (size_t) n * sizeof (int32_t)));
     CU (cudaMemsetAsync (w.pos, 0, (size_t) n * sizeof (int32_t), st));
     w.pk_stride = ((size_t) 4 * n + 8 + 31) & ~(size_t) 31;
-    CU (cudaHostAlloc (&w.h_packet, w.pk_stride * PK_RING * sizeof (int32_t), cudaHostAllocMapped));
+    CU (host_pool_alloc ((void **) &w.h_packet, w.pk_stride * PK_RING * sizeof (int32_t)));
     CU (cudaHostGetDevicePointer ((void **) &w.h_packet_dev, w.h_packet, 0));
     for (int i = 0; i < PK_RING; ++i) CU (cudaEventCreateWithFlags (&w.pk_ev[i], cudaEventDisableTiming));
     return SLIPCU_OK;
@@ -2513,7 +2555,7 @@ extern "C" void slipcu_factor_free (slipcu_factor *F)
         if (sl.w.st) cudaStreamDestroy (sl.w.st);
     }
     if (F->ev_commit) cudaEventDestroy (F->ev_commit);
-    if (F->h_info) cudaFreeHost (F->h_info);
+    host_pool_free (F->h_info);
     if (F->ev) cudaEventDestroy (F->ev);
     if (F->ev0) cudaEventDestroy (F->ev0);
     if (F->ev1) cudaEventDestroy (F->ev1);
@@ -2622,6 +2664,14 @@ static int session_common_init (slipcu_factor *F, int n, int channels)
     F->frac = env_int ("SLIP_B200_FRAC", 1);
     F->frac_margin = std::max (0, env_int ("SLIP_B200_FRAC_MARGIN", 12));      // 0 in tests: forces the add-words retry
     F->frac_verify = env_int ("SLIP_B200_FRAC_VERIFY", 0);
+    static std::mutex attr_mutex;
+    static std::vector<int> attr_done;
+    bool configure = false;
+    {
+        std::lock_guard<std::mutex> lk (attr_mutex);
+        if (std::find (attr_done.begin (), attr_done.end (), F->device) == attr_done.end ()) { attr_done.push_back (F->device); configure = true; }
+    }
+    if (configure) {
     CU (cudaFuncSetAttribute (k_garner_small, cudaFuncAttributeMaxDynamicSharedMemorySize, GS_MAX * GS_MAX * (int) sizeof (u32)));
     CU (cudaFuncSetAttribute (k_garner_flow<1, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     CU (cudaFuncSetAttribute (k_garner_flow<2, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
@@ -2629,6 +2679,7 @@ static int session_common_init (slipcu_factor *F, int n, int channels)
     CU (cudaFuncSetAttribute (k_garner_flow<4, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     CU (cudaFuncSetAttribute (k_garner_flow<5, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     CU (cudaFuncSetAttribute (k_garner_flow<6, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    }
     F->garner_e = env_int ("SLIP_B200_GARNER_E", 0);       // 0: chosen per launch
     int smem_optin = 0;
     cudaDeviceGetAttribute (&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, F->device);
@@ -2636,8 +2687,11 @@ static int session_common_init (slipcu_factor *F, int n, int channels)
     F->cpt = env_int ("SLIP_B200_CPT", 4);             // channels per thread of k_trisolve: 4 or 2
     if (F->cpt != 2 && F->cpt != 4) F->cpt = 4;
     F->threads = TRI_THREADS * 4 / F->cpt;
-    rc = tri_configure (smem_optin - 1024);      // static shared memory of the kernels (a few words) comes out of the same budget
-    if (rc) return rc;
+    if (configure)
+    {
+        rc = tri_configure (smem_optin - 1024);      // static shared memory of the kernels (a few words) comes out of the same budget
+        if (rc) return rc;
+    }
 
     CU (cudaStreamCreateWithFlags (&F->st, cudaStreamNonBlocking));
     F->wst = F->st;
@@ -2662,7 +2716,8 @@ static int session_common_init (slipcu_factor *F, int n, int channels)
     CU (cudaEventCreateWithFlags (&F->ev_commit, cudaEventDisableTiming));
     // the scan result goes straight into mapped host memory (a 48-byte store over PCIe instead of a
     // copy-engine operation per column); the event behind the kernel publishes it to the host
-    CU (cudaHostAlloc (&F->h_info, sizeof (slipcu_pivot_info), cudaHostAllocMapped));
+    CU (host_pool_alloc ((void **) &F->h_info, sizeof (slipcu_pivot_info)));
+    memset (F->h_info, 0, sizeof (slipcu_pivot_info));
     CU (cudaHostGetDevicePointer ((void **) &F->d_info, F->h_info, 0));
     F->cols.resize (n);
     return SLIPCU_OK;
@@ -3560,44 +3615,19 @@ extern "C" int slipcu_factor_download (slipcu_factor *F, slipcu_column_sink sink
     size_t maxw = 0; int maxc = 0;
     for (auto &hc : F->cols) { maxw = std::max (maxw, (size_t) hc.cnt * hc.stride); maxc = std::max (maxc, hc.cnt); }
     u32 *h_limbs = nullptr; int32_t *h_nl = nullptr; int8_t *h_sign = nullptr;
-    CU (cudaHostAlloc (&h_limbs, std::max<size_t> (maxw, 1) * sizeof (u32), cudaHostAllocDefault));
-    CU (cudaHostAlloc (&h_nl, (size_t) std::max (maxc, 1) * sizeof (int32_t), cudaHostAllocDefault));
-    CU (cudaHostAlloc (&h_sign, (size_t) std::max (maxc, 1), cudaHostAllocDefault));
+    CU (host_pool_alloc ((void **) &h_limbs, std::max<size_t> (maxw, 1) * sizeof (u32)));
+    CU (host_pool_alloc ((void **) &h_nl, (size_t) std::max (maxc, 1) * sizeof (int32_t)));
+    CU (host_pool_alloc ((void **) &h_sign, (size_t) std::max (maxc, 1)));
     int rc = SLIPCU_OK;
     for (int k = 0; k < F->n && rc == SLIPCU_OK; ++k)
         rc = stream_column (F, k, F->cols[k], sink, user, h_limbs, h_nl, h_sign);
-    cudaFreeHost (h_limbs); cudaFreeHost (h_nl); cudaFreeHost (h_sign);
+    host_pool_free (h_limbs); host_pool_free (h_nl); host_pool_free (h_sign);
     return rc;
 }
 
 // ------------------------------------------------------------------------------------------------
 // solve
 // ------------------------------------------------------------------------------------------------
-// pinned host buffers are expensive to create (cudaHostAlloc runs at ~0.3 s per GB): kept per process
-static std::mutex g_hpool_mutex;
-static std::multimap<size_t, void *> g_hpool_free;
-static std::map<void *, size_t> g_hpool_size;
-static cudaError_t host_pool_alloc (void **out, size_t bytes)
-{
-    const size_t want = pool_round (std::max<size_t> (bytes, 1));
-    {
-        std::lock_guard<std::mutex> lk (g_hpool_mutex);
-        auto it = g_hpool_free.find (want);
-        if (it != g_hpool_free.end ()) { *out = it->second; g_hpool_free.erase (it); return cudaSuccess; }
-    }
-    cudaError_t e = cudaHostAlloc (out, want, cudaHostAllocPortable);
-    if (e == cudaSuccess) { std::lock_guard<std::mutex> lk (g_hpool_mutex); g_hpool_size[*out] = want; }
-    return e;
-}
-static void host_pool_free (void *ptr)
-{
-    if (!ptr) return;
-    std::lock_guard<std::mutex> lk (g_hpool_mutex);
-    auto it = g_hpool_size.find (ptr);
-    if (it == g_hpool_size.end ()) { cudaFreeHost (ptr); return; }
-    g_hpool_free.insert ({it->second, ptr});
-}
-
 // b: nrhs right-hand sides of n entries, entry (row i, right-hand side c) at index c * n + i.
 //
 // The right-hand sides go through in batches.  A batch is one launch of every kernel: the residues
@@ -3804,11 +3834,27 @@ extern "C" void slipcu_get_counters (slipcu_counters *o)
     o->trisolve_ms = g_tri_ms; o->trisolve_bytes = g_tri_bytes; o->trisolve_modmul = g_tri_modmul;
     o->recon_ms = g_recon_ms; o->recon_mac = g_recon_mac;
     o->h2d_bytes = g_h2d_bytes; o->d2h_bytes = g_d2h_bytes; o->device_ms = g_device_ms; o->other_ms = g_other_ms;
+    {   // union of the k_trisolve intervals
+        std::lock_guard<std::mutex> lk (g_event_mutex);
+        std::vector<std::pair<float, float>> iv = g_tri_intervals;
+        std::sort (iv.begin (), iv.end ());
+        double total = 0; float lo = 0, hi = -1;
+        for (auto &p : iv)
+        {
+            if (hi < lo || p.first > hi) { if (hi >= lo) total += hi - lo; lo = p.first; hi = p.second; }
+            else hi = std::max (hi, p.second);
+        }
+        if (hi >= lo) total += hi - lo;
+        o->trisolve_union_ms = total;
+    }
 }
 extern "C" void slipcu_reset_counters (void)
 {
     g_launches = 0; g_tri_launches = 0;
     g_tri_ms = g_tri_bytes = g_tri_modmul = g_recon_ms = g_recon_mac = 0;
     g_h2d_bytes = g_d2h_bytes = g_device_ms = g_other_ms = 0;
+    std::lock_guard<std::mutex> lk (g_event_mutex);
+    g_tri_intervals.clear ();
+    if (g_base_ev) { g_event_pool.push_back (g_base_ev); g_base_ev = nullptr; }
 }
 extern "C" void slipcu_set_profiling (int enabled) { g_profiling = enabled; }

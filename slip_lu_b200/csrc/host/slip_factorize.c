@@ -351,13 +351,16 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
         const int S_dev = slipcu_factor_channels (dev) ;
         const int cap_units = slipcu_factor_capacity_units (dev) ;
         /* lookahead depth: with few channels one column cannot fill the GPU, so the bulk parts of
-           the next columns run beside it; with thousands of channels a column is HBM-bound on
-           its own and the second launch per column costs more than it hides */
-        int look = S_dev <= 512 ? 6 : 0 ;
+           the next columns run beside it (NSR8K: 1.5 s without, 0.5 s with six).  With thousands of
+           channels a column is HBM-bound on its own, but the GPU idles between a column and its pivot
+           (pivot search, host turn): the bulk parts of the next two columns, queued on their own
+           streams, fill those gaps -- 2.13 -> 1.87 s on the device at n = 2000 (round 1 measured
+           this slower; its second launch per column was three times as expensive) */
+        int look = S_dev <= 512 ? 6 : 2 ;
         { const char *lk = getenv ("SLIP_B200_LOOKAHEAD") ; if (lk && *lk) look = atoi (lk) ; }
         double look_min = 1e6 ;          /* element updates (rows x channels) below which a bulk part is not launched */
         { const char *lm = getenv ("SLIP_B200_LOOK_MIN") ; if (lm && *lm) look_min = atof (lm) ; }
-        int look_steps = 32 ;            /* elimination steps from which a bulk part is launched whatever its volume */
+        int look_steps = 1 << 30 ;       /* elimination steps from which a bulk part is launched whatever its volume (off: measured neutral to negative) */
         { const char *ls = getenv ("SLIP_B200_LOOK_STEPS") ; if (ls && *ls) look_steps = atoi (ls) ; }
         if (look < 0) look = 0 ;
         if (look > SLIPCU_SPEC_SLOTS - 1) look = SLIPCU_SPEC_SLOTS - 1 ;

@@ -61,6 +61,9 @@ int  slipcu_set_device (int device);
 /* diagnostics: measured 32-bit integer-multiply peaks of the device (register-resident chains of
  * IMAD.WIDE, IMAD and IMAD.HI), the denominators of bench.py's roofline.int_mul */
 int  slipcu_measure_imad_peak (double *wide_per_s, double *lo_per_s, double *hi_per_s);
+/* ... and of the modular multiply-subtract of k_trisolve itself (w <- w + l*y mod p, Montgomery:
+ * IMAD.WIDE + IMAD + IMAD.HI + three integer ALU operations) on registers only */
+int  slipcu_measure_modmul_peak (double *modmul_per_s);
 
 /* -- factorization session -------------------------------------------------------------------
  * slipcu_factor_begin: uploads A (CSC; values as limb strings) and reduces it into `channels`

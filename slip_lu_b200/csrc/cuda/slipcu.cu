@@ -2454,7 +2454,12 @@ __global__ void __launch_bounds__ (256) k_imad_peak (int iters, u32 *out)
             // every multiplicand depends on the previous result, so nothing is loop-invariant
             if (KIND == 0) w[i] = (u64) (u32) w[i] * b + w[i];
             else if (KIND == 1) a[i] = a[i] * b + a[(i + 1) & 7];
-            else a[i] = __umulhi (a[i], b) + 0x9e3779b9u;
+            else if (KIND == 2) a[i] = __umulhi (a[i], b) + 0x9e3779b9u;
+            else
+            {   // KIND 3: the update of k_trisolve itself, w <- w + l * ny mod p (Montgomery), on registers
+                const u32 p = 0x7fffffffu - 18u, ninv = b | 1u;      // (any odd word: only the instruction mix matters)
+                a[i] = add_mod (a[i] & 0x3fffffffu, mont_mul (a[i], b >> 2, p, ninv) & 0x3fffffffu, p);
+            }
         }
     }
     u64 t = 0;
@@ -2463,6 +2468,7 @@ __global__ void __launch_bounds__ (256) k_imad_peak (int iters, u32 *out)
     if ((u32) t == 0xdeadbeefu) out[0] = (u32) (t >> 32);    // practically never true: keeps the chains alive
 }
 
+extern "C" int slipcu_measure_modmul_peak (double *modmul_per_s);
 extern "C" int slipcu_measure_imad_peak (double *wide_per_s, double *lo_per_s, double *hi_per_s)
 {
     int dev = 0, sms = 148;
@@ -2494,6 +2500,36 @@ extern "C" int slipcu_measure_imad_peak (double *wide_per_s, double *lo_per_s, d
         }
         if (res[kind]) *res[kind] = best;
     }
+    cudaEventDestroy (e0); cudaEventDestroy (e1); cudaFree (out);
+    return SLIPCU_OK;
+}
+
+// peak rate of the modular multiply-subtract of k_trisolve when nothing but registers is involved
+extern "C" int slipcu_measure_modmul_peak (double *modmul_per_s)
+{
+    int dev = 0, sms = 148;
+    if (g_device.load () >= 0) CU (cudaSetDevice (g_device.load ()));
+    CU (cudaGetDevice (&dev));
+    cudaDeviceGetAttribute (&sms, cudaDevAttrMultiProcessorCount, dev);
+    u32 *out = nullptr;
+    CU (cudaMalloc (&out, 4));
+    cudaEvent_t e0, e1;
+    CU (cudaEventCreate (&e0)); CU (cudaEventCreate (&e1));
+    const int grid = sms * 8, iters = 1 << 13;
+    const double ops = (double) grid * 256.0 * (double) iters * 8.0;
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep)
+    {
+        CU (cudaEventRecord (e0, 0));
+        k_imad_peak<3><<<grid, 256>>> (iters, out);
+        CU (cudaEventRecord (e1, 0));
+        CU (cudaEventSynchronize (e1));
+        float ms = 0;
+        CU (cudaEventElapsedTime (&ms, e0, e1));
+        if (rep > 0 && ms > 0) best = std::max (best, ops / (ms * 1e-3));
+        g_launches++;
+    }
+    if (modmul_per_s) *modmul_per_s = best;
     cudaEventDestroy (e0); cudaEventDestroy (e1); cudaFree (out);
     return SLIPCU_OK;
 }

@@ -332,7 +332,7 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
 
     for (int attempt = 0 ; ; attempt++)
     {
-        int retry = 0, grow = 0, tight = 0 ;
+        int retry = 0, grow = 0, tight = 0, predict = 0 ;
         /* fewer channels than the a-priori bound: sessions whose factors go to the host prove every
            column's size (mode 1); SLIP_solve_* sessions verify their result exactly at the end, so
            measured sizes are enough there (mode 2, see slip_b200_device.h).  SLIP_B200_BOUND=proven
@@ -344,6 +344,7 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
             bound_mode = (want_host_factors || (bm && bm [0] == 'p')) ? 1 : 2 ;
         }
         SLIP_TRY (patterns_init (&P, n, (int64_t) S->lnz + S->unz)) ;
+        const double t_attempt = now_s () ;
         tt = now_s () ;
         SLIP_TRY (slip_from_device_status (slipcu_factor_begin (&dev, n, nz, A->p, A->i, Al.limbs, Al.off,
             Al.sign, channels, want_host_factors, bound_mode))) ;
@@ -500,6 +501,14 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
                    close to the bound (random wide entries: ratio ~0.97) no smaller channel count
                    will do, and the next attempt goes straight to the a-priori count */
                 tight = cum_bits > 64.0 && (double) info.bound_units / 64.0 >= 0.75 * cum_bits ;
+                /* the sizes seen so far, extrapolated along the Hadamard prefix to the last column
+                   (they grow roughly in proportion to it), with half as much again on top */
+                if (cum_bits > 1.0)
+                    predict = (int) ceil (1.5 * ((double) info.bound_units / 64.0) * ((total_bits + extra) / cum_bits)
+                                          / SLIP_B200_CHANNEL_BITS) + SLIP_B200_SPARE_CHANNELS ;
+                if (timing)
+                    fprintf (stderr, "slip_lu_b200 timing: column %d of %d does not fit %d channels (size %.0f bits, Hadamard prefix %.0f of %.0f bits, %.3fs into the attempt)\n",
+                        k, n, S_dev, (double) info.bound_units / 64.0, cum_bits, total_bits, now_s () - t_attempt) ;
                 retry = 1 ; break ;
             }
             int32_t slot = -1 ;
@@ -545,9 +554,12 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
             if (res) { slip_resident_free (res) ; res = NULL ; }
             patterns_free (&P) ;
             if (grow)
-            {   /* bound mode ran out of room: four times the channels, at least what the failed
-                   column asked for, at most the Hadamard count (which needs no proof) */
-                int next = 4 * channels ;
+            {   /* ran out of room: the extrapolated need (lp n=10000: 32 -> 288 channels in one step
+                   where quadrupling took 32 -> 128 -> 480 and 40 % of the time in aborted attempts),
+                   at least twice the channels and what the failed column asked for, at most the
+                   Hadamard count (which needs no proof) */
+                int next = 2 * channels ;
+                if (next < predict) next = predict ;
                 if (next < grow + grow / 4) next = grow + grow / 4 ;
                 next = (next + 31) & ~31 ;
                 channels = (!tight && 2 * next <= channels_full) ? next : channels_full ;

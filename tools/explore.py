@@ -17,7 +17,7 @@ class Counters(C.Structure):
     _fields_ = [("launches", C.c_uint64), ("trisolve_launches", C.c_uint64), ("trisolve_ms", C.c_double),
                 ("trisolve_bytes", C.c_double), ("trisolve_modmul", C.c_double), ("recon_ms", C.c_double),
                 ("recon_mac", C.c_double), ("h2d_bytes", C.c_double), ("d2h_bytes", C.c_double),
-                ("device_ms", C.c_double), ("other_ms", C.c_double)]
+                ("device_ms", C.c_double), ("other_ms", C.c_double), ("trisolve_union_ms", C.c_double)]
 
 
 def main():

@@ -114,7 +114,10 @@ int slipcu_factor_column_wait (slipcu_factor *F, slipcu_pivot_info *info);
 /* A column with exactly one candidate (cnt - nU == 1) has its pivot without a search: the caller may
  * go straight to slipcu_factor_set_pivot (k, nU) and on to the next column without _wait; the
  * column's reconstruction and scan still run (sizes, zero test) and report through the running
- * fields of the next slipcu_pivot_info. */
+ * fields of the next slipcu_pivot_info.  A caller that does so for every such column except the
+ * last says so with slipcu_factor_nowait_singles (F, 1): sessions that need neither sizes nor
+ * digits then replace the reconstruction of those columns by a zero test of the residues. */
+void slipcu_factor_nowait_singles (slipcu_factor *F, int on);
 
 /* lookahead: the bulk part of the column that will be column k, i.e. the steps of
  * slip_REF_triangular_solve.c:150-232 with every pivot committed so far, on the pattern reachable

@@ -556,6 +556,7 @@ struct slipcu_factor
     int32_t *run_flags = nullptr;            // device: [0] first column (k+1) without a nonzero candidate, [1] largest measured size so far
     struct { int k, slot; } pending_commit = { -1, -1 };     // pivot chosen, commit folded into the next column's first kernel
     int frac_min_s = 256;                    // approximate pivot search only from this many channels on
+    int nowait_singles = 0;                  // the caller does not wait for single-candidate columns (slipcu_factor_nowait_singles)
     int mag_on = 0;
     int measured = 0;                        // measured mode: sizes of the candidates are measured, the result is verified exactly by the caller
     int32_t *Amag = nullptr;                 // [nz] 64 log2 |a| of the input entries, rounded up
@@ -2387,6 +2388,22 @@ __device__ __forceinline__ void pivot_commit_body (const CommitArgs &a, int c)
 }
 __global__ void k_pivot_commit (CommitArgs a) { pivot_commit_body (a, blockIdx.x * blockDim.x + threadIdx.x); }
 
+// Zero test of a single candidate from its residues (the value is below the product of the channel
+// primes, so it is zero iff every residue is): all a column with one candidate needs when neither
+// sizes nor digits are wanted.
+__global__ void __launch_bounds__ (256) k_zero_test (int k, int S, int CH, int cnt, int slot, const u32 *base, int32_t *run_flags)
+{
+    __shared__ int s_nz;
+    if (threadIdx.x == 0) s_nz = 0;
+    __syncthreads ();
+    int nz = 0;
+    for (int c = threadIdx.x; c < S; c += blockDim.x)
+        nz |= base[((size_t) (c / CH) * cnt + slot) * CH + (c % CH)] != 0;
+    if (nz) s_nz = 1;
+    __syncthreads ();
+    if (threadIdx.x == 0 && !s_nz) atomicCAS (&run_flags[0], 0, k + 1);
+}
+
 // First kernel of a column: brings the pattern packet over from mapped host memory (no copy-engine
 // operation), fills the row -> slot map, and commits the PREVIOUS column's pivot in its spare
 // blocks (the host decided it a moment ago; nothing of this kernel depends on it).
@@ -3371,7 +3388,16 @@ extern "C" int slipcu_factor_column_launch (slipcu_factor *F, int k, int col, in
     F->frac_col = -1;
     F->cur_launch = k;
     const bool single = (cnt - nU == 1);             // no search needed: exact zero test and size only
-    if (F->frac && !F->keep_positional && mode != 2 && s >= F->frac_min_s && !single)
+    if (single && F->nowait_singles && k < F->n - 1 && !F->keep_positional && !F->measured && !F->mag_on)
+    {   // one candidate, a-priori channel count, factors stay on the device: its pivot needs a zero
+        // test and nothing else (the caller does not wait for this column)
+        k_zero_test<<<1, 256, 0, F->st>>> (k, S, CH, cnt, nU, hc.base, F->run_flags);
+        g_launches++;
+        CU (cudaGetLastError ());
+        if (debug_check ("k_zero_test", F->st)) return fail (SLIPCU_CUDA_ERROR, "k_zero_test", "debug");
+        g_hw[3] += wall_s () - tw; tw = wall_s ();
+    }
+    else if (F->frac && !F->keep_positional && mode != 2 && s >= F->frac_min_s && !single)
     {   // magnitudes only: no digits unless the choice turns out to be too close to call
         const int W = std::min (std::max (F->fracW, 8), frac_word_cap (s));
         rc = run_frac (F, hc, cnt, nU, s, mode, diag_slot, W);
@@ -3414,6 +3440,8 @@ extern "C" int slipcu_factor_column_launch (slipcu_factor *F, int k, int col, in
     F->cur = k;
     return SLIPCU_OK;
 }
+
+extern "C" void slipcu_factor_nowait_singles (slipcu_factor *F, int on) { if (F) F->nowait_singles = on ? 1 : 0; }
 
 extern "C" int slipcu_factor_column_wait (slipcu_factor *F, slipcu_pivot_info *info)
 {

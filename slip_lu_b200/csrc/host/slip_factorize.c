@@ -349,6 +349,7 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
         SLIP_TRY (slip_from_device_status (slipcu_factor_begin (&dev, n, nz, A->p, A->i, Al.limbs, Al.off,
             Al.sign, channels, want_host_factors, bound_mode))) ;
         t_begin += now_s () - tt ;
+        slipcu_factor_nowait_singles (dev, use_single) ;
         const int S_dev = slipcu_factor_channels (dev) ;
         const int cap_units = slipcu_factor_capacity_units (dev) ;
         /* lookahead depth: with few channels one column cannot fill the GPU, so the bulk parts of

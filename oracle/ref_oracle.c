@@ -19,8 +19,10 @@
  * PARITY PIN: the reference ships no golden output vectors for this path (its demos only
  * print timings and run SLIP_check_solution), so this oracle is pinned against outputs of
  * the reference itself: oracle/_ref/libslip_ref.so (the unmodified reference compiled by
- * oracle/Makefile) in tests/test_oracle.py, and against the committed fixtures
- * tests/golden/*.json generated from that library by tests/golden/make_golden.py.
+ * oracle/Makefile) in tests/test_oracle.py, against the committed fixtures
+ * tests/golden/*.json generated from that library by tests/golden/make_golden.py, and at size
+ * against the reference's digests of L, U, rhos and pinv on its own ExampleMats / BasisLIB
+ * matrices (tests/golden/refmats.json, tests/test_refmats.py).
  *
  * The REF update is written once in its closed form
  *     x_i <- ( rho_j * rho_{j-1}/rho_{h_i} * x_i  -  l_ij * x_j ) / rho_{j-1},   rho_{-1} = 1

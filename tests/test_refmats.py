@@ -25,11 +25,8 @@ def have(name):
 # systems the CPU oracle finishes in seconds
 ORACLE_CASES = ["prob159", "basislib/25fv47", "basislib/bas1lp", "basislib/neos7", "basislib/qiu",
                 "basislib/rosen2", "basislib/route", "basislib/stair"]
-# through SLIP_solve_mpq on the GPU (every family, every regime of the channel sizing)
-SOLVE_CASES = ["NSR8K", "prob159", "synth/rand240", "synth/rand600", "synth/lap24", "synth/lap32",
-               "basislib/gen2", "basislib/rat7a", "basislib/newman2", "basislib/aa01", "basislib/cr42",
-               "basislib/ch", "basislib/complex", "basislib/t0331-4l", "basislib/delf000", "basislib/nug07",
-               "basislib/pds-20.pre", "basislib/model4", "basislib/ulevimin", "basislib/grow22"]
+# through SLIP_solve_mpq on the GPU: every recorded system (61 of the reference's own + 4 synthetic at size)
+SOLVE_CASES = sorted(RECS)
 # through SLIP_LU_factorize + SLIP_LU_solve on the GPU (L and U come to the host as mpz_t)
 FACTOR_CASES = ["NSR8K", "prob159", "synth/rand240", "synth/rand600", "synth/lap24",
                 "basislib/rat7a", "basislib/newman2", "basislib/aa01", "basislib/cr42", "basislib/complex",

@@ -546,6 +546,19 @@ def sharded_block(lib, args, rank, world, barrier, reduce_max, reduce_sum):
                         "columns_checked_exactly": int(tot[0]), "columns_exact": int(tot[1]),
                         "verification": "SLIP_check_solution on the first and last column of every rank; bound-mode results are also verified inside the library (A N = det b)"}
     lib.free_analysis(S); lib.free_sparse(A); lib.free_options(o)
+    if world == 1 and not args.no_cpu_baseline:
+        leg = cpu_leg_subprocess(["--cpu-leg", f"sharded:{seed}", "--batch-n", str(nb), "--mrhs-n", str(n3), "--mrhs-rhs", str(nrhs)])
+        if "batch_sample_s" in leg:
+            cpu_batch = leg["batch_sample_s"] * nsys / leg["batch_sample_systems"]
+            cpu_mrhs = leg["mrhs_factorize_s"] + leg["mrhs_solve_4_rhs_s"] * nrhs / 4.0
+            out["batch"]["cpu"] = {"kind": leg["kind"], "sample": "the first 64 of the systems, one after the other",
+                                   "sample_seconds": leg["batch_sample_s"], "whole_job_seconds_extrapolated": cpu_batch,
+                                   "ratio_vs_gpu": cpu_batch / out["batch"]["seconds"]}
+            out["multi_rhs"]["cpu"] = {"kind": leg["kind"], "sample": "SLIP_LU_analyze + SLIP_LU_factorize in full, SLIP_LU_solve on 4 of the right-hand sides",
+                                       "factorize_seconds": leg["mrhs_factorize_s"], "solve_4_rhs_seconds": leg["mrhs_solve_4_rhs_s"],
+                                       "whole_job_seconds_extrapolated": cpu_mrhs, "ratio_vs_gpu": cpu_mrhs / out["multi_rhs"]["seconds"]}
+        else:
+            out["cpu_error"] = leg.get("error")
     return out
 
 
@@ -610,6 +623,43 @@ def main():
         ref = reference_lib()
         if ref is None:
             emit({"error": "oracle/_ref/libslip_ref.so is not built"})
+            return
+        if args.cpu_leg.startswith("sharded:"):
+            # bounded samples of the two sharded jobs on the host: 64 of the configs[4] systems, and the
+            # configs[3] factorization with 4 of its right-hand sides (seed of the matrix after the colon)
+            from slip_lu_b200 import capi, synth
+            t_batch = 0.0
+            done = 0
+            for g in range(64):
+                n, cp, ri, vals, b = synth.lp_basis(args.batch_n, seed=5000 + g, nrhs=1)
+                A = ref.sparse_from_csc(n, cp, ri, vals); B = ref.dense_from_rows(b); o = ref.default_options()
+                t0 = time.perf_counter()                       # the interface calls only, as in the GPU leg
+                S = ref.analyze(A, o)
+                try:
+                    x = ref.solve_mpq(A, S, B, o)
+                    t_batch += time.perf_counter() - t0
+                    ref.free_mpq_mat(x, n, 1)
+                    done += 1
+                except capi.SlipError:
+                    t_batch += time.perf_counter() - t0
+                ref.free_analysis(S); ref.free_dense(B); ref.free_sparse(A); ref.free_options(o)
+            seed = int(args.cpu_leg.split(":")[1])
+            n, cp, ri, vals, _ = synth.lp_basis(args.mrhs_n, seed=seed, nrhs=1)
+            import numpy as np
+            ball = np.random.default_rng(1234).integers(-(1 << 20), 1 << 20, size=(n, args.mrhs_rhs), dtype=np.int32)
+            ball[ball == 0] = 1
+            A = ref.sparse_from_csc(n, cp, ri, vals); o = ref.default_options()
+            B = ref.dense_from_rows([[int(v) for v in ball[r, :4]] for r in range(n)])
+            t0 = time.perf_counter()
+            S = ref.analyze(A, o)
+            L, U, rhos, pinv = ref.factorize(A, S, o)
+            t_fac = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            x = ref.lu_solve(B, rhos, L, U, pinv)
+            t_sol = time.perf_counter() - t0
+            emit({"kind": "unmodified reference (oracle/_ref), 1 thread, this box, own process",
+                  "batch_sample_systems": 64, "batch_sample_s": t_batch, "batch_sample_solved": done,
+                  "mrhs_factorize_s": t_fac, "mrhs_solve_4_rhs_s": t_sol})
             return
         emit({"cpu_s": cpu_solve_system(ref, refmats.system(args.cpu_leg)), "workload": args.cpu_leg,
               "kind": "unmodified reference (oracle/_ref), 1 thread, this box, own process"})

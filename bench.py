@@ -796,18 +796,22 @@ def main():
     }
 
     if "intmul" in extras and rank == 0:
-        w, l, h, m = C.c_double(), C.c_double(), C.c_double(), C.c_double()
-        if lib.dll.slipcu_measure_imad_peak(C.byref(w), C.byref(l), C.byref(h)) == 0 and w.value > 0 \
-                and lib.dll.slipcu_measure_modmul_peak(C.byref(m)) == 0 and m.value > 0:
+        pk = (C.c_double * 8)()
+        if lib.dll.slipcu_measure_int_peaks(pk) == 0 and pk[7] > 0:
             mm = out["roofline"]["modmul_per_s"] or 0.0
+            sms = 148
+            mhz = float(clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965)
+            peak = pk[7] * sms * mhz * 1e6          # modular multiply-subtracts/s at the clock of the timed region
             out["roofline"]["int_mul"] = {
                 "what": "k_trisolve's modular multiply-subtracts per second against the rate of the same operation on registers only",
                 "unit": "modular multiply-subtracts/s (each: IMAD.WIDE + IMAD + IMAD.HI + 3 integer ALU operations)",
-                "achieved": mm, "peak": m.value, "frac": mm / m.value,
-                "imad_per_s": 3.0 * mm,
-                "peak_imad_wide": w.value, "peak_imad": l.value, "peak_imad_hi": h.value,
-                "peak_source": "measured live: register-resident chains, 8 per thread, 8 CTAs x 256 threads per SM "
-                               "(slipcu_measure_modmul_peak / slipcu_measure_imad_peak); IMAD.WIDE and IMAD.HI issue at half the rate of IMAD"}
+                "achieved": mm, "peak": peak, "frac": mm / peak if peak else None,
+                "peak_per_sm_cycle": {"modmul": pk[7], "imad_wide": pk[4], "imad": pk[5], "imad_hi": pk[6]},
+                "peak_as_run_per_s": {"modmul": pk[3], "imad_wide": pk[0], "imad": pk[1], "imad_hi": pk[2]},
+                "sm_mhz_used": mhz, "imad_per_s": 3.0 * mm,
+                "peak_source": "measured live (slipcu_measure_int_peaks): register-resident chains, 8 per thread, 8 CTAs x 256 threads per SM, "
+                               "operations per SM cycle from clock64 inside the kernel x 148 SMs x the SM clock sampled during the timed region "
+                               "(the microbenchmark itself runs power-capped at a lower clock: peak_as_run_per_s)"}
 
     block_s = {}
 

@@ -64,6 +64,10 @@ int  slipcu_measure_imad_peak (double *wide_per_s, double *lo_per_s, double *hi_
 /* ... and of the modular multiply-subtract of k_trisolve itself (w <- w + l*y mod p, Montgomery:
  * IMAD.WIDE + IMAD + IMAD.HI + three integer ALU operations) on registers only */
 int  slipcu_measure_modmul_peak (double *modmul_per_s);
+/* all four at once: out[0..3] operations per second as run, out[4..7] operations per SM clock cycle
+ * (clock64 inside the kernels: independent of the clock the GPU holds under this power-hungry load),
+ * for IMAD.WIDE, IMAD, IMAD.HI, modular multiply-subtract */
+int  slipcu_measure_int_peaks (double *out8);
 
 /* -- factorization session -------------------------------------------------------------------
  * slipcu_factor_begin: uploads A (CSC; values as limb strings) and reduces it into `channels`
@@ -200,7 +204,10 @@ typedef struct
 } slipcu_counters;
 void slipcu_get_counters (slipcu_counters *out);
 void slipcu_reset_counters (void);
-void slipcu_set_profiling (int enabled);   /* 1: bracket kernels with CUDA events (adds syncs) */
+void slipcu_set_profiling (int enabled);
+/* device blocks and pinned host buffers of finished sessions are cached per process (cudaMalloc and
+ * cudaHostAlloc cost milliseconds and serialise the device); this hands every cached one back */
+void slipcu_release_cached_memory (void);   /* 1: bracket kernels with CUDA events (adds syncs) */
 
 #ifdef __cplusplus
 }

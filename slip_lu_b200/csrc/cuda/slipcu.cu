@@ -392,7 +392,13 @@ static void pool_free (void *ptr)
     if (it == g_pool_size.end ()) { cudaFree (ptr); return; }
     g_pool_free.insert ({it->second, ptr});
     g_pool_cached += it->second.second;
+    // cached blocks are bounded: beyond the cap (SLIP_B200_POOL_CAP_MB, default 64 GB, about a third
+    // of the device) everything cached goes back to the driver
+    static const size_t cap = (size_t) [] { const char *v = getenv ("SLIP_B200_POOL_CAP_MB"); return (v && *v) ? atoll (v) : 65536ll; } () << 20;
+    if (g_pool_cached > cap) pool_trim_locked ();
 }
+// returns every cached device block and pinned host buffer to the driver (SLIP_finalize)
+extern "C" void slipcu_release_cached_memory (void);
 template <typename T> static cudaError_t pool_alloc_t (T **out, size_t bytes) { return pool_alloc ((void **) out, bytes); }
 
 // pinned host buffers are expensive to create (cudaHostAlloc runs at ~0.3 s per GB, and both it and
@@ -2463,6 +2469,8 @@ __global__ void __launch_bounds__ (256) k_imad_peak (int iters, u32 *out)
     u64 w[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { a[i] = (threadIdx.x + 1u) * 2654435761u + i; w[i] = a[i]; }
+    __syncthreads ();
+    const long long c0 = clock64 ();
     for (int it = 0; it < iters; ++it)
     {
 #pragma unroll
@@ -2474,81 +2482,85 @@ __global__ void __launch_bounds__ (256) k_imad_peak (int iters, u32 *out)
             else if (KIND == 2) a[i] = __umulhi (a[i], b) + 0x9e3779b9u;
             else
             {   // KIND 3: the update of k_trisolve itself, w <- w + l * ny mod p (Montgomery), on registers
-                const u32 p = 0x7fffffffu - 18u, ninv = b | 1u;      // (any odd word: only the instruction mix matters)
-                a[i] = add_mod (a[i] & 0x3fffffffu, mont_mul (a[i], b >> 2, p, ninv) & 0x3fffffffu, p);
+                // (operands are not kept reduced: only the instruction mix matters here)
+                const u32 p = 0x7fffffffu - 18u, ninv = b | 1u;
+                a[i] = add_mod (a[i], mont_mul (a[i], b, p, ninv), p);
             }
         }
     }
+    const long long c1 = clock64 ();
     u64 t = 0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += w[i] + a[i];
     if ((u32) t == 0xdeadbeefu) out[0] = (u32) (t >> 32);    // practically never true: keeps the chains alive
+    if (threadIdx.x == 0) out[1 + blockIdx.x] = (u32) (c1 - c0);          // SM cycles of this CTA's loop
 }
 
-extern "C" int slipcu_measure_modmul_peak (double *modmul_per_s);
-extern "C" int slipcu_measure_imad_peak (double *wide_per_s, double *lo_per_s, double *hi_per_s)
+// Runs one kind: returns operations per second (wall) and per SM clock cycle (all 8 CTAs of an SM run
+// side by side for the same number of cycles, so the per-cycle rate does not depend on the clock the
+// GPU happens to hold under this -- power-hungry -- load).
+static int run_imad_kind (int kind, double *per_s, double *per_sm_cycle)
 {
     int dev = 0, sms = 148;
     if (g_device.load () >= 0) CU (cudaSetDevice (g_device.load ()));
     CU (cudaGetDevice (&dev));
     cudaDeviceGetAttribute (&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int per_sm = 8, grid = sms * per_sm, iters = 1 << 13;
     u32 *out = nullptr;
-    CU (cudaMalloc (&out, 4));
+    CU (cudaMalloc (&out, (size_t) (grid + 1) * sizeof (u32)));
     cudaEvent_t e0, e1;
     CU (cudaEventCreate (&e0)); CU (cudaEventCreate (&e1));
-    const int grid = sms * 8, iters = 1 << 14;
     const double ops = (double) grid * 256.0 * (double) iters * 8.0;
-    double *res[3] = { wide_per_s, lo_per_s, hi_per_s };
-    for (int kind = 0; kind < 3; ++kind)
-    {
-        double best = 0;
-        for (int rep = 0; rep < 4; ++rep)
-        {
-            CU (cudaEventRecord (e0, 0));
-            if (kind == 0) k_imad_peak<0><<<grid, 256>>> (iters, out);
-            else if (kind == 1) k_imad_peak<1><<<grid, 256>>> (iters, out);
-            else k_imad_peak<2><<<grid, 256>>> (iters, out);
-            CU (cudaEventRecord (e1, 0));
-            CU (cudaEventSynchronize (e1));
-            float ms = 0;
-            CU (cudaEventElapsedTime (&ms, e0, e1));
-            if (rep > 0 && ms > 0) best = std::max (best, ops / (ms * 1e-3));
-            g_launches++;
-        }
-        if (res[kind]) *res[kind] = best;
-    }
-    cudaEventDestroy (e0); cudaEventDestroy (e1); cudaFree (out);
-    return SLIPCU_OK;
-}
-
-// peak rate of the modular multiply-subtract of k_trisolve when nothing but registers is involved
-extern "C" int slipcu_measure_modmul_peak (double *modmul_per_s)
-{
-    int dev = 0, sms = 148;
-    if (g_device.load () >= 0) CU (cudaSetDevice (g_device.load ()));
-    CU (cudaGetDevice (&dev));
-    cudaDeviceGetAttribute (&sms, cudaDevAttrMultiProcessorCount, dev);
-    u32 *out = nullptr;
-    CU (cudaMalloc (&out, 4));
-    cudaEvent_t e0, e1;
-    CU (cudaEventCreate (&e0)); CU (cudaEventCreate (&e1));
-    const int grid = sms * 8, iters = 1 << 13;
-    const double ops = (double) grid * 256.0 * (double) iters * 8.0;
-    double best = 0;
+    double best = 0, best_cyc = 0;
+    std::vector<u32> cyc (grid + 1);
     for (int rep = 0; rep < 4; ++rep)
     {
         CU (cudaEventRecord (e0, 0));
-        k_imad_peak<3><<<grid, 256>>> (iters, out);
+        if (kind == 0) k_imad_peak<0><<<grid, 256>>> (iters, out);
+        else if (kind == 1) k_imad_peak<1><<<grid, 256>>> (iters, out);
+        else if (kind == 2) k_imad_peak<2><<<grid, 256>>> (iters, out);
+        else k_imad_peak<3><<<grid, 256>>> (iters, out);
         CU (cudaEventRecord (e1, 0));
         CU (cudaEventSynchronize (e1));
         float ms = 0;
         CU (cudaEventElapsedTime (&ms, e0, e1));
-        if (rep > 0 && ms > 0) best = std::max (best, ops / (ms * 1e-3));
         g_launches++;
+        if (rep == 0 || ms <= 0) continue;
+        CU (cudaMemcpy (cyc.data (), out, (size_t) (grid + 1) * sizeof (u32), cudaMemcpyDeviceToHost));
+        double mean = 0;
+        for (int i = 1; i <= grid; ++i) mean += cyc[i];
+        mean /= grid;
+        const double rate = ops / (ms * 1e-3), pc = (double) per_sm * 256.0 * iters * 8.0 / mean;
+        if (rate > best) best = rate;
+        if (pc > best_cyc) best_cyc = pc;
     }
-    if (modmul_per_s) *modmul_per_s = best;
+    if (per_s) *per_s = best;
+    if (per_sm_cycle) *per_sm_cycle = best_cyc;
     cudaEventDestroy (e0); cudaEventDestroy (e1); cudaFree (out);
     return SLIPCU_OK;
+}
+
+// out[0..3] = operations per second, out[4..7] = operations per SM clock cycle, for
+// IMAD.WIDE, IMAD, IMAD.HI and the modular multiply-subtract of k_trisolve
+extern "C" int slipcu_measure_int_peaks (double *out8)
+{
+    if (!out8) return fail (SLIPCU_BAD_INPUT, "slipcu_measure_int_peaks", "bad argument");
+    for (int k = 0; k < 4; ++k) { int rc = run_imad_kind (k, &out8[k], &out8[4 + k]); if (rc) return rc; }
+    return SLIPCU_OK;
+}
+extern "C" int slipcu_measure_imad_peak (double *wide_per_s, double *lo_per_s, double *hi_per_s)
+{
+    double o[8];
+    int rc = slipcu_measure_int_peaks (o);
+    if (rc) return rc;
+    if (wide_per_s) *wide_per_s = o[0];
+    if (lo_per_s) *lo_per_s = o[1];
+    if (hi_per_s) *hi_per_s = o[2];
+    return SLIPCU_OK;
+}
+extern "C" int slipcu_measure_modmul_peak (double *modmul_per_s)
+{
+    return run_imad_kind (3, modmul_per_s, nullptr);
 }
 
 static int env_int (const char *name, int dflt)
@@ -3922,3 +3934,11 @@ extern "C" void slipcu_reset_counters (void)
     if (g_base_ev) { g_event_pool.push_back (g_base_ev); g_base_ev = nullptr; }
 }
 extern "C" void slipcu_set_profiling (int enabled) { g_profiling = enabled; }
+
+extern "C" void slipcu_release_cached_memory (void)
+{
+    { std::lock_guard<std::mutex> lk (g_pool_mutex); pool_trim_locked (); }
+    std::lock_guard<std::mutex> lk (g_hpool_mutex);
+    for (auto &kv : g_hpool_free) { cudaFreeHost (kv.second); g_hpool_size.erase (kv.second); }
+    g_hpool_free.clear ();
+}

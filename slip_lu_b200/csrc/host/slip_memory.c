@@ -36,6 +36,7 @@ void SLIP_initialize_expert (void *(*MyMalloc) (size_t), void *(*MyRealloc) (voi
 void SLIP_finalize (void)
 {
     slip_resident_drop_all () ;       /* GPU-resident factors of objects the caller never deleted */
+    slipcu_release_cached_memory () ; /* cached device blocks and pinned buffers back to the driver */
     mpfr_free_cache () ;
 }
 

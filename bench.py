@@ -796,18 +796,20 @@ def main():
     }
 
     if "intmul" in extras and rank == 0:
-        pk = (C.c_double * 8)()
-        if lib.dll.slipcu_measure_int_peaks(pk) == 0 and pk[7] > 0:
+        pk = (C.c_double * 10)()
+        if lib.dll.slipcu_measure_int_peaks(pk) == 0 and pk[9] > 0:
             mm = out["roofline"]["modmul_per_s"] or 0.0
             sms = 148
             mhz = float(clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965)
-            peak = pk[7] * sms * mhz * 1e6          # modular multiply-subtracts/s at the clock of the timed region
+            peak = pk[9] * sms * mhz * 1e6          # modular multiply-subtracts/s at the clock of the timed region
             out["roofline"]["int_mul"] = {
                 "what": "k_trisolve's modular multiply-subtracts per second against the rate of the same operation on registers only",
-                "unit": "modular multiply-subtracts/s (each: IMAD.WIDE + IMAD + IMAD.HI + 3 integer ALU operations)",
+                "unit": "modular multiply-subtracts/s (each: a Shoup product by the step's fixed multiplier, IMAD.HI + 2 IMAD, + 3 integer ALU operations)",
                 "achieved": mm, "peak": peak, "frac": mm / peak if peak else None,
-                "peak_per_sm_cycle": {"modmul": pk[7], "imad_wide": pk[4], "imad": pk[5], "imad_hi": pk[6]},
-                "peak_as_run_per_s": {"modmul": pk[3], "imad_wide": pk[0], "imad": pk[1], "imad_hi": pk[2]},
+                "peak_per_sm_cycle": {"shoup_multiply_subtract": pk[9], "montgomery_multiply_subtract": pk[8],
+                                      "imad_wide": pk[5], "imad": pk[6], "imad_hi": pk[7]},
+                "peak_as_run_per_s": {"shoup_multiply_subtract": pk[4], "montgomery_multiply_subtract": pk[3],
+                                      "imad_wide": pk[0], "imad": pk[1], "imad_hi": pk[2]},
                 "sm_mhz_used": mhz, "imad_per_s": 3.0 * mm,
                 "peak_source": "measured live (slipcu_measure_int_peaks): register-resident chains, 8 per thread, 8 CTAs x 256 threads per SM, "
                                "operations per SM cycle from clock64 inside the kernel x 148 SMs x the SM clock sampled during the timed region "

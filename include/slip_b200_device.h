@@ -61,13 +61,14 @@ int  slipcu_set_device (int device);
 /* diagnostics: measured 32-bit integer-multiply peaks of the device (register-resident chains of
  * IMAD.WIDE, IMAD and IMAD.HI), the denominators of bench.py's roofline.int_mul */
 int  slipcu_measure_imad_peak (double *wide_per_s, double *lo_per_s, double *hi_per_s);
-/* ... and of the modular multiply-subtract of k_trisolve itself (w <- w + l*y mod p, Montgomery:
- * IMAD.WIDE + IMAD + IMAD.HI + three integer ALU operations) on registers only */
+/* ... and of the modular multiply-subtract of k_trisolve itself (w <- w + l*y mod p with a Shoup
+ * product: IMAD.HI + 2 IMAD + three integer ALU operations) on registers only */
 int  slipcu_measure_modmul_peak (double *modmul_per_s);
-/* all four at once: out[0..3] operations per second as run, out[4..7] operations per SM clock cycle
+/* all at once: out[0..4] operations per second as run, out[5..9] operations per SM clock cycle
  * (clock64 inside the kernels: independent of the clock the GPU holds under this power-hungry load),
- * for IMAD.WIDE, IMAD, IMAD.HI, modular multiply-subtract */
-int  slipcu_measure_int_peaks (double *out8);
+ * for IMAD.WIDE, IMAD, IMAD.HI, the Montgomery multiply-subtract (IMAD.WIDE + IMAD + IMAD.HI) and the
+ * Shoup multiply-subtract of k_trisolve (IMAD.HI + 2 IMAD) */
+int  slipcu_measure_int_peaks (double *out10);
 
 /* -- factorization session -------------------------------------------------------------------
  * slipcu_factor_begin: uploads A (CSC; values as limb strings) and reduces it into `channels`

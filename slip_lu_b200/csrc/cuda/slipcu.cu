@@ -131,6 +131,7 @@ struct Tables
     std::vector<u32> hp;       // host copy of the primes
     std::vector<double> cumbits;   // cumbits[c] = log2(p_0 ... p_{c-1})
     u32 *p = nullptr, *ninv = nullptr, *r2 = nullptr, *one = nullptr;
+    u32 *c62 = nullptr;        // floor(2^62 / p): reciprocal for the Shoup companion of a step's multiplier
     u32 *C = nullptr;          // [S][S]  C[u][t] = (p_0..p_{u-1}) mod p_t, Montgomery form, u < t
     u32 *invB = nullptr;       // [S]     (p_0..p_{t-1})^-1 mod p_t, Montgomery form
     u32 *Bpos = nullptr;       // [S][LB] limbs of p_0..p_{t-1}
@@ -141,7 +142,7 @@ struct Tables
     int32_t *cum_ub = nullptr; // [S+1] upper bound of 64 log2 (p_0..p_{c-1}) (bound mode)
     ~Tables ()
     {
-        cudaFree (p); cudaFree (ninv); cudaFree (r2); cudaFree (one);
+        cudaFree (p); cudaFree (ninv); cudaFree (r2); cudaFree (one); cudaFree (c62);
         cudaFree (C); cudaFree (invB); cudaFree (Bpos); cudaFree (Minv); cudaFree (Urec); cudaFree (cum_ub);
     }
 };
@@ -221,7 +222,7 @@ static int build_tables (int S, std::shared_ptr<Tables> &out)
     T->S = S;
     extend_primes ((size_t) S);
     T->hp.assign (g_primes.begin (), g_primes.begin () + S);
-    std::vector<u32> ninv (S), r2 (S), one (S);
+    std::vector<u32> ninv (S), r2 (S), one (S), c62 (S);
     T->cumbits.resize (S + 1);
     T->cumbits[0] = 0.0;
     for (int c = 0; c < S; ++c)
@@ -233,6 +234,7 @@ static int build_tables (int S, std::shared_ptr<Tables> &out)
         u64 r = ((u64) 1 << 32) % p;
         one[c] = (u32) r;
         r2[c] = (u32) ((r * r) % p);
+        c62[c] = (u32) ((((unsigned __int128) 1) << 62) / p);      // 2^31 < c62 < 2^32 for 2^30 < p < 2^31
         T->cumbits[c + 1] = T->cumbits[c] + log2 ((double) p);
     }
     // prefix products as limb strings: row t = p_0 .. p_{t-1}  (t limbs at most)
@@ -257,6 +259,8 @@ static int build_tables (int S, std::shared_ptr<Tables> &out)
     CU (cudaMalloc (&T->ninv, S * sizeof (u32)));
     CU (cudaMalloc (&T->r2, S * sizeof (u32)));
     CU (cudaMalloc (&T->one, S * sizeof (u32)));
+    CU (cudaMalloc (&T->c62, S * sizeof (u32)));
+    CU (cudaMemcpy (T->c62, c62.data (), S * sizeof (u32), cudaMemcpyHostToDevice));
     CU (cudaMalloc (&T->invB, S * sizeof (u32)));
     CU (cudaMalloc (&T->C, (size_t) S * S * sizeof (u32)));
     CU (cudaMalloc (&T->Bpos, (size_t) (S + 4) * T->LB * sizeof (u32)));
@@ -787,6 +791,7 @@ struct TriArgs
     u32 *out;                // result: channel block cb of right-hand side y at out + cb * out_cb_stride + y * out_y_stride
     size_t out_y_stride, out_cb_stride;      // (one column: out_cb_stride = cnt * CH)
     const u32 *rho, *invrho, *p, *ninv;      // [n][S] pivots and their inverses (Montgomery form)
+    const u32 *c62;          // [S] floor(2^62 / p)
     const int32_t *pos;      // [n] row -> slot
     int x_in_smem;
     int nchunks;             // total pipeline chunks of this launch
@@ -878,6 +883,33 @@ template <int CPT> __device__ __forceinline__ ChanVec<CPT> sub_mulv (const ChanV
     ChanVec<CPT> r;
 #pragma unroll
     for (int i = 0; i < CPT; ++i) r.v[i] = add_mod (w.v[i], mont_mul (l.v[i], ny.v[i], p.v[i], ni.v[i]), p.v[i]);
+    return r;
+}
+// Shoup multiplication by a multiplier that stays fixed over many products (the -yhat_j of an
+// elimination step): with the companion yq = floor (y 2^32 / p), q = hi32 (l yq) and
+// r = l y - q p lies in [0, 2p), computed in 32-bit wrap-around arithmetic.  One IMAD.HI and two
+// IMAD per product where the Montgomery product needs IMAD.WIDE + IMAD + IMAD.HI; IMAD.WIDE and
+// IMAD.HI issue at less than half the rate of IMAD (46 / 55 / 113 per SM cycle, measured), and the
+// integer multiplies are what bounds k_trisolve.  y is a PLAIN residue; l in Montgomery form gives
+// the product in Montgomery form.
+__device__ __forceinline__ u32 shoup_companion (u32 y, u32 p, u32 c62)
+{   // floor (y 2^32 / p) exactly: estimate with the reciprocal (low by at most 2), then correct
+    u32 q = (u32) (((u64) y * c62) >> 30);
+    u64 rem = ((u64) y << 32) - (u64) q * p;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) if (rem >= p) { rem -= p; ++q; }
+    return q;
+}
+template <int CPT> __device__ __forceinline__ ChanVec<CPT> sub_mul_shoup (const ChanVec<CPT> &w, const ChanVec<CPT> &l, const ChanVec<CPT> &ny, const ChanVec<CPT> &nyq, const ChanVec<CPT> &p)
+{   // w + l * ny mod p  (ny = -yhat, plain)
+    ChanVec<CPT> r;
+#pragma unroll
+    for (int i = 0; i < CPT; ++i)
+    {
+        const u32 q = __umulhi (l.v[i], nyq.v[i]);
+        const u32 t = l.v[i] * ny.v[i] - q * p.v[i];           // in [0, 2p)
+        r.v[i] = csub (w.v[i] + csub (t, p.v[i]), p.v[i]);
+    }
     return r;
 }
 template <int CPT> __device__ __forceinline__ ChanVec<CPT> negv (const ChanVec<CPT> &y, const ChanVec<CPT> &p)
@@ -1154,10 +1186,15 @@ __global__ void __launch_bounds__ (TRI_THREADS * 4 / CPT, CH == 4 ? 1 : 2) k_tri
     const int qc = (tid % TPR) * CPT, rg = tid / TPR;  // first channel of this thread inside the block, row group
     const int c0 = cb * CH + qc;
     const V pv = ldv<CPT> (a.p + c0), niv = ldv<CPT> (a.ninv + c0);
+    // the multiplier of a step (-yhat_j and its Shoup companion) is worked out ONCE per warp: lane c
+    // does channel c of the block, the others fetch theirs with shuffles (every thread doing its own
+    // four would spend more instructions on a step's set-up than on a short step's updates)
+    const int ch1 = (tid & 31) % CH;
+    const u32 p1 = a.p[cb * CH + ch1], ni1 = a.ninv[cb * CH + ch1], c62_1 = a.c62[cb * CH + ch1];
     unsigned char *xb = (unsigned char *) xs + qc * 4;             // this thread's channels of row 0
-    V negy;
+    V negy, negyq;                                     // -yhat_j as a plain residue, and its Shoup companion
 #pragma unroll
-    for (int i = 0; i < CPT; ++i) negy.v[i] = 0;
+    for (int i = 0; i < CPT; ++i) { negy.v[i] = 0; negyq.v[i] = 0; }
     int u = a.u0;                                      // elimination step (= U slot) of the current chunk
     int bc = 0, bi = TRI_BUFS - 1;                     // buffers of the chunk consumed / requested
     for (int c = 0; c < nchunks; ++c)
@@ -1171,8 +1208,18 @@ __global__ void __launch_bounds__ (TRI_THREADS * 4 / CPT, CH == 4 ? 1 : 2) k_tri
         const u32 meta = lds64 (ring + (u32) (c % TRI_RING) * (u32) sizeof (ChunkInfo) + 16).y;
         if (meta & 0x10000u)
         {   // yhat_j = w_j / rho_j
-            const V wj = ldv<CPT> (xb + (size_t) u * CH * 4);
-            negy = negv<CPT> (mont_mulv<CPT> (wj, ldsv<CPT> (sb + SM::L_BYTES + SM::S_BYTES + qc * 4), pv, niv), pv);
+            const u32 wj1 = xs[(size_t) u * CH + ch1];
+            u32 ir1;
+            asm volatile ("ld.shared.u32 %0, [%1];" : "=r"(ir1) : "r"(sb + SM::L_BYTES + SM::S_BYTES + (u32) ch1 * 4));
+            const u32 y1 = mont_redc (mont_mul (wj1, ir1, p1, ni1), p1, ni1);      // yhat_j, out of Montgomery form
+            const u32 ny1 = y1 ? p1 - y1 : 0u;
+            const u32 nyq1 = shoup_companion (ny1, p1, c62_1);
+#pragma unroll
+            for (int i = 0; i < CPT; ++i)
+            {
+                negy.v[i] = __shfl_sync (0xffffffffu, ny1, qc + i);
+                negyq.v[i] = __shfl_sync (0xffffffffu, nyq1, qc + i);
+            }
         }
         // rows of one step hit distinct slots: the four rows of a thread are loaded, updated and
         // stored together so that their latencies overlap
@@ -1202,13 +1249,13 @@ __global__ void __launch_bounds__ (TRI_THREADS * 4 / CPT, CH == 4 ? 1 : 2) k_tri
             {
                 if (XS && CPT == 4)
                 {
-                    const V r = sub_mulv<CPT> (w[q], l[q], negy, pv, niv);
+                    const V r = sub_mul_shoup<CPT> (w[q], l[q], negy, negyq, pv);
                     asm volatile ("{\n .reg .pred p;\n setp.ne.u32 p, %4, %5;\n"
                                   " @p st.shared.v4.u32 [%6], {%0,%1,%2,%3};\n}"
                                   :: "r"(r.v[0]), "r"(r.v[1]), "r"(r.v[2]), "r"(r.v[3]),
                                      "r"(t[q]), "r"(spare), "r"(xsa + t[q]) : "memory");
                 }
-                else if (XS || t[q] != spare) stv<CPT> (xb + t[q], sub_mulv<CPT> (w[q], l[q], negy, pv, niv));
+                else if (XS || t[q] != spare) stv<CPT> (xb + t[q], sub_mul_shoup<CPT> (w[q], l[q], negy, negyq, pv));
             }
         }
         if (meta & 0x20000u) ++u;
@@ -2480,11 +2527,19 @@ __global__ void __launch_bounds__ (256) k_imad_peak (int iters, u32 *out)
             if (KIND == 0) w[i] = (u64) (u32) w[i] * b + w[i];
             else if (KIND == 1) a[i] = a[i] * b + a[(i + 1) & 7];
             else if (KIND == 2) a[i] = __umulhi (a[i], b) + 0x9e3779b9u;
-            else
-            {   // KIND 3: the update of k_trisolve itself, w <- w + l * ny mod p (Montgomery), on registers
-                // (operands are not kept reduced: only the instruction mix matters here)
+            else if (KIND == 3)
+            {   // the Montgomery multiply-subtract w <- w + l * ny mod p (k_trisolve of round 1; still the
+                // operation of the other kernels), on registers.  Operands are not kept reduced: only
+                // the instruction mix matters here.
                 const u32 p = 0x7fffffffu - 18u, ninv = b | 1u;
                 a[i] = add_mod (a[i], mont_mul (a[i], b, p, ninv), p);
+            }
+            else
+            {   // KIND 4: the update of k_trisolve itself, the same with a Shoup product (sub_mul_shoup)
+                const u32 p = 0x7fffffffu - 18u, ny = b >> 2, nyq = b | 1u;
+                const u32 q = __umulhi (a[i], nyq);
+                const u32 t = a[i] * ny - q * p;
+                a[i] = csub (a[i] + csub (t, p), p);
             }
         }
     }
@@ -2519,7 +2574,8 @@ static int run_imad_kind (int kind, double *per_s, double *per_sm_cycle)
         if (kind == 0) k_imad_peak<0><<<grid, 256>>> (iters, out);
         else if (kind == 1) k_imad_peak<1><<<grid, 256>>> (iters, out);
         else if (kind == 2) k_imad_peak<2><<<grid, 256>>> (iters, out);
-        else k_imad_peak<3><<<grid, 256>>> (iters, out);
+        else if (kind == 3) k_imad_peak<3><<<grid, 256>>> (iters, out);
+        else k_imad_peak<4><<<grid, 256>>> (iters, out);
         CU (cudaEventRecord (e1, 0));
         CU (cudaEventSynchronize (e1));
         float ms = 0;
@@ -2540,17 +2596,17 @@ static int run_imad_kind (int kind, double *per_s, double *per_sm_cycle)
     return SLIPCU_OK;
 }
 
-// out[0..3] = operations per second, out[4..7] = operations per SM clock cycle, for
-// IMAD.WIDE, IMAD, IMAD.HI and the modular multiply-subtract of k_trisolve
-extern "C" int slipcu_measure_int_peaks (double *out8)
+// out[0..4] = operations per second, out[5..9] = operations per SM clock cycle, for IMAD.WIDE,
+// IMAD, IMAD.HI, the Montgomery multiply-subtract and the Shoup multiply-subtract of k_trisolve
+extern "C" int slipcu_measure_int_peaks (double *out10)
 {
-    if (!out8) return fail (SLIPCU_BAD_INPUT, "slipcu_measure_int_peaks", "bad argument");
-    for (int k = 0; k < 4; ++k) { int rc = run_imad_kind (k, &out8[k], &out8[4 + k]); if (rc) return rc; }
+    if (!out10) return fail (SLIPCU_BAD_INPUT, "slipcu_measure_int_peaks", "bad argument");
+    for (int k = 0; k < 5; ++k) { int rc = run_imad_kind (k, &out10[k], &out10[5 + k]); if (rc) return rc; }
     return SLIPCU_OK;
 }
 extern "C" int slipcu_measure_imad_peak (double *wide_per_s, double *lo_per_s, double *hi_per_s)
 {
-    double o[8];
+    double o[10];
     int rc = slipcu_measure_int_peaks (o);
     if (rc) return rc;
     if (wide_per_s) *wide_per_s = o[0];
@@ -2560,7 +2616,7 @@ extern "C" int slipcu_measure_imad_peak (double *wide_per_s, double *lo_per_s, d
 }
 extern "C" int slipcu_measure_modmul_peak (double *modmul_per_s)
 {
-    return run_imad_kind (3, modmul_per_s, nullptr);
+    return run_imad_kind (4, modmul_per_s, nullptr);
 }
 
 static int env_int (const char *name, int dflt)
@@ -3282,7 +3338,7 @@ extern "C" int slipcu_factor_spec_launch (slipcu_factor *F, int slot, int k, int
     a.src_y_stride = 0;
     a.out = sl.buf; a.out_y_stride = 0; a.out_cb_stride = (size_t) cnt * CH;
     a.rho = F->rho; a.invrho = F->invrho;
-    a.p = T.p; a.ninv = T.ninv; a.pos = w.pos;
+    a.p = T.p; a.ninv = T.ninv; a.c62 = T.c62; a.pos = w.pos;
     a.nchunks = nchunks; a.upos = d + cnt; a.publish = 0; a.u0 = 0;
     a.mag_on = F->mag_on; a.mag_src = F->mag_on ? F->Amag + F->hAp[col] : nullptr; a.mag_out = sl.mag;
     a.rho_mag = F->rho_mag; a.bound_out = nullptr;
@@ -3353,7 +3409,7 @@ extern "C" int slipcu_factor_column_launch (slipcu_factor *F, int k, int col, in
     a.src_y_stride = 0;
     a.out = hc.base; a.out_y_stride = 0; a.out_cb_stride = (size_t) cnt * CH;
     a.rho = F->rho; a.invrho = F->invrho;
-    a.p = T.p; a.ninv = T.ninv; a.pos = w.pos;
+    a.p = T.p; a.ninv = T.ninv; a.c62 = T.c62; a.pos = w.pos;
     a.nchunks = nchunks; a.upos = hc.rows + cnt; a.publish = 1; a.u0 = first_step;
     a.mag_on = F->mag_on; a.mag_out = hc.mag; a.rho_mag = F->rho_mag; a.bound_out = F->bound;
     size_t smem = 0;
@@ -3829,7 +3885,7 @@ extern "C" int slipcu_solve (slipcu_factor *F, int nrhs, const u32 *blimbs, cons
             a.src_y_stride = (size_t) n;
             a.out = dz; a.out_y_stride = (size_t) n * CH; a.out_cb_stride = cntb * CH;
             a.rho = F->rho; a.invrho = F->invrho;
-            a.p = T.p; a.ninv = T.ninv; a.pos = F->mc.pos;
+            a.p = T.p; a.ninv = T.ninv; a.c62 = T.c62; a.pos = F->mc.pos;
             a.nchunks = fwd_chunks; a.upos = dident; a.publish = 1; a.u0 = 0;
             a.rhs_fastest = 1;
             size_t smem = 0;

@@ -428,7 +428,8 @@ def sharded_block(lib, args, rank, world, barrier, reduce_max, reduce_sum):
         cores = len(os.sched_getaffinity(0))
     except AttributeError:
         cores = os.cpu_count() or 1
-    threads = max(1, min(8, cores // max(1, world)))
+    # (under torchrun every rank is already pinned to its own share of the cores, see main)
+    threads = max(1, min(8, cores if world > 1 else cores))
 
     # (i) configs[4]: batch of independent LP-basis systems
     nsys, nb = args.batch_systems, args.batch_n

@@ -235,14 +235,14 @@ def roofline_of(c, peak, peak_src, t_dev=None):
     achieved = (c.trisolve_bytes / 1e9) / (tri_ms / 1e3) if tri_ms > 0 else 0.0
     traffic = None
     try:   # DRAM bytes / algorithmic bytes of one `ncu --set full` capture of this kernel
-        cap = json.load(open(os.path.join(ROOT, "profiles", "r01_trisolve_ncu_full.json")))
+        cap = json.load(open(os.path.join(ROOT, "profiles", "r02_trisolve_ncu_full.json")))
         traffic = cap["traffic_over_algorithmic"] * c.trisolve_bytes / max(1, c.trisolve_launches)
     except Exception:
         pass
     return {"bound": "hbm", "kernel": "k_trisolve", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak if peak else None, "peak_source": peak_src,
             "launches": int(c.trisolve_launches), "traffic": traffic,
-            "traffic_source": "algorithmic bytes x the DRAM/algorithmic ratio of profiles/r01_trisolve_ncu_full.json (one ncu --set full capture)",
+            "traffic_source": "algorithmic bytes x the DRAM/algorithmic ratio (1.011) of profiles/r02_trisolve_ncu_full.json (one ncu --set full capture of this kernel)",
             "algorithmic_bytes_per_launch": c.trisolve_bytes / max(1, c.trisolve_launches),
             "modmul_per_s": c.trisolve_modmul / (tri_ms / 1e3) if tri_ms > 0 else None,
             "kernel_ms": tri_ms, "kernel_ms_sum_of_launches": c.trisolve_ms,

@@ -724,9 +724,11 @@ __global__ void k_setpos (int cnt, const int32_t *rows, int32_t *pos)
 // load gives a thread its four targets.  A target is the BYTE offset of the slot's row in the work
 // vector; rows without a target (past the end of the chunk, or the pivot row itself) point at the
 // spare row `cnt` of the vector, which absorbs their updates.
+// upart = 1: the steps use the U parts of the columns (slots 0..nU-1, no pivot among them): the back
+// substitution, z_i -= U_ij z_j for the rows above the diagonal of column j.
 __global__ void k_slots (int nU, int total, int CH, int cnt, const int32_t *upos, const int32_t *uoff,
                          const int32_t *uchunk, const ColDesc *desc, const int32_t *pos, int32_t *slots,
-                         StepInfo *steps, ChunkInfo *chunks)
+                         StepInfo *steps, ChunkInfo *chunks, int upart)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
@@ -735,16 +737,17 @@ __global__ void k_slots (int nU, int total, int CH, int cnt, const int32_t *upos
     const int u = lo, o = i - uoff[u];
     const int R = tri_chunk_rows (CH), RG = tri_row_groups (CH);
     const ColDesc d = desc[upos[u]];
-    const int len = d.cnt - d.nU;
+    const int first = upart ? 0 : d.nU;           // first slot of the part the step streams
+    const int len = upart ? d.nU : d.cnt - d.nU;
     const int ci = o / R, q = o % R;              // chunk of the step, entry inside the chunk
     const int r = ci * R + (q & 3) * RG + (q >> 2);
-    const int m = d.nU + r;
+    const int m = first + r;
     const int rowbytes = CH * 4;
-    slots[i] = (r < len && m != d.pivslot) ? pos[d.rows[m]] * rowbytes : cnt * rowbytes;
+    slots[i] = (r < len && (upart || m != d.pivslot)) ? pos[d.rows[m]] * rowbytes : cnt * rowbytes;
     if (o == 0)
     {
         StepInfo si;
-        si.lbase = d.base + (size_t) d.nU * CH; si.j = upos[u]; si.len = len; si.cbstride = d.cnt * CH;
+        si.lbase = d.base + (size_t) first * CH; si.j = upos[u]; si.len = len; si.cbstride = d.cnt * CH;
         si.slot_off = uoff[u]; si.chunk0 = uchunk[u]; si.pad = 0;
         steps[u] = si;
     }
@@ -752,10 +755,10 @@ __global__ void k_slots (int nU, int total, int CH, int cnt, const int32_t *upos
     {
         ChunkInfo c;
         const int r0 = ci * R;
-        c.lsrc = d.base + (size_t) (d.nU + r0) * CH; c.cbstride = d.cnt * CH;
+        c.lsrc = d.base + (size_t) (first + r0) * CH; c.cbstride = d.cnt * CH;
         c.slot_off = uoff[u] + r0; c.j = upos[u];
         c.meta = min (R, len - r0) | ((r0 == 0) << 16) | ((r0 + R >= len) << 17);
-        c.msrc = d.mag ? d.mag + d.nU + r0 : nullptr;
+        c.msrc = d.mag ? d.mag + first + r0 : nullptr;
         chunks[uchunk[u] + ci] = c;
     }
 }
@@ -807,6 +810,12 @@ struct TriArgs
     int32_t *bound_out;      // largest published bound of this launch
     int smem_bytes;          // dynamic shared memory of the launch
     int rhs_fastest;         // 1: blockIdx.x = right-hand side, blockIdx.y = channel block (see slipcu_solve)
+    // back substitution (slots are positions): the slot of a step's pivot is its position j from the
+    // chunk descriptor (steps run n-1..0 and columns without a U part have no chunk at all), the
+    // source vector is multiplied by src_scale (det) on the way in, and the result by 1/rho_t on
+    // the way out (publish == 2):  z = det y;  for j = n-1..0: x_j = z_j / rho_j, z_i -= U_ij x_j
+    int j_is_slot;
+    const u32 *src_scale;    // [S] or nullptr
 };
 
 template <int CH>
@@ -1168,10 +1177,14 @@ __global__ void __launch_bounds__ (TRI_THREADS * 4 / CPT, CH == 4 ? 1 : 2) k_tri
         {   // long source (dense right-hand side, speculative first part): CPT channels per access,
             // one slot lookup per row
             const int qs = (tid % TPR) * CPT;
+            V sc, pq, nq;
+            if (a.src_scale) { sc = ldv<CPT> (a.src_scale + cb * CH + qs); pq = ldv<CPT> (a.p + cb * CH + qs); nq = ldv<CPT> (a.ninv + cb * CH + qs); }
             for (int e = tid / TPR; e < a.src_cnt; e += NT / TPR)
             {
                 const int row = a.src_rows ? a.src_rows[e] : e;
-                stv<CPT> (xs + (size_t) a.pos[row] * CH + qs, ldv<CPT> (src + (first + (size_t) e * a.src_step) * CH + qs));
+                V v = ldv<CPT> (src + (first + (size_t) e * a.src_step) * CH + qs);
+                if (a.src_scale) v = mont_mulv<CPT> (v, sc, pq, nq);
+                stv<CPT> (xs + (size_t) a.pos[row] * CH + qs, v);
             }
         }
         else
@@ -1179,7 +1192,9 @@ __global__ void __launch_bounds__ (TRI_THREADS * 4 / CPT, CH == 4 ? 1 : 2) k_tri
             {
                 const int e = i / CH, ch = i % CH;
                 const int row = a.src_rows ? a.src_rows[e] : e;
-                xs[a.pos[row] * CH + ch] = src[(first + (size_t) e * a.src_step) * CH + ch];
+                u32 v = src[(first + (size_t) e * a.src_step) * CH + ch];
+                if (a.src_scale) v = mont_mul (v, a.src_scale[cb * CH + ch], a.p[cb * CH + ch], a.ninv[cb * CH + ch]);
+                xs[a.pos[row] * CH + ch] = v;
             }
     }
 
@@ -1205,10 +1220,12 @@ __global__ void __launch_bounds__ (TRI_THREADS * 4 / CPT, CH == 4 ? 1 : 2) k_tri
         if (tid < 2 && c + 2 * TRI_BUFS - 2 < nchunks) fetch_desc (c + 2 * TRI_BUFS - 2, tid);
         cp_async_commit ();
         const u32 sb = stage0 + (u32) bc * SM::STAGE;
-        const u32 meta = lds64 (ring + (u32) (c % TRI_RING) * (u32) sizeof (ChunkInfo) + 16).y;
+        const uint2 jm = lds64 (ring + (u32) (c % TRI_RING) * (u32) sizeof (ChunkInfo) + 16);
+        const u32 meta = jm.y;
         if (meta & 0x10000u)
         {   // yhat_j = w_j / rho_j
-            const u32 wj1 = xs[(size_t) u * CH + ch1];
+            const int uu = a.j_is_slot ? (int) jm.x : u;
+            const u32 wj1 = xs[(size_t) uu * CH + ch1];
             u32 ir1;
             asm volatile ("ld.shared.u32 %0, [%1];" : "=r"(ir1) : "r"(sb + SM::L_BYTES + SM::S_BYTES + (u32) ch1 * 4));
             const u32 y1 = mont_redc (mont_mul (wj1, ir1, p1, ni1), p1, ni1);      // yhat_j, out of Montgomery form
@@ -1267,8 +1284,12 @@ __global__ void __launch_bounds__ (TRI_THREADS * 4 / CPT, CH == 4 ? 1 : 2) k_tri
     for (int t = rg; t < cnt; t += RG)
     {
         V v = ldv<CPT> (xs + t * CH + qc);
-        const int lvl = a.publish ? ((t < nU) ? a.upos[t] : a.k) : 0;      // level the entry is brought to
-        if (lvl >= 1) v = mont_mulv<CPT> (v, ldv<CPT> (a.rho + (size_t) (lvl - 1) * S + c0), pv, niv);
+        if (a.publish == 2) v = mont_mulv<CPT> (v, ldv<CPT> (a.invrho + (size_t) t * S + c0), pv, niv);      // x_t = z_t / rho_t
+        else
+        {
+            const int lvl = a.publish ? ((t < nU) ? a.upos[t] : a.k) : 0;      // level the entry is brought to
+            if (lvl >= 1) v = mont_mulv<CPT> (v, ldv<CPT> (a.rho + (size_t) (lvl - 1) * S + c0), pv, niv);
+        }
         stv<CPT> (xg + t * CH + qc, v);
     }
 }
@@ -2982,7 +3003,7 @@ static int flush_commit (slipcu_factor *F)
 // pattern (rows), step positions (upos) and slot-list offsets (uoff, nU+1 entries) are on the device
 static int prepare_steps (slipcu_factor *F, WorkCtx &w, int cnt, int nU, const int32_t *rows, const int32_t *upos,
                           const int32_t *uoff, const int32_t *uchunk, int total, int nchunks,
-                          int packet_ints = 0, bool with_commit = false)
+                          int packet_ints = 0, bool with_commit = false, int upart = 0)
 {
     if ((size_t) nchunks > w.chunks_cap)
     {
@@ -3040,7 +3061,7 @@ static int prepare_steps (slipcu_factor *F, WorkCtx &w, int cnt, int nU, const i
     }
     if (nU > 0 && total > 0)
     {
-        k_slots<<<(total + 255) / 256, 256, 0, w.st>>> (nU, total, F->CH, cnt, upos, uoff, uchunk, F->desc, w.pos, w.slots, w.steps, w.chunks);
+        k_slots<<<(total + 255) / 256, 256, 0, w.st>>> (nU, total, F->CH, cnt, upos, uoff, uchunk, F->desc, w.pos, w.slots, w.steps, w.chunks, upart);
         g_launches++;
         CU (cudaGetLastError ());
         if (debug_check ("k_slots", w.st)) return fail (SLIPCU_CUDA_ERROR, "k_slots", "debug");
@@ -3792,7 +3813,7 @@ extern "C" int slipcu_solve (slipcu_factor *F, int nrhs, const u32 *blimbs, cons
     // batch size: work vectors, digit scratch and limb buffers of a batch within the memory budget,
     // and at least four batches when there are many right-hand sides (so that host and GPU overlap)
     const size_t budget = (size_t) std::max (1, env_int ("SLIP_B200_SOLVE_BATCH_MB", 1024)) << 20;
-    const size_t per_rhs = (size_t) n * ((size_t) S * 4 + ((size_t) S + 4) * 4 + 2 * (size_t) stride * 4);
+    const size_t per_rhs = (size_t) n * (2 * (size_t) S * 4 + ((size_t) S + 4) * 4 + 2 * (size_t) stride * 4);
     int batch = (int) std::max<size_t> (1, std::min<size_t> ((size_t) nrhs, budget / std::max<size_t> (per_rhs, 1)));
     if (nrhs >= 8) batch = std::min (batch, (nrhs + 3) / 4);
     if ((int64_t) batch * n > (int64_t) INT32_MAX / 2) batch = std::max (1, (int) ((int64_t) (INT32_MAX / 2) / n));
@@ -3800,7 +3821,11 @@ extern "C" int slipcu_solve (slipcu_factor *F, int nrhs, const u32 *blimbs, cons
     const size_t bn = (size_t) batch * n;
 
     u32 *dl = nullptr, *dB = nullptr, *dz = nullptr; int64_t *doff = nullptr; int8_t *dsg = nullptr;
-    int32_t *drow_at = nullptr, *dident = nullptr, *dpinv = nullptr, *duoff = nullptr;
+    int32_t *drow_at = nullptr, *dident = nullptr, *dpinv = nullptr, *duoff = nullptr, *dboff = nullptr, *drev = nullptr;
+    u32 *dz2 = nullptr;
+    WorkCtx bw;                           // step lists of the back substitution (pos[] shared with F->mc)
+    int bwd_chunks = 0;
+    const bool legacy_backsub = env_int ("SLIP_B200_BACKSUB", 1) == 0;      // k_backsub: one serial loop over the columns per CTA
     struct Buf { u32 *dlimbs = nullptr; int32_t *dnl = nullptr; int8_t *dsign = nullptr;
                  u32 *h_limbs = nullptr; int32_t *h_nl = nullptr; int8_t *h_sign = nullptr; int32_t *h_topd = nullptr;
                  cudaEvent_t done = nullptr; int r0 = 0, nb = 0; bool busy = false; } buf[2];
@@ -3858,6 +3883,30 @@ extern "C" int slipcu_solve (slipcu_factor *F, int nrhs, const u32 *blimbs, cons
         rc = prepare_steps (F, F->mc, n, n, F->rows_are_positions ? dident : drow_at, dident, duoff, duoff + n + 1, (int) tot, (int) nch);
         if (rc) goto done;
     }
+    if (!legacy_backsub)
+    {   // ... and of the back substitution: the U part of every column is one step, columns n-1..0
+        std::vector<int32_t> boff (2 * (size_t) n + 2), rev (n);
+        int64_t tot = 0, nch = 0;
+        for (int u = 0; u < n; ++u)
+        {
+            const int k = n - 1 - u, len = F->cols[k].nU;
+            rev[u] = k;
+            boff[u] = (int32_t) tot; boff[n + 1 + u] = (int32_t) nch;
+            tot += tri_slot_extent (len, CH); nch += (len + tri_chunk_rows (CH) - 1) / tri_chunk_rows (CH);
+        }
+        boff[n] = (int32_t) tot; boff[2 * n + 1] = (int32_t) nch;
+        bwd_chunks = (int) nch;
+        if (tot > INT32_MAX) { rc = fail (SLIPCU_BAD_INPUT, "slipcu_solve", "U has too many entries"); goto done; }
+        CUG (pool_alloc_t (&dboff, (2 * (size_t) n + 2) * sizeof (int32_t)));
+        CUG (pool_alloc_t (&drev, (size_t) n * sizeof (int32_t)));
+        CUG (pool_alloc_t (&dz2, bn * S * sizeof (u32)));
+        CUG (cudaMemcpyAsync (dboff, boff.data (), (2 * (size_t) n + 2) * sizeof (int32_t), cudaMemcpyHostToDevice, F->st));
+        CUG (cudaMemcpyAsync (drev, rev.data (), (size_t) n * sizeof (int32_t), cudaMemcpyHostToDevice, F->st));
+        CUG (cudaStreamSynchronize (F->st));
+        bw.st = F->st; bw.pos = F->mc.pos;
+        rc = prepare_steps (F, bw, n, n, F->rows_are_positions ? dident : drow_at, drev, dboff, dboff + n + 1, (int) tot, (int) nch, 0, false, 1);
+        if (rc) goto done;
+    }
     for (int bi = 0; bi <= nbatches; ++bi)
     {
         double tw0 = wall_s ();
@@ -3893,6 +3942,23 @@ extern "C" int slipcu_solve (slipcu_factor *F, int nrhs, const u32 *blimbs, cons
             if (rc) goto done;
             CUG (launch_tri_any (CH, F->cpt, a, dim3 (nb, S / CH), smem, F->st));
             if (debug_check ("k_trisolve(forward)", F->st)) { rc = fail (SLIPCU_CUDA_ERROR, "k_trisolve(forward)", "debug"); goto done; }
+            u32 *dres = dz;                 // where the numerators end up
+            if (!legacy_backsub)
+            {   // back substitution through the same chunked pipeline: z = det y on the way in, the U
+                // parts as steps n-1..0, x_t = z_t / rho_t on the way out
+                TriArgs bq = a;
+                bq.chunks = bw.chunks; bq.slots = bw.slots; bq.steps = bw.steps; bq.nchunks = bwd_chunks;
+                bq.src = dz; bq.src_total = cntb; bq.src_first = 0; bq.src_step = 1; bq.src_cnt = n;
+                bq.src_rows = nullptr;                        // dz is in slot (position) order already
+                bq.pos = dident;                              // ... so entry e goes to slot e
+                bq.src_y_stride = (size_t) n;
+                bq.out = dz2; bq.src_scale = F->rho + (size_t) (n - 1) * S; bq.j_is_slot = 1; bq.publish = 2;
+                CUG (launch_tri_any (CH, F->cpt, bq, dim3 (nb, S / CH), smem, F->st));
+                if (debug_check ("k_trisolve(backward)", F->st)) { rc = fail (SLIPCU_CUDA_ERROR, "k_trisolve(backward)", "debug"); goto done; }
+                dres = dz2;
+            }
+            else
+            {
             BackArgs b;
             b.n = n; b.S = S; b.z = dz; b.z_y_stride = (size_t) n * CH; b.z_cb_stride = cntb * CH; b.rhs_fastest = 1;
             b.desc = F->desc; b.rho = F->rho; b.invrho = F->invrho; b.p = T.p; b.ninv = T.ninv; b.pos = F->mc.pos;
@@ -3903,8 +3969,9 @@ extern "C" int slipcu_solve (slipcu_factor *F, int nrhs, const u32 *blimbs, cons
             else k_backsub<32><<<dim3 (nb, S / CH), 256, 0, F->st>>> (b);
             CUG (cudaGetLastError ());
             if (debug_check ("k_backsub", F->st)) { rc = fail (SLIPCU_CUDA_ERROR, "k_backsub", "debug"); goto done; }
+            }
             // numerators of the whole batch: one reconstruction launch, one limb launch
-            rc = run_garner (F, dz, (int) cntb, 0, (int) cntb, s, B.dsign);
+            rc = run_garner (F, dres, (int) cntb, 0, (int) cntb, s, B.dsign);
             if (rc) goto done;
             rc = run_limbs (F, 0, (int) cntb, 0, stride, s, B.dlimbs, B.dnl);
             if (rc) goto done;
@@ -3946,6 +4013,8 @@ done:
     }
     pool_free (dl); pool_free (doff); pool_free (dsg); pool_free (dB); pool_free (dz);
     pool_free (drow_at); pool_free (dident); pool_free (dpinv); pool_free (duoff);
+    pool_free (dboff); pool_free (drev); pool_free (dz2);
+    pool_free (bw.slots); pool_free (bw.steps); pool_free (bw.chunks);
     for (int i = 0; i < 2; ++i)
     {
         pool_free (buf[i].dlimbs); pool_free (buf[i].dnl); pool_free (buf[i].dsign);

@@ -254,6 +254,7 @@ def test_channel_prime_dividing_a_pivot_is_retired(gpu, oracle):
                                  {"SLIP_B200_CH": "4", "SLIP_B200_CPT": "2"}, {"SLIP_B200_CANON_GMP": "1"},
                                  {"SLIP_B200_LOOKAHEAD": "0"}, {"SLIP_B200_LOOKAHEAD": "3", "SLIP_B200_LOOK_MIN": "0"},
                                  {"SLIP_B200_SINGLE": "0"}, {"SLIP_B200_LOOKAHEAD": "6", "SLIP_B200_LOOK_STEPS": "1"},
+                                 {"SLIP_B200_BACKSUB": "0"}, {"SLIP_B200_BACKSUB": "0", "SLIP_B200_CH": "4"},
                                  {"SLIP_B200_CH": "16"}, {"SLIP_B200_CH": "32"}, {"SLIP_B200_X_GLOBAL": "1"},
                                  {"SLIP_B200_CH": "32", "SLIP_B200_X_GLOBAL": "1"}, {"SLIP_B200_GARNER": "1"},
                                  {"SLIP_B200_GARNER": "0"}, {"SLIP_B200_CPT": "2"}, {"SLIP_B200_CPT": "4"},

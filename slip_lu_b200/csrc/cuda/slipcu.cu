@@ -565,7 +565,7 @@ struct slipcu_factor
     unsigned *done_ctr = nullptr;            // device counter of the fused reconstruction + scan launches
     int32_t *run_flags = nullptr;            // device: [0] first column (k+1) without a nonzero candidate, [1] largest measured size so far
     struct { int k, slot; } pending_commit = { -1, -1 };     // pivot chosen, commit folded into the next column's first kernel
-    int frac_min_s = 256;                    // approximate pivot search only from this many channels on
+    int frac_min_s = 64;                     // approximate pivot search only from this many channels on
     int nowait_singles = 0;                  // the caller does not wait for single-candidate columns (slipcu_factor_nowait_singles)
     int mag_on = 0;
     int measured = 0;                        // measured mode: sizes of the candidates are measured, the result is verified exactly by the caller
@@ -2852,7 +2852,7 @@ static int session_common_init (slipcu_factor *F, int n, int channels)
         CU (pool_alloc_t (&F->run_flags, 2 * sizeof (int32_t)));
         CU (cudaMemcpy (F->run_flags, init, sizeof (init), cudaMemcpyHostToDevice));
     }
-    F->frac_min_s = std::max (16, env_int ("SLIP_B200_FRAC_MIN_S", 256));
+    F->frac_min_s = std::max (16, env_int ("SLIP_B200_FRAC_MIN_S", 64));
     rc = init_workctx (F->mc, n, F->st);
     if (rc) return rc;
     CU (cudaEventCreateWithFlags (&F->ev_commit, cudaEventDisableTiming));
@@ -3560,9 +3560,6 @@ extern "C" int slipcu_factor_column_wait (slipcu_factor *F, slipcu_pivot_info *i
         {
             F->frac_fallbacks++;
             F->frac_col = -1;
-            // matrices full of ties (small integer entries) send most columns here: the exact path
-            // alone is cheaper than a failed approximate search in front of it
-            if (F->frac_cols >= 32 && 4 * F->frac_fallbacks > F->frac_cols) F->frac = 0;
             int rc = run_garner (F, hc.base, F->fq.cnt, F->fq.nU, F->fq.cnt - F->fq.nU, F->fq.s, hc.sign);
             if (rc == SLIPCU_OK) rc = run_exact_scan (F, hc, F->fq.cnt, F->fq.nU, F->fq.mode, F->fq.diag_slot);
             if (rc) return rc;
@@ -3589,6 +3586,10 @@ extern "C" int slipcu_factor_column_wait (slipcu_factor *F, slipcu_pivot_info *i
             }
         }
         info->reserved[0] = info->reserved[1] = info->reserved[2] = 0;
+        // matrices full of ties (small integer entries) send most columns to the exact scan or to a
+        // repeat with more words: the exact path alone is then cheaper than a failed approximate
+        // search in front of it
+        if (F->frac_cols >= 24 && 4 * (F->frac_fallbacks + F->frac_retries) > F->frac_cols) F->frac = 0;
     }
     g_hw[5] += wall_s () - tw;
     // a zero pivot of a column the host did not wait for also raises the bad-channel flag: singular first

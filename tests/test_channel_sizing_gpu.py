@@ -112,3 +112,18 @@ def test_adaptive_off_gives_the_same_result(gpu, oracle, monkeypatch):
     st = stats(gpu)
     assert st["restarts"] == 0 and st["channels"] >= st["hadamard"]
     assert pinv == want["pinv"] and x == want["x"]
+
+
+def test_finalize_releases_cached_memory_and_the_library_keeps_working(gpu, oracle):
+    """SLIP_finalize hands the cached device blocks and pinned buffers back to the driver (and drops
+    resident factors); the next call allocates afresh and gives the same bits."""
+    n, cp, ri, vals, b = synth.random_sparse(60, 5, 24, seed=91, nrhs=2)
+    q = cases.colamd_like_order(n, cp, ri)
+    want = cases.run_oracle(oracle, n, cp, ri, vals, b, q)
+    x1, p1 = solve_mpq_py(gpu, n, cp, ri, vals, b, q)
+    gpu.dll.SLIP_finalize()
+    gpu.dll.SLIP_initialize()
+    x2, p2 = solve_mpq_py(gpu, n, cp, ri, vals, b, q)
+    got = cases.run_library(gpu, n, cp, ri, vals, b, q)
+    assert x1 == want["x"] and x2 == want["x"] and p1 == p2 == want["pinv"]
+    cases.assert_same_factorization(got, want, "after SLIP_finalize")

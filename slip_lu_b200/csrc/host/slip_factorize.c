@@ -33,12 +33,20 @@ typedef struct
     int32_t *prows ;
     int32_t *pend ;      /* n */
     int8_t *pruned ;     /* n */
+    /* row-wise view of the L parts: for every row r the finished columns j whose L part holds r,
+     * as linked nodes (node m: column rl_col[m], next node rl_next[m]); rl_head[r] = first node.
+     * Lets the pruning find the columns that hold the new pivot row without searching them. */
+    int32_t *rl_head ;   /* n */
+    int32_t *rl_col, *rl_next ;
+    int64_t rl_cap, rl_used ;
+    int32_t *ustamp ;    /* n: ustamp[j] == k+1 <=> column j is in the U part of column k */
 } pattern_store ;
 
 static void patterns_free (pattern_store *P)
 {
     SLIP_free (P->rows) ; SLIP_free (P->ptr) ; SLIP_free (P->nU) ; SLIP_free (P->piv) ;
     SLIP_free (P->prows) ; SLIP_free (P->pend) ; SLIP_free (P->pruned) ;
+    SLIP_free (P->rl_head) ; SLIP_free (P->rl_col) ; SLIP_free (P->rl_next) ; SLIP_free (P->ustamp) ;
     memset (P, 0, sizeof (*P)) ;
 }
 
@@ -53,8 +61,15 @@ static SLIP_info patterns_init (pattern_store *P, int32_t n, int64_t guess)
     P->prows = (int32_t *) SLIP_malloc ((size_t) P->cap * sizeof (int32_t)) ;
     P->pend = (int32_t *) SLIP_calloc ((size_t) n, sizeof (int32_t)) ;
     P->pruned = (int8_t *) SLIP_calloc ((size_t) n, sizeof (int8_t)) ;
-    if (!P->rows || !P->ptr || !P->nU || !P->piv || !P->prows || !P->pend || !P->pruned)
+    P->rl_cap = P->cap ; P->rl_used = 0 ;
+    P->rl_head = (int32_t *) SLIP_malloc ((size_t) n * sizeof (int32_t)) ;
+    P->rl_col = (int32_t *) SLIP_malloc ((size_t) P->rl_cap * sizeof (int32_t)) ;
+    P->rl_next = (int32_t *) SLIP_malloc ((size_t) P->rl_cap * sizeof (int32_t)) ;
+    P->ustamp = (int32_t *) SLIP_calloc ((size_t) n, sizeof (int32_t)) ;
+    if (!P->rows || !P->ptr || !P->nU || !P->piv || !P->prows || !P->pend || !P->pruned
+        || !P->rl_head || !P->rl_col || !P->rl_next || !P->ustamp)
     { patterns_free (P) ; return SLIP_OUT_OF_MEMORY ; }
+    for (int32_t r = 0 ; r < n ; r++) P->rl_head [r] = -1 ;
     return SLIP_OK ;
 }
 
@@ -113,19 +128,19 @@ static int32_t reach_unordered (const SLIP_sparse *A, int32_t col, int32_t klim,
  * them through prow -> column k.  Only the pivotal rows of L(:,j) stay visible: in the dense
  * trailing part a search then costs O(columns) instead of O(entries).  The reach SET is unchanged,
  * and the order of a pattern is fixed afterwards by order_by_position, so nothing else is affected. */
-static void prune_columns (pattern_store *P, int32_t k, int32_t prow, int32_t nU, const int32_t *upos,
+static SLIP_info prune_columns (pattern_store *P, int32_t k, int32_t prow, int32_t nU, const int32_t *upos,
     const int32_t *pinv)
 {
-    for (int32_t u = 0 ; u < nU ; u++)
+    /* the columns of the U part of column k ... */
+    for (int32_t u = 0 ; u < nU ; u++) P->ustamp [upos [u]] = k + 1 ;
+    /* ... whose L part holds the new pivot row: read off the row's list (total cost over the
+       factorization: nnz(L); searching every L(:,j) for prow cost as much as the numerical work) */
+    for (int32_t m = P->rl_head [prow] ; m >= 0 ; m = P->rl_next [m])
     {
-        const int32_t j = upos [u] ;
-        if (P->pruned [j]) continue ;
+        const int32_t j = P->rl_col [m] ;
+        if (P->pruned [j] || P->ustamp [j] != k + 1) continue ;
         int32_t *rj = P->prows + P->ptr [j] + P->nU [j] ;
-        const int32_t lj = P->pend [j] ;
-        int32_t m = 0 ;
-        while (m < lj && rj [m] != prow) m++ ;
-        if (m == lj) continue ;
-        int32_t head = 0, tail = lj ;
+        int32_t head = 0, tail = P->pend [j] ;
         while (head < tail)
         {
             if (pinv [rj [head]] <= k) head++ ;
@@ -134,6 +149,28 @@ static void prune_columns (pattern_store *P, int32_t k, int32_t prow, int32_t nU
         P->pend [j] = tail ;
         P->pruned [j] = 1 ;
     }
+    /* column k joins the row lists: every row of its L part except the pivot row itself */
+    const int32_t cnt = (int32_t) (P->ptr [k + 1] - P->ptr [k]), nUk = P->nU [k] ;
+    if (P->rl_used + cnt > P->rl_cap)
+    {
+        int64_t ncap = P->rl_cap ;
+        while (ncap < P->rl_used + cnt) ncap *= 2 ;
+        int32_t *nc = (int32_t *) realloc (P->rl_col, (size_t) ncap * sizeof (int32_t)) ;
+        if (!nc) return SLIP_OUT_OF_MEMORY ;
+        P->rl_col = nc ;
+        int32_t *nn = (int32_t *) realloc (P->rl_next, (size_t) ncap * sizeof (int32_t)) ;
+        if (!nn) return SLIP_OUT_OF_MEMORY ;
+        P->rl_next = nn ; P->rl_cap = ncap ;
+    }
+    const int32_t *rk = P->rows + P->ptr [k] ;
+    for (int32_t t = nUk ; t < cnt ; t++)
+    {
+        const int32_t r = rk [t] ;
+        if (r == prow) continue ;
+        const int32_t m = (int32_t) P->rl_used++ ;
+        P->rl_col [m] = k ; P->rl_next [m] = P->rl_head [r] ; P->rl_head [r] = m ;
+    }
+    return SLIP_OK ;
 }
 
 /* order a pattern by current row position (slip_sort_xi.c): positions are a permutation, so a
@@ -485,7 +522,7 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
                 P.used += cnt ;
                 P.ptr [k + 1] = P.used ; P.nU [k] = nU ; P.piv [k] = nU ;
                 P.pend [k] = cnt - nU ; P.pruned [k] = 0 ;
-                if (use_pruning) prune_columns (&P, k, prow1, nU, upos, pinv) ;
+                if (use_pruning) SLIP_TRY (prune_columns (&P, k, prow1, nU, upos, pinv)) ;
                 t_piv += now_s () - tt ;
                 continue ;
             }
@@ -524,7 +561,7 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
             P.used += cnt ;
             P.ptr [k + 1] = P.used ; P.nU [k] = nU ; P.piv [k] = slot ;
             P.pend [k] = cnt - nU ; P.pruned [k] = 0 ;
-            if (use_pruning) prune_columns (&P, k, prow, nU, upos, pinv) ;
+            if (use_pruning) SLIP_TRY (prune_columns (&P, k, prow, nU, upos, pinv)) ;
             if (k == n - 1)
             {   /* det = rho[n-1], kept with the resident factors for the rational solve */
                 res = (slip_resident *) SLIP_calloc (1, sizeof (slip_resident)) ;

@@ -173,21 +173,33 @@ static SLIP_info prune_columns (pattern_store *P, int32_t k, int32_t prow, int32
     return SLIP_OK ;
 }
 
-/* order a pattern by current row position (slip_sort_xi.c): positions are a permutation, so a
- * flag per position and one sweep replace the sort */
+/* order a pattern by current row position (slip_sort_xi.c): positions are a permutation, so a bit
+ * per position and one sweep over the words in use replace the sort (posbits: n/64+1 zero words,
+ * left zero again) */
 static void order_by_position (int32_t n, int32_t cnt, int32_t *pat, const int32_t *pinv,
-    const int32_t *row_at, int32_t *posflag, int32_t stamp)
+    const int32_t *row_at, uint64_t *posbits)
 {
-    int32_t lo = n, hi = -1 ;
+    (void) n ;
+    int32_t lo = INT32_MAX, hi = -1 ;
     for (int32_t t = 0 ; t < cnt ; t++)
     {
         const int32_t pos = pinv [pat [t]] ;
-        posflag [pos] = stamp ;
+        posbits [pos >> 6] |= (uint64_t) 1 << (pos & 63) ;
         if (pos < lo) lo = pos ;
         if (pos > hi) hi = pos ;
     }
     int32_t w = 0 ;
-    for (int32_t pos = lo ; pos <= hi ; pos++) if (posflag [pos] == stamp) pat [w++] = row_at [pos] ;
+    for (int32_t q = lo >> 6 ; hi >= 0 && q <= (hi >> 6) ; q++)
+    {
+        uint64_t word = posbits [q] ;
+        posbits [q] = 0 ;
+        while (word)
+        {
+            const int bit = __builtin_ctzll (word) ;
+            pat [w++] = row_at [(q << 6) + bit] ;
+            word &= word - 1 ;
+        }
+    }
 }
 
 /* ---- the rational tolerance test on two reconstructed entries ---- */
@@ -326,7 +338,7 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
     int32_t *upos = (int32_t *) SLIP_malloc ((size_t) n * sizeof (int32_t)) ;
     int32_t *spat = (int32_t *) SLIP_malloc ((size_t) n * sizeof (int32_t)) ;      /* bulk-part pattern, ordered */
     int32_t *supos = (int32_t *) SLIP_malloc ((size_t) n * sizeof (int32_t)) ;
-    int32_t *posflag = (int32_t *) SLIP_calloc ((size_t) n, sizeof (int32_t)) ;
+    uint64_t *posflag = (uint64_t *) SLIP_calloc ((size_t) n / 64 + 2, sizeof (uint64_t)) ;      /* position bitmap of order_by_position */
     if (!colbits || !row_at || !stack || !upos || !cumbits_at || !posflag || !spat || !supos) { status = SLIP_OUT_OF_MEMORY ; goto cleanup ; }
 
     for (int32_t a = 0 ; a < nz ; a++)
@@ -413,7 +425,7 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
             memset (ring [i].mark, 0, (size_t) n * sizeof (int32_t)) ;
             ring [i].cnt = 0 ; ring [i].spec_slot = -1 ;
         }
-        for (int32_t r = 0 ; r < n ; r++) { pinv [r] = r ; row_at [r] = r ; posflag [r] = 0 ; }
+        for (int32_t r = 0 ; r < n ; r++) { pinv [r] = r ; row_at [r] = r ; }
         double cum_bits = 0 ;
         work_updates = 0 ; work_limbmul = 0 ;
         /* the patterns of the first D columns start from the entries of A alone */
@@ -446,7 +458,7 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
                     if (e->mark [rr] != e->stamp) { e->mark [rr] = e->stamp ; pat [cnt++] = rr ; }
                 }
             }
-            order_by_position (n, cnt, pat, pinv, row_at, posflag, k + 1) ;
+            order_by_position (n, cnt, pat, pinv, row_at, posflag) ;
             int32_t nU = 0, diag_slot = -1 ;
             for (int32_t t = 0 ; t < cnt ; t++)
             {
@@ -472,7 +484,7 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
                 if (look > 0 && k > 0)
                 {
                     memcpy (spat, f->pat, (size_t) f->cnt * sizeof (int32_t)) ;
-                    order_by_position (n, f->cnt, spat, pinv, row_at, posflag, n + c + 2) ;
+                    order_by_position (n, f->cnt, spat, pinv, row_at, posflag) ;
                     int32_t snU = 0 ;
                     for (int32_t t = 0 ; t < f->cnt ; t++)
                     {

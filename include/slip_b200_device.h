@@ -42,7 +42,10 @@ typedef struct
                                caller may skip slipcu_factor_column_wait for columns with a single
                                candidate, whose pivot needs no search, and learns of a zero there
                                from the next column it does wait for) */
-    int32_t pad[2];
+    int32_t seq;            /* written last by the kernel that filled the record (sequence number of the
+                               scan): the record lives in mapped host memory and slipcu_factor_column_wait
+                               polls this word instead of sleeping on an event */
+    int32_t pad[1];
 } slipcu_pivot_info;
 
 /* receives column k of the factorization as positional integers.  `limbs` holds `cnt` rows of

@@ -566,6 +566,8 @@ struct slipcu_factor
     int32_t *run_flags = nullptr;            // device: [0] first column (k+1) without a nonzero candidate, [1] largest measured size so far
     struct { int k, slot; } pending_commit = { -1, -1 };     // pivot chosen, commit folded into the next column's first kernel
     int frac_min_s = 64;                     // approximate pivot search only from this many channels on
+    int32_t info_seq = 0;                    // sequence number of the last scan / selection launched
+    bool counted = false;                    // this session is in g_live_sessions
     int nowait_singles = 0;                  // the caller does not wait for single-candidate columns (slipcu_factor_nowait_singles)
     int mag_on = 0;
     int measured = 0;                        // measured mode: sizes of the candidates are measured, the result is verified exactly by the caller
@@ -1373,6 +1375,7 @@ struct ScanArgs
     slipcu_pivot_info *info;          // mapped host memory
     int32_t *mag; const int32_t *cum_ub; const int32_t *bound; int measured;
     int k; int32_t *run_flags;        // see slipcu_factor::run_flags
+    int32_t seq;                      // written to info->seq last
 };
 
 // the scan itself, by all threads of one CTA of any size (<= 512 threads)
@@ -1434,6 +1437,8 @@ __device__ __noinline__ void pivot_scan_body (const ScanArgs &a)
             info->singular_col = a.run_flags[0];
             if (a.measured) { atomicMax (&a.run_flags[1], s_meas); info->bound_units = a.run_flags[1]; }
             else info->bound_units = a.bound ? *a.bound : 0;
+            __threadfence_system ();
+            *(volatile int32_t *) &info->seq = a.seq;
         }
     }
 }
@@ -2362,6 +2367,7 @@ struct FracSel
     const FracKey *key; const int32_t *bad;
     slipcu_pivot_info *info;
     int k; int32_t *run_flags;
+    int32_t seq;
 };
 // order of the approximate magnitudes: more leading zero words is smaller, then the key words
 __device__ __forceinline__ int frac_cmp (const FracKey &x, const FracKey &y)
@@ -2439,6 +2445,8 @@ __global__ void __launch_bounds__ (256) k_fracselect (FracSel a)
         info->reserved[0] = s_uncertain ? 0 : 1;      // 1: the choice is proven
         info->reserved[1] = best >= 0 ? a.key[best].lead : 0;
         info->reserved[2] = a.W;
+        __threadfence_system ();
+        *(volatile int32_t *) &info->seq = a.seq;
     }
 }
 
@@ -2516,6 +2524,7 @@ extern "C" int slipcu_device_count (void)
 // device 0.  Sessions take g_device when it is set, and every entry point makes the session's own
 // device current before it touches the runtime.
 static std::atomic<int> g_device{-1};
+static std::atomic<int> g_live_sessions{0};       // sessions alive in the process (polling is for a lone session only)
 extern "C" int slipcu_set_device (int device)
 {
     CU (cudaSetDevice (device));
@@ -2668,6 +2677,7 @@ static int init_workctx (WorkCtx &w, int n, cudaStream_t st)
 extern "C" void slipcu_factor_free (slipcu_factor *F)
 {
     if (!F) return;
+    if (F->counted) g_live_sessions--;
     if (getenv ("SLIP_B200_TIMING"))
         fprintf (stderr, "slipcu host wall: alloc %.3f packet+prepass %.3f trisolve-launch %.3f garner-launch %.3f scan-launch %.3f wait %.3f\n",
                  g_hw[0], g_hw[1], g_hw[2], g_hw[3], g_hw[4], g_hw[5]);
@@ -2781,6 +2791,7 @@ static int session_common_init (slipcu_factor *F, int n, int channels)
     }
     if (g_device.load () >= 0) { F->device = g_device.load (); CU (cudaSetDevice (F->device)); }
     else CU (cudaGetDevice (&F->device));
+    g_live_sessions++; F->counted = true;
     F->n = n;
     const int S = (channels + 31) & ~31;
     int rc = get_tables (S, F->tab);
@@ -3210,7 +3221,7 @@ static int run_frac (slipcu_factor *F, const HostCol &hc, int cnt, int nU, int s
     }
     FracSel q;
     q.ne = ne; q.nU = nU; q.mode = mode; q.diag_slot = diag_slot; q.W = W;
-    q.key = F->frackey; q.bad = F->bad; q.info = F->d_info; q.k = F->cur_launch; q.run_flags = F->run_flags;
+    q.key = F->frackey; q.bad = F->bad; q.info = F->d_info; q.k = F->cur_launch; q.run_flags = F->run_flags; q.seq = ++F->info_seq;
     {
         ScopedTimer tm (F, &g_other_ms);
         k_fracselect<<<1, 256, 0, F->st>>> (q);
@@ -3252,6 +3263,7 @@ static ScanArgs make_scan_args (slipcu_factor *F, const HostCol &hc, int cnt, in
     a.mag = F->mag_on ? hc.mag : nullptr; a.cum_ub = F->tab->cum_ub; a.bound = F->mag_on ? F->bound : nullptr;
     a.measured = F->measured;
     a.k = F->cur_launch; a.run_flags = F->run_flags;
+    a.seq = ++F->info_seq;
     return a;
 }
 
@@ -3537,7 +3549,25 @@ extern "C" int slipcu_factor_column_wait (slipcu_factor *F, slipcu_pivot_info *i
     if (!F || !info || F->cur < 0) return fail (SLIPCU_BAD_INPUT, "slipcu_factor_column_wait", "bad argument");
     USE_DEVICE (F);
     double tw = wall_s ();
-    CU (cudaEventSynchronize (F->ev));
+    {   // the record is complete when its sequence word (written last, after a system-wide fence) shows
+        // the number of the launch: polled here, which returns microseconds before an event wait would
+        const int32_t want = F->info_seq;
+        volatile int32_t *sq = &F->h_info->seq;
+        bool seen = false;
+        // (several sessions in flight on host threads: spinning threads get in each other's way --
+        // 128 small systems on 8 threads took twice as long -- so those sleep on the event)
+        const int max_spins = g_live_sessions.load () <= 1 ? (1 << 22) : 0;
+        for (int spins = 0; spins < max_spins; ++spins)
+        {
+            if (*sq == want) { seen = true; break; }
+            if ((spins & 2047) == 2047 && cudaEventQuery (F->ev) != cudaErrorNotReady) break;      // finished, or failed
+#if defined(__x86_64__) || defined(__i386__)
+            __builtin_ia32_pause ();
+#endif
+        }
+        if (!seen) CU (cudaEventSynchronize (F->ev));
+        else std::atomic_thread_fence (std::memory_order_acquire);
+    }
     g_d2h_bytes += sizeof (slipcu_pivot_info);
     *info = *F->h_info;
     if (F->frac_col == F->cur)

@@ -598,6 +598,59 @@ static cudaEvent_t take_event ()
     cudaEventCreate (&e);
     return e;
 }
+// Events and streams of finished sessions are kept too (creating and destroying them takes a
+// driver-wide lock: eight sessions starting and ending on eight host threads queue up behind it).
+static std::mutex g_obj_mutex;
+static std::multimap<int, cudaEvent_t> g_ev_free;          // kind = 2 * device + timing
+static std::map<cudaEvent_t, int> g_ev_kind;
+static std::multimap<int, cudaStream_t> g_st_free;         // device
+static std::map<cudaStream_t, int> g_st_dev;
+static cudaError_t pooled_event (cudaEvent_t *out, bool timing)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice (&dev);
+    if (e != cudaSuccess) return e;
+    const int kind = 2 * dev + (timing ? 1 : 0);
+    {
+        std::lock_guard<std::mutex> lk (g_obj_mutex);
+        auto it = g_ev_free.find (kind);
+        if (it != g_ev_free.end ()) { *out = it->second; g_ev_free.erase (it); return cudaSuccess; }
+    }
+    e = timing ? cudaEventCreate (out) : cudaEventCreateWithFlags (out, cudaEventDisableTiming);
+    if (e == cudaSuccess) { std::lock_guard<std::mutex> lk (g_obj_mutex); g_ev_kind[*out] = kind; }
+    return e;
+}
+static void release_event (cudaEvent_t ev)
+{
+    if (!ev) return;
+    std::lock_guard<std::mutex> lk (g_obj_mutex);
+    auto it = g_ev_kind.find (ev);
+    if (it == g_ev_kind.end ()) { cudaEventDestroy (ev); return; }
+    g_ev_free.insert ({it->second, ev});
+}
+static cudaError_t pooled_stream (cudaStream_t *out)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice (&dev);
+    if (e != cudaSuccess) return e;
+    {
+        std::lock_guard<std::mutex> lk (g_obj_mutex);
+        auto it = g_st_free.find (dev);
+        if (it != g_st_free.end ()) { *out = it->second; g_st_free.erase (it); return cudaSuccess; }
+    }
+    e = cudaStreamCreateWithFlags (out, cudaStreamNonBlocking);
+    if (e == cudaSuccess) { std::lock_guard<std::mutex> lk (g_obj_mutex); g_st_dev[*out] = dev; }
+    return e;
+}
+static void release_stream (cudaStream_t st)
+{   // the caller has synchronised it
+    if (!st) return;
+    std::lock_guard<std::mutex> lk (g_obj_mutex);
+    auto it = g_st_dev.find (st);
+    if (it == g_st_dev.end ()) { cudaStreamDestroy (st); return; }
+    g_st_free.insert ({it->second, st});
+}
+
 struct ScopedTimer
 {
     slipcu_factor *F; double *acc; cudaEvent_t a = nullptr; cudaStream_t st;
@@ -2659,7 +2712,7 @@ static void free_workctx (WorkCtx &w)
 {
     pool_free (w.pos); pool_free (w.slots); pool_free (w.steps); pool_free (w.chunks);
     host_pool_free (w.h_packet);
-    for (cudaEvent_t e : w.pk_ev) if (e) cudaEventDestroy (e);
+    for (cudaEvent_t e : w.pk_ev) if (e) release_event (e);
     w = WorkCtx ();
 }
 static int init_workctx (WorkCtx &w, int n, cudaStream_t st)
@@ -2670,7 +2723,7 @@ static int init_workctx (WorkCtx &w, int n, cudaStream_t st)
     w.pk_stride = ((size_t) 4 * n + 8 + 31) & ~(size_t) 31;
     CU (host_pool_alloc ((void **) &w.h_packet, w.pk_stride * PK_RING * sizeof (int32_t)));
     CU (cudaHostGetDevicePointer ((void **) &w.h_packet_dev, w.h_packet, 0));
-    for (int i = 0; i < PK_RING; ++i) CU (cudaEventCreateWithFlags (&w.pk_ev[i], cudaEventDisableTiming));
+    for (int i = 0; i < PK_RING; ++i) CU (pooled_event (&w.pk_ev[i], false));
     return SLIPCU_OK;
 }
 
@@ -2702,23 +2755,23 @@ extern "C" void slipcu_factor_free (slipcu_factor *F)
         if (sl.w.st) cudaStreamSynchronize (sl.w.st);
         free_workctx (sl.w);
         pool_free (sl.buf); pool_free (sl.mag);
-        if (sl.done) cudaEventDestroy (sl.done);
-        if (sl.consumed) cudaEventDestroy (sl.consumed);
-        if (sl.w.st) cudaStreamDestroy (sl.w.st);
+        if (sl.done) release_event (sl.done);
+        if (sl.consumed) release_event (sl.consumed);
+        if (sl.w.st) release_stream (sl.w.st);
     }
-    if (F->ev_commit) cudaEventDestroy (F->ev_commit);
+    if (F->ev_commit) release_event (F->ev_commit);
     host_pool_free (F->h_info);
-    if (F->ev) cudaEventDestroy (F->ev);
-    if (F->ev0) cudaEventDestroy (F->ev0);
-    if (F->ev1) cudaEventDestroy (F->ev1);
-    if (F->ev_start) cudaEventDestroy (F->ev_start);
-    if (F->ev_end) cudaEventDestroy (F->ev_end);
-    if (F->ev_tri) cudaEventDestroy (F->ev_tri);
-    if (F->ev_gl) cudaEventDestroy (F->ev_gl);
-    if (F->ev_side[0]) cudaEventDestroy (F->ev_side[0]);
-    if (F->ev_side[1]) cudaEventDestroy (F->ev_side[1]);
-    if (F->st2) cudaStreamDestroy (F->st2);
-    if (F->st) cudaStreamDestroy (F->st);
+    if (F->ev) release_event (F->ev);
+    if (F->ev0) release_event (F->ev0);
+    if (F->ev1) release_event (F->ev1);
+    if (F->ev_start) release_event (F->ev_start);
+    if (F->ev_end) release_event (F->ev_end);
+    if (F->ev_tri) release_event (F->ev_tri);
+    if (F->ev_gl) release_event (F->ev_gl);
+    if (F->ev_side[0]) release_event (F->ev_side[0]);
+    if (F->ev_side[1]) release_event (F->ev_side[1]);
+    if (F->st2) release_stream (F->st2);
+    if (F->st) release_stream (F->st);
     delete F;
 }
 
@@ -2846,11 +2899,11 @@ static int session_common_init (slipcu_factor *F, int n, int channels)
         if (rc) return rc;
     }
 
-    CU (cudaStreamCreateWithFlags (&F->st, cudaStreamNonBlocking));
+    CU (pooled_stream (&F->st));
     F->wst = F->st;
-    CU (cudaEventCreateWithFlags (&F->ev, cudaEventDisableTiming));
-    CU (cudaEventCreate (&F->ev0)); CU (cudaEventCreate (&F->ev1));
-    CU (cudaEventCreate (&F->ev_start)); CU (cudaEventCreate (&F->ev_end));
+    CU (pooled_event (&F->ev, false));
+    CU (pooled_event (&F->ev0, true)); CU (pooled_event (&F->ev1, true));
+    CU (pooled_event (&F->ev_start, true)); CU (pooled_event (&F->ev_end, true));
     CU (pool_alloc_t (&F->rho, (size_t) n * S * sizeof (u32)));
     CU (pool_alloc_t (&F->invrho, (size_t) n * S * sizeof (u32)));
     CU (pool_alloc_t (&F->desc, (size_t) n * sizeof (ColDesc)));
@@ -2866,7 +2919,7 @@ static int session_common_init (slipcu_factor *F, int n, int channels)
     F->frac_min_s = std::max (16, env_int ("SLIP_B200_FRAC_MIN_S", 64));
     rc = init_workctx (F->mc, n, F->st);
     if (rc) return rc;
-    CU (cudaEventCreateWithFlags (&F->ev_commit, cudaEventDisableTiming));
+    CU (pooled_event (&F->ev_commit, false));
     // the scan result goes straight into mapped host memory (a 48-byte store over PCIe instead of a
     // copy-engine operation per column); the event behind the kernel publishes it to the host
     CU (host_pool_alloc ((void **) &F->h_info, sizeof (slipcu_pivot_info)));
@@ -2918,11 +2971,11 @@ extern "C" int slipcu_factor_begin (slipcu_factor **out, int n, int nz, const in
     if (F->keep_positional && env_int ("SLIP_B200_OVERLAP", 1))
     {   // second stream for the positional reconstruction (see the session struct)
         F->overlap = 1;
-        CU (cudaStreamCreateWithFlags (&F->st2, cudaStreamNonBlocking));
-        CU (cudaEventCreateWithFlags (&F->ev_tri, cudaEventDisableTiming));
-        CU (cudaEventCreateWithFlags (&F->ev_gl, cudaEventDisableTiming));
-        CU (cudaEventCreateWithFlags (&F->ev_side[0], cudaEventDisableTiming));
-        CU (cudaEventCreateWithFlags (&F->ev_side[1], cudaEventDisableTiming));
+        CU (pooled_stream (&F->st2));
+        CU (pooled_event (&F->ev_tri, false));
+        CU (pooled_event (&F->ev_gl, false));
+        CU (pooled_event (&F->ev_side[0], false));
+        CU (pooled_event (&F->ev_side[1], false));
     }
     const int S = F->S, CH = F->CH;
     CU (pool_alloc_t (&F->dAp, (size_t) (n + 1) * sizeof (int32_t)));
@@ -3332,11 +3385,11 @@ extern "C" int slipcu_factor_spec_launch (slipcu_factor *F, int slot, int k, int
     if (!sl.w.st)
     {
         cudaStream_t st = nullptr;
-        CU (cudaStreamCreateWithFlags (&st, cudaStreamNonBlocking));
+        CU (pooled_stream (&st));
         int rc0 = init_workctx (sl.w, F->n, st);
         if (rc0) return rc0;
-        CU (cudaEventCreateWithFlags (&sl.done, cudaEventDisableTiming));
-        CU (cudaEventCreateWithFlags (&sl.consumed, cudaEventDisableTiming));
+        CU (pooled_event (&sl.done, false));
+        CU (pooled_event (&sl.consumed, false));
     }
     WorkCtx &w = sl.w;
     // the slot's previous vector may still be read by the column launch that consumed it
@@ -3885,7 +3938,7 @@ extern "C" int slipcu_solve (slipcu_factor *F, int nrhs, const u32 *blimbs, cons
         CUG (host_pool_alloc ((void **) &buf[i].h_nl, bn * sizeof (int32_t)));
         CUG (host_pool_alloc ((void **) &buf[i].h_sign, bn));
         CUG (host_pool_alloc ((void **) &buf[i].h_topd, bn * sizeof (int32_t)));
-        CUG (cudaEventCreateWithFlags (&buf[i].done, cudaEventDisableTiming));
+        CUG (pooled_event (&buf[i].done, false));
     }
     CUG (cudaMemcpyAsync (dl, blimbs, nl * sizeof (u32), cudaMemcpyHostToDevice, F->st));
     CUG (cudaMemcpyAsync (doff, boff, (total + 1) * sizeof (int64_t), cudaMemcpyHostToDevice, F->st));
@@ -4050,7 +4103,7 @@ done:
     {
         pool_free (buf[i].dlimbs); pool_free (buf[i].dnl); pool_free (buf[i].dsign);
         host_pool_free (buf[i].h_limbs); host_pool_free (buf[i].h_nl); host_pool_free (buf[i].h_sign); host_pool_free (buf[i].h_topd);
-        if (buf[i].done) cudaEventDestroy (buf[i].done);
+        if (buf[i].done) release_event (buf[i].done);
     }
 #undef CUG
     return rc;

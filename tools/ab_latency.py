@@ -47,9 +47,10 @@ for g in range(128):
     systems.append((lib.sparse_from_csc(n, cp, ri, vals), lib.dense_from_rows(b), lib.default_options()))
 solve(*systems[0])
 t = time.perf_counter()
-with ThreadPoolExecutor(max_workers=8) as pool:
+NT = int(os.environ.get("AB_THREADS", "8"))
+with ThreadPoolExecutor(max_workers=NT) as pool:
     list(pool.map(lambda s: solve(*s), systems))
-out.append(f"128 x lp500 (8 threads) {(time.perf_counter() - t) * 1e3:.0f} ms")
+out.append(f"128 x lp500 ({NT} threads) {(time.perf_counter() - t) * 1e3:.0f} ms")
 n, cp, ri, vals, b = synth.lp_basis(10000, seed=4, nrhs=1)
 A = lib.sparse_from_csc(n, cp, ri, vals); B = lib.dense_from_rows(b); o = lib.default_options()
 best = 1e9

@@ -9,12 +9,17 @@
 // 32-bit-limb carry-chain pass.  See DESIGN.md for layout, bounds and rooflines.
 //
 // Reference routines replaced (cjh10644/SLIP_LU):
-//   k_trisolve        slip_REF_triangular_solve.c:84-262, slip_forward_sub.c:64-155
-//   k_backsub         slip_array_mul.c, slip_back_sub.c:30-56
-//   k_garner,k_limbs  (GMP keeps values positional; here reconstruction is explicit)
-//   k_pivot_scan      slip_get_pivot.c:46-150, slip_get_{smallest,largest,nonzero}_pivot.c
-//   k_pivot_commit    slip_get_pivot.c:152-175
+//   k_trisolve        slip_REF_triangular_solve.c:84-262, slip_forward_sub.c:64-155, and (the U parts
+//                     as steps n-1..0) slip_array_mul.c + slip_back_sub.c:30-56
+//   k_prep, k_slots   the index arithmetic of the reference's inner loops (pinv[L->i[m]]), once per
+//                     column for all channels; k_prep also commits the previous pivot
+//   k_garner*, k_limbs  (GMP keeps values positional; here reconstruction is explicit)
+//   pivot_scan_body   slip_get_pivot.c:46-150, slip_get_{smallest,largest,nonzero}_pivot.c (run by the
+//                     last CTA of the reconstruction launch); k_fraccrt/k_fracselect: the same search
+//                     on approximate magnitudes with a proven-choice rule
+//   pivot_commit_body slip_get_pivot.c:152-175
 //   k_residues        slip_get_column.c (input side)
+//   k_backsub         round 1's back substitution (kept behind SLIP_B200_BACKSUB=0)
 
 #include <cuda_runtime.h>
 #include <stdint.h>

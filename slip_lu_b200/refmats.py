@@ -88,6 +88,7 @@ SYNTH = {
     "synth/rand600": dict(family="configs[1] generator (random sparse, 10 nnz/col, 32-bit)", gen="random", n=600, seed=BENCH_SEED),
     "synth/lap24": dict(family="configs[2] generator (2D Laplacian pattern, 64-bit)", gen="laplacian", m=24, seed=7),
     "synth/lap32": dict(family="configs[2] generator (2D Laplacian pattern, 64-bit)", gen="laplacian", m=32, seed=7),
+    "synth/lap40": dict(family="configs[2] generator (2D Laplacian pattern, 64-bit)", gen="laplacian", m=40, seed=7),
 }
 
 

@@ -345,7 +345,7 @@ def cpu_leg_subprocess(argv, timeout=900):
 H2H = ["synth/rand240", "NSR8K", "prob159", "synth/lap24"]
 # GPU leg live, CPU seconds as recorded with the reference's digests in the build container (minutes
 # of CPU each: not repeated in every bench run); the ratio of these rows is labelled accordingly
-H2H_RECORDED = ["synth/rand600", "synth/lap32", "basislib/gen2", "basislib/rat7a"]
+H2H_RECORDED = ["synth/rand600", "synth/lap32", "synth/lap40", "basislib/gen2", "basislib/rat7a"]
 
 
 def head_to_head(lib, with_cpu):

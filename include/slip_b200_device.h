@@ -201,7 +201,9 @@ typedef struct
     double   recon_mac;           /* 32x32 multiply-accumulates in reconstruction */
     double   h2d_bytes, d2h_bytes;/* bytes this library copied host->device / device->host */
     double   device_ms;           /* CUDA-event time from "A resident in HBM" to "solution numerators
-                                     reconstructed in HBM", accumulated over slipcu_solve calls */
+                                     reconstructed in HBM", accumulated over slipcu_solve calls; sessions that
+                                     never reach a solve (attempts aborted for more channels or a retired prime)
+                                     add their time when they are freed */
     double   other_ms;            /* symbolic pre-pass + pivot scan kernels (profiling mode) */
     double   trisolve_union_ms;   /* time during which at least one k_trisolve launch was running (launches
                                      on the lookahead streams overlap: trisolve_ms counts shared time twice) */

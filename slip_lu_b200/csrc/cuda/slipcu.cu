@@ -573,6 +573,7 @@ struct slipcu_factor
     int frac_min_s = 64;                     // approximate pivot search only from this many channels on
     int32_t info_seq = 0;                    // sequence number of the last scan / selection launched
     bool counted = false;                    // this session is in g_live_sessions
+    bool timed = false;                      // its device time has been added to g_device_ms (slipcu_solve)
     int nowait_singles = 0;                  // the caller does not wait for single-candidate columns (slipcu_factor_nowait_singles)
     int mag_on = 0;
     int measured = 0;                        // measured mode: sizes of the candidates are measured, the result is verified exactly by the caller
@@ -2741,6 +2742,16 @@ extern "C" void slipcu_factor_free (slipcu_factor *F)
                  g_hw[0], g_hw[1], g_hw[2], g_hw[3], g_hw[4], g_hw[5]);
     for (double &v : g_hw) v = 0;
     cudaSetDevice (F->device);
+    if (F->st && F->ev_start && F->ev_end && !F->timed && !F->rows_are_positions && F->cur >= 0)
+    {   // a session that never reached its solve (an attempt aborted for more channels, a prime
+        // retired, a singular matrix): its device time belongs to the job as well
+        if (cudaEventRecord (F->ev_end, F->st) == cudaSuccess && cudaEventSynchronize (F->ev_end) == cudaSuccess)
+        {
+            float ms = 0;
+            if (cudaEventElapsedTime (&ms, F->ev_start, F->ev_end) == cudaSuccess) g_device_ms += ms; else cudaGetLastError ();
+        }
+        else cudaGetLastError ();
+    }
     if (F->st) cudaStreamSynchronize (F->st);
     if (F->st2) cudaStreamSynchronize (F->st2);
     flush_timers (F);
@@ -4098,7 +4109,7 @@ done:
     if (rc == SLIPCU_OK && !F->rows_are_positions)
     {   // device-side job time: A resident -> solution numerators reconstructed on the device
         float ms = 0;
-        if (cudaEventElapsedTime (&ms, F->ev_start, F->ev_end) == cudaSuccess) g_device_ms += ms; else cudaGetLastError ();
+        if (cudaEventElapsedTime (&ms, F->ev_start, F->ev_end) == cudaSuccess) { g_device_ms += ms; F->timed = true; } else cudaGetLastError ();
     }
     pool_free (dl); pool_free (doff); pool_free (dsg); pool_free (dB); pool_free (dz);
     pool_free (drow_at); pool_free (dident); pool_free (dpinv); pool_free (duoff);

@@ -3822,20 +3822,6 @@ extern "C" int slipcu_factor_upload (slipcu_factor **out, int n, int channels, c
     return check_channels (F);
 }
 
-// D2H of a column's limbs through pinned staging, handed to the sink
-static int stream_column (slipcu_factor *F, int k, const HostCol &hc, slipcu_column_sink sink, void *user,
-                          u32 *h_limbs, int32_t *h_nl, int8_t *h_sign)
-{
-    CU (cudaMemcpyAsync (h_limbs, hc.limbs, (size_t) hc.cnt * hc.stride * sizeof (u32), cudaMemcpyDeviceToHost, F->st));
-    CU (cudaMemcpyAsync (h_nl, hc.nl, (size_t) hc.cnt * sizeof (int32_t), cudaMemcpyDeviceToHost, F->st));
-    CU (cudaMemcpyAsync (h_sign, hc.sign, (size_t) hc.cnt, cudaMemcpyDeviceToHost, F->st));
-    CU (cudaStreamSynchronize (F->st));
-    g_d2h_bytes += (double) hc.cnt * hc.stride * 4 + (double) hc.cnt * 5;
-    int rc = sink (user, k, hc.cnt, hc.stride, h_limbs, h_nl, h_sign);
-    if (rc) return fail (rc, "column sink", "host sink failed");
-    return SLIPCU_OK;
-}
-
 // a channel prime that divides a pivot makes that channel's inverses meaningless
 static int check_channels (slipcu_factor *F)
 {
@@ -3859,22 +3845,85 @@ extern "C" int slipcu_factor_bad_prime (slipcu_factor *F, uint32_t *prime)
     return SLIPCU_OK;
 }
 
+// The columns come to the host in batches of up to DL_BATCH_BYTES of limbs, two pinned buffer sets
+// alternating: while the sink turns batch i into mpz_t (the host's share: allocation and copy of
+// every entry), the copy engine brings batch i + 1 (round 1: one copy, one stream synchronisation
+// and one sink call per column, strictly one after the other).
+#define DL_BATCH_BYTES ((size_t) 64 << 20)
 extern "C" int slipcu_factor_download (slipcu_factor *F, slipcu_column_sink sink, void *user)
 {
     if (!F || !sink) return fail (SLIPCU_BAD_INPUT, "slipcu_factor_download", "bad argument");
     USE_DEVICE (F);
     { int rcf = flush_commit (F); if (rcf) return rcf; }
     { int rcb = check_channels (F); if (rcb) return rcb; }
-    size_t maxw = 0; int maxc = 0;
-    for (auto &hc : F->cols) { maxw = std::max (maxw, (size_t) hc.cnt * hc.stride); maxc = std::max (maxc, hc.cnt); }
-    u32 *h_limbs = nullptr; int32_t *h_nl = nullptr; int8_t *h_sign = nullptr;
-    CU (host_pool_alloc ((void **) &h_limbs, std::max<size_t> (maxw, 1) * sizeof (u32)));
-    CU (host_pool_alloc ((void **) &h_nl, (size_t) std::max (maxc, 1) * sizeof (int32_t)));
-    CU (host_pool_alloc ((void **) &h_sign, (size_t) std::max (maxc, 1)));
+    const int n = F->n;
+    // batches of consecutive columns
+    std::vector<int> first;              // first column of every batch, then n
+    size_t maxw = 0, maxc = 0;
+    {
+        size_t w = 0, c = 0;
+        for (int k = 0; k < n; ++k)
+        {
+            const size_t cw = (size_t) F->cols[k].cnt * F->cols[k].stride;
+            if (first.empty () || (w > 0 && (w + cw) * sizeof (u32) > DL_BATCH_BYTES))
+            {
+                maxw = std::max (maxw, w); maxc = std::max (maxc, c);
+                first.push_back (k); w = 0; c = 0;
+            }
+            w += cw; c += (size_t) F->cols[k].cnt;
+        }
+        maxw = std::max (maxw, w); maxc = std::max (maxc, c);
+        first.push_back (n);
+    }
+    const int nbatch = (int) first.size () - 1;
+    struct Buf { u32 *limbs = nullptr; int32_t *nl = nullptr; int8_t *sign = nullptr; cudaEvent_t done = nullptr; } buf[2];
     int rc = SLIPCU_OK;
-    for (int k = 0; k < F->n && rc == SLIPCU_OK; ++k)
-        rc = stream_column (F, k, F->cols[k], sink, user, h_limbs, h_nl, h_sign);
-    host_pool_free (h_limbs); host_pool_free (h_nl); host_pool_free (h_sign);
+    const int nbuf = nbatch > 1 ? 2 : 1;
+    for (int i = 0; i < nbuf && rc == SLIPCU_OK; ++i)
+    {
+        if (host_pool_alloc ((void **) &buf[i].limbs, std::max<size_t> (maxw, 1) * sizeof (u32)) != cudaSuccess
+            || host_pool_alloc ((void **) &buf[i].nl, std::max<size_t> (maxc, 1) * sizeof (int32_t)) != cudaSuccess
+            || host_pool_alloc ((void **) &buf[i].sign, std::max<size_t> (maxc, 1)) != cudaSuccess
+            || pooled_event (&buf[i].done, false) != cudaSuccess)
+        { cudaGetLastError (); rc = fail (SLIPCU_OUT_OF_MEMORY, "slipcu_factor_download", "pinned host memory"); }
+    }
+    auto enqueue = [&] (int bi) -> int
+    {
+        Buf &B = buf[bi % nbuf];
+        size_t w = 0, c = 0;
+        for (int k = first[bi]; k < first[bi + 1]; ++k)
+        {
+            const HostCol &hc = F->cols[k];
+            CU (cudaMemcpyAsync (B.limbs + w, hc.limbs, (size_t) hc.cnt * hc.stride * sizeof (u32), cudaMemcpyDeviceToHost, F->st));
+            CU (cudaMemcpyAsync (B.nl + c, hc.nl, (size_t) hc.cnt * sizeof (int32_t), cudaMemcpyDeviceToHost, F->st));
+            CU (cudaMemcpyAsync (B.sign + c, hc.sign, (size_t) hc.cnt, cudaMemcpyDeviceToHost, F->st));
+            g_d2h_bytes += (double) hc.cnt * hc.stride * 4 + (double) hc.cnt * 5;
+            w += (size_t) hc.cnt * hc.stride; c += (size_t) hc.cnt;
+        }
+        CU (cudaEventRecord (B.done, F->st));
+        return SLIPCU_OK;
+    };
+    if (rc == SLIPCU_OK && nbatch > 0) rc = enqueue (0);
+    for (int bi = 0; bi < nbatch && rc == SLIPCU_OK; ++bi)
+    {
+        if (bi + 1 < nbatch) { rc = enqueue (bi + 1); if (rc) break; }
+        Buf &B = buf[bi % nbuf];
+        if (cudaEventSynchronize (B.done) != cudaSuccess) { rc = fail (SLIPCU_CUDA_ERROR, "slipcu_factor_download", "copy failed"); break; }
+        size_t w = 0, c = 0;
+        for (int k = first[bi]; k < first[bi + 1]; ++k)
+        {
+            const HostCol &hc = F->cols[k];
+            const int rs = sink (user, k, hc.cnt, hc.stride, B.limbs + w, B.nl + c, B.sign + c);
+            if (rs) { rc = fail (rs, "column sink", "host sink failed"); break; }
+            w += (size_t) hc.cnt * hc.stride; c += (size_t) hc.cnt;
+        }
+    }
+    cudaStreamSynchronize (F->st);
+    for (int i = 0; i < 2; ++i)
+    {
+        host_pool_free (buf[i].limbs); host_pool_free (buf[i].nl); host_pool_free (buf[i].sign);
+        release_event (buf[i].done);
+    }
     return rc;
 }
 

@@ -802,11 +802,11 @@ def main():
             mm = out["roofline"]["modmul_per_s"] or 0.0
             sms = 148
             mhz = float(clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965)
-            peak = pk[9] * sms * mhz * 1e6          # modular multiply-subtracts/s at the clock of the timed region
+            int_peak = pk[9] * sms * mhz * 1e6      # modular multiply-subtracts/s at the clock of the timed region
             out["roofline"]["int_mul"] = {
                 "what": "k_trisolve's modular multiply-subtracts per second against the rate of the same operation on registers only",
                 "unit": "modular multiply-subtracts/s (each: a Shoup product by the step's fixed multiplier, IMAD.HI + 2 IMAD, + 3 integer ALU operations)",
-                "achieved": mm, "peak": peak, "frac": mm / peak if peak else None,
+                "achieved": mm, "peak": int_peak, "frac": mm / int_peak if int_peak else None,
                 "peak_per_sm_cycle": {"shoup_multiply_subtract": pk[9], "montgomery_multiply_subtract": pk[8],
                                       "imad_wide": pk[5], "imad": pk[6], "imad_hi": pk[7]},
                 "peak_as_run_per_s": {"shoup_multiply_subtract": pk[4], "montgomery_multiply_subtract": pk[3],

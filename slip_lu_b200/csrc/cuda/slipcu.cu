@@ -562,6 +562,7 @@ struct slipcu_factor
     slipcu_pivot_info *d_info = nullptr;
     size_t smem_limit = 0;
     int keep_positional = 1, rows_are_positions = 0, x_global = 0, cur = -1, cur_launch = 0;
+    int slot_sort = 0;                  // k_slots hands rows to threads by bank group (see there)
     std::vector<struct TimedRange> ranges;      // profiling: event pairs not yet read
     u32 *tmp_limbs = nullptr; int32_t *tmp_nl = nullptr; int tmp_stride = 0;
     int sms = 148;
@@ -746,12 +747,27 @@ static __host__ __device__ constexpr int tri_ring (int CH) { return CH == 4 ? 16
 // TRI_THREADS/(CH/4) rows at a time; a pipeline chunk is four such row groups (16 KB of L).
 static __host__ __device__ inline int tri_row_groups (int CH) { return TRI_THREADS / (CH / 4); }
 static __host__ __device__ inline int tri_chunk_rows (int CH) { return 4 * tri_row_groups (CH); }
+// A row of the work vector is CH*4 bytes, so 32/CH consecutive row groups (the lanes of a
+// quarter-warp) make one 128-byte wavefront of a 16-byte-per-lane shared-memory access: the number
+// of 'bank groups' a row can fall into.  The slot lists hand the rows of a chunk to the threads in
+// units of that many row groups (see k_slots).
+static __host__ __device__ constexpr int tri_bank_groups (int CH) { return 32 / CH; }
+// row groups of a chunk of nrows rows whose threads have anything to do
+static __host__ __device__ inline int tri_active_groups (int nrows, int CH)
+{
+    const int G = tri_bank_groups (CH), RG = tri_row_groups (CH), up = (nrows + G - 1) / G * G;
+    return up < RG ? up : RG;
+}
 // entries of the slot list of a step with len rows: full chunks, then 4 entries per thread in use
 static __host__ __device__ inline int tri_slot_extent (int len, int CH)
 {
-    const int R = tri_chunk_rows (CH), RG = tri_row_groups (CH), rem = len % R;
-    return (len / R) * R + 4 * (rem < RG ? rem : RG);
+    const int R = tri_chunk_rows (CH), rem = len % R;
+    return (len / R) * R + 4 * tri_active_groups (rem, CH);
 }
+// A slot-list entry: target slot of the work vector (the spare row `cnt` when the row has no
+// target) in the low 22 bits, the row of the chunk whose L entry goes there in the high 10.
+#define TRI_SLOT_BITS 22
+#define TRI_SLOT_MASK ((1u << TRI_SLOT_BITS) - 1u)
 
 struct StepInfo           // one elimination step of a column: eliminate with column j of L
 {
@@ -780,47 +796,91 @@ __global__ void k_setpos (int cnt, const int32_t *rows, int32_t *pos)
     if (t < cnt) pos[rows[t]] = t;
 }
 
-// Slot lists.  For each chunk the list is stored in the order the consumer threads read it: entry
-// 4*g + q is the target of chunk row g + q*RG (g = row group of the thread), so that one 16-byte
-// load gives a thread its four targets.  A target is the BYTE offset of the slot's row in the work
-// vector; rows without a target (past the end of the chunk, or the pivot row itself) point at the
-// spare row `cnt` of the vector, which absorbs their updates.
+// Slot lists, one CTA per pipeline chunk.  Entry 4*g + q of a chunk's list belongs to the thread
+// of row group g (one 16-byte load gives a thread its four entries) and names BOTH the row of the
+// chunk it takes its L entry from and the slot of the work vector that entry updates (packed, see
+// TRI_SLOT_BITS); rows without a target (past the end of the chunk, or the pivot row itself) point
+// at the spare row `cnt` of the vector and are skipped by the consumer.
+//
+// Which row goes to which thread is free, and it decides the shared-memory bank conflicts of
+// k_trisolve: the G = 32/CH row groups of a quarter-warp read G rows of L and read-modify-write G
+// rows of w in one access each, conflict-free iff the G rows fall into G distinct bank groups
+// (row index mod G for L in the stage buffer, slot mod G for w).  With sort == 0 thread g takes
+// rows g + q*RG (consecutive rows of L, targets wherever the pattern puts them: about two
+// wavefronts per access on scattered patterns).  With sort == 1 warp a of this CTA owns the rows
+// r = a (mod G) of the chunk (always 128 of them) and orders them by (slot - a) mod G, stable;
+// the i-th row of every class goes to the same quarter-warp access (q = i / 32, g = (i mod 32) G + a):
+// the L rows of an access are one of each class, and so are the targets wherever the four classes
+// are in the same stretch of their order (all of them, up to the imbalance of the counts).
 // upart = 1: the steps use the U parts of the columns (slots 0..nU-1, no pivot among them): the back
 // substitution, z_i -= U_ij z_j for the rows above the diagonal of column j.
-__global__ void k_slots (int nU, int total, int CH, int cnt, const int32_t *upos, const int32_t *uoff,
+__global__ void __launch_bounds__ (256) k_slots (int nU, int CH, int cnt, const int32_t *upos, const int32_t *uoff,
                          const int32_t *uchunk, const ColDesc *desc, const int32_t *pos, int32_t *slots,
-                         StepInfo *steps, ChunkInfo *chunks, int upart)
+                         StepInfo *steps, ChunkInfo *chunks, int upart, int sort)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    int lo = 0, hi = nU - 1;                      // last u with uoff[u] <= i
-    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (uoff[mid] <= i) lo = mid; else hi = mid - 1; }
-    const int u = lo, o = i - uoff[u];
-    const int R = tri_chunk_rows (CH), RG = tri_row_groups (CH);
+    const int ci = blockIdx.x, lane = threadIdx.x & 31, a = threadIdx.x >> 5;    // chunk, lane, class
+    const int G = tri_bank_groups (CH), R = tri_chunk_rows (CH);
+    int lo = 0, hi = nU - 1;                      // last u with uchunk[u] <= ci: the step of the chunk
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (uchunk[mid] <= ci) lo = mid; else hi = mid - 1; }
+    const int u = lo;
     const ColDesc d = desc[upos[u]];
     const int first = upart ? 0 : d.nU;           // first slot of the part the step streams
     const int len = upart ? d.nU : d.cnt - d.nU;
-    const int ci = o / R, q = o % R;              // chunk of the step, entry inside the chunk
-    const int r = ci * R + (q & 3) * RG + (q >> 2);
-    const int m = first + r;
-    const int rowbytes = CH * 4;
-    slots[i] = (r < len && (upart || m != d.pivslot)) ? pos[d.rows[m]] * rowbytes : cnt * rowbytes;
-    if (o == 0)
+    const int r0 = (ci - uchunk[u]) * R;          // first row of the chunk within the step
+    const int nrows = min (R, len - r0);
+    const int active = (nrows == R) ? tri_row_groups (CH) : tri_active_groups (nrows, CH);
+    const int npass = (((nrows + G - 1) / G) + 31) >> 5;        // passes of 32 rows of a class that hold rows at all
+    const unsigned lt = (1u << lane) - 1u;
+    int slot[4], key[4], idx[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
     {
-        StepInfo si;
-        si.lbase = d.base + (size_t) first * CH; si.j = upos[u]; si.len = len; si.cbstride = d.cnt * CH;
-        si.slot_off = uoff[u]; si.chunk0 = uchunk[u]; si.pad = 0;
-        steps[u] = si;
+        const int r = a + G * (p * 32 + lane);
+        const int m = first + r0 + r;
+        const bool target = r < nrows && (upart || m != d.pivslot);
+        slot[p] = target ? pos[d.rows[m]] : cnt;
+        key[p] = target ? (sort ? ((slot[p] - a) & (G - 1)) : 0) : G;
+        idx[p] = p * 32 + lane;                   // passes without rows keep their place at the end
     }
-    if (q == 0)
+    if (sort || npass < 4)
+    {   // stable order by key: targets first (by bank group relative to the class), rows without one last
+        int run = 0;
+        for (int k = 0; k <= G; ++k)
+        {
+            if (!sort && k > 0 && k < G) continue;
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+            {
+                if (p >= npass) continue;
+                const unsigned b = __ballot_sync (0xffffffffu, key[p] == k);
+                if (key[p] == k) idx[p] = run + __popc (b & lt);
+                run += __popc (b);
+            }
+        }
+    }
+    int32_t *out = slots + (size_t) uoff[u] + r0;
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
     {
+        const int g = (idx[p] & 31) * G + a, q = idx[p] >> 5;
+        const int r = a + G * (p * 32 + lane);
+        if (g < active) out[4 * g + q] = (int32_t) ((u32) slot[p] | ((u32) r << TRI_SLOT_BITS));
+    }
+    if (threadIdx.x == 0)
+    {
+        if (r0 == 0)
+        {
+            StepInfo si;
+            si.lbase = d.base + (size_t) first * CH; si.j = upos[u]; si.len = len; si.cbstride = d.cnt * CH;
+            si.slot_off = uoff[u]; si.chunk0 = uchunk[u]; si.pad = 0;
+            steps[u] = si;
+        }
         ChunkInfo c;
-        const int r0 = ci * R;
         c.lsrc = d.base + (size_t) (first + r0) * CH; c.cbstride = d.cnt * CH;
         c.slot_off = uoff[u] + r0; c.j = upos[u];
-        c.meta = min (R, len - r0) | ((r0 == 0) << 16) | ((r0 + R >= len) << 17);
+        c.meta = nrows | ((r0 == 0) << 16) | ((r0 + R >= len) << 17);
         c.msrc = d.mag ? d.mag + first + r0 : nullptr;
-        chunks[uchunk[u] + ci] = c;
+        chunks[ci] = c;
     }
 }
 
@@ -1026,9 +1086,9 @@ __device__ __forceinline__ void cp_async4 (u32 dst_smem, const void *src)
     asm volatile ("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst_smem), "l"(src) : "memory");
 }
 
-// The bound CTA of a k_trisolve launch.  Same chunk descriptors, same slot lists (stored in the
-// order the consumer threads of the residue CTAs read them: entry 4g+q is chunk row g + q*RG) and
-// the same three-stage cp.async ring, but a row is one int32 instead of CH residues.
+// The bound CTA of a k_trisolve launch.  Same chunk descriptors, same slot lists (every entry names
+// its chunk row and its target slot, see k_slots) and the same three-stage cp.async ring, but a
+// row is one int32 instead of CH residues.
 template <int CH, int NT>
 __device__ __noinline__ void tri_mag_cta (const TriArgs &a, unsigned char *smem_raw)
 {
@@ -1043,7 +1103,6 @@ __device__ __noinline__ void tri_mag_cta (const TriArgs &a, unsigned char *smem_
     int32_t *mb = in_smem ? (int32_t *) smem_raw : a.mag_out;      // working vector (global when the pattern is too long)
     const u32 ring = smem0 + vec_bytes;
     const u32 stage0 = ring + RING_BYTES;
-    const int spare = cnt * CH * 4;
 
     auto fetch_desc = [&] (int X, int half)
     {
@@ -1057,7 +1116,7 @@ __device__ __noinline__ void tri_mag_cta (const TriArgs &a, unsigned char *smem_
         const uint4 d1 = lds128 (da + 16);             // j, meta, msrc (lo, hi)
         const int nrows = (int) (d1.y & 0xffffu);
         const int32_t *msrc = (const int32_t *) (((unsigned long long) d1.w << 32) | d1.z);
-        if (tid < min (nrows, RG)) cp_async16 (sb + (u32) tid * 16, a.slots + (size_t) d0.w + (size_t) tid * 4);
+        if (tid < tri_active_groups (nrows, CH)) cp_async16 (sb + (u32) tid * 16, a.slots + (size_t) d0.w + (size_t) tid * 4);
         for (int r = tid; r < nrows; r += NT) cp_async4 (sb + R * 4 + (u32) r * 4, msrc + r);
         if ((d1.y & 0x10000u) && tid == 0) cp_async4 (sb + 2 * R * 4, a.rho_mag + (int) d1.x);
     };
@@ -1097,19 +1156,15 @@ __device__ __noinline__ void tri_mag_cta (const TriArgs &a, unsigned char *smem_
         }
         if (y != MAG_NEG)
         {
-            const int ext = (nrows == R) ? R : 4 * min (nrows, RG);
+            const int ext = (nrows == R) ? R : 4 * tri_active_groups (nrows, CH);
             for (int e = tid; e < ext; e += NT)
             {
-                const int t = reinterpret_cast<const int32_t *> (sbp)[e];
-                const int r = (e >> 2) + (e & 3) * RG;
-                if (t != spare && r < nrows)
+                const u32 t = reinterpret_cast<const u32 *> (sbp)[e];
+                const int slot = (int) (t & TRI_SLOT_MASK), r = (int) (t >> TRI_SLOT_BITS);
+                if (slot != cnt && r < nrows)
                 {
                     const int32_t lm = reinterpret_cast<const int32_t *> (sbp + R * 4)[r];
-                    if (lm != MAG_NEG)
-                    {
-                        const int slot = t / (CH * 4);
-                        mb[slot] = mag_lse (mb[slot], lm + y);
-                    }
+                    if (lm != MAG_NEG) mb[slot] = mag_lse (mb[slot], lm + y);
                 }
             }
         }
@@ -1212,7 +1267,7 @@ __global__ void __launch_bounds__ (TRI_THREADS * 4 / CPT, CH == 4 ? 1 : 2) k_tri
                 if (tid + 2 * NT < lp) cp_async16_off<2 * NT * 16> (ldst, lsrc);
                 if (tid + 3 * NT < lp) cp_async16_off<3 * NT * 16> (ldst, lsrc);
             }
-            if (tid < min (nrows, RG))                 // one 16-byte group of targets per row group in use
+            if (tid < tri_active_groups (nrows, CH))   // one 16-byte group of entries per row group in use
                 cp_async16 (sb + SM::L_BYTES + (u32) tid * 16, a.slots + (size_t) d0.w + (size_t) tid * 4);
         }
         if ((d1.y & 0x10000u) && tid < CH / 4)
@@ -1301,17 +1356,20 @@ __global__ void __launch_bounds__ (TRI_THREADS * 4 / CPT, CH == 4 ? 1 : 2) k_tri
         }
         // rows of one step hit distinct slots: the four rows of a thread are loaded, updated and
         // stored together so that their latencies overlap
-        if (rg < (int) (meta & 0xffffu))
+        if (rg < tri_active_groups ((int) (meta & 0xffffu), CH))
         {
+            // four slot-list entries: the chunk row each L entry comes from and the slot it updates
             const uint4 tq = lds128 (sb + SM::L_BYTES + (u32) rg * 16);
-            const u32 t[4] = { tq.x, tq.y, tq.z, tq.w };
-            const u32 lrow = sb + (u32) rg * (CH * 4) + qc * 4;
+            const u32 en[4] = { tq.x, tq.y, tq.z, tq.w };
+            u32 t[4];
+            const u32 lrow = sb + qc * 4;
             V l[4], w[4];
             const u32 xsa = smem0 + qc * 4;            // (XS) shared-memory address of this thread's channels of row 0
 #pragma unroll
             for (int q = 0; q < 4; ++q)
             {
-                l[q] = ldsv<CPT> (lrow + q * RG * CH * 4);
+                t[q] = (en[q] & TRI_SLOT_MASK) * (CH * 4);             // byte offset of the target row
+                l[q] = ldsv<CPT> (lrow + (en[q] >> TRI_SLOT_BITS) * (CH * 4));
                 if (XS && CPT == 4)
                 {   // predicated in place (no branch, the four rows stay interleaved): rows without
                     // a target neither load nor store
@@ -2909,6 +2967,11 @@ static int session_common_init (slipcu_factor *F, int n, int channels)
     F->cpt = env_int ("SLIP_B200_CPT", 4);             // channels per thread of k_trisolve: 4 or 2
     if (F->cpt != 2 && F->cpt != 4) F->cpt = 4;
     F->threads = TRI_THREADS * 4 / F->cpt;
+    // sessions of thousands of channels are bound by k_trisolve's shared-memory traffic: their slot lists
+    // are ordered by bank group; sessions of few channels are bound by the latency of a column,
+    // where the plain order (no ballots in k_slots) is the shorter path
+    F->slot_sort = env_int ("SLIP_B200_SLOT_SORT", F->S > 512 ? 1 : 0) ? 1 : 0;
+    if (F->n >= (int) TRI_SLOT_MASK) return fail (SLIPCU_BAD_INPUT, "session", "more than 4M rows");
     if (configure)
     {
         rc = tri_configure (smem_optin - 1024);      // static shared memory of the kernels (a few words) comes out of the same budget
@@ -3139,9 +3202,9 @@ static int prepare_steps (slipcu_factor *F, WorkCtx &w, int cnt, int nU, const i
         CU (cudaGetLastError ());
         if (debug_check ("k_setpos", w.st)) return fail (SLIPCU_CUDA_ERROR, "k_setpos", "debug");
     }
-    if (nU > 0 && total > 0)
+    if (nU > 0 && total > 0 && nchunks > 0)
     {
-        k_slots<<<(total + 255) / 256, 256, 0, w.st>>> (nU, total, F->CH, cnt, upos, uoff, uchunk, F->desc, w.pos, w.slots, w.steps, w.chunks, upart);
+        k_slots<<<nchunks, 32 * tri_bank_groups (F->CH), 0, w.st>>> (nU, F->CH, cnt, upos, uoff, uchunk, F->desc, w.pos, w.slots, w.steps, w.chunks, upart, F->slot_sort);
         g_launches++;
         CU (cudaGetLastError ());
         if (debug_check ("k_slots", w.st)) return fail (SLIPCU_CUDA_ERROR, "k_slots", "debug");

@@ -233,16 +233,20 @@ def roofline_of(c, peak, peak_src, t_dev=None):
     # launches on the lookahead streams overlap: the kernel's time is the union of its launch intervals
     tri_ms = c.trisolve_union_ms if c.trisolve_union_ms > 0 else c.trisolve_ms
     achieved = (c.trisolve_bytes / 1e9) / (tri_ms / 1e3) if tri_ms > 0 else 0.0
-    traffic = None
-    try:   # DRAM bytes / algorithmic bytes of one `ncu --set full` capture of this kernel
-        cap = json.load(open(os.path.join(ROOT, "profiles", "r02_trisolve_ncu_full.json")))
-        traffic = cap["traffic_over_algorithmic"] * c.trisolve_bytes / max(1, c.trisolve_launches)
-    except Exception:
-        pass
+    traffic, ratio, cap_name = None, None, None
+    for name in ("r02_trisolve_ncu_full_sorted.json", "r02_trisolve_ncu_full.json"):
+        try:   # DRAM bytes / algorithmic bytes of one `ncu --set full` capture of this kernel
+            cap = json.load(open(os.path.join(ROOT, "profiles", name)))
+            ratio = cap["k_trisolve"][0]["traffic_over_algorithmic"] if "k_trisolve" in cap else cap["traffic_over_algorithmic"]
+            traffic = ratio * c.trisolve_bytes / max(1, c.trisolve_launches)
+            cap_name = name
+            break
+        except Exception:
+            continue
     return {"bound": "hbm", "kernel": "k_trisolve", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak if peak else None, "peak_source": peak_src,
             "launches": int(c.trisolve_launches), "traffic": traffic,
-            "traffic_source": "algorithmic bytes x the DRAM/algorithmic ratio (1.011) of profiles/r02_trisolve_ncu_full.json (one ncu --set full capture of this kernel)",
+            "traffic_source": ("algorithmic bytes x the DRAM/algorithmic ratio (%.4f) of profiles/%s (one ncu --set full capture of this kernel)" % (ratio, cap_name)) if cap_name else None,
             "algorithmic_bytes_per_launch": c.trisolve_bytes / max(1, c.trisolve_launches),
             "modmul_per_s": c.trisolve_modmul / (tri_ms / 1e3) if tri_ms > 0 else None,
             "kernel_ms": tri_ms, "kernel_ms_sum_of_launches": c.trisolve_ms,

@@ -136,7 +136,6 @@ struct Tables
     std::vector<u32> hp;       // host copy of the primes
     std::vector<double> cumbits;   // cumbits[c] = log2(p_0 ... p_{c-1})
     u32 *p = nullptr, *ninv = nullptr, *r2 = nullptr, *one = nullptr;
-    u32 *c62 = nullptr;        // floor(2^62 / p): reciprocal for the Shoup companion of a step's multiplier
     u32 *C = nullptr;          // [S][S]  C[u][t] = (p_0..p_{u-1}) mod p_t, Montgomery form, u < t
     u32 *invB = nullptr;       // [S]     (p_0..p_{t-1})^-1 mod p_t, Montgomery form
     u32 *Bpos = nullptr;       // [S][LB] limbs of p_0..p_{t-1}
@@ -147,7 +146,7 @@ struct Tables
     int32_t *cum_ub = nullptr; // [S+1] upper bound of 64 log2 (p_0..p_{c-1}) (bound mode)
     ~Tables ()
     {
-        cudaFree (p); cudaFree (ninv); cudaFree (r2); cudaFree (one); cudaFree (c62);
+        cudaFree (p); cudaFree (ninv); cudaFree (r2); cudaFree (one);
         cudaFree (C); cudaFree (invB); cudaFree (Bpos); cudaFree (Minv); cudaFree (Urec); cudaFree (cum_ub);
     }
 };
@@ -227,7 +226,7 @@ static int build_tables (int S, std::shared_ptr<Tables> &out)
     T->S = S;
     extend_primes ((size_t) S);
     T->hp.assign (g_primes.begin (), g_primes.begin () + S);
-    std::vector<u32> ninv (S), r2 (S), one (S), c62 (S);
+    std::vector<u32> ninv (S), r2 (S), one (S);
     T->cumbits.resize (S + 1);
     T->cumbits[0] = 0.0;
     for (int c = 0; c < S; ++c)
@@ -239,7 +238,6 @@ static int build_tables (int S, std::shared_ptr<Tables> &out)
         u64 r = ((u64) 1 << 32) % p;
         one[c] = (u32) r;
         r2[c] = (u32) ((r * r) % p);
-        c62[c] = (u32) ((((unsigned __int128) 1) << 62) / p);      // 2^31 < c62 < 2^32 for 2^30 < p < 2^31
         T->cumbits[c + 1] = T->cumbits[c] + log2 ((double) p);
     }
     // prefix products as limb strings: row t = p_0 .. p_{t-1}  (t limbs at most)
@@ -264,8 +262,6 @@ static int build_tables (int S, std::shared_ptr<Tables> &out)
     CU (cudaMalloc (&T->ninv, S * sizeof (u32)));
     CU (cudaMalloc (&T->r2, S * sizeof (u32)));
     CU (cudaMalloc (&T->one, S * sizeof (u32)));
-    CU (cudaMalloc (&T->c62, S * sizeof (u32)));
-    CU (cudaMemcpy (T->c62, c62.data (), S * sizeof (u32), cudaMemcpyHostToDevice));
     CU (cudaMalloc (&T->invB, S * sizeof (u32)));
     CU (cudaMalloc (&T->C, (size_t) S * S * sizeof (u32)));
     CU (cudaMalloc (&T->Bpos, (size_t) (S + 4) * T->LB * sizeof (u32)));
@@ -765,9 +761,12 @@ static __host__ __device__ inline int tri_slot_extent (int len, int CH)
     return (len / R) * R + 4 * tri_active_groups (rem, CH);
 }
 // A slot-list entry: target slot of the work vector (the spare row `cnt` when the row has no
-// target) in the low 22 bits, the row of the chunk whose L entry goes there in the high 10.
+// target) in the high 22 bits, the row of the chunk whose L entry goes there in the low 10
+// (one shift gives the slot, one mask the row).
 #define TRI_SLOT_BITS 22
 #define TRI_SLOT_MASK ((1u << TRI_SLOT_BITS) - 1u)
+#define TRI_ROW_BITS 10
+#define TRI_ROW_MASK ((1u << TRI_ROW_BITS) - 1u)
 
 struct StepInfo           // one elimination step of a column: eliminate with column j of L
 {
@@ -864,7 +863,7 @@ __global__ void __launch_bounds__ (256) k_slots (int nU, int CH, int cnt, const 
     {
         const int g = (idx[p] & 31) * G + a, q = idx[p] >> 5;
         const int r = a + G * (p * 32 + lane);
-        if (g < active) out[4 * g + q] = (int32_t) ((u32) slot[p] | ((u32) r << TRI_SLOT_BITS));
+        if (g < active) out[4 * g + q] = (int32_t) (((u32) slot[p] << TRI_ROW_BITS) | (u32) r);
     }
     if (threadIdx.x == 0)
     {
@@ -915,7 +914,6 @@ struct TriArgs
     u32 *out;                // result: channel block cb of right-hand side y at out + cb * out_cb_stride + y * out_y_stride
     size_t out_y_stride, out_cb_stride;      // (one column: out_cb_stride = cnt * CH)
     const u32 *rho, *invrho, *p, *ninv;      // [n][S] pivots and their inverses (Montgomery form)
-    const u32 *c62;          // [S] floor(2^62 / p)
     const int32_t *pos;      // [n] row -> slot
     int x_in_smem;
     int nchunks;             // total pipeline chunks of this launch
@@ -963,6 +961,16 @@ __device__ __forceinline__ void cp_async16 (u32 dst_smem, const void *src)
 template <int OFF> __device__ __forceinline__ void cp_async16_off (u32 dst_smem, const void *src)
 {   // same displacement on both sides, folded into the instruction
     asm volatile ("cp.async.cg.shared.global [%0+%2], [%1+%2], 16;" :: "r"(dst_smem), "l"(src), "n"(OFF) : "memory");
+}
+__device__ __forceinline__ void cp_async16_if (bool on, u32 dst_smem, const void *src)
+{   // predicated in place: a branch would start a new basic block (and ptxas pads the first LDGSTS of a block)
+    asm volatile ("{\n .reg .pred p;\n setp.ne.u32 p, %2, 0;\n @p cp.async.cg.shared.global [%0], [%1], 16;\n}"
+                  :: "r"(dst_smem), "l"(src), "r"((u32) on) : "memory");
+}
+template <int OFF> __device__ __forceinline__ void cp_async16_off_if (bool on, u32 dst_smem, const void *src)
+{
+    asm volatile ("{\n .reg .pred p;\n setp.ne.u32 p, %3, 0;\n @p cp.async.cg.shared.global [%0+%2], [%1+%2], 16;\n}"
+                  :: "r"(dst_smem), "l"(src), "n"(OFF), "r"((u32) on) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit () { asm volatile ("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait () { asm volatile ("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
@@ -1022,14 +1030,6 @@ template <int CPT> __device__ __forceinline__ ChanVec<CPT> sub_mulv (const ChanV
 // IMAD.HI issue at less than half the rate of IMAD (46 / 55 / 113 per SM cycle, measured), and the
 // integer multiplies are what bounds k_trisolve.  y is a PLAIN residue; l in Montgomery form gives
 // the product in Montgomery form.
-__device__ __forceinline__ u32 shoup_companion (u32 y, u32 p, u32 c62)
-{   // floor (y 2^32 / p) exactly: estimate with the reciprocal (low by at most 2), then correct
-    u32 q = (u32) (((u64) y * c62) >> 30);
-    u64 rem = ((u64) y << 32) - (u64) q * p;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) if (rem >= p) { rem -= p; ++q; }
-    return q;
-}
 template <int CPT> __device__ __forceinline__ ChanVec<CPT> sub_mul_shoup (const ChanVec<CPT> &w, const ChanVec<CPT> &l, const ChanVec<CPT> &ny, const ChanVec<CPT> &nyq, const ChanVec<CPT> &p)
 {   // w + l * ny mod p  (ny = -yhat, plain)
     ChanVec<CPT> r;
@@ -1160,7 +1160,7 @@ __device__ __noinline__ void tri_mag_cta (const TriArgs &a, unsigned char *smem_
             for (int e = tid; e < ext; e += NT)
             {
                 const u32 t = reinterpret_cast<const u32 *> (sbp)[e];
-                const int slot = (int) (t & TRI_SLOT_MASK), r = (int) (t >> TRI_SLOT_BITS);
+                const int slot = (int) (t >> TRI_ROW_BITS), r = (int) (t & TRI_ROW_MASK);
                 if (slot != cnt && r < nrows)
                 {
                     const int32_t lm = reinterpret_cast<const int32_t *> (sbp + R * 4)[r];
@@ -1256,23 +1256,22 @@ __global__ void __launch_bounds__ (TRI_THREADS * 4 / CPT, CH == 4 ? 1 : 2) k_tri
                 cp_async16_off<2 * NT * 16> (ldst, lsrc);
                 cp_async16_off<3 * NT * 16> (ldst, lsrc);
             }
-            if (tid < RG) cp_async16 (sb + SM::L_BYTES + (u32) tid * 16, a.slots + (size_t) d0.w + (size_t) tid * 4);
         }
         else
         {
-            if (tid < lp) cp_async16_off<0> (ldst, lsrc);
-            if (tid + NT < lp) cp_async16_off<NT * 16> (ldst, lsrc);
+            cp_async16_off_if<0> (tid < lp, ldst, lsrc);
+            cp_async16_off_if<NT * 16> (tid + NT < lp, ldst, lsrc);
             if (CPT == 4)
             {
-                if (tid + 2 * NT < lp) cp_async16_off<2 * NT * 16> (ldst, lsrc);
-                if (tid + 3 * NT < lp) cp_async16_off<3 * NT * 16> (ldst, lsrc);
+                cp_async16_off_if<2 * NT * 16> (tid + 2 * NT < lp, ldst, lsrc);
+                cp_async16_off_if<3 * NT * 16> (tid + 3 * NT < lp, ldst, lsrc);
             }
-            if (tid < tri_active_groups (nrows, CH))   // one 16-byte group of entries per row group in use
-                cp_async16 (sb + SM::L_BYTES + (u32) tid * 16, a.slots + (size_t) d0.w + (size_t) tid * 4);
         }
-        if ((d1.y & 0x10000u) && tid < CH / 4)
-            cp_async16 (sb + SM::L_BYTES + SM::S_BYTES + (u32) tid * 16,
-                        a.invrho + (size_t) d1.x * S + (size_t) cb * CH + 4 * tid);
+        // one 16-byte group of entries per row group in use; the step's 1/rho_j with its first chunk
+        cp_async16_if (tid < tri_active_groups (nrows, CH), sb + SM::L_BYTES + (u32) tid * 16,
+                       a.slots + (size_t) d0.w + (size_t) tid * 4);
+        cp_async16_if ((d1.y & 0x10000u) && tid < CH / 4, sb + SM::L_BYTES + SM::S_BYTES + (u32) tid * 16,
+                       a.invrho + (size_t) d1.x * S + (size_t) cb * CH + 4 * tid);
     };
 
     // prologue: the first descriptors, then the first chunks, are requested while the vector is initialised
@@ -1321,7 +1320,7 @@ __global__ void __launch_bounds__ (TRI_THREADS * 4 / CPT, CH == 4 ? 1 : 2) k_tri
     // does channel c of the block, the others fetch theirs with shuffles (every thread doing its own
     // four would spend more instructions on a step's set-up than on a short step's updates)
     const int ch1 = (tid & 31) % CH;
-    const u32 p1 = a.p[cb * CH + ch1], ni1 = a.ninv[cb * CH + ch1], c62_1 = a.c62[cb * CH + ch1];
+    const u32 p1 = a.p[cb * CH + ch1], ni1 = a.ninv[cb * CH + ch1];
     unsigned char *xb = (unsigned char *) xs + qc * 4;             // this thread's channels of row 0
     V negy, negyq;                                     // -yhat_j as a plain residue, and its Shoup companion
 #pragma unroll
@@ -1333,7 +1332,11 @@ __global__ void __launch_bounds__ (TRI_THREADS * 4 / CPT, CH == 4 ? 1 : 2) k_tri
         cp_async_wait<TRI_BUFS - 2> ();                // this thread's copies of chunk c have landed
         __syncthreads ();                              // ... and everyone's; chunk c-1 is fully applied
         if (c + TRI_BUFS - 1 < nchunks) issue ((c + TRI_BUFS - 1) % TRI_RING, stage0 + (u32) bi * SM::STAGE);
-        if (tid < 2 && c + 2 * TRI_BUFS - 2 < nchunks) fetch_desc (c + 2 * TRI_BUFS - 2, tid);
+        {   // descriptor 2 BUFS - 2 chunks ahead (two threads, 16 bytes each)
+            const int X = c + 2 * TRI_BUFS - 2;
+            cp_async16_if (tid < 2 && X < nchunks, ring + (u32) (X % TRI_RING) * (u32) sizeof (ChunkInfo) + (u32) (tid & 1) * 16,
+                           (const unsigned char *) (a.chunks + X) + (tid & 1) * 16);
+        }
         cp_async_commit ();
         const u32 sb = stage0 + (u32) bc * SM::STAGE;
         const uint2 jm = lds64 (ring + (u32) (c % TRI_RING) * (u32) sizeof (ChunkInfo) + 16);
@@ -1344,9 +1347,14 @@ __global__ void __launch_bounds__ (TRI_THREADS * 4 / CPT, CH == 4 ? 1 : 2) k_tri
             const u32 wj1 = xs[(size_t) uu * CH + ch1];
             u32 ir1;
             asm volatile ("ld.shared.u32 %0, [%1];" : "=r"(ir1) : "r"(sb + SM::L_BYTES + SM::S_BYTES + (u32) ch1 * 4));
-            const u32 y1 = mont_redc (mont_mul (wj1, ir1, p1, ni1), p1, ni1);      // yhat_j, out of Montgomery form
-            const u32 ny1 = y1 ? p1 - y1 : 0u;
-            const u32 nyq1 = shoup_companion (ny1, p1, c62_1);
+            // -yhat_j as a plain residue and its Shoup companion floor (ny 2^32 / p).  The Montgomery
+            // form nym = ny 2^32 mod p is at hand, ny 2^32 - nym is a multiple of p below p 2^32, and an
+            // exact division by p is a multiplication by 1/p modulo 2^32: the companion is
+            // nym * (-1/p) mod 2^32, one IMAD with the Montgomery constant
+            const u32 ym = mont_mul (wj1, ir1, p1, ni1);                           // yhat_j, Montgomery form
+            const u32 nym = ym ? p1 - ym : 0u;
+            const u32 ny1 = mont_redc (nym, p1, ni1);                              // out of Montgomery form
+            const u32 nyq1 = nym * ni1;
 #pragma unroll
             for (int i = 0; i < CPT; ++i)
             {
@@ -1368,8 +1376,8 @@ __global__ void __launch_bounds__ (TRI_THREADS * 4 / CPT, CH == 4 ? 1 : 2) k_tri
 #pragma unroll
             for (int q = 0; q < 4; ++q)
             {
-                t[q] = (en[q] & TRI_SLOT_MASK) * (CH * 4);             // byte offset of the target row
-                l[q] = ldsv<CPT> (lrow + (en[q] >> TRI_SLOT_BITS) * (CH * 4));
+                t[q] = (en[q] >> TRI_ROW_BITS) * (CH * 4);             // byte offset of the target row
+                l[q] = ldsv<CPT> (lrow + (en[q] & TRI_ROW_MASK) * (CH * 4));
                 if (XS && CPT == 4)
                 {   // predicated in place (no branch, the four rows stay interleaved): rows without
                     // a target neither load nor store
@@ -3503,7 +3511,7 @@ extern "C" int slipcu_factor_spec_launch (slipcu_factor *F, int slot, int k, int
     a.src_y_stride = 0;
     a.out = sl.buf; a.out_y_stride = 0; a.out_cb_stride = (size_t) cnt * CH;
     a.rho = F->rho; a.invrho = F->invrho;
-    a.p = T.p; a.ninv = T.ninv; a.c62 = T.c62; a.pos = w.pos;
+    a.p = T.p; a.ninv = T.ninv; a.pos = w.pos;
     a.nchunks = nchunks; a.upos = d + cnt; a.publish = 0; a.u0 = 0;
     a.mag_on = F->mag_on; a.mag_src = F->mag_on ? F->Amag + F->hAp[col] : nullptr; a.mag_out = sl.mag;
     a.rho_mag = F->rho_mag; a.bound_out = nullptr;
@@ -3574,7 +3582,7 @@ extern "C" int slipcu_factor_column_launch (slipcu_factor *F, int k, int col, in
     a.src_y_stride = 0;
     a.out = hc.base; a.out_y_stride = 0; a.out_cb_stride = (size_t) cnt * CH;
     a.rho = F->rho; a.invrho = F->invrho;
-    a.p = T.p; a.ninv = T.ninv; a.c62 = T.c62; a.pos = w.pos;
+    a.p = T.p; a.ninv = T.ninv; a.pos = w.pos;
     a.nchunks = nchunks; a.upos = hc.rows + cnt; a.publish = 1; a.u0 = first_step;
     a.mag_on = F->mag_on; a.mag_out = hc.mag; a.rho_mag = F->rho_mag; a.bound_out = F->bound;
     size_t smem = 0;
@@ -4146,7 +4154,7 @@ extern "C" int slipcu_solve (slipcu_factor *F, int nrhs, const u32 *blimbs, cons
             a.src_y_stride = (size_t) n;
             a.out = dz; a.out_y_stride = (size_t) n * CH; a.out_cb_stride = cntb * CH;
             a.rho = F->rho; a.invrho = F->invrho;
-            a.p = T.p; a.ninv = T.ninv; a.c62 = T.c62; a.pos = F->mc.pos;
+            a.p = T.p; a.ninv = T.ninv; a.pos = F->mc.pos;
             a.nchunks = fwd_chunks; a.upos = dident; a.publish = 1; a.u0 = 0;
             a.rhs_fastest = 1;
             size_t smem = 0;

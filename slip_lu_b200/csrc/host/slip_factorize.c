@@ -368,7 +368,11 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
             if (start < 32) start = 32 ;
             if (start < min_channels) start = min_channels ;
             start = (start + 31) & ~31 ;
-            if (2 * start <= channels_full) channels = start ;
+            /* Up to 128 channels a column costs the same whatever the count (at most 32 CTAs of 4
+               channels on 148 SMs, reconstruction by k_garner_small out of shared memory), so a
+               fraction buys nothing there and a restart costs an attempt: prob159 (88 channels
+               needed of 97) and six BasisLIB bases were started at 32 and always restarted. */
+            if (2 * start <= channels_full && ((sc && *sc) || channels_full > 128)) channels = start ;
         }
     }
 

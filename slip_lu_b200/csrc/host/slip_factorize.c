@@ -13,6 +13,9 @@
 #include <time.h>
 #include "slip_internal.h"
 
+/* Hadamard channel counts up to this are carried in full from the start (see slip_factorize_driver) */
+#define SLIP_B200_FULL_START_MAX 768
+
 static double now_s (void)
 {
     struct timespec t ;
@@ -368,11 +371,14 @@ SLIP_info slip_factorize_driver (SLIP_sparse *L, SLIP_sparse *U, SLIP_sparse *A,
             if (start < 32) start = 32 ;
             if (start < min_channels) start = min_channels ;
             start = (start + 31) & ~31 ;
-            /* Up to 128 channels a column costs the same whatever the count (at most 32 CTAs of 4
-               channels on 148 SMs, reconstruction by k_garner_small out of shared memory), so a
-               fraction buys nothing there and a restart costs an attempt: prob159 (88 channels
-               needed of 97) and six BasisLIB bases were started at 32 and always restarted. */
-            if (2 * start <= channels_full && ((sc && *sc) || channels_full > 128)) channels = start ;
+            /* Up to a few hundred channels a column costs about the same whatever the count (the
+               CTAs of its channel blocks fit one wave of the 148 SMs), so a fraction buys little
+               there and a restart costs an attempt plus ~10 ms of set-up: prob159 (88 channels
+               needed of 97) and 23 of the 24 BasisLIB bases with Hadamard counts of 64..768
+               channels were started on a fraction and always restarted with (nearly) the full
+               count.  The fraction pays where the bound is far off: NSR8K 64 of 956, the
+               model/newman bases 544-896 of 1900-4300. */
+            if (2 * start <= channels_full && ((sc && *sc) || channels_full > SLIP_B200_FULL_START_MAX)) channels = start ;
         }
     }
 

@@ -276,9 +276,9 @@ def exact_check_integers(lib, system, x):
     return True
 
 
-def gpu_solve_system(lib, name, system, rec, repeat=2, profile=False):
+def gpu_solve_system(lib, name, system, rec, repeat=3, profile=False):
     """analyze + solve_mpq of a named system (triplets); best wall time of `repeat` runs after one
-    warm-up, parity of x and of the row permutation against the reference's recorded digests."""
+    warm-up (the 10-100 ms systems vary by tens of per cent from run to run on a shared box), parity of x and of the row permutation against the reference's recorded digests."""
     from slip_lu_b200 import refmats
     n, I, J, X, b = system
     A = lib.sparse_from_triplets(n, I, J, X)
